@@ -1,0 +1,137 @@
+/* ORACLE — TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Plain-C, scalar, one-stream-at-a-time restatement of the reference hot path
+ * (wexiangis/wmix: src/webrtc.c handle layer + the WebRTC C cores in pkg/webrtc_cut.tar.gz +
+ * src/g711codec.c + the same-format branch of wmix_load_data).  Written from the algorithm,
+ * not copied; every function cites the reference file:line it follows
+ * (R: = /root/reference, T: = inside R:pkg/webrtc_cut.tar.gz).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs
+ * may load this library.  Nothing under wmix_b200/ includes, links or dlopens it.
+ *
+ * Parity pin: tests/test_oracle_pin.py checks every function here against the unmodified
+ * reference compiled by oracle/build_ref.sh (oracle/_ref/libwmix_ref.so), against the
+ * known-answer vectors transcribed from the reference's own unit tests, and against the
+ * committed fixtures under tests/golden/.
+ */
+#ifndef WMIX_ORACLE_H
+#define WMIX_ORACLE_H
+#include <stdint.h>
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- G.711 (R:src/g711codec.c) ---- */
+uint8_t orc_linear2alaw(int pcm);
+uint8_t orc_linear2ulaw(int pcm);
+int16_t orc_alaw2linear(uint8_t code);
+int16_t orc_ulaw2linear(uint8_t code);
+int orc_PCM2G711a(const char *in, char *out, int in_bytes);   /* returns samples */
+int orc_PCM2G711u(const char *in, char *out, int in_bytes);
+int orc_G711a2PCM(const char *in, char *out, int n_codes);    /* returns bytes   */
+int orc_G711u2PCM(const char *in, char *out, int n_codes);
+
+/* ---- mix bus (R:src/wmix.c:1617-1702) ---- */
+int16_t orc_volume_add(int16_t a, int16_t b);
+/* bus[i] = volumeAdd(bus[i], src[i] / rdce) over a ring that wraps at ring_len samples.
+ * Returns the new write position (in samples). */
+uint32_t orc_mix_same_format(int16_t *ring, uint32_t ring_len, uint32_t pos,
+                             const int16_t *src, uint32_t n, uint8_t rdce);
+/* exact int32 conference bus and N-minus-one read-out (not in the reference) */
+void orc_bus_sum(int32_t *bus, const int16_t *pcm, int n_part, int frame);
+void orc_bus_nminus1(int16_t *out, const int32_t *bus, const int16_t *own, int frame);
+
+/* ---- signal-processing primitives (T:webrtc/common_audio/signal_processing) ---- */
+int16_t orc_norm_w32(int32_t a);
+int16_t orc_norm_u32(uint32_t a);
+int16_t orc_size_in_bits(uint32_t n);
+int16_t orc_sat16(int32_t v);
+int32_t orc_div_w32_w16(int32_t num, int16_t den);
+int32_t orc_energy(const int16_t *v, int n, int *scale);
+int32_t orc_sqrt(int32_t value);
+void orc_downsample_by2(const int16_t *in, int len, int16_t *out, int32_t st[8]);
+
+/* ---- VAD (T:webrtc/common_audio/vad) ---- */
+typedef struct {
+    int32_t ds_state[4];
+    int16_t noise_means[12], speech_means[12], noise_stds[12], speech_stds[12];
+    int32_t frame_counter;
+    int16_t over_hang, num_of_speech;
+    int16_t age[96], low_value[96];
+    int16_t mean_value[6];
+    int16_t upper_state[5], lower_state[5], hp_state[4];
+    int16_t over_hang_max_1[3], over_hang_max_2[3], individual[3], total[3];
+    int vad;
+} orc_vad_core;
+void orc_vad_core_init(orc_vad_core *v, int mode);
+int16_t orc_vad_features(orc_vad_core *v, const int16_t *in, int len, int16_t feat[6]);
+int32_t orc_vad_gaussian(int16_t input, int16_t mean, int16_t std, int16_t *delta);
+void orc_vad_downsample(const int16_t *in, int16_t *out, int32_t st[2], int in_len);
+int16_t orc_vad_find_minimum(orc_vad_core *v, int16_t feature, int channel);
+int orc_vad_core_process(orc_vad_core *v, int fs, const int16_t *frame, int len); /* -1/0/1 */
+
+/* handle layer: R:src/webrtc.c:40-167 (mono; chn>1 averaged exactly as the reference) */
+typedef struct {
+    orc_vad_core core;
+    int chn, freq, interval_ms, pkg, reduce;
+} orc_vad;
+orc_vad *orc_vad_init(int chn, int freq, int interval_ms);
+void orc_vad_process(orc_vad *h, int16_t *frame, int frame_num);
+void orc_vad_release(orc_vad *h);
+
+/* ---- AGC (T:webrtc/modules/audio_processing/agc/legacy) ---- */
+typedef struct {
+    int32_t down[8];
+    int16_t hp, counter, log_ratio, mean_long;
+    int32_t var_long;
+    int16_t std_long, mean_short;
+    int32_t var_short;
+    int16_t std_short;
+} orc_agc_vad;
+typedef struct {
+    int32_t cap_slow, cap_fast, gain;
+    int32_t table[32];
+    int16_t gate_prev;
+    orc_agc_vad near_vad;
+    int fs;
+    int16_t comp_db, target_dbfs, analog_target;
+    uint8_t limiter;
+} orc_agc_core;
+int orc_agc_gain_table(int32_t table[32], int16_t comp_db, int16_t target_dbfs,
+                       uint8_t limiter, int16_t analog_target);
+int16_t orc_agc_analog_target(int16_t comp_db);
+void orc_agc_core_init(orc_agc_core *a, int fs, int comp_db);
+int orc_agc_core_set_gain(orc_agc_core *a, int comp_db);
+int16_t orc_agc_process_vad(orc_agc_vad *s, const int16_t *in, int n);
+int orc_agc_core_process(orc_agc_core *a, const int16_t *in, int16_t *out, int n);
+
+typedef struct {
+    orc_agc_core core;
+    int chn, freq, interval_ms, pkg;
+} orc_agc;
+orc_agc *orc_agc_init(int chn, int freq, int interval_ms, int value);
+int orc_agc_process(orc_agc *h, int16_t *in, int16_t *out, int frame_num);
+void orc_agc_addition(orc_agc *h, uint8_t value);
+void orc_agc_release(orc_agc *h);
+
+/* ---- Ooura real FFT as used by NS (T:webrtc/common_audio/fft4g.c) ---- */
+void orc_rdft(int n, int isgn, float *a, int *ip, float *w);
+
+/* ---- NS float core (T:webrtc/modules/audio_processing/ns/ns_core.c) ---- */
+typedef struct orc_ns_core orc_ns_core;
+typedef struct {
+    orc_ns_core *core;
+    int chn, freq, pkg;
+} orc_ns;
+orc_ns *orc_ns_init(int chn, int freq);
+void orc_ns_process(orc_ns *h, const int16_t *in, int16_t *out, int frame_num);
+void orc_ns_release(orc_ns *h);
+/* introspection for tests */
+int orc_ns_block_index(const orc_ns *h);
+const float *orc_ns_prior_model(const orc_ns *h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,104 @@
+"""ctypes loaders for the two checkers: oracle/liboracle.so (our C restatement) and
+oracle/_ref/libwmix_ref.so (the unmodified reference, when it was built in this tree).
+Test infrastructure only."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ORACLE_DIR = os.path.join(ROOT, "oracle")
+
+
+def P(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def fnv1a64(b: bytes) -> str:
+    h = 0xCBF29CE484222325
+    for x in b:
+        h = ((h ^ x) * 0x100000001B3) & 0xFFFFFFFFFFFFFFFF
+    return "%016x" % h
+
+
+_oracle = None
+_ref = None
+
+
+def oracle():
+    global _oracle
+    if _oracle is None:
+        so = os.path.join(ORACLE_DIR, "liboracle.so")
+        srcs = [os.path.join(ORACLE_DIR, f) for f in os.listdir(ORACLE_DIR) if f.endswith((".c", ".h"))]
+        if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+            subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, so])
+        L = C.CDLL(so)
+        for f in ("orc_vad_init", "orc_agc_init", "orc_ns_init"):
+            getattr(L, f).restype = C.c_void_p
+        L.orc_ns_prior_model.restype = C.POINTER(C.c_float)
+        L.orc_mix_same_format.restype = C.c_uint32
+        for f in ("orc_linear2alaw", "orc_linear2ulaw"):
+            getattr(L, f).restype = C.c_uint8
+        for f in ("orc_alaw2linear", "orc_ulaw2linear", "orc_norm_w32", "orc_norm_u32", "orc_size_in_bits",
+                  "orc_sat16", "orc_vad_find_minimum", "orc_vad_features", "orc_agc_process_vad",
+                  "orc_volume_add", "orc_agc_analog_target"):
+            getattr(L, f).restype = C.c_int16
+        _oracle = L
+    return _oracle
+
+
+def ref():
+    """The real reference, or None when oracle/_ref was not built (no /root/reference)."""
+    global _ref
+    if _ref is None:
+        so = os.path.join(ORACLE_DIR, "_ref", "libwmix_ref.so")
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        for f in ("ns_init", "vad_init", "agc_init", "aec_init"):
+            getattr(L, f).restype = C.c_void_p
+        _ref = L
+    return _ref
+
+
+class RefChain:
+    """NS -> AGC -> VAD through the reference's own handle API, one 10 ms frame at a time."""
+
+    def __init__(self, L, freq, ns=True, agc=True, vad=True, gain=5, prefix=""):
+        self.L, self.freq, self.n = L, freq, freq // 100
+        g = lambda name: getattr(L, prefix + name)
+        self.g = g
+        self.ns = C.c_void_p(g("ns_init")(1, freq, None) if prefix == "" else g("ns_init")(1, freq)) if ns else None
+        if prefix == "":
+            self.agc = C.c_void_p(g("agc_init")(1, freq, 10, gain, None)) if agc else None
+            self.vad = C.c_void_p(g("vad_init")(1, freq, 10, None)) if vad else None
+        else:
+            self.agc = C.c_void_p(g("agc_init")(1, freq, 10, gain)) if agc else None
+            self.vad = C.c_void_p(g("vad_init")(1, freq, 10)) if vad else None
+
+    def frame(self, x):
+        x = np.ascontiguousarray(x, dtype=np.int16).copy()
+        if self.ns:
+            self.g("ns_process")(self.ns, P(x), P(x), self.n)
+        if self.agc:
+            self.g("agc_process")(self.agc, P(x), P(x), self.n)
+        if self.vad:
+            self.g("vad_process")(self.vad, P(x), self.n)
+        return x
+
+    def run(self, pcm):
+        pcm = np.asarray(pcm, dtype=np.int16)
+        nf = len(pcm) // self.n
+        out = np.empty(nf * self.n, dtype=np.int16)
+        for i in range(nf):
+            out[i * self.n:(i + 1) * self.n] = self.frame(pcm[i * self.n:(i + 1) * self.n])
+        return out
+
+    def close(self):
+        if self.ns:
+            self.g("ns_release")(self.ns)
+        if self.agc:
+            self.g("agc_release")(self.agc)
+        if self.vad:
+            self.g("vad_release")(self.vad)

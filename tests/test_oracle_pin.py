@@ -1,0 +1,319 @@
+"""Pins oracle/liboracle.so (our C restatement) to
+  (1) the known-answer vectors transcribed from the reference's own unit tests,
+  (2) the unmodified reference compiled here (oracle/_ref/libwmix_ref.so) on seeded inputs,
+  (3) the committed fixtures in tests/golden/ (made by tests/golden/make_golden.py from (2)).
+CPU only."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+from tests._oracle import P, RefChain, fnv1a64, oracle, ref
+from wmix_b200.synth import make_frames
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+need_ref = pytest.mark.skipif(ref() is None, reason="oracle/_ref not built (no /root/reference here)")
+
+
+def i16(*a):
+    return np.array(a, dtype=np.int16)
+
+
+# ---------------------------------------------------------------- G.711
+def _g711_all(L, prefix):
+    x = np.arange(-32768, 32768, dtype=np.int16)
+    ea = np.zeros(65536, np.uint8)
+    eu = np.zeros(65536, np.uint8)
+    c = np.arange(256, dtype=np.uint8)
+    da = np.zeros(256, np.int16)
+    du = np.zeros(256, np.int16)
+    if prefix:
+        assert L.orc_PCM2G711a(P(x), P(ea), 131072) == 65536
+        assert L.orc_PCM2G711u(P(x), P(eu), 131072) == 65536
+        assert L.orc_G711a2PCM(P(c), P(da), 256) == 512
+        assert L.orc_G711u2PCM(P(c), P(du), 256) == 512
+    else:
+        assert L.PCM2G711a(P(x), P(ea), 131072, 0) == 65536
+        assert L.PCM2G711u(P(x), P(eu), 131072, 0) == 65536
+        assert L.G711a2PCM(P(c), P(da), 256, 0) == 512
+        assert L.G711u2PCM(P(c), P(du), 256, 0) == 512
+    return ea, eu, da, du
+
+
+def test_g711_spot_values_from_survey():
+    L = oracle()
+    # SURVEY.md §8c spot values (reference probe)
+    assert [L.orc_linear2alaw(v) for v in (0, -1, -32768, 32767, -8, 255, 256)] == [0xD5, 0x5A, 0x2A, 0xAA, 0x55, 0xDA, 0xC5]
+    assert [L.orc_linear2ulaw(v) for v in (0, -1, -32768, 32767)] == [0xFF, 0x7F, 0x00, 0x80]
+    assert L.orc_alaw2linear(0x2A) == -32256 and L.orc_ulaw2linear(0x00) == -32124
+
+
+def test_g711_golden_hashes():
+    g = json.load(open(os.path.join(GOLDEN, "hashes.json")))
+    ea, eu, da, du = _g711_all(oracle(), "orc_")
+    assert fnv1a64(ea.tobytes()) == g["g711_alaw_enc"]
+    assert fnv1a64(eu.tobytes()) == g["g711_ulaw_enc"]
+    assert fnv1a64(da.tobytes()) == g["g711_alaw_dec"]
+    assert fnv1a64(du.tobytes()) == g["g711_ulaw_dec"]
+
+
+@need_ref
+def test_g711_full_domain_vs_reference():
+    for a, b in zip(_g711_all(oracle(), "orc_"), _g711_all(ref(), "")):
+        assert np.array_equal(a, b)
+
+
+# ---------------------------------------------------------------- mix
+def test_mix_kat_from_survey():
+    L = oracle()
+    ring = i16(15648, -25396)
+    src = i16(-5670, -4786)
+    assert L.orc_mix_same_format(P(ring), 2, 0, P(src), 2, 3) == 0
+    assert ring.tolist() == [13758, -26991]
+    assert L.orc_volume_add(30000, 30000) == 32767 and L.orc_volume_add(-30000, -30000) == -32768
+
+
+@need_ref
+def test_mix_vs_reference_wmix_load_data():
+    R, L = ref(), oracle()
+    rng = np.random.default_rng(7)
+    ring_bytes = R.oracle_ref_wmix_buff_size()
+    n = ring_bytes // 2
+
+    class WPoint(C.Union):
+        _fields_ = [("U8", C.c_void_p)]
+
+    R.wmix_load_data.restype = WPoint
+    R.wmix_load_data.argtypes = [C.c_void_p, WPoint, C.c_uint32, C.c_uint16, C.c_uint8, C.c_uint8, WPoint,
+                                 C.c_uint8, C.POINTER(C.c_uint32)]
+    wm = (C.c_uint8 * R.oracle_ref_sizeof_wmix())()
+    for rdce_mode, reduce in ((1, 1), (3, 0), (3, 3), (16, 2)):
+        ring_ref = (rng.integers(-32768, 32768, n)).astype(np.int16)
+        ring_ref[::7] = 0
+        ring_orc = ring_ref.copy()
+        head_off = (n - 100) * 2
+        R.oracle_ref_wmix_seat(wm, P(ring_ref), ring_bytes, rdce_mode, 0, 0)
+        src = rng.integers(-32768, 32768, 480).astype(np.int16)
+        src[::5] = 0
+        tick = C.c_uint32(0)
+        head = WPoint(ring_ref.ctypes.data + head_off)
+        out = R.wmix_load_data(wm, WPoint(src.ctypes.data), src.nbytes, R.oracle_ref_wmix_freq(), 1, 16, head,
+                               reduce, C.byref(tick))
+        d = 1 if reduce == rdce_mode else rdce_mode
+        pos = L.orc_mix_same_format(P(ring_orc), n, head_off // 2, P(src), len(src), d)
+        assert np.array_equal(ring_ref, ring_orc)
+        assert out.U8 - ring_ref.ctypes.data == pos * 2
+
+
+# ---------------------------------------------------------------- SPL primitives (reference unit-test KATs)
+def test_spl_kats():
+    L = oracle()
+    # T:.../signal_processing/signal_processing_unittest.cc:92-157
+    assert L.orc_norm_w32(111121) == 14 and L.orc_norm_u32(111121) == 15 and L.orc_size_in_bits(111121) == 17
+    assert L.orc_norm_w32(0) == 0 and L.orc_norm_w32(-1) == 31 and L.orc_norm_w32(-2147483648) == 0
+    assert L.orc_sqrt(1134567892) == 33700
+    assert L.orc_div_w32_w16(117, -5) == -23 and L.orc_div_w32_w16(5, 0) == 0x7FFFFFFF
+    assert L.orc_sat16(40000) == 32767 and L.orc_sat16(-40000) == -32768
+
+
+@need_ref
+def test_spl_vs_reference_random():
+    R, L = ref(), oracle()
+    rng = np.random.default_rng(3)
+    R.WebRtcSpl_Sqrt.restype = C.c_int32
+    for v in list(rng.integers(-2**31, 2**31, 4000)) + [0, 1, 2, 3, 2**31 - 1, -2**31, 73632]:
+        assert L.orc_sqrt(int(v)) == R.WebRtcSpl_Sqrt(int(v)), v
+    for n in (5, 10, 20, 40, 80):
+        for scale in (1, 100, 32767):
+            v = (rng.integers(-scale, scale + 1, n)).astype(np.int16)
+            if scale == 32767:
+                v[0] = -32768
+            s1, s2 = C.c_int(0), C.c_int(0)
+            assert L.orc_energy(P(v), n, C.byref(s1)) == R.WebRtcSpl_Energy(P(v), n, C.byref(s2))
+            assert s1.value == s2.value
+    st1 = np.zeros(8, np.int32)
+    st2 = np.zeros(8, np.int32)
+    for _ in range(50):
+        x = rng.integers(-32768, 32768, 8).astype(np.int16)
+        o1 = np.zeros(4, np.int16)
+        o2 = np.zeros(4, np.int16)
+        L.orc_downsample_by2(P(x), 8, P(o1), P(st1))
+        R.WebRtcSpl_DownsampleBy2(P(x), 8, P(o2), P(st2))
+        assert np.array_equal(o1, o2) and np.array_equal(st1, st2)
+
+
+# ---------------------------------------------------------------- VAD (reference unit-test KATs)
+class VadCore(C.Structure):
+    _fields_ = [("ds_state", C.c_int32 * 4), ("noise_means", C.c_int16 * 12), ("speech_means", C.c_int16 * 12),
+                ("noise_stds", C.c_int16 * 12), ("speech_stds", C.c_int16 * 12), ("frame_counter", C.c_int32),
+                ("over_hang", C.c_int16), ("num_of_speech", C.c_int16), ("age", C.c_int16 * 96),
+                ("low_value", C.c_int16 * 96), ("mean_value", C.c_int16 * 6), ("upper_state", C.c_int16 * 5),
+                ("lower_state", C.c_int16 * 5), ("hp_state", C.c_int16 * 4), ("oh1", C.c_int16 * 3),
+                ("oh2", C.c_int16 * 3), ("individual", C.c_int16 * 3), ("total", C.c_int16 * 3), ("vad", C.c_int)]
+
+
+def _speech_ii(n):
+    return (np.arange(n, dtype=np.int64) ** 2).astype(np.int16)  # (int16_t)(i*i)
+
+
+def test_vad_filterbank_kat():
+    # T:.../vad/vad_filterbank_unittest.cc:26-90
+    L = oracle()
+    ref_energy = {80: 48, 160: 11, 240: 11}
+    ref_feat = {80: [1213, 759, 587, 462, 434, 272], 160: [1479, 1385, 1291, 1200, 1103, 1099],
+                240: [1732, 1692, 1681, 1629, 1436, 1436]}
+    speech = _speech_ii(240)
+    core = VadCore()
+    L.orc_vad_core_init(C.byref(core), 0)  # one init, state carried across the three lengths
+    for n in (80, 160, 240):
+        feat = np.zeros(6, np.int16)
+        assert L.orc_vad_features(C.byref(core), P(speech), n, P(feat)) == ref_energy[n]
+        assert feat.tolist() == ref_feat[n]
+    core = VadCore()
+    L.orc_vad_core_init(C.byref(core), 0)
+    for n in (80, 160, 240):
+        feat = np.zeros(6, np.int16)
+        x = np.zeros(240, np.int16)
+        assert L.orc_vad_features(C.byref(core), P(x), n, P(feat)) == 0
+        assert feat.tolist() == [368, 368, 272, 176, 176, 176]
+    for n in (80, 160, 240):
+        core = VadCore()
+        L.orc_vad_core_init(C.byref(core), 0)
+        feat = np.zeros(6, np.int16)
+        x = np.ones(240, np.int16)
+        assert L.orc_vad_features(C.byref(core), P(x), n, P(feat)) == 0
+        assert feat.tolist() == [368, 368, 272, 176, 176, 176]
+
+
+def test_vad_gmm_kat():
+    # T:.../vad/vad_gmm_unittest.cc:21-42
+    L = oracle()
+    d = C.c_int16(0)
+    for (x, m, s), (p, dd) in {(0, 0, 128): (1048576, 0), (16, 128, 128): (1048576, 0), (-16, -128, 128): (1048576, 0),
+                               (59, 0, 128): (1024, 7552), (75, 128, 128): (1024, 7552), (-75, -128, 128): (1024, -7552),
+                               (105, 0, 128): (0, 13440)}.items():
+        assert L.orc_vad_gaussian(x, m, s, C.byref(d)) == p and d.value == dd
+
+
+def test_vad_sp_kat():
+    # T:.../vad/vad_sp_unittest.cc:24-73
+    L = oracle()
+    zeros = np.zeros(960, np.int16)
+    data = _speech_ii(960)
+    out = np.zeros(480, np.int16)
+    st = np.zeros(2, np.int32)
+    L.orc_vad_downsample(P(zeros), P(out), P(st), 960)
+    assert st.tolist() == [0, 0] and not out.any()
+    L.orc_vad_downsample(P(data), P(out), P(st), 960)
+    assert st.tolist() == [207, 2270]
+    ref_min = [1600, 720, 509, 512, 532, 552, 570, 588, 606, 624, 642, 659, 675, 691, 707, 723, 1600, 544, 502, 522,
+               542, 561, 579, 597, 615, 633, 651, 667, 683, 699, 715, 731]
+    core = VadCore()
+    L.orc_vad_core_init(C.byref(core), 0)
+    for i in range(16):
+        v = 500 * (i + 1)
+        for ch in range(6):
+            assert L.orc_vad_find_minimum(C.byref(core), v, ch) == ref_min[i]
+            assert L.orc_vad_find_minimum(C.byref(core), 12000, ch) == ref_min[i + 16]
+        core.frame_counter += 1
+
+
+def test_vad_core_kat():
+    # T:.../vad/vad_core_unittest.cc:57-104 — ONE InitCore, then zeros -> 0 and (i*i) -> 1 for every
+    # valid (rate, length) pair in kFrameLengths order, state carried from call to call.  The 48 kHz
+    # calls of the original are left out (that resampler is not on wmix's path and has its own state).
+    L = oracle()
+    lengths = [80, 120, 160, 240, 320, 480, 640, 960, 1440]
+    speech = _speech_ii(1440)
+    zeros = np.zeros(1440, np.int16)
+    valid = lambda fs, n: n in (fs // 100, fs // 50, fs * 3 // 100)
+    core = VadCore()
+    L.orc_vad_core_init(C.byref(core), 0)
+    for x, want in ((zeros, 0), (speech, 1)):
+        for n in lengths:
+            for fs in (8000, 16000, 32000):
+                if valid(fs, n):
+                    assert L.orc_vad_core_process(C.byref(core), fs, P(x), n) == want, (fs, n, want)
+    assert L.orc_vad_core_process(C.byref(core), 9999, P(zeros), 160) == -1
+    assert L.orc_vad_core_process(C.byref(core), 16000, P(zeros), 161) == -1
+    assert L.orc_vad_core_process(C.byref(core), 16000, None, 160) == -1
+
+
+# ---------------------------------------------------------------- AGC
+def test_agc_gain_table_kat():
+    # CalculateGainTable(comp=5,target=0,limiter=0,analogTarget=6)
+    L = oracle()
+    tab = np.zeros(32, np.int32)
+    assert L.orc_agc_analog_target(5) == 6
+    assert L.orc_agc_gain_table(P(tab), 5, 0, 0, 6) == 0
+    assert tab[:4].tolist() == [74652, 91180, 113772, 126764] and tab[28:].tolist() == [130796] * 4
+
+
+@need_ref
+def test_agc_gain_table_all_gains_vs_reference():
+    R, L = ref(), oracle()
+    for comp in range(0, 91):
+        for lim in (0, 1):
+            at = L.orc_agc_analog_target(comp)
+            a = np.zeros(32, np.int32)
+            b = np.zeros(32, np.int32)
+            ra = L.orc_agc_gain_table(P(a), comp, 0, lim, at)
+            rb = R.WebRtcAgc_CalculateGainTable(P(b), comp, 0, lim, at)
+            assert ra == rb and np.array_equal(a, b), (comp, lim)
+
+
+# ---------------------------------------------------------------- streams vs the reference
+def _streams(freq, n_streams, n_ticks, seed):
+    return make_frames(n_streams, freq, 0, n_ticks, seed=seed)  # [T, S, L]
+
+
+@need_ref
+@pytest.mark.parametrize("freq", [8000, 16000])
+@pytest.mark.parametrize("stage", ["vad", "agc", "ns", "chain"])
+def test_stage_vs_reference(freq, stage):
+    R, L = ref(), oracle()
+    S, T = (6, 700) if stage in ("ns", "chain") else (8, 400)
+    x = _streams(freq, S, T, seed=11)
+    kw = dict(ns=stage in ("ns", "chain"), agc=stage in ("agc", "chain"), vad=stage in ("vad", "chain"))
+    for s in range(S):
+        pcm = np.ascontiguousarray(x[:, s, :]).reshape(-1)
+        a = RefChain(R, freq, **kw)
+        b = RefChain(L, freq, prefix="orc_", **kw)
+        ya, yb = a.run(pcm), b.run(pcm)
+        a.close()
+        b.close()
+        assert np.array_equal(ya, yb), (stage, freq, s, int(np.abs(ya.astype(int) - yb).max()))
+
+
+@need_ref
+def test_config1_wav_vs_reference():
+    """BASELINE config 1: NS on audio/1x8000.wav through src/webrtc.c, then AGC(5) and VAD(10 ms) in place."""
+    wav = "/root/reference/audio/1x8000.wav"
+    if not os.path.exists(wav):
+        pytest.skip("fixture wav not on this box")
+    pcm = np.fromfile(wav, dtype=np.int16, offset=44)
+    pcm = pcm[: len(pcm) // 80 * 80]
+    a = RefChain(ref(), 8000)
+    b = RefChain(oracle(), 8000, prefix="orc_")
+    ya, yb = a.run(pcm), b.run(pcm)
+    assert np.array_equal(ya, yb)
+    g = json.load(open(os.path.join(GOLDEN, "hashes.json")))
+    assert fnv1a64(yb.tobytes()) == g["config1_ns_agc_vad"]
+
+
+def test_golden_streams():
+    """Committed fixtures: first/last samples + hash of reference output on seeded streams."""
+    g = json.load(open(os.path.join(GOLDEN, "hashes.json")))
+    for key, spec in g["streams"].items():
+        freq, stage, S, T, seed = spec["freq"], spec["stage"], spec["n_streams"], spec["n_ticks"], spec["seed"]
+        x = _streams(freq, S, T, seed)
+        kw = dict(ns=stage in ("ns", "chain"), agc=stage in ("agc", "chain"), vad=stage in ("vad", "chain"))
+        outs = []
+        for s in range(S):
+            c = RefChain(oracle(), freq, prefix="orc_", **kw)
+            outs.append(c.run(np.ascontiguousarray(x[:, s, :]).reshape(-1)))
+            c.close()
+        y = np.stack(outs)
+        assert fnv1a64(y.tobytes()) == spec["hash"], key
