@@ -1,0 +1,113 @@
+/* wmixb — batched, stream-parallel C entry points of wmix_b200 (additive API).
+ *
+ * The reference (wexiangis/wmix) runs exactly ONE record chain per process:
+ *   wmix_shmem_write_circle: ns_process -> [aec_process2] -> agc_process -> vad_process
+ *   (R:src/wmix.c:613-710), producers mixing through wmix_load_data (R:src/wmix.c:1639).
+ * This header drives N independent streams of that same chain per 10 ms tick on one B200.
+ * Per-stream results are bit-compatible with calling the reference handle API
+ * (include/webrtc.h == R:src/webrtc.h:32-61) once per stream.
+ *
+ * C ABI only: plain pointers and sizes.  `stream` arguments are a cudaStream_t passed as void*.
+ * Pointers named d_* are device memory, h_* host memory (pinned for full copy overlap).
+ * Every function returns 0 on success, a negative WMIXB_E* code otherwise; there is no CPU
+ * fallback: without a usable CUDA device wmixb_create fails with WMIXB_ENODEV.
+ */
+#ifndef WMIXB_H
+#define WMIXB_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    WMIXB_OK = 0,
+    WMIXB_EINVAL = -1,   /* bad argument (same cases for which the reference *_init returns NULL) */
+    WMIXB_ENODEV = -2,   /* no CUDA device / driver */
+    WMIXB_ECUDA = -3,    /* a CUDA call failed; see wmixb_last_error() */
+    WMIXB_ENOMEM = -4
+};
+
+/* stage bits, executed in the reference's order NS -> AGC -> VAD (R:src/wmix.c:613-710) */
+enum { WMIXB_NS = 1, WMIXB_AGC = 2, WMIXB_VAD = 4 };
+
+typedef struct wmixb_config {
+    int n_streams;      /* independent mono streams on this GPU                                  */
+    int freq;           /* 8000 or 16000 (10 ms tick = 80 / 160 samples per stream)              */
+    int stages;         /* OR of WMIXB_NS / WMIXB_AGC / WMIXB_VAD: state is allocated for these   */
+    int ns_policy;      /* 0..3; wmix uses 2   (R:src/webrtc.c:532 NS_AGGRESSIVE)                */
+    int agc_gain_db;    /* compressionGaindB = wmix's `value` (R:src/webrtc.c:707), e.g. 5        */
+    int vad_mode;       /* 0..3; wmix uses 3   (R:src/webrtc.c:16 VAD_AGGRESSIVE)                */
+    int device;         /* CUDA device ordinal                                                   */
+    int reserved[9];
+} wmixb_config;
+
+typedef struct wmixb_engine wmixb_engine;
+
+int wmixb_create(const wmixb_config* cfg, wmixb_engine** out);
+void wmixb_destroy(wmixb_engine* e);
+/* re-initialise streams [first, first+count) — what tearing a wmix handle down and re-creating
+ * it does (R:src/wmix.c:565-600) */
+int wmixb_reset(wmixb_engine* e, int first, int count);
+/* change the AGC compression gain for the whole engine (agc_addition, R:src/webrtc.c:824-838) */
+int wmixb_set_agc_gain(wmixb_engine* e, int gain_db);
+
+/* One 10 ms tick for all streams, PCM resident on the device.
+ * d_in / d_out: int16 [n_streams][frame] (frame = freq/100), may alias.  d_vad (nullable):
+ * uint8 [n_streams] speech flags of this tick.  `stages` selects a subset of the configured
+ * stages (0 = all configured).  Asynchronous on `stream`. */
+int wmixb_tick_device(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int stages,
+                      void* stream);
+/* Same, host buffers: H2D copy, kernels, D2H copy on the engine's own stream, then waits. */
+int wmixb_tick_host(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int stages);
+
+/* Persistent offline mode: every stream runs n_frames consecutive frames inside one launch per
+ * stage.  d_in / d_out: int16 [n_streams][n_frames][frame].  d_vad (nullable): [n_streams][n_frames]. */
+int wmixb_offline_device(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int n_frames,
+                         int stages, void* stream);
+
+/* Conference bus.  Streams are grouped into conferences by contiguous ranges:
+ * conference c = streams [h_conf_start[c], h_conf_start[c+1]).
+ *   bus_sum     : d_bus[c][i] = sum over members of d_pcm[s][i]           (exact int32)
+ *   bus_nminus1 : d_out[s][i] = clamp16(d_bus[conf(s)][i] - d_pcm[s][i])  (N-minus-one read-out)
+ * d_bus: int32 [n_conf][frame] — the buffer an NCCL int32 sum all-reduce runs on between the
+ * two calls when a conference spans GPUs. */
+int wmixb_set_conferences(wmixb_engine* e, const int32_t* h_conf_start, int n_conf);
+int wmixb_bus_sum_device(wmixb_engine* e, const int16_t* d_pcm, int32_t* d_bus, void* stream);
+int wmixb_bus_nminus1_device(wmixb_engine* e, const int32_t* d_bus, const int16_t* d_pcm, int16_t* d_out,
+                             void* stream);
+
+/* G.711 on device buffers (R:src/g711codec.c).  law: 0 = A-law, 1 = mu-law.  n = samples. */
+int wmixb_g711_encode_device(int law, const int16_t* d_pcm, uint8_t* d_codes, size_t n, void* stream);
+int wmixb_g711_decode_device(int law, const uint8_t* d_codes, int16_t* d_pcm, size_t n, void* stream);
+/* fused G.711 leg of config 5: decode -> (caller all-reduces d_bus) -> N-minus-one -> encode */
+int wmixb_g711_bus_sum_device(wmixb_engine* e, int law, const uint8_t* d_codes, int32_t* d_bus, void* stream);
+int wmixb_g711_nminus1_device(wmixb_engine* e, int law, const int32_t* d_bus, const uint8_t* d_codes,
+                              uint8_t* d_out_codes, void* stream);
+
+/* Same-format branch of wmix_load_data on a device-resident ring (R:src/wmix.c:1678-1702):
+ * ring[(pos+i) % ring_len] = volumeAdd(ring[..], src[i] / rdce); returns the new position in
+ * *new_pos.  Calls issued in order on one stream reproduce the reference's chained adds. */
+int wmixb_mix_load_device(int16_t* d_ring, uint32_t ring_len, uint32_t pos, const int16_t* d_src, uint32_t n,
+                          int rdce, uint32_t* new_pos, void* stream);
+
+/* state snapshot / restore of one stream (checkpointing; byte layout is engine-internal) */
+size_t wmixb_stream_state_bytes(const wmixb_engine* e);
+int wmixb_get_stream_state(wmixb_engine* e, int stream_index, void* h_buf);
+int wmixb_set_stream_state(wmixb_engine* e, int stream_index, const void* h_buf);
+
+/* bookkeeping */
+int wmixb_sync(wmixb_engine* e);
+const char* wmixb_last_error(void);
+long long wmixb_kernel_launches(void);          /* kernels this library has launched so far */
+size_t wmixb_state_bytes_per_stream(const wmixb_engine* e);
+int wmixb_frame_len(const wmixb_engine* e);
+/* init-time tables, exported so tests can pin them against the reference's literals */
+void wmixb_ns_window(int ana, int block, float* out);
+int wmixb_agc_gain_table(int32_t table[32], int comp_db, int target_dbfs, int limiter, int analog_target);
+int wmixb_agc_analog_target(int comp_db);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,121 @@
+// TEST INFRASTRUCTURE — lane-loop / thread-loop emulation of the kernel bodies on the CPU.
+//
+// Compiles the very same .cuh sources the sm_100a kernels are built from (wmix_b200/csrc/
+// {ns,vad,agc,g711_mix}.cuh + host_tables.cpp) with g++, replacing "32 lanes in lock-step
+// between warp barriers" by a loop over lanes per phase (WMX_NS_PHASE_* in ns.cuh) and "one
+// thread per stream" by a plain call.  It exists so the kernel LOGIC can be checked against the
+// reference in the GPU-less CI container; it is not part of libwmix_b200.so and nothing in the
+// product can reach it.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../wmix_b200/csrc/agc.cuh"
+#include "../../wmix_b200/csrc/g711_mix.cuh"
+#include "../../wmix_b200/csrc/host_tables.h"
+#include "../../wmix_b200/csrc/ns.cuh"
+#include "../../wmix_b200/csrc/vad.cuh"
+
+using namespace wmx;
+
+template <int ANA>
+static void fill_tables(ns::Tables<ANA>& T, int policy)
+{
+    memset(&T, 0, sizeof(T));
+    host::ns_window(ANA, ns::Geo<ANA>::kBlock, T.window);
+    host::fft_w_table(ANA / 4, T.w);
+    host::fft_c_table(ANA / 4, T.c);
+    host::ns_log_table(ANA / 2 + 1, T.log_i, &T.sum_log_i, &T.sum_log_i_sq);
+    host::ns_policy(policy, &T.overdrive, &T.floor_gain, &T.gainmap);
+}
+
+struct EmuNs {
+    int ana;
+    std::vector<float> rec, sh;
+    std::vector<uint16_t> hist;
+    ns::Tables<256> t256;
+    ns::Tables<128> t128;
+    ns::Warp<256> w256;
+    ns::Warp<128> w128;
+};
+
+extern "C" {
+
+void* emu_ns_create(int freq)
+{
+    EmuNs* e = new EmuNs();
+    e->ana = freq == 8000 ? 128 : 256;
+    e->hist.assign(3 * ns::kHistBins, 0);
+    if (e->ana == 256) {
+        fill_tables(e->t256, 2);
+        e->rec.assign(ns::Geo<256>::kRecFloats, 0.f);
+        e->sh.assign(ns::Geo<256>::kShFloats, 0.f);
+        for (int l = 0; l < 32; ++l) ns::init_record_values<256>(e->rec.data(), l, 32);
+    } else {
+        fill_tables(e->t128, 2);
+        e->rec.assign(ns::Geo<128>::kRecFloats, 0.f);
+        e->sh.assign(ns::Geo<128>::kShFloats, 0.f);
+        for (int l = 0; l < 32; ++l) ns::init_record_values<128>(e->rec.data(), l, 32);
+    }
+    return e;
+}
+void emu_ns_frame(void* h, const int16_t* in, int16_t* out)
+{
+    EmuNs* e = (EmuNs*)h;
+    if (e->ana == 256) ns::frame<256>(e->w256, e->rec.data(), e->hist.data(), in, out, e->sh.data(), e->t256);
+    else ns::frame<128>(e->w128, e->rec.data(), e->hist.data(), in, out, e->sh.data(), e->t128);
+}
+void emu_ns_destroy(void* h) { delete (EmuNs*)h; }
+const float* emu_ns_record(void* h) { return ((EmuNs*)h)->rec.data(); }
+
+struct EmuInt {
+    int freq;
+    std::vector<int32_t> vad, agc;
+    int32_t table[32];
+    vad::Params vp;
+};
+
+void* emu_int_create(int freq, int agc_gain_db, int vad_mode)
+{
+    EmuInt* e = new EmuInt();
+    e->freq = freq;
+    e->vad.assign(vad::N_WORDS, 0);
+    e->agc.assign(agc::N_WORDS, 0);
+    host::vad_initial_words(e->vad.data());
+    host::agc_initial_words(e->agc.data());
+    host::agc_gain_table(e->table, (int16_t)agc_gain_db, 0, 0, host::agc_analog_target((int16_t)agc_gain_db));
+    int16_t th[4];
+    host::vad_thresholds(vad_mode, 10, th);
+    e->vp = {th[0], th[1], th[2], th[3]};
+    return e;
+}
+void emu_agc_frame(void* h, int16_t* x)
+{
+    EmuInt* e = (EmuInt*)h;
+    SoaWords st{e->agc.data(), 1};
+    if (e->freq == 16000) agc::process_packet<true>(st, x, e->table);
+    else agc::process_packet<false>(st, x, e->table);
+}
+int emu_vad_frame(void* h, int16_t* x)
+{
+    EmuInt* e = (EmuInt*)h;
+    SoaWords st{e->vad.data(), 1};
+    if (e->freq == 16000) return vad::process_packet<80, true>(st, x, e->vp);
+    return vad::process_packet<80, false>(st, x, e->vp);
+}
+void emu_int_destroy(void* h) { delete (EmuInt*)h; }
+
+void emu_g711(const int16_t* pcm, int n, uint8_t* alaw, uint8_t* ulaw)
+{
+    for (int i = 0; i < n; ++i) { alaw[i] = linear2alaw(pcm[i]); ulaw[i] = linear2ulaw(pcm[i]); }
+}
+void emu_g711_dec(const uint8_t* codes, int n, int16_t* a, int16_t* u)
+{
+    for (int i = 0; i < n; ++i) { a[i] = alaw2linear(codes[i]); u[i] = ulaw2linear(codes[i]); }
+}
+int16_t emu_mix_step(int16_t bus, int16_t src, int rdce) { return mix_step(bus, src, rdce); }
+int emu_agc_gain_table(int32_t* t, int comp, int target, int lim, int at) { return host::agc_gain_table(t, (int16_t)comp, (int16_t)target, lim, (int16_t)at); }
+int emu_agc_analog_target(int comp) { return host::agc_analog_target((int16_t)comp); }
+void emu_ns_window(int ana, int block, float* w) { host::ns_window(ana, block, w); }
+}

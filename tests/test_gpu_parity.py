@@ -1,0 +1,375 @@
+"""GPU parity tests (run on the B200 box): every call goes through the C-ABI of
+libwmix_b200.so; the checkers are oracle/liboracle.so (C restatement) and, when it travelled
+with the snapshot, oracle/_ref/libwmix_ref.so (the unmodified reference).
+
+Bar: bit-exact for G.711 / mix / VAD / AGC.  NS is float: the kernel keeps the reference's
+operation order (no FMA, serial sums, double transcendentals), so the expectation is also
+bit-exact; the stated tolerance, should CUDA's libm ever round one double log/exp/pow/tanh
+differently from glibc, is max-abs <= 2 LSB and >= 99.9 % identical samples per stream."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import wmix_b200  # noqa: E402
+from tests._oracle import P, RefChain, fnv1a64, oracle, ref  # noqa: E402
+from wmix_b200 import AGC, NS, VAD  # noqa: E402
+from wmix_b200.synth import make_frames  # noqa: E402
+
+DEV = "cuda:0"
+NS_MAX_ABS = 2
+NS_MIN_EQUAL = 0.999
+
+
+def checkers():
+    out = [("oracle", oracle(), "orc_")]
+    if ref() is not None:
+        out.append(("reference", ref(), ""))
+    return out
+
+
+def run_gpu(x, freq, stages, gain=5, offline=0):
+    """x: int16 [T, S, L] -> (out [T, S, L], vad [T, S])"""
+    T, S, L = x.shape
+    eng = wmix_b200.Engine(S, freq, stages=stages, agc_gain_db=gain)
+    out = np.empty_like(x)
+    vad = np.zeros((T, S), np.uint8)
+    if offline:
+        assert T % offline == 0
+        for t0 in range(0, T, offline):
+            blk = np.ascontiguousarray(x[t0:t0 + offline].transpose(1, 0, 2))       # [S, K, L]
+            d_in = torch.from_numpy(blk).to(DEV)
+            d_out = torch.empty_like(d_in)
+            d_v = torch.zeros((S, offline), dtype=torch.uint8, device=DEV)
+            eng.offline_device(d_in, d_out, offline, d_v)
+            out[t0:t0 + offline] = d_out.cpu().numpy().transpose(1, 0, 2)
+            vad[t0:t0 + offline] = d_v.cpu().numpy().T
+    else:
+        d_in = torch.empty((S, L), dtype=torch.int16, device=DEV)
+        d_v = torch.zeros((S,), dtype=torch.uint8, device=DEV)
+        for t in range(T):
+            d_in.copy_(torch.from_numpy(x[t]))
+            eng.tick_device(d_in, d_in, d_v)                                          # in place, like wmix
+            out[t] = d_in.cpu().numpy()
+            vad[t] = d_v.cpu().numpy()
+    eng.close()
+    return out, vad
+
+
+def run_checker(L, prefix, x, freq, stages, gain=5):
+    T, S, _ = x.shape
+    kw = dict(ns=bool(stages & NS), agc=bool(stages & AGC), vad=bool(stages & VAD), gain=gain)
+    out = np.empty_like(x)
+    for s in range(S):
+        c = RefChain(L, freq, prefix=prefix, **kw)
+        for t in range(T):
+            out[t, s] = c.frame(x[t, s])
+        c.close()
+    return out
+
+
+# ---------------------------------------------------------------- G.711
+def test_g711_full_domain_device():
+    L = oracle()
+    x = np.arange(-32768, 32768, dtype=np.int16)
+    d_x = torch.from_numpy(x).to(DEV)
+    for law, enc, dec in ((0, L.orc_linear2alaw, L.orc_alaw2linear), (1, L.orc_linear2ulaw, L.orc_ulaw2linear)):
+        d_c = torch.empty(65536, dtype=torch.uint8, device=DEV)
+        wmix_b200.g711_encode(law, d_x, d_c, 65536)
+        want = np.array([enc(int(v)) for v in x], np.uint8)
+        assert np.array_equal(d_c.cpu().numpy(), want)
+        codes = np.arange(256, dtype=np.uint8)
+        d_codes = torch.from_numpy(codes).to(DEV)
+        d_p = torch.empty(256, dtype=torch.int16, device=DEV)
+        wmix_b200.g711_decode(law, d_codes, d_p, 256)
+        assert np.array_equal(d_p.cpu().numpy(), np.array([dec(int(c)) for c in codes], np.int16))
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hashes.json")))
+    d_c = torch.empty(65536, dtype=torch.uint8, device=DEV)
+    wmix_b200.g711_encode(0, d_x, d_c, 65536)
+    assert fnv1a64(d_c.cpu().numpy().tobytes()) == g["g711_alaw_enc"]
+    wmix_b200.g711_encode(1, d_x, d_c, 65536)
+    assert fnv1a64(d_c.cpu().numpy().tobytes()) == g["g711_ulaw_enc"]
+
+
+def test_g711_ragged_lengths_and_dropin_api():
+    lib = wmix_b200.lib()
+    L = oracle()
+    rng = np.random.default_rng(1)
+    for n in (1, 7, 8, 9, 80, 161, 1000):
+        x = rng.integers(-32768, 32768, n).astype(np.int16)
+        got = np.zeros(n, np.uint8)
+        want = np.zeros(n, np.uint8)
+        assert lib.PCM2G711a(x.ctypes.data, got.ctypes.data, 2 * n, 0) == n
+        assert L.orc_PCM2G711a(P(x), P(want), 2 * n) == n
+        assert np.array_equal(got, want)
+        assert lib.PCM2G711u(x.ctypes.data, got.ctypes.data, 2 * n, 0) == n
+        L.orc_PCM2G711u(P(x), P(want), 2 * n)
+        assert np.array_equal(got, want)
+        back = np.zeros(n, np.int16)
+        wback = np.zeros(n, np.int16)
+        assert lib.G711a2PCM(want.ctypes.data, back.ctypes.data, n, 0) == 2 * n
+        L.orc_G711a2PCM(P(want), P(wback), n)
+        assert np.array_equal(back, wback)
+    assert lib.PCM2G711a(None, None, 0, 0) == -1          # the reference's only argument check
+    # round trip is idempotent after one pass: enc(dec(enc(x))) == enc(x)
+    x = torch.from_numpy(rng.integers(-32768, 32768, 1 << 20).astype(np.int16)).to(DEV)
+    c1 = torch.empty(1 << 20, dtype=torch.uint8, device=DEV)
+    c2 = torch.empty_like(c1)
+    p = torch.empty_like(x)
+    for law in (0, 1):
+        wmix_b200.g711_encode(law, x, c1, 1 << 20)
+        wmix_b200.g711_decode(law, c1, p, 1 << 20)
+        wmix_b200.g711_encode(law, p, c2, 1 << 20)
+        if law == 1:
+            assert torch.equal(c1, c2)
+        else:
+            # A-law of -1..-8 is the one place the reference is not idempotent (its -pcm-8 quirk)
+            m = (x >= 0) | (x < -8)
+            assert torch.equal(c1[m], c2[m])
+
+
+# ---------------------------------------------------------------- mix
+def test_mix_load_ring_vs_oracle():
+    L = oracle()
+    rng = np.random.default_rng(2)
+    n = 16000
+    ring = rng.integers(-32768, 32768, n).astype(np.int16)
+    ring[::7] = 0
+    d_ring = torch.from_numpy(ring.copy()).to(DEV)
+    pos_g = pos_o = n - 100
+    for rdce in (1, 3, 16, 2):
+        src = rng.integers(-32768, 32768, 480).astype(np.int16)
+        src[::5] = 0
+        d_src = torch.from_numpy(src).to(DEV)
+        pos_g = wmix_b200.mix_load(d_ring, n, pos_g, d_src, len(src), rdce)
+        pos_o = L.orc_mix_same_format(P(ring), n, pos_o, P(src), len(src), rdce)
+        assert pos_g == pos_o
+    assert np.array_equal(d_ring.cpu().numpy(), ring)
+    # survey KAT
+    d_r = torch.tensor([15648, -25396], dtype=torch.int16, device=DEV)
+    d_s = torch.tensor([-5670, -4786], dtype=torch.int16, device=DEV)
+    wmix_b200.mix_load(d_r, 2, 0, d_s, 2, 3)
+    assert d_r.cpu().tolist() == [13758, -26991]
+
+
+@pytest.mark.parametrize("sizes", [[1, 2, 3, 58], [1024] * 3, [16] * 40, [5000]])
+def test_conference_bus(sizes):
+    rng = np.random.default_rng(3)
+    S, Lf = sum(sizes), 160
+    starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    pcm = rng.integers(-32768, 32768, (S, Lf)).astype(np.int16)
+    eng = wmix_b200.Engine(S, 16000, stages=0)
+    eng.set_conferences(starts)
+    d_pcm = torch.from_numpy(pcm).to(DEV)
+    d_bus = torch.empty((len(sizes), Lf), dtype=torch.int32, device=DEV)
+    d_out = torch.empty_like(d_pcm)
+    eng.bus_sum(d_pcm, d_bus)
+    eng.bus_nminus1(d_bus, d_pcm, d_out)
+    bus = np.stack([pcm[starts[c]:starts[c + 1]].astype(np.int64).sum(0) for c in range(len(sizes))])
+    assert np.array_equal(d_bus.cpu().numpy(), bus.astype(np.int32))
+    want = np.clip(np.repeat(bus, sizes, axis=0) - pcm, -32768, 32767).astype(np.int16)
+    assert np.array_equal(d_out.cpu().numpy(), want)
+    # oracle cross-check on the first conference
+    L = oracle()
+    n0 = sizes[0]
+    b0 = np.zeros(Lf, np.int32)
+    L.orc_bus_sum(P(b0), P(np.ascontiguousarray(pcm[:n0])), n0, Lf)
+    assert np.array_equal(b0, bus[0].astype(np.int32))
+    eng.close()
+
+
+def test_g711_conference_leg():
+    rng = np.random.default_rng(4)
+    sizes = [16] * 32
+    S, Lf = sum(sizes), 80
+    starts = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    codes = rng.integers(0, 256, (S, Lf)).astype(np.uint8)
+    L = oracle()
+    for law, dec, enc in ((0, L.orc_alaw2linear, L.orc_linear2alaw), (1, L.orc_ulaw2linear, L.orc_linear2ulaw)):
+        lut = np.array([dec(c) for c in range(256)], np.int16)
+        pcm = lut[codes]
+        eng = wmix_b200.Engine(S, 8000, stages=0)
+        eng.set_conferences(starts)
+        d_codes = torch.from_numpy(codes).to(DEV)
+        d_bus = torch.empty((len(sizes), Lf), dtype=torch.int32, device=DEV)
+        d_out = torch.empty_like(d_codes)
+        eng.g711_bus_sum(law, d_codes, d_bus)
+        eng.g711_nminus1(law, d_bus, d_codes, d_out)
+        bus = np.stack([pcm[starts[c]:starts[c + 1]].astype(np.int64).sum(0) for c in range(len(sizes))])
+        lin = np.clip(np.repeat(bus, sizes, axis=0) - pcm, -32768, 32767).astype(np.int16)
+        want = np.array([enc(int(v)) for v in lin.reshape(-1)], np.uint8).reshape(S, Lf)
+        assert np.array_equal(d_out.cpu().numpy(), want)
+        eng.close()
+
+
+# ---------------------------------------------------------------- the record chain
+@pytest.mark.parametrize("freq", [16000, 8000])
+@pytest.mark.parametrize("stages,name", [(VAD, "vad"), (AGC, "agc"), (AGC | VAD, "agc+vad")])
+def test_integer_stages_bit_exact(freq, stages, name):
+    x = make_frames(130, freq, 0, 320, seed=31)
+    got, _ = run_gpu(x, freq, stages)
+    for cname, L, prefix in checkers():
+        want = run_checker(L, prefix, x[:, :40], freq, stages)
+        assert np.array_equal(got[:, :40], want), (name, cname)
+    # every stream checked against the oracle on a shorter run is covered by the cohorts above;
+    # streams 40.. exercise the partial last CTA / SoA padding: compare with the oracle too
+    want = run_checker(oracle(), "orc_", x[:120, 120:], freq, stages)
+    assert np.array_equal(got[:120, 120:], want)
+
+
+def _ns_compare(got, want, what):
+    diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    per_stream_equal = (diff == 0).mean(axis=(0, 2))
+    info = dict(max_abs=int(diff.max()), mismatching=int((diff > 0).sum()), total=int(diff.size),
+                worst_stream_equal=float(per_stream_equal.min()))
+    print("[ns parity %s] %s" % (what, info))
+    assert diff.max() <= NS_MAX_ABS, info
+    assert per_stream_equal.min() >= NS_MIN_EQUAL, info
+    return info
+
+
+@pytest.mark.parametrize("freq", [16000, 8000])
+def test_ns_vs_checkers(freq):
+    # 650 ticks: passes frame 50 (start-up model off), 200 (gain map on) and 500 (first re-learn)
+    x = make_frames(70, freq, 0, 650, seed=41)
+    got, _ = run_gpu(x, freq, NS)
+    for cname, L, prefix in checkers():
+        want = run_checker(L, prefix, x[:, :24], freq, NS)
+        info = _ns_compare(got[:, :24], want, "%s %d Hz" % (cname, freq))
+        if info["mismatching"] == 0:
+            print("  -> bit-exact")
+
+
+def test_full_chain_16k_and_vad_flags():
+    x = make_frames(66, 16000, 0, 560, seed=51)
+    got, vad = run_gpu(x, 16000, NS | AGC | VAD)
+    want = run_checker(oracle(), "orc_", x[:, :16], 16000, NS | AGC | VAD)
+    diff = np.abs(got[:, :16].astype(np.int32) - want)
+    print("[chain parity] max_abs=%d mismatching=%d/%d" % (diff.max(), (diff > 0).sum(), diff.size))
+    assert diff.max() <= 2 * NS_MAX_ABS and (diff == 0).mean() >= NS_MIN_EQUAL
+    assert vad[:, 1].sum() == 0              # the all-zero cohort never triggers
+    assert vad[300:, 2].mean() > 0.9         # the full-scale square does
+
+
+def test_config1_wav_fixture_hash():
+    """BASELINE config 1 through the GPU: committed hash of the reference's output on audio/1x8000.wav
+    is only checkable where the wav is; elsewhere the seeded-stream fixtures stand in."""
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hashes.json")))
+    for key in ("vad_16000", "agc_16000", "vad_8000", "agc_8000"):
+        spec = g["streams"][key]
+        stages = {"vad": VAD, "agc": AGC}[spec["stage"]]
+        x = make_frames(spec["n_streams"], spec["freq"], 0, spec["n_ticks"], seed=spec["seed"])
+        got, _ = run_gpu(x, spec["freq"], stages)
+        y = np.ascontiguousarray(got.transpose(1, 0, 2)).reshape(spec["n_streams"], -1)
+        assert fnv1a64(y.tobytes()) == spec["hash"], key
+    for key in ("ns_16000", "chain_16000", "ns_8000", "chain_8000"):
+        spec = g["streams"][key]
+        stages = NS if spec["stage"] == "ns" else NS | AGC | VAD
+        x = make_frames(spec["n_streams"], spec["freq"], 0, spec["n_ticks"], seed=spec["seed"])
+        got, _ = run_gpu(x, spec["freq"], stages)
+        y = np.ascontiguousarray(got.transpose(1, 0, 2)).reshape(spec["n_streams"], -1)
+        ok = fnv1a64(y.tobytes()) == spec["hash"]
+        print("[golden %s] %s" % (key, "bit-exact" if ok else "differs (within NS tolerance is checked elsewhere)"))
+        assert np.array_equal(y[:, :8], np.array(spec["head"], np.int16))
+
+
+def test_wav_config1_when_available():
+    wav = "/root/reference/audio/1x8000.wav"
+    if not os.path.exists(wav):
+        pytest.skip("reference wav is not on the GPU box (by design)")
+
+
+def test_offline_mode_equals_ticks():
+    x = make_frames(40, 16000, 0, 60, seed=61)
+    a, va = run_gpu(x, 16000, NS | AGC | VAD)
+    b, vb = run_gpu(x, 16000, NS | AGC | VAD, offline=20)
+    assert np.array_equal(a, b) and np.array_equal(va, vb)
+
+
+def test_snapshot_restore_and_reset():
+    x = make_frames(8, 16000, 0, 80, seed=71)
+    S, L = 8, 160
+    eng = wmix_b200.Engine(S, 16000)
+    d = torch.empty((S, L), dtype=torch.int16, device=DEV)
+    for t in range(40):
+        d.copy_(torch.from_numpy(x[t]))
+        eng.tick_device(d, d)
+    snap = [eng.get_state(s) for s in range(S)]
+    tail = []
+    for t in range(40, 80):
+        d.copy_(torch.from_numpy(x[t]))
+        eng.tick_device(d, d)
+        tail.append(d.cpu().numpy().copy())
+    for s in range(S):
+        eng.set_state(s, snap[s])
+    for t in range(40, 80):
+        d.copy_(torch.from_numpy(x[t]))
+        eng.tick_device(d, d)
+        assert np.array_equal(d.cpu().numpy(), tail[t - 40])
+    # reset == fresh engine
+    eng.reset()
+    fresh, _ = run_gpu(x[:20], 16000, NS | AGC | VAD)
+    for t in range(20):
+        d.copy_(torch.from_numpy(x[t]))
+        eng.tick_device(d, d)
+        assert np.array_equal(d.cpu().numpy(), fresh[t])
+    eng.close()
+
+
+def test_dropin_handle_api():
+    lib = wmix_b200.lib()
+    L = oracle()
+    x = make_frames(4, 16000, 0, 60, seed=81)[:, 0, :]
+    ns = lib.ns_init(1, 16000, None)
+    agc = lib.agc_init(1, 16000, 10, 5, None)
+    vad = lib.vad_init(1, 16000, 10, None)
+    assert ns and agc and vad
+    chain = RefChain(L, 16000, prefix="orc_")
+    for t in range(60):
+        f = x[t].copy()
+        lib.ns_process(ns, f.ctypes.data, f.ctypes.data, 160)
+        assert lib.agc_process(agc, f.ctypes.data, f.ctypes.data, 160) == 0
+        lib.vad_process(vad, f.ctypes.data, 160)
+        assert np.array_equal(f, chain.frame(x[t]))
+    lib.agc_addition(agc, 9)
+    lib.ns_release(ns)
+    lib.agc_release(agc)
+    lib.vad_release(vad)
+    # error behaviour of the reference: unsupported rates give NULL
+    assert not lib.ns_init(1, 44100, None) and not lib.vad_init(1, 48000, 10, None)
+    assert not lib.agc_init(1, 12000, 10, 5, None) and not lib.aec_init(1, 32000, 10, None)
+
+
+def test_full_size_replication_property():
+    """Config 3 size (100k streams): stream s is fed the input of stream s % 64, so its output
+    must equal that of stream s % 64 at every tick — checks indexing/occupancy paths at scale."""
+    S, base, T = 100_000, 64, 12
+    x = make_frames(base, 16000, 0, T, seed=91)
+    eng = wmix_b200.Engine(S, 16000)
+    d = torch.empty((S, 160), dtype=torch.int16, device=DEV)
+    small, _ = run_gpu(x, 16000, NS | AGC | VAD)
+    for t in range(T):
+        d.copy_(torch.from_numpy(x[t]).to(DEV).repeat((S + base - 1) // base, 1)[:S])
+        eng.tick_device(d, d)
+        y = d.view(-1)[: (S // base) * base * 160].view(S // base, base, 160)
+        assert bool((y == y[0:1]).all())
+        assert np.array_equal(y[0].cpu().numpy(), small[t])
+    eng.close()
+
+
+def test_errors_are_loud():
+    with pytest.raises(wmix_b200.WmixError):
+        wmix_b200.Engine(16, 44100)
+    with pytest.raises(wmix_b200.WmixError):
+        wmix_b200.Engine(0, 16000)
+    eng = wmix_b200.Engine(4, 16000, stages=NS)
+    d = torch.zeros((4, 160), dtype=torch.int16, device=DEV)
+    with pytest.raises(wmix_b200.WmixError):
+        eng.tick_device(d, d, stages=AGC)
+    eng.close()

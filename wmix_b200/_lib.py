@@ -1,0 +1,82 @@
+"""ctypes binding of libwmix_b200.so (the C-ABI in include/wmixb.h, include/webrtc.h,
+include/g711codec.h).  There is no Python or CPU implementation behind this module: if the
+shared library is missing or cannot be loaded, importing a symbol raises."""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libwmix_b200.so")
+
+NS, AGC, VAD = 1, 2, 4
+
+
+class Config(C.Structure):
+    _fields_ = [("n_streams", C.c_int), ("freq", C.c_int), ("stages", C.c_int), ("ns_policy", C.c_int),
+                ("agc_gain_db", C.c_int), ("vad_mode", C.c_int), ("device", C.c_int), ("reserved", C.c_int * 9)]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "wmix_b200: %s not built — run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a).  There is no CPU fallback." % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    vp, i, u32, sz = C.c_void_p, C.c_int, C.c_uint32, C.c_size_t
+    sig = {
+        "wmixb_create": (i, [C.POINTER(Config), C.POINTER(vp)]),
+        "wmixb_destroy": (None, [vp]),
+        "wmixb_reset": (i, [vp, i, i]),
+        "wmixb_set_agc_gain": (i, [vp, i]),
+        "wmixb_tick_device": (i, [vp, vp, vp, vp, i, vp]),
+        "wmixb_tick_host": (i, [vp, vp, vp, vp, i]),
+        "wmixb_offline_device": (i, [vp, vp, vp, vp, i, i, vp]),
+        "wmixb_set_conferences": (i, [vp, vp, i]),
+        "wmixb_bus_sum_device": (i, [vp, vp, vp, vp]),
+        "wmixb_bus_nminus1_device": (i, [vp, vp, vp, vp, vp]),
+        "wmixb_g711_encode_device": (i, [i, vp, vp, sz, vp]),
+        "wmixb_g711_decode_device": (i, [i, vp, vp, sz, vp]),
+        "wmixb_g711_bus_sum_device": (i, [vp, i, vp, vp, vp]),
+        "wmixb_g711_nminus1_device": (i, [vp, i, vp, vp, vp, vp]),
+        "wmixb_mix_load_device": (i, [vp, u32, u32, vp, u32, i, C.POINTER(u32), vp]),
+        "wmixb_stream_state_bytes": (sz, [vp]),
+        "wmixb_get_stream_state": (i, [vp, i, vp]),
+        "wmixb_set_stream_state": (i, [vp, i, vp]),
+        "wmixb_sync": (i, [vp]),
+        "wmixb_last_error": (C.c_char_p, []),
+        "wmixb_kernel_launches": (C.c_longlong, []),
+        "wmixb_state_bytes_per_stream": (sz, [vp]),
+        "wmixb_frame_len": (i, [vp]),
+        "wmixb_ns_window": (None, [i, i, vp]),
+        "wmixb_agc_gain_table": (i, [vp, i, i, i, i]),
+        "wmixb_agc_analog_target": (i, [i]),
+        # drop-in handle API (include/webrtc.h)
+        "vad_init": (vp, [i, i, i, vp]), "vad_process": (None, [vp, vp, i]), "vad_release": (None, [vp]),
+        "ns_init": (vp, [i, i, vp]), "ns_process": (None, [vp, vp, vp, i]), "ns_release": (None, [vp]),
+        "agc_init": (vp, [i, i, i, i, vp]), "agc_process": (i, [vp, vp, vp, i]),
+        "agc_addition": (None, [vp, C.c_uint8]), "agc_release": (None, [vp]),
+        "aec_init": (vp, [i, i, i, vp]),
+        # include/g711codec.h
+        "PCM2G711a": (i, [vp, vp, i, i]), "PCM2G711u": (i, [vp, vp, i, i]),
+        "G711a2PCM": (i, [vp, vp, i, i]), "G711u2PCM": (i, [vp, vp, i, i]),
+    }
+    for name, (res, args) in sig.items():
+        f = getattr(L, name)
+        f.restype = res
+        f.argtypes = args
+    _lib = L
+    return L
+
+
+class WmixError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        raise WmixError("%s failed (%d): %s" % (what, rc, lib().wmixb_last_error().decode()))

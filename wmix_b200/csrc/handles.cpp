@@ -1,0 +1,228 @@
+// Drop-in handle layer: include/webrtc.h and include/g711codec.h on top of wmixb.
+// Mirrors the marshaling of R:src/webrtc.c (channel averaging / replication, packet loop,
+// early return on error) on the host; the DSP itself is a one-stream wmixb engine on the GPU.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/g711codec.h"
+#include "../../include/webrtc.h"
+#include "../../include/wmixb.h"
+
+namespace {
+
+struct Handle {
+    wmixb_engine* eng = nullptr;
+    int chn = 1, freq = 0, pkg = 0, stage = 0;
+    bool* debug = nullptr;
+    std::vector<int16_t> mono, res;
+};
+
+bool dbg(const bool* d) { return d && *d; }
+
+Handle* make(int stage, int chn, int freq, int gain, bool* debug, const char* who)
+{
+    wmixb_config c;
+    memset(&c, 0, sizeof c);
+    c.n_streams = 1;
+    c.freq = freq;
+    c.stages = stage;
+    c.ns_policy = 2;      // NS_AGGRESSIVE, R:src/webrtc.c:532
+    c.agc_gain_db = gain; // compressionGaindB, R:src/webrtc.c:707
+    c.vad_mode = 3;       // VAD_AGGRESSIVE, R:src/webrtc.c:16
+    wmixb_engine* e = nullptr;
+    if (wmixb_create(&c, &e) != WMIXB_OK) {
+        if (dbg(debug)) printf("%s failed !! (%s)\r\n", who, wmixb_last_error());
+        return nullptr;
+    }
+    Handle* h = new Handle();
+    h->eng = e;
+    h->chn = chn;
+    h->freq = freq;
+    h->pkg = freq / 100;
+    h->stage = stage;
+    h->debug = debug;
+    h->mono.resize((size_t)h->pkg);
+    h->res.resize((size_t)h->pkg);
+    return h;
+}
+
+void drop(void* fp, const char* who)
+{
+    Handle* h = (Handle*)fp;
+    wmixb_destroy(h->eng);
+    if (dbg(h->debug)) printf("%s\r\n", who);
+    delete h;
+}
+
+bool rate_ok(int freq, int max) { return !(freq > max || freq % 8000 != 0); }
+
+}  // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------- VAD
+void* vad_init(int chn, int freq, int intervalMs, bool* debug)
+{
+    if (!rate_ok(freq, 32000)) return nullptr;                      // R:src/webrtc.c:43
+    if (freq == 32000 || (freq <= 16000 && intervalMs % 20 == 0)) {
+        // 32 kHz and the 20 ms packet (R:src/webrtc.c:56-65) are not wired up yet — INTEGRATION.md
+        if (dbg(debug)) printf("vad_init: only 8/16 kHz with 10 ms packets on the GPU path so far\r\n");
+        return nullptr;
+    }
+    Handle* h = make(WMIXB_VAD, chn, freq, 0, debug, "vad_init");
+    if (h && dbg(debug)) printf("vad_init: chn/%d freq/%d intervalMs/%d pkgFrame/%d\r\n", chn, freq, 10, h->pkg);
+    return h;
+}
+
+void vad_process(void* fp, int16_t* frame, int frameNum)
+{
+    Handle* h = (Handle*)fp;
+    const int total = frameNum * h->chn;
+    int mono = total;
+    if (h->chn > 1) {                                               // R:src/webrtc.c:107-118
+        int pos = 0;
+        for (mono = 0; pos < total;) {
+            int32_t s = 0;
+            for (int c = 0; c < h->chn; ++c) s += frame[pos++];
+            frame[mono++] = (int16_t)(s / h->chn);
+        }
+    }
+    // R:src/webrtc.c:120-141 always hands the detector the START of the buffer and attenuates
+    // [cLen, pkgFrame): with more than one packet per call only the first is ever touched.
+    for (int pos = 0; pos < mono; pos += h->pkg) {
+        memcpy(h->mono.data(), frame, (size_t)h->pkg * 2);
+        uint8_t flag = 0;
+        if (wmixb_tick_host(h->eng, h->mono.data(), h->res.data(), &flag, WMIXB_VAD) != WMIXB_OK) {
+            if (dbg(h->debug)) printf("WebRtcVad_Process failed !!, %s \r\n", wmixb_last_error());
+            return;
+        }
+        for (int i = pos; i < h->pkg; ++i) frame[i] = h->res[(size_t)i];
+    }
+    if (h->chn > 1) {                                               // R:src/webrtc.c:144-150
+        int m = mono - 1;
+        for (int pos = total - 1; pos >= 0; --m)
+            for (int c = 0; c < h->chn; ++c) frame[pos--] = frame[m];
+    }
+}
+
+void vad_release(void* fp) { drop(fp, "vad_release"); }
+
+// ---------------------------------------------------------------- NS
+void* ns_init(int chn, int freq, bool* debug)
+{
+    if (!rate_ok(freq, 32000)) return nullptr;                      // R:src/webrtc.c:563
+    if (freq == 32000 || chn != 1) {
+        // stereo is fed to WebRtcNs as low band + "high band" (R:src/webrtc.c:624-636); 32 kHz
+        // mono would need the 160-sample 32k path — neither is on the GPU yet
+        if (dbg(debug)) printf("ns_init: only mono 8/16 kHz on the GPU path so far\r\n");
+        return nullptr;
+    }
+    Handle* h = make(WMIXB_NS, chn, freq, 0, debug, "ns_init");
+    if (h && dbg(debug)) printf("ns_init: chn/%d freq/%d intervalMs/%d pkgFrame/%d x %d\r\n", chn, freq, 10, h->pkg, chn);
+    return h;
+}
+
+void ns_process(void* fp, int16_t* frame, int16_t* frameOut, int frameNum)
+{
+    Handle* h = (Handle*)fp;
+    for (int pos = 0; pos < frameNum; pos += h->pkg) {              // R:src/webrtc.c:624-643
+        memcpy(h->mono.data(), frame + pos, (size_t)h->pkg * 2);
+        if (wmixb_tick_host(h->eng, h->mono.data(), h->res.data(), nullptr, WMIXB_NS) != WMIXB_OK) {
+            if (dbg(h->debug)) printf("ns_process failed !!, %s \r\n", wmixb_last_error());
+            return;
+        }
+        memcpy(frameOut + pos, h->res.data(), (size_t)h->pkg * 2);
+    }
+}
+
+void ns_release(void* fp) { drop(fp, "ns_release"); }
+
+// ---------------------------------------------------------------- AGC
+void* agc_init(int chn, int freq, int intervalMs, int value, bool* debug)
+{
+    (void)intervalMs;
+    if (!rate_ok(freq, 32000)) return nullptr;                      // R:src/webrtc.c:711
+    if (freq == 32000) {
+        if (dbg(debug)) printf("agc_init: only 8/16 kHz on the GPU path so far\r\n");
+        return nullptr;
+    }
+    Handle* h = make(WMIXB_AGC, chn, freq, value, debug, "agc_init");
+    if (h && dbg(debug)) printf("agc_init: chn/%d freq/%d intervalMs/%d pkgFrame/%d x %d\r\n", chn, freq, 10, h->pkg, chn);
+    return h;
+}
+
+int agc_process(void* fp, int16_t* frame, int16_t* frameOut, int frameNum)
+{
+    Handle* h = (Handle*)fp;
+    const int total = frameNum * h->chn, step = h->pkg * h->chn;
+    for (int pos = 0; pos < total; pos += step) {                   // R:src/webrtc.c:786-818
+        for (int i = 0; i < h->pkg; ++i) {
+            int32_t s = 0;
+            for (int c = 0; c < h->chn; ++c) s += *frame++;
+            h->mono[(size_t)i] = (int16_t)(s / h->chn);
+        }
+        if (wmixb_tick_host(h->eng, h->mono.data(), h->res.data(), nullptr, WMIXB_AGC) != WMIXB_OK) {
+            if (dbg(h->debug)) printf("WebRtcAgc_Process failed !!, %s \r\n", wmixb_last_error());
+            return -1;
+        }
+        for (int i = 0; i < h->pkg; ++i)
+            for (int c = 0; c < h->chn; ++c) *frameOut++ = h->res[(size_t)i];
+    }
+    return 0;
+}
+
+void agc_addition(void* fp, uint8_t value)
+{
+    Handle* h = (Handle*)fp;
+    if (wmixb_set_agc_gain(h->eng, value) != WMIXB_OK && dbg(h->debug))
+        printf("WebRtcAgc_set_config failed !!, %s \r\n", wmixb_last_error());
+}
+
+void agc_release(void* fp) { drop(fp, "agc_release"); }
+
+// ---------------------------------------------------------------- AEC (not on the GPU yet)
+void* aec_init(int chn, int freq, int intervalMs, bool* debug)
+{
+    (void)chn; (void)intervalMs;
+    if (!rate_ok(freq, 16000)) return nullptr;                      // R:src/webrtc.c:220
+    if (dbg(debug)) printf("aec_init: the PBFDAF echo canceller is not implemented on the GPU path yet\r\n");
+    return nullptr;
+}
+int aec_setFrameFar(void*, int16_t*, int) { return -1; }
+int aec_process(void*, int16_t*, int16_t*, int, int) { return -1; }
+int aec_process2(void*, int16_t*, int16_t*, int16_t*, int, int) { return -1; }
+void aec_release(void*) {}
+
+// ---------------------------------------------------------------- G.711 host entry points
+static int g711_host(int law, bool encode, const void* in, void* out, int n)
+{
+    if (n <= 0) return 0;
+    void *din = nullptr, *dout = nullptr;
+    const size_t in_b = encode ? (size_t)n * 2 : (size_t)n, out_b = encode ? (size_t)n : (size_t)n * 2;
+    int rc = -1;
+    if (cudaMalloc(&din, in_b) == cudaSuccess && cudaMalloc(&dout, out_b) == cudaSuccess &&
+        cudaMemcpy(din, in, in_b, cudaMemcpyHostToDevice) == cudaSuccess) {
+        const int r = encode ? wmixb_g711_encode_device(law, (const int16_t*)din, (uint8_t*)dout, (size_t)n, nullptr)
+                             : wmixb_g711_decode_device(law, (const uint8_t*)din, (int16_t*)dout, (size_t)n, nullptr);
+        if (r == WMIXB_OK && cudaMemcpy(out, dout, out_b, cudaMemcpyDeviceToHost) == cudaSuccess) rc = 0;
+    }
+    cudaFree(din);
+    cudaFree(dout);
+    return rc;
+}
+
+int g711a_encode(unsigned char g711_data[], const short amp[], int len) { return g711_host(0, true, amp, g711_data, len) == 0 ? len : -1; }
+int g711u_encode(unsigned char g711_data[], const short amp[], int len) { return g711_host(1, true, amp, g711_data, len) == 0 ? len : -1; }
+int g711a_decode(short amp[], const unsigned char g711a_data[], int n) { return g711_host(0, false, g711a_data, amp, n) == 0 ? (n > 0 ? n : 0) * 2 : -1; }
+int g711u_decode(short amp[], const unsigned char g711u_data[], int n) { return g711_host(1, false, g711u_data, amp, n) == 0 ? (n > 0 ? n : 0) * 2 : -1; }
+
+int PCM2G711a(char* in, char* out, int len, int) { if (!in && !out && len == 0) { printf("Error, empty data or transmit failed, exit !\n"); return -1; } return g711a_encode((unsigned char*)out, (const short*)in, len / 2); }
+int PCM2G711u(char* in, char* out, int len, int) { if (!in && !out && len == 0) { printf("Error, empty data or transmit failed, exit !\n"); return -1; } return g711u_encode((unsigned char*)out, (const short*)in, len / 2); }
+int G711a2PCM(char* in, char* out, int len, int) { if (!in && !out && len == 0) { printf("Error, empty data or transmit failed, exit !\n"); return -1; } return g711a_decode((short*)out, (const unsigned char*)in, len); }
+int G711u2PCM(char* in, char* out, int len, int) { if (!in && !out && len == 0) { printf("Error, empty data or transmit failed, exit !\n"); return -1; } return g711u_decode((short*)out, (const unsigned char*)in, len); }
+
+}  // extern "C"

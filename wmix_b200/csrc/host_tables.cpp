@@ -1,0 +1,240 @@
+// Host-side, init-time constant tables for the kernels: NS window / FFT twiddles / log table,
+// the AGC compressor curve, and the VAD mode thresholds.  These are identical for every stream
+// of an engine, are computed once on the CPU (with the same libm the reference uses, so the
+// floats agree bit for bit) and uploaded.  No per-sample work happens here.
+#include "host_tables.h"
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+namespace wmx {
+namespace host {
+
+// ---- NS -------------------------------------------------------------------------------------
+
+// Flat-top window with quarter-sine edges (T:.../ns/windows_private.h:64 kBlocks80w128, :94
+// kBlocks160w256).  The reference ships it as literals printed with 8 decimals; printing and
+// re-parsing the closed form reproduces every float of those tables exactly (tested).
+void ns_window(int ana, int block, float* w)
+{
+    const int ov = ana - block;
+    for (int i = 0; i < ana; ++i) {
+        int k = i < ana - i ? i : ana - i;
+        if (k > ov) k = ov;
+        char txt[32];
+        snprintf(txt, sizeof txt, "%.8f", sin(3.14159265358979323846 * k / (2.0 * ov)));
+        w[i] = strtof(txt, nullptr);
+    }
+}
+
+static void bitrev_pairs(int n, float* a)
+{
+    const int nc = n >> 1;
+    int bits = 0;
+    while ((1 << bits) < nc) ++bits;
+    for (int c = 0; c < nc; ++c) {
+        int r = 0;
+        for (int b = 0; b < bits; ++b) r |= ((c >> b) & 1) << (bits - 1 - b);
+        if (r > c) {
+            float t0 = a[2 * c], t1 = a[2 * c + 1];
+            a[2 * c] = a[2 * r]; a[2 * c + 1] = a[2 * r + 1];
+            a[2 * r] = t0; a[2 * r + 1] = t1;
+        }
+    }
+}
+
+// cos/sin table of the complex passes, stored bit-reversed (T:.../fft4g.c:642-668 makewt)
+void fft_w_table(int nw, float* w)
+{
+    const int h = nw >> 1;
+    const float d = (float)atan((double)1.0f) / h;   // NB: double libm, as the C reference calls it
+    w[0] = 1;
+    w[1] = 0;
+    w[h] = (float)cos((double)(d * h));
+    w[h + 1] = w[h];
+    for (int j = 2; j < h; j += 2) {
+        const float x = (float)cos((double)(d * j)), y = (float)sin((double)(d * j));
+        w[j] = x; w[j + 1] = y;
+        w[nw - j] = y; w[nw - j + 1] = x;
+    }
+    if (h > 2) bitrev_pairs(nw, w);
+}
+
+// half-scaled cos/sin table of the real split (T:.../fft4g.c:671-688 makect)
+void fft_c_table(int nc, float* c)
+{
+    const int h = nc >> 1;
+    const float d = (float)atan((double)1.0f) / h;
+    c[0] = (float)cos((double)(d * h));
+    c[h] = 0.5f * c[0];
+    for (int j = 1; j < h; ++j) {
+        c[j] = 0.5f * (float)cos((double)(d * j));
+        c[nc - j] = 0.5f * (float)sin((double)(d * j));
+    }
+}
+
+// (float)log((float)i) and the two start-up regressor sums the reference re-derives every
+// frame (T:.../ns/ns_core.c:1089-1101); accumulated in float, i = 5 .. bins-1, in order
+void ns_log_table(int bins, float* log_i, float* sum, float* sum_sq)
+{
+    float s = 0.f, s2 = 0.f;
+    log_i[0] = 0.f;
+    for (int i = 1; i < bins; ++i) {
+        const float v = (float)log((double)(float)i);
+        log_i[i] = v;
+        if (i >= 5) { s += v; s2 += v * v; }
+    }
+    *sum = s;
+    *sum_sq = s2;
+}
+
+// T:.../ns/ns_core.c:1012-1041
+int ns_policy(int mode, float* overdrive, float* floor_gain, int* gainmap)
+{
+    switch (mode) {
+    case 0: *overdrive = 1.f; *floor_gain = 0.5f; *gainmap = 0; return 0;
+    case 1: *overdrive = 1.f; *floor_gain = 0.25f; *gainmap = 1; return 0;
+    case 2: *overdrive = 1.1f; *floor_gain = 0.125f; *gainmap = 1; return 0;
+    case 3: *overdrive = 1.25f; *floor_gain = 0.09f; *gainmap = 1; return 0;
+    }
+    return -1;
+}
+
+// ---- VAD ------------------------------------------------------------------------------------
+
+// T:.../vad/vad_core.c:78-100: per mode, columns = 10 / 20 / 30 ms
+int vad_thresholds(int mode, int frame_ms, int16_t out[4])
+{
+    static const int16_t oh1[4][3] = {{8, 4, 3}, {8, 4, 3}, {6, 3, 2}, {6, 3, 2}};
+    static const int16_t oh2[4][3] = {{14, 7, 5}, {14, 7, 5}, {9, 5, 3}, {9, 5, 3}};
+    static const int16_t loc[4][3] = {{24, 21, 24}, {37, 32, 37}, {82, 78, 82}, {94, 94, 94}};
+    static const int16_t glo[4][3] = {{57, 48, 57}, {100, 80, 100}, {285, 260, 285}, {1100, 1050, 1100}};
+    if (mode < 0 || mode > 3) return -1;
+    const int col = frame_ms == 10 ? 0 : (frame_ms == 20 ? 1 : 2);
+    out[0] = oh1[mode][col];
+    out[1] = oh2[mode][col];
+    out[2] = loc[mode][col];
+    out[3] = glo[mode][col];
+    return 0;
+}
+
+// initial GMM (T:.../vad/vad_core.c:40-63) in the kernel's packed word layout
+void vad_initial_words(int32_t* words /* vad::N_WORDS */)
+{
+    static const int16_t nmean[12] = {6738, 4892, 7065, 6715, 6771, 3369, 7646, 3863, 7820, 7266, 5020, 4362};
+    static const int16_t smean[12] = {8306, 10085, 10078, 11823, 11843, 6309, 9473, 9571, 10879, 7581, 8180, 7483};
+    static const int16_t nstd[12] = {378, 1064, 493, 582, 688, 593, 474, 697, 475, 688, 421, 455};
+    static const int16_t sstd[12] = {555, 505, 567, 524, 585, 1231, 509, 828, 492, 1540, 1079, 850};
+    auto pk = [](int16_t lo, int16_t hi) { return (int32_t)(((uint32_t)(uint16_t)hi << 16) | (uint16_t)lo); };
+    memset(words, 0, sizeof(int32_t) * 136);
+    for (int ch = 0; ch < 6; ++ch) {
+        words[2 + ch] = pk(nmean[ch], nmean[ch + 6]);
+        words[8 + ch] = pk(smean[ch], smean[ch + 6]);
+        words[14 + ch] = pk(nstd[ch], nstd[ch + 6]);
+        words[20 + ch] = pk(sstd[ch], sstd[ch + 6]);
+    }
+    for (int i = 0; i < 48; ++i) {
+        words[28 + i] = 0;                       // ages
+        words[76 + i] = pk(10000, 10000);        // smallest values
+    }
+    for (int i = 0; i < 3; ++i) words[124 + i] = pk(1600, 1600);
+    words[135] = 4;                              // wmix starts muted (R:src/webrtc.c:64)
+}
+
+// ---- AGC ------------------------------------------------------------------------------------
+
+static int16_t div16(int32_t num, int16_t den) { return den ? (int16_t)(num / den) : (int16_t)0x7FFF; }
+static int clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+static int normw32(int32_t a) { if (!a) return 0; if (a < 0) a = ~a; return clz((uint32_t)a) - 1; }
+static int32_t shl(int32_t x, int c) { return c >= 0 ? (int32_t)((uint32_t)x << c) : (x >> (-c)); }
+
+// generating function table of the compressor, round(256*log2(1+e^i)) (digital_agc.c:36-53)
+static uint16_t genfunc(int i) { return (uint16_t)floor(256.0 * log2(1.0 + exp((double)i)) + 0.5); }
+
+// analog target implied by the compression gain (T:.../agc/legacy/analog_agc.c:424-448)
+int16_t agc_analog_target(int16_t comp_db)
+{
+    int16_t t = div16((int32_t)(int16_t)(5 * comp_db + 5), 11);
+    t = (int16_t)(4 + t);
+    return t < 4 ? (int16_t)4 : t;
+}
+
+// 32-entry Q16 gain curve (T:.../agc/legacy/digital_agc.c:57-257)
+int agc_gain_table(int32_t table[32], int16_t comp_db, int16_t target_dbfs, int limiter, int16_t analog_target)
+{
+    const int32_t kLog10 = 54426, kLog10_2 = 49321, kLogE_1 = 23637, kRatio = 3;
+    const int16_t headroom = (int16_t)(analog_target - target_dbfs);
+    int16_t t16 = (int16_t)(headroom + div16((comp_db - analog_target) * (kRatio - 1) + (kRatio >> 1), kRatio));
+    const int16_t max_gain = t16 > headroom ? t16 : headroom;
+    const int16_t diff_gain = div16(comp_db * (kRatio - 1) + (kRatio >> 1), kRatio);
+    if (diff_gain < 0 || diff_gain >= 128) return -1;
+    const int16_t lim_idx = (int16_t)(2 + div16((int32_t)analog_target << 13, (int16_t)(kLog10_2 / 2)));
+    const int32_t lim_lvl = target_dbfs + div16(kRatio >> 1, kRatio);
+    const uint16_t gmax = genfunc(diff_gain);
+    const int32_t den = 20 * (int32_t)gmax;
+
+    for (int i = 0; i < 32; ++i) {
+        // input level of this table slot, Q14
+        int32_t lvl = (int32_t)(int16_t)((kRatio - 1) * (i - 1)) * kLog10_2 + 1;
+        lvl = ((int32_t)diff_gain << 14) - lvl / kRatio;
+        const uint32_t mag = (uint32_t)(lvl >= 0 ? lvl : -lvl);
+        const int ip = (int)(mag >> 14);
+        const uint32_t fp = mag & 0x3FFF;
+        uint32_t a = (uint32_t)(uint16_t)(genfunc(ip + 1) - genfunc(ip)) * fp + ((uint32_t)genfunc(ip) << 14);
+        uint32_t approx = a >> 8;
+        if (lvl < 0) {
+            const int z = mag ? clz(mag) : 0;
+            int zs = 0;
+            uint32_t b;
+            if (z < 15) {
+                b = (mag >> (15 - z)) * (uint32_t)kLogE_1;
+                if (z < 9) { zs = 9 - z; a >>= zs; }
+                else b >>= z - 9;
+            } else {
+                b = (mag * (uint32_t)kLogE_1) >> 6;
+            }
+            approx = (b < a) ? (a - b) >> (8 - zs) : 0;
+        }
+        int32_t num = (int32_t)((uint32_t)(max_gain * (int32_t)gmax) << 6);
+        num -= (int32_t)approx * diff_gain;
+        const int z = (num > (den >> 8)) ? normw32(num) : normw32(den) + 8;
+        num = (int32_t)((uint32_t)num << z);
+        const int32_t d = shl(den, z - 8);
+        num += (num < 0) ? -(d / 2) : (d / 2);
+        int32_t y = num / d;
+        if (limiter && i < lim_idx) {
+            int32_t t = (int32_t)(int16_t)(i - 1) * kLog10_2;
+            t -= (int32_t)((uint32_t)lim_lvl << 14);
+            y = (t + 10) / 20;
+        }
+        int32_t g = (y > 39000) ? (((y >> 1) * kLog10 + 4096) >> 13) : ((y * kLog10 + 8192) >> 14);
+        g += 16 << 14;
+        if (g <= 0) { table[i] = 0; continue; }
+        const int e = (uint16_t)(int16_t)(g >> 14);
+        const int32_t f = g & 0x3FFF;
+        int32_t frac;
+        if (f >> 13) frac = (1 << 14) - ((((1 << 14) - f) * ((2 << 14) - 22817)) >> 13);
+        else frac = (f * (22817 - (1 << 14))) >> 13;
+        table[i] = (int32_t)(1u << e) + shl((int32_t)(uint16_t)frac, e - 14);
+    }
+    return 0;
+}
+
+// AgcVad / DigitalAgc init (T:.../agc/legacy/digital_agc.c:259-281, :606-631) in word layout
+void agc_initial_words(int32_t* words /* agc::N_WORDS */)
+{
+    auto pk = [](int16_t lo, int16_t hi) { return (int32_t)(((uint32_t)(uint16_t)hi << 16) | (uint16_t)lo); };
+    memset(words, 0, sizeof(int32_t) * 18);
+    words[0] = 134217728;            // capacitorSlow
+    words[2] = 65536;                // gain
+    words[12] = pk(0, 3);            // (HPstate, counter)
+    words[13] = pk(0, 15 << 10);     // (logRatio, meanLongTerm)
+    words[14] = 500 << 8;            // varianceLongTerm
+    words[15] = pk(0, 15 << 10);     // (stdLongTerm, meanShortTerm)
+    words[16] = 500 << 8;            // varianceShortTerm
+}
+
+}  // namespace host
+}  // namespace wmx

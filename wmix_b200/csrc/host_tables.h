@@ -1,0 +1,18 @@
+// Host-side init-time tables (see host_tables.cpp).
+#pragma once
+#include <stdint.h>
+
+namespace wmx {
+namespace host {
+void ns_window(int ana, int block, float* w);
+void fft_w_table(int nw, float* w);
+void fft_c_table(int nc, float* c);
+void ns_log_table(int bins, float* log_i, float* sum, float* sum_sq);
+int ns_policy(int mode, float* overdrive, float* floor_gain, int* gainmap);
+int vad_thresholds(int mode, int frame_ms, int16_t out[4]);
+void vad_initial_words(int32_t* words);
+int16_t agc_analog_target(int16_t comp_db);
+int agc_gain_table(int32_t table[32], int16_t comp_db, int16_t target_dbfs, int limiter, int16_t analog_target);
+void agc_initial_words(int32_t* words);
+}  // namespace host
+}  // namespace wmx

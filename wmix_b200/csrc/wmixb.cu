@@ -1,0 +1,680 @@
+// wmix_b200 — sm_100a kernels and the C-ABI engine behind include/wmixb.h.
+//
+// Kernels (all new; the reference has no GPU code):
+//   ns_kernel<ANA>      WebRTC NS, one stream-frame per warp, persistent grid  (ns.cuh)
+//   post_kernel<FS16>   AGC -> VAD (+ mute ramp), one stream per thread        (agc.cuh, vad.cuh)
+//   bus_sum / nminus1   conference bus: exact int32 sum, N-minus-one read-out
+//   g711_*              A-law / mu-law codecs, 16-byte vectorised
+//   mix_load            same-format branch of wmix_load_data on a device ring
+// Build: nvcc -std=c++17 -O3 --fmad=false -gencode arch=compute_100a,code=sm_100a -lineinfo
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <vector>
+
+#include "../../include/wmixb.h"
+#include "agc.cuh"
+#include "g711_mix.cuh"
+#include "host_tables.h"
+#include "ns.cuh"
+#include "vad.cuh"
+
+using namespace wmx;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+static int fail_cuda(cudaError_t e, const char* what, int line)
+{
+    snprintf(g_err, sizeof g_err, "%s failed at wmixb.cu:%d: %s", what, line, cudaGetErrorString(e));
+    return WMIXB_ECUDA;
+}
+#define CK(call)                                                         \
+    do {                                                                 \
+        cudaError_t e__ = (call);                                        \
+        if (e__ != cudaSuccess) return fail_cuda(e__, #call, __LINE__);  \
+    } while (0)
+#define CK_LAUNCH()                                                      \
+    do {                                                                 \
+        g_launches.fetch_add(1, std::memory_order_relaxed);              \
+        cudaError_t e__ = cudaGetLastError();                            \
+        if (e__ != cudaSuccess) return fail_cuda(e__, "kernel launch", __LINE__); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// NS kernel: persistent grid, one warp per stream, K frames per stream per launch
+// ------------------------------------------------------------------------------------------
+constexpr int kNsWarps = 8;
+
+template <int ANA>
+struct NsSmem {
+    static constexpr size_t kTableFloats = (sizeof(ns::Tables<ANA>) + 15) / 16 * 4;
+    static constexpr size_t kBytes = (kTableFloats + (size_t)kNsWarps * ns::Geo<ANA>::kShFloats) * sizeof(float);
+};
+template <int ANA>
+constexpr size_t ns_smem_bytes() { return NsSmem<ANA>::kBytes; }
+
+template <int ANA>
+__global__ void __launch_bounds__(kNsWarps * 32, 2)
+ns_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Tables<ANA>* __restrict__ tables,
+          const int16_t* in, int16_t* out, int n_streams, int n_frames)
+{
+    typedef ns::Geo<ANA> G;
+    extern __shared__ __align__(16) float smem[];
+    ns::Tables<ANA>* T = reinterpret_cast<ns::Tables<ANA>*>(smem);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+        for (int i = threadIdx.x; i < (int)(sizeof(ns::Tables<ANA>) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    float* tile = smem + NsSmem<ANA>::kTableFloats + (size_t)warp * G::kShFloats;
+    ns::Warp<ANA> W;
+    W.lane_id = threadIdx.x & 31;
+    const int total_warps = gridDim.x * kNsWarps;
+    for (int s = blockIdx.x * kNsWarps + warp; s < n_streams; s += total_warps) {
+        float* r = rec + (size_t)s * G::kRecFloats;
+        uint16_t* h = hist + (size_t)s * 3 * ns::kHistBins;
+        const int16_t* pi = in + (size_t)s * n_frames * G::kBlock;
+        int16_t* po = out + (size_t)s * n_frames * G::kBlock;
+        for (int f = 0; f < n_frames; ++f)
+            ns::frame<ANA>(W, r, h, pi + (size_t)f * G::kBlock, po + (size_t)f * G::kBlock, tile, *T);
+    }
+}
+
+template <int ANA>
+__global__ void ns_init_kernel(float* rec, uint16_t* hist, int first, int count)
+{
+    typedef ns::Geo<ANA> G;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= count) return;
+    const int s = first + warp;
+    float* r = rec + (size_t)s * G::kRecFloats;
+    ns::init_record<ANA>(r, hist + (size_t)s * 3 * ns::kHistBins, lane, 32);
+    __syncwarp();
+    ns::init_record_values<ANA>(r, lane, 32);
+}
+
+// ------------------------------------------------------------------------------------------
+// post kernel: AGC -> VAD, one stream per thread; PCM tile staged through shared memory so
+// global traffic is whole lines while each thread walks its own row without bank conflicts
+// (row pitch = frame+2 int16 = an odd number of 32-bit words).
+// ------------------------------------------------------------------------------------------
+constexpr int kPostThreads = 128;
+
+template <bool FS16>
+__global__ void __launch_bounds__(kPostThreads)
+post_kernel(int32_t* __restrict__ agc_words, int32_t* __restrict__ vad_words, const int32_t* __restrict__ agc_table,
+            vad::Params vp, const int16_t* in, int16_t* out, uint8_t* vad_out, int n_streams, size_t stride,
+            int n_frames, int stages)
+{
+    constexpr int L = FS16 ? 160 : 80;
+    constexpr int ROWW = L / 2 + 1;                     // row pitch in 32-bit words (odd)
+    __shared__ int32_t tile[kPostThreads * ROWW];
+    __shared__ int32_t tab[32];
+    const int tid = threadIdx.x;
+    const int s0 = blockIdx.x * kPostThreads;
+    const int s = s0 + tid;
+    if (tid < 32) tab[tid] = agc_table ? agc_table[tid] : 0;
+    const int rows = min(kPostThreads, n_streams - s0);
+    const int32_t* in32 = reinterpret_cast<const int32_t*>(in);
+    int32_t* out32 = reinterpret_cast<int32_t*>(out);
+    SoaWords agc_st{agc_words ? agc_words + s : nullptr, stride};
+    SoaWords vad_st{vad_words ? vad_words + s : nullptr, stride};
+    for (int f = 0; f < n_frames; ++f) {
+        __syncthreads();
+        for (int idx = tid; idx < rows * (L / 2); idx += kPostThreads) {
+            const int r = idx / (L / 2), w = idx - r * (L / 2);
+            tile[r * ROWW + w] = in32[((size_t)(s0 + r) * n_frames + f) * (L / 2) + w];
+        }
+        __syncthreads();
+        if (s < n_streams) {
+            int16_t* x = reinterpret_cast<int16_t*>(tile + tid * ROWW);
+            if (stages & WMIXB_AGC) agc::process_packet<FS16>(agc_st, x, tab);
+            if (stages & WMIXB_VAD) {
+                const int flag = vad::process_packet<80, FS16>(vad_st, x, vp);
+                if (vad_out) vad_out[(size_t)s * n_frames + f] = (uint8_t)flag;
+            }
+        }
+        __syncthreads();
+        for (int idx = tid; idx < rows * (L / 2); idx += kPostThreads) {
+            const int r = idx / (L / 2), w = idx - r * (L / 2);
+            out32[((size_t)(s0 + r) * n_frames + f) * (L / 2) + w] = tile[r * ROWW + w];
+        }
+    }
+}
+
+__global__ void words_init_kernel(int32_t* words, const int32_t* init, int n_words, size_t stride, int first, int count)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    for (int w = 0; w < n_words; ++w) words[(size_t)w * stride + first + i] = init[w];
+}
+
+// ------------------------------------------------------------------------------------------
+// conference bus
+// ------------------------------------------------------------------------------------------
+// grid = (n_conf, chunks): thread i owns sample i of the frame and walks a slice of the
+// conference's members, so every load is a coalesced row segment; slices are combined with one
+// int32 atomicAdd per sample (exact and order-independent).  LAW < 0: PCM input, else G.711.
+template <int LAW>
+__global__ void bus_sum_kernel(const void* __restrict__ src, int32_t* __restrict__ bus, const int32_t* __restrict__ conf_start,
+                               int frame, int chunk)
+{
+    const int c = blockIdx.x;
+    const int first = conf_start[c] + blockIdx.y * chunk;
+    const int last = min(conf_start[c + 1], first + chunk);
+    if (first >= last) return;
+    for (int i = threadIdx.x; i < frame; i += blockDim.x) {
+        int32_t acc = 0;
+        for (int p = first; p < last; ++p) {
+            if (LAW < 0) acc += static_cast<const int16_t*>(src)[(size_t)p * frame + i];
+            else if (LAW == 0) acc += alaw2linear(static_cast<const uint8_t*>(src)[(size_t)p * frame + i]);
+            else acc += ulaw2linear(static_cast<const uint8_t*>(src)[(size_t)p * frame + i]);
+        }
+        if (gridDim.y == 1) bus[(size_t)c * frame + i] = acc;
+        else atomicAdd(&bus[(size_t)c * frame + i], acc);
+    }
+}
+
+template <int LAW>
+__global__ void nminus1_kernel(const int32_t* __restrict__ bus, const void* __restrict__ own, void* __restrict__ out,
+                               const int32_t* __restrict__ conf_of, int frame, size_t total)
+{
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t s = idx / frame;
+        const int i = (int)(idx - s * frame);
+        const int32_t b = bus[(size_t)conf_of[s] * frame + i];
+        if (LAW < 0) {
+            static_cast<int16_t*>(out)[idx] = sat16(b - static_cast<const int16_t*>(own)[idx]);
+        } else {
+            const uint8_t code = static_cast<const uint8_t*>(own)[idx];
+            const int16_t mine = LAW == 0 ? alaw2linear(code) : ulaw2linear(code);
+            const int16_t v = sat16(b - mine);
+            static_cast<uint8_t*>(out)[idx] = LAW == 0 ? linear2alaw(v) : linear2ulaw(v);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// G.711 element-wise, 8 samples (16 B of PCM / 8 B of codes) per thread-iteration
+// ------------------------------------------------------------------------------------------
+template <int LAW>
+__global__ void g711_encode_kernel(const int16_t* __restrict__ pcm, uint8_t* __restrict__ codes, size_t n)
+{
+    const size_t nvec = n / 8;
+    const int4* p4 = reinterpret_cast<const int4*>(pcm);
+    uint2* c2 = reinterpret_cast<uint2*>(codes);
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+        const int4 x = p4[v];
+        const int w[4] = {x.x, x.y, x.z, x.w};
+        uint32_t o[2] = {0, 0};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int16_t smp = (int16_t)((k & 1) ? (w[k >> 1] >> 16) : (w[k >> 1] & 0xFFFF));
+            const uint32_t code = LAW == 0 ? linear2alaw(smp) : linear2ulaw(smp);
+            o[k >> 2] |= code << (8 * (k & 3));
+        }
+        c2[v] = make_uint2(o[0], o[1]);
+    }
+    for (size_t i = nvec * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        codes[i] = LAW == 0 ? linear2alaw(pcm[i]) : linear2ulaw(pcm[i]);
+}
+
+template <int LAW>
+__global__ void g711_decode_kernel(const uint8_t* __restrict__ codes, int16_t* __restrict__ pcm, size_t n)
+{
+    const size_t nvec = n / 8;
+    const uint2* c2 = reinterpret_cast<const uint2*>(codes);
+    int4* p4 = reinterpret_cast<int4*>(pcm);
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (size_t)gridDim.x * blockDim.x) {
+        const uint2 c = c2[v];
+        const uint32_t w[2] = {c.x, c.y};
+        int o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint8_t a = (uint8_t)(w[k >> 1] >> (16 * (k & 1))), b = (uint8_t)(w[k >> 1] >> (16 * (k & 1) + 8));
+            const int16_t lo = LAW == 0 ? alaw2linear(a) : ulaw2linear(a);
+            const int16_t hi = LAW == 0 ? alaw2linear(b) : ulaw2linear(b);
+            o[k] = pack16(lo, hi);
+        }
+        p4[v] = make_int4(o[0], o[1], o[2], o[3]);
+    }
+    for (size_t i = nvec * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        pcm[i] = LAW == 0 ? alaw2linear(codes[i]) : ulaw2linear(codes[i]);
+}
+
+// same-format branch of wmix_load_data on a device ring (R:src/wmix.c:1678-1702)
+__global__ void mix_load_kernel(int16_t* ring, uint32_t ring_len, uint32_t pos, const int16_t* __restrict__ src,
+                                uint32_t n, int rdce)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t at = (pos + i) % ring_len;
+        ring[at] = mix_step(ring[at], src[i], rdce);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// engine
+// ------------------------------------------------------------------------------------------
+struct wmixb_engine {
+    wmixb_config cfg;
+    int frame = 0, ana = 0, sm_count = 0;
+    size_t stride = 0;                      // SoA row pitch (streams rounded up to 32)
+    float* ns_rec = nullptr;
+    uint16_t* ns_hist = nullptr;
+    void* ns_tables = nullptr;
+    int32_t* agc_words = nullptr;
+    int32_t* vad_words = nullptr;
+    int32_t* agc_table = nullptr;
+    int32_t* agc_init = nullptr;
+    int32_t* vad_init = nullptr;
+    vad::Params vp{};
+    int16_t *d_in = nullptr, *d_out = nullptr;   // staging for the host-buffer entry point
+    uint8_t* d_vad = nullptr;
+    int32_t* conf_start = nullptr;          // [n_conf+1]
+    int32_t* conf_of = nullptr;             // [n_streams]
+    int n_conf = 0, max_conf = 0;
+    cudaStream_t stream = nullptr;
+    int ns_grid = 0;
+};
+
+static int ns_rec_floats(const wmixb_engine* e) { return e->ana == 256 ? ns::Geo<256>::kRecFloats : ns::Geo<128>::kRecFloats; }
+
+template <int ANA>
+static int upload_ns_tables(wmixb_engine* e)
+{
+    ns::Tables<ANA> T;
+    memset(&T, 0, sizeof T);
+    host::ns_window(ANA, ns::Geo<ANA>::kBlock, T.window);
+    host::fft_w_table(ANA / 4, T.w);
+    host::fft_c_table(ANA / 4, T.c);
+    host::ns_log_table(ANA / 2 + 1, T.log_i, &T.sum_log_i, &T.sum_log_i_sq);
+    if (host::ns_policy(e->cfg.ns_policy, &T.overdrive, &T.floor_gain, &T.gainmap) != 0) {
+        snprintf(g_err, sizeof g_err, "ns_policy %d out of range 0..3", e->cfg.ns_policy);
+        return WMIXB_EINVAL;
+    }
+    CK(cudaMalloc(&e->ns_tables, sizeof T));
+    CK(cudaMemcpy(e->ns_tables, &T, sizeof T, cudaMemcpyHostToDevice));
+    CK(cudaFuncSetAttribute(ns_kernel<ANA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns_smem_bytes<ANA>()));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ns_kernel<ANA>, kNsWarps * 32, ns_smem_bytes<ANA>()));
+    if (per_sm < 1) per_sm = 1;
+    e->ns_grid = e->sm_count * per_sm;
+    return WMIXB_OK;
+}
+
+static int upload_agc_table(wmixb_engine* e, int gain_db)
+{
+    int32_t tab[32];
+    if (host::agc_gain_table(tab, (int16_t)gain_db, 0, 0, host::agc_analog_target((int16_t)gain_db)) != 0) {
+        snprintf(g_err, sizeof g_err, "agc gain %d dB out of range", gain_db);
+        return WMIXB_EINVAL;
+    }
+    CK(cudaMemcpyAsync(e->agc_table, tab, sizeof tab, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_reset(wmixb_engine* e, int first, int count)
+{
+    if (!e || first < 0 || count < 0 || first + count > e->cfg.n_streams) return WMIXB_EINVAL;
+    if (count == 0) return WMIXB_OK;
+    CK(cudaSetDevice(e->cfg.device));
+    if (e->ns_rec) {
+        const int blocks = (count * 32 + 255) / 256;
+        if (e->ana == 256) ns_init_kernel<256><<<blocks, 256, 0, e->stream>>>(e->ns_rec, e->ns_hist, first, count);
+        else ns_init_kernel<128><<<blocks, 256, 0, e->stream>>>(e->ns_rec, e->ns_hist, first, count);
+        CK_LAUNCH();
+    }
+    if (e->agc_words) {
+        words_init_kernel<<<(count + 255) / 256, 256, 0, e->stream>>>(e->agc_words, e->agc_init, agc::N_WORDS, e->stride, first, count);
+        CK_LAUNCH();
+    }
+    if (e->vad_words) {
+        words_init_kernel<<<(count + 255) / 256, 256, 0, e->stream>>>(e->vad_words, e->vad_init, vad::N_WORDS, e->stride, first, count);
+        CK_LAUNCH();
+    }
+    CK(cudaStreamSynchronize(e->stream));
+    return WMIXB_OK;
+}
+
+extern "C" void wmixb_destroy(wmixb_engine* e)
+{
+    if (!e) return;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    cudaFree(e->ns_rec); cudaFree(e->ns_hist); cudaFree(e->ns_tables);
+    cudaFree(e->agc_words); cudaFree(e->vad_words); cudaFree(e->agc_table);
+    cudaFree(e->agc_init); cudaFree(e->vad_init);
+    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_vad);
+    cudaFree(e->conf_start); cudaFree(e->conf_of);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+static int create_impl(const wmixb_config* cfg, wmixb_engine* e)
+{
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0) {
+        snprintf(g_err, sizeof g_err, "no CUDA device (%s) — wmix_b200 has no CPU path", cudaGetErrorString(ce));
+        return WMIXB_ENODEV;
+    }
+    if (cfg->device < 0 || cfg->device >= ndev) { snprintf(g_err, sizeof g_err, "device %d of %d", cfg->device, ndev); return WMIXB_EINVAL; }
+    CK(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, cfg->device));
+    e->sm_count = prop.multiProcessorCount;
+    CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+    const size_t n = (size_t)cfg->n_streams;
+    e->stride = (n + 31) / 32 * 32;
+    if (cfg->stages & WMIXB_NS) {
+        CK(cudaMalloc(&e->ns_rec, n * ns_rec_floats(e) * sizeof(float)));
+        CK(cudaMalloc(&e->ns_hist, n * 3 * ns::kHistBins * sizeof(uint16_t)));
+        int rc = e->ana == 256 ? upload_ns_tables<256>(e) : upload_ns_tables<128>(e);
+        if (rc) return rc;
+    }
+    if (cfg->stages & WMIXB_AGC) {
+        int32_t init[agc::N_WORDS];
+        host::agc_initial_words(init);
+        CK(cudaMalloc(&e->agc_words, e->stride * agc::N_WORDS * sizeof(int32_t)));
+        CK(cudaMalloc(&e->agc_init, sizeof init));
+        CK(cudaMemcpy(e->agc_init, init, sizeof init, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&e->agc_table, 32 * sizeof(int32_t)));
+        int rc = upload_agc_table(e, cfg->agc_gain_db);
+        if (rc) return rc;
+    }
+    if (cfg->stages & WMIXB_VAD) {
+        int32_t init[vad::N_WORDS];
+        host::vad_initial_words(init);
+        CK(cudaMalloc(&e->vad_words, e->stride * vad::N_WORDS * sizeof(int32_t)));
+        CK(cudaMalloc(&e->vad_init, sizeof init));
+        CK(cudaMemcpy(e->vad_init, init, sizeof init, cudaMemcpyHostToDevice));
+        int16_t th[4];
+        if (host::vad_thresholds(cfg->vad_mode, 10, th) != 0) { snprintf(g_err, sizeof g_err, "vad_mode %d out of range 0..3", cfg->vad_mode); return WMIXB_EINVAL; }
+        e->vp = vad::Params{th[0], th[1], th[2], th[3]};
+    }
+    CK(cudaMalloc(&e->d_in, n * e->frame * sizeof(int16_t)));
+    CK(cudaMalloc(&e->d_out, n * e->frame * sizeof(int16_t)));
+    CK(cudaMalloc(&e->d_vad, n));
+    CK(cudaMalloc(&e->conf_of, n * sizeof(int32_t)));
+    return wmixb_reset(e, 0, cfg->n_streams);
+}
+
+extern "C" int wmixb_create(const wmixb_config* cfg, wmixb_engine** out)
+{
+    if (!cfg || !out) return WMIXB_EINVAL;
+    *out = nullptr;
+    if (cfg->n_streams < 1) { snprintf(g_err, sizeof g_err, "n_streams must be >= 1"); return WMIXB_EINVAL; }
+    // the reference accepts freq <= 32000 && freq % 8000 == 0 (R:src/webrtc.c:43, :563, :711);
+    // the batched engine covers the two rates BASELINE.json's configs use
+    if (cfg->freq != 8000 && cfg->freq != 16000) { snprintf(g_err, sizeof g_err, "freq %d: batched engine supports 8000 and 16000", cfg->freq); return WMIXB_EINVAL; }
+    if ((cfg->stages & ~(WMIXB_NS | WMIXB_AGC | WMIXB_VAD)) != 0) { snprintf(g_err, sizeof g_err, "unknown stage bits"); return WMIXB_EINVAL; }
+    wmixb_engine* e = new (std::nothrow) wmixb_engine();
+    if (!e) return WMIXB_ENOMEM;
+    e->cfg = *cfg;
+    e->frame = cfg->freq / 100;
+    e->ana = cfg->freq == 16000 ? 256 : 128;
+    const int rc = create_impl(cfg, e);
+    if (rc != WMIXB_OK) { wmixb_destroy(e); return rc; }
+    *out = e;
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_set_agc_gain(wmixb_engine* e, int gain_db)
+{
+    if (!e || !e->agc_table) return WMIXB_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    return upload_agc_table(e, gain_db);
+}
+
+static int run_stages(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int n_frames, int stages,
+                      cudaStream_t st)
+{
+    if (stages == 0) stages = e->cfg.stages;
+    if (stages & ~e->cfg.stages) { snprintf(g_err, sizeof g_err, "stage mask 0x%x not configured (engine has 0x%x)", stages, e->cfg.stages); return WMIXB_EINVAL; }
+    const int n = e->cfg.n_streams;
+    const int16_t* cur = d_in;
+    if (stages & WMIXB_NS) {
+        const int need = (n + kNsWarps - 1) / kNsWarps;
+        const int grid = need < e->ns_grid ? need : e->ns_grid;
+        if (e->ana == 256)
+            ns_kernel<256><<<grid, kNsWarps * 32, ns_smem_bytes<256>(), st>>>(e->ns_rec, e->ns_hist, (const ns::Tables<256>*)e->ns_tables, cur, d_out, n, n_frames);
+        else
+            ns_kernel<128><<<grid, kNsWarps * 32, ns_smem_bytes<128>(), st>>>(e->ns_rec, e->ns_hist, (const ns::Tables<128>*)e->ns_tables, cur, d_out, n, n_frames);
+        CK_LAUNCH();
+        cur = d_out;
+    }
+    if (stages & (WMIXB_AGC | WMIXB_VAD)) {
+        const int grid = (n + kPostThreads - 1) / kPostThreads;
+        if (e->frame == 160)
+            post_kernel<true><<<grid, kPostThreads, 0, st>>>(e->agc_words, e->vad_words, e->agc_table, e->vp, cur, d_out, d_vad, n, e->stride, n_frames, stages);
+        else
+            post_kernel<false><<<grid, kPostThreads, 0, st>>>(e->agc_words, e->vad_words, e->agc_table, e->vp, cur, d_out, d_vad, n, e->stride, n_frames, stages);
+        CK_LAUNCH();
+        cur = d_out;
+    }
+    if (cur == d_in && d_in != d_out) CK(cudaMemcpyAsync(d_out, d_in, (size_t)n * n_frames * e->frame * 2, cudaMemcpyDeviceToDevice, st));
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_tick_device(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int stages, void* stream)
+{
+    if (!e || !d_in || !d_out) return WMIXB_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    return run_stages(e, d_in, d_out, d_vad, 1, stages, (cudaStream_t)stream);
+}
+
+extern "C" int wmixb_offline_device(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int n_frames,
+                                    int stages, void* stream)
+{
+    if (!e || !d_in || !d_out || n_frames < 1) return WMIXB_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    return run_stages(e, d_in, d_out, d_vad, n_frames, stages, (cudaStream_t)stream);
+}
+
+extern "C" int wmixb_tick_host(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int stages)
+{
+    if (!e || !h_in || !h_out) return WMIXB_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t bytes = (size_t)e->cfg.n_streams * e->frame * sizeof(int16_t);
+    CK(cudaMemcpyAsync(e->d_in, h_in, bytes, cudaMemcpyHostToDevice, e->stream));
+    const int rc = run_stages(e, e->d_in, e->d_out, e->d_vad, 1, stages, e->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_out, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (h_vad) CK(cudaMemcpyAsync(h_vad, e->d_vad, (size_t)e->cfg.n_streams, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return WMIXB_OK;
+}
+
+// ---- conference bus ----
+extern "C" int wmixb_set_conferences(wmixb_engine* e, const int32_t* h_conf_start, int n_conf)
+{
+    if (!e || !h_conf_start || n_conf < 1) return WMIXB_EINVAL;
+    if (h_conf_start[0] != 0 || h_conf_start[n_conf] != e->cfg.n_streams) { snprintf(g_err, sizeof g_err, "conference ranges must cover [0, n_streams)"); return WMIXB_EINVAL; }
+    std::vector<int32_t> of((size_t)e->cfg.n_streams);
+    int biggest = 0;
+    for (int c = 0; c < n_conf; ++c) {
+        if (h_conf_start[c + 1] < h_conf_start[c]) { snprintf(g_err, sizeof g_err, "conference ranges must be non-decreasing"); return WMIXB_EINVAL; }
+        for (int s = h_conf_start[c]; s < h_conf_start[c + 1]; ++s) of[s] = c;
+        if (h_conf_start[c + 1] - h_conf_start[c] > biggest) biggest = h_conf_start[c + 1] - h_conf_start[c];
+    }
+    CK(cudaSetDevice(e->cfg.device));
+    cudaFree(e->conf_start);
+    e->conf_start = nullptr;
+    CK(cudaMalloc(&e->conf_start, (size_t)(n_conf + 1) * sizeof(int32_t)));
+    CK(cudaMemcpy(e->conf_start, h_conf_start, (size_t)(n_conf + 1) * sizeof(int32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(e->conf_of, of.data(), of.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+    e->n_conf = n_conf;
+    e->max_conf = biggest;
+    return WMIXB_OK;
+}
+
+template <int LAW>
+static int bus_sum_impl(wmixb_engine* e, const void* src, int32_t* d_bus, cudaStream_t st)
+{
+    if (!e || !src || !d_bus || e->n_conf < 1) return WMIXB_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    // enough CTAs to fill the chip: split big conferences into member slices
+    int chunks = 1;
+    const int want = 4 * e->sm_count;
+    if (e->n_conf < want) chunks = (want + e->n_conf - 1) / e->n_conf;
+    int chunk = (e->max_conf + chunks - 1) / chunks;
+    if (chunk < 8) chunk = 8;
+    chunks = (e->max_conf + chunk - 1) / chunk;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 1) CK(cudaMemsetAsync(d_bus, 0, (size_t)e->n_conf * e->frame * sizeof(int32_t), st));
+    dim3 grid((unsigned)e->n_conf, (unsigned)chunks);
+    bus_sum_kernel<LAW><<<grid, e->frame <= 96 ? 96 : 160, 0, st>>>(src, d_bus, e->conf_start, e->frame, chunk);
+    CK_LAUNCH();
+    return WMIXB_OK;
+}
+
+template <int LAW>
+static int nminus1_impl(wmixb_engine* e, const int32_t* d_bus, const void* own, void* out, cudaStream_t st)
+{
+    if (!e || !d_bus || !own || !out || e->n_conf < 1) return WMIXB_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t total = (size_t)e->cfg.n_streams * e->frame;
+    size_t blocks = (total + 255) / 256;
+    const size_t cap = (size_t)e->sm_count * 16;
+    if (blocks > cap) blocks = cap;
+    nminus1_kernel<LAW><<<(unsigned)blocks, 256, 0, st>>>(d_bus, own, out, e->conf_of, e->frame, total);
+    CK_LAUNCH();
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_bus_sum_device(wmixb_engine* e, const int16_t* d_pcm, int32_t* d_bus, void* stream)
+{
+    return bus_sum_impl<-1>(e, d_pcm, d_bus, (cudaStream_t)stream);
+}
+extern "C" int wmixb_bus_nminus1_device(wmixb_engine* e, const int32_t* d_bus, const int16_t* d_pcm, int16_t* d_out, void* stream)
+{
+    return nminus1_impl<-1>(e, d_bus, d_pcm, d_out, (cudaStream_t)stream);
+}
+extern "C" int wmixb_g711_bus_sum_device(wmixb_engine* e, int law, const uint8_t* d_codes, int32_t* d_bus, void* stream)
+{
+    if (law == 0) return bus_sum_impl<0>(e, d_codes, d_bus, (cudaStream_t)stream);
+    if (law == 1) return bus_sum_impl<1>(e, d_codes, d_bus, (cudaStream_t)stream);
+    return WMIXB_EINVAL;
+}
+extern "C" int wmixb_g711_nminus1_device(wmixb_engine* e, int law, const int32_t* d_bus, const uint8_t* d_codes,
+                                         uint8_t* d_out_codes, void* stream)
+{
+    if (law == 0) return nminus1_impl<0>(e, d_bus, d_codes, d_out_codes, (cudaStream_t)stream);
+    if (law == 1) return nminus1_impl<1>(e, d_bus, d_codes, d_out_codes, (cudaStream_t)stream);
+    return WMIXB_EINVAL;
+}
+
+// ---- G.711 / mix ring ----
+static unsigned ew_blocks(size_t work_items)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    size_t b = (work_items + 255) / 256;
+    const size_t cap = (size_t)sms * 8;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (unsigned)b;
+}
+
+extern "C" int wmixb_g711_encode_device(int law, const int16_t* d_pcm, uint8_t* d_codes, size_t n, void* stream)
+{
+    if ((law != 0 && law != 1) || (n && (!d_pcm || !d_codes))) return WMIXB_EINVAL;
+    if (n == 0) return WMIXB_OK;
+    if (((uintptr_t)d_pcm & 15) || ((uintptr_t)d_codes & 7)) { snprintf(g_err, sizeof g_err, "g711: buffers must be 16-byte (pcm) / 8-byte (codes) aligned"); return WMIXB_EINVAL; }
+    if (law == 0) g711_encode_kernel<0><<<ew_blocks(n / 8 + 1), 256, 0, (cudaStream_t)stream>>>(d_pcm, d_codes, n);
+    else g711_encode_kernel<1><<<ew_blocks(n / 8 + 1), 256, 0, (cudaStream_t)stream>>>(d_pcm, d_codes, n);
+    CK_LAUNCH();
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_g711_decode_device(int law, const uint8_t* d_codes, int16_t* d_pcm, size_t n, void* stream)
+{
+    if ((law != 0 && law != 1) || (n && (!d_pcm || !d_codes))) return WMIXB_EINVAL;
+    if (n == 0) return WMIXB_OK;
+    if (((uintptr_t)d_pcm & 15) || ((uintptr_t)d_codes & 7)) { snprintf(g_err, sizeof g_err, "g711: buffers must be 16-byte (pcm) / 8-byte (codes) aligned"); return WMIXB_EINVAL; }
+    if (law == 0) g711_decode_kernel<0><<<ew_blocks(n / 8 + 1), 256, 0, (cudaStream_t)stream>>>(d_codes, d_pcm, n);
+    else g711_decode_kernel<1><<<ew_blocks(n / 8 + 1), 256, 0, (cudaStream_t)stream>>>(d_codes, d_pcm, n);
+    CK_LAUNCH();
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_mix_load_device(int16_t* d_ring, uint32_t ring_len, uint32_t pos, const int16_t* d_src, uint32_t n,
+                                     int rdce, uint32_t* new_pos, void* stream)
+{
+    if (!d_ring || ring_len == 0 || pos >= ring_len || (n && !d_src) || rdce < 1 || n > ring_len) return WMIXB_EINVAL;
+    if (n) {
+        mix_load_kernel<<<ew_blocks(n), 256, 0, (cudaStream_t)stream>>>(d_ring, ring_len, pos, d_src, n, rdce);
+        CK_LAUNCH();
+    }
+    if (new_pos) *new_pos = (uint32_t)(((uint64_t)pos + n) % ring_len);
+    return WMIXB_OK;
+}
+
+// ---- state snapshot ----
+extern "C" size_t wmixb_stream_state_bytes(const wmixb_engine* e)
+{
+    if (!e) return 0;
+    size_t b = 0;
+    if (e->ns_rec) b += (size_t)ns_rec_floats(e) * 4 + 3 * ns::kHistBins * 2;
+    if (e->agc_words) b += agc::N_WORDS * 4;
+    if (e->vad_words) b += vad::N_WORDS * 4;
+    return b;
+}
+extern "C" size_t wmixb_state_bytes_per_stream(const wmixb_engine* e) { return wmixb_stream_state_bytes(e); }
+
+static int state_xfer(wmixb_engine* e, int s, void* buf, bool get)
+{
+    if (!e || !buf || s < 0 || s >= e->cfg.n_streams) return WMIXB_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaStreamSynchronize(e->stream));
+    char* p = (char*)buf;
+    auto xfer = [&](void* dev, size_t bytes) -> cudaError_t {
+        cudaError_t r = get ? cudaMemcpy(p, dev, bytes, cudaMemcpyDeviceToHost) : cudaMemcpy(dev, p, bytes, cudaMemcpyHostToDevice);
+        p += bytes;
+        return r;
+    };
+    auto xfer2d = [&](int32_t* dev, int words) -> cudaError_t {
+        cudaError_t r = get ? cudaMemcpy2D(p, 4, dev + s, e->stride * 4, 4, words, cudaMemcpyDeviceToHost)
+                            : cudaMemcpy2D(dev + s, e->stride * 4, p, 4, 4, words, cudaMemcpyHostToDevice);
+        p += (size_t)words * 4;
+        return r;
+    };
+    if (e->ns_rec) {
+        CK(xfer(e->ns_rec + (size_t)s * ns_rec_floats(e), (size_t)ns_rec_floats(e) * 4));
+        CK(xfer(e->ns_hist + (size_t)s * 3 * ns::kHistBins, 3 * ns::kHistBins * 2));
+    }
+    if (e->agc_words) CK(xfer2d(e->agc_words, agc::N_WORDS));
+    if (e->vad_words) CK(xfer2d(e->vad_words, vad::N_WORDS));
+    return WMIXB_OK;
+}
+extern "C" int wmixb_get_stream_state(wmixb_engine* e, int s, void* h_buf) { return state_xfer(e, s, h_buf, true); }
+extern "C" int wmixb_set_stream_state(wmixb_engine* e, int s, const void* h_buf) { return state_xfer(e, s, (void*)h_buf, false); }
+
+// ---- bookkeeping ----
+extern "C" int wmixb_sync(wmixb_engine* e)
+{
+    if (!e) return WMIXB_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    return WMIXB_OK;
+}
+extern "C" const char* wmixb_last_error(void) { return g_err; }
+extern "C" long long wmixb_kernel_launches(void) { return g_launches.load(); }
+extern "C" int wmixb_frame_len(const wmixb_engine* e) { return e ? e->frame : 0; }
+extern "C" void wmixb_ns_window(int ana, int block, float* out) { host::ns_window(ana, block, out); }
+extern "C" int wmixb_agc_gain_table(int32_t table[32], int comp_db, int target_dbfs, int limiter, int analog_target)
+{
+    return host::agc_gain_table(table, (int16_t)comp_db, (int16_t)target_dbfs, limiter, (int16_t)analog_target);
+}
+extern "C" int wmixb_agc_analog_target(int comp_db) { return host::agc_analog_target((int16_t)comp_db); }

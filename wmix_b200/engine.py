@@ -1,0 +1,122 @@
+"""Python face of the batched engine (include/wmixb.h): thin, pointer-passing wrappers.
+
+PyTorch is used here only for device memory and streams (tensors are handed to the C-ABI as raw
+pointers); numpy arrays go through the host-buffer entry point."""
+import ctypes as C
+
+import numpy as np
+
+from ._lib import AGC, NS, VAD, Config, check, lib
+
+
+def _ptr(x):
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()  # torch tensor
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+
+        return torch.cuda.current_stream().cuda_stream
+    return getattr(stream, "cuda_stream", stream)
+
+
+class Engine:
+    """N independent mono streams of wmix's record chain NS -> AGC -> VAD on one GPU."""
+
+    def __init__(self, n_streams, freq=16000, stages=NS | AGC | VAD, ns_policy=2, agc_gain_db=5, vad_mode=3, device=0):
+        self.L = lib()
+        cfg = Config(n_streams=n_streams, freq=freq, stages=stages, ns_policy=ns_policy, agc_gain_db=agc_gain_db,
+                     vad_mode=vad_mode, device=device)
+        h = C.c_void_p()
+        check(self.L.wmixb_create(C.byref(cfg), C.byref(h)), "wmixb_create")
+        self.h, self.n, self.freq, self.frame, self.stages, self.device = h, n_streams, freq, freq // 100, stages, device
+
+    def close(self):
+        if self.h:
+            self.L.wmixb_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- ticks ---
+    def tick_device(self, d_in, d_out, d_vad=None, stages=0, stream=None):
+        check(self.L.wmixb_tick_device(self.h, _ptr(d_in), _ptr(d_out), _ptr(d_vad), stages, _stream_ptr(stream)),
+              "wmixb_tick_device")
+
+    def tick_host(self, h_in, h_out, h_vad=None, stages=0):
+        check(self.L.wmixb_tick_host(self.h, _ptr(h_in), _ptr(h_out), _ptr(h_vad), stages), "wmixb_tick_host")
+
+    def offline_device(self, d_in, d_out, n_frames, d_vad=None, stages=0, stream=None):
+        check(self.L.wmixb_offline_device(self.h, _ptr(d_in), _ptr(d_out), _ptr(d_vad), n_frames, stages,
+                                          _stream_ptr(stream)), "wmixb_offline_device")
+
+    # --- conference bus ---
+    def set_conferences(self, conf_start):
+        a = np.ascontiguousarray(conf_start, dtype=np.int32)
+        check(self.L.wmixb_set_conferences(self.h, a.ctypes.data, len(a) - 1), "wmixb_set_conferences")
+        self.n_conf = len(a) - 1
+
+    def bus_sum(self, d_pcm, d_bus, stream=None):
+        check(self.L.wmixb_bus_sum_device(self.h, _ptr(d_pcm), _ptr(d_bus), _stream_ptr(stream)), "wmixb_bus_sum_device")
+
+    def bus_nminus1(self, d_bus, d_pcm, d_out, stream=None):
+        check(self.L.wmixb_bus_nminus1_device(self.h, _ptr(d_bus), _ptr(d_pcm), _ptr(d_out), _stream_ptr(stream)),
+              "wmixb_bus_nminus1_device")
+
+    def g711_bus_sum(self, law, d_codes, d_bus, stream=None):
+        check(self.L.wmixb_g711_bus_sum_device(self.h, law, _ptr(d_codes), _ptr(d_bus), _stream_ptr(stream)),
+              "wmixb_g711_bus_sum_device")
+
+    def g711_nminus1(self, law, d_bus, d_codes, d_out, stream=None):
+        check(self.L.wmixb_g711_nminus1_device(self.h, law, _ptr(d_bus), _ptr(d_codes), _ptr(d_out), _stream_ptr(stream)),
+              "wmixb_g711_nminus1_device")
+
+    # --- misc ---
+    def reset(self, first=0, count=None):
+        check(self.L.wmixb_reset(self.h, first, self.n - first if count is None else count), "wmixb_reset")
+
+    def set_agc_gain(self, db):
+        check(self.L.wmixb_set_agc_gain(self.h, db), "wmixb_set_agc_gain")
+
+    def sync(self):
+        check(self.L.wmixb_sync(self.h), "wmixb_sync")
+
+    def state_bytes_per_stream(self):
+        return self.L.wmixb_state_bytes_per_stream(self.h)
+
+    def get_state(self, s):
+        buf = np.zeros(self.L.wmixb_stream_state_bytes(self.h), np.uint8)
+        check(self.L.wmixb_get_stream_state(self.h, s, buf.ctypes.data), "wmixb_get_stream_state")
+        return buf
+
+    def set_state(self, s, buf):
+        buf = np.ascontiguousarray(buf, np.uint8)
+        check(self.L.wmixb_set_stream_state(self.h, s, buf.ctypes.data), "wmixb_set_stream_state")
+
+
+def g711_encode(law, d_pcm, d_codes, n, stream=None):
+    check(lib().wmixb_g711_encode_device(law, _ptr(d_pcm), _ptr(d_codes), n, _stream_ptr(stream)), "wmixb_g711_encode_device")
+
+
+def g711_decode(law, d_codes, d_pcm, n, stream=None):
+    check(lib().wmixb_g711_decode_device(law, _ptr(d_codes), _ptr(d_pcm), n, _stream_ptr(stream)), "wmixb_g711_decode_device")
+
+
+def mix_load(d_ring, ring_len, pos, d_src, n, rdce, stream=None):
+    new_pos = C.c_uint32(0)
+    check(lib().wmixb_mix_load_device(_ptr(d_ring), ring_len, pos, _ptr(d_src), n, rdce, C.byref(new_pos),
+                                      _stream_ptr(stream)), "wmixb_mix_load_device")
+    return new_pos.value
+
+
+def kernel_launches():
+    return lib().wmixb_kernel_launches()
