@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of wmix_b200 (contract: see the task prompt / DESIGN.md §6).
+
+Metric (BASELINE.json): real-time 16 kHz mono streams sustained per GPU through
+NS -> AGC -> VAD -> conference-bus mix inside a 10 ms tick, and the fraction of the measured
+B200 HBM roofline the dominant kernel (ns_kernel) reaches.
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (CUDA)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference C path on host cores
+
+A "step" is one 10 ms tick over every stream of the job: ns_kernel, post_kernel (AGC+VAD) and
+bus_sum_kernel.  Workload: BASELINE config 3, 100 000 streams per GPU (weak scaling: every rank
+owns its own 100 000 streams and its own conferences; the path has no cross-stream exchange, so
+there is no collective).  value = streams_total * 10 ms / ms_per_step.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FREQ = 16000
+FRAME = 160
+CONF_SIZE = 16
+NS_BYTES_PER_STREAM_TICK = 14.4e3      # NS state R+W + PCM in/out
+CHAIN_BYTES_PER_STREAM_TICK = 16.0e3   # NS + VAD + AGC + mix
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_pool(n_streams, n_ring, seed):
+    """[n_ring, n_streams, FRAME] int16: n_ring consecutive ticks (speech active) of 2048 distinct seeded
+    streams, tiled over n_streams.  Synthetic speech + noise, SURVEY.md §8(d)."""
+    from wmix_b200.synth import make_frames
+
+    base = min(2048, n_streams)
+    x = make_frames(base, FREQ, 300, n_ring, seed=seed)                   # [R, base, L]
+    reps = (n_streams + base - 1) // base
+    return np.ascontiguousarray(np.tile(x, (1, reps, 1))[:, :n_streams])
+
+
+def cpu_leg(n_streams, n_ticks, kind_pref="reference"):
+    """The reference C chain on the host cores (bounded sample).  Returns dict for cpu_baseline."""
+    from tests._oracle import oracle, P
+
+    L = oracle()
+    L.orc_bench_chain.restype = C.c_double
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libwmix_ref.so")
+    kind = "reference" if (kind_pref == "reference" and os.path.exists(ref_so)) else "port"
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n_streams = max(CONF_SIZE * cores, n_streams // (CONF_SIZE * cores) * (CONF_SIZE * cores))
+    x = make_pool(n_streams, n_ticks, seed=7)
+    bus = np.zeros((n_ticks, n_streams // CONF_SIZE, FRAME), np.int32)
+    sec = L.orc_bench_chain(ref_so.encode() if kind == "reference" else None, FREQ, n_streams, n_ticks, CONF_SIZE, cores,
+                            P(x), None, P(bus))
+    if sec <= 0:
+        raise RuntimeError("orc_bench_chain failed: %r" % sec)
+    ms_per_tick = sec * 1e3 / n_ticks
+    return {"value": n_streams * 10.0 / ms_per_tick, "unit": "real-time 16 kHz streams (10 ms tick)", "cores": cores,
+            "kind": kind, "sample": "%d streams x %d ticks, NS->AGC->VAD->bus, -O2 build, one pthread per core" % (n_streams, n_ticks),
+            "ms_per_tick": ms_per_tick, "us_per_stream_tick_per_core": sec * 1e6 * cores / (n_streams * n_ticks)}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    n_streams = CONF_SIZE * cores * max(1, 2048 // (CONF_SIZE * cores))
+    # one "step" = one tick over the bounded sample; warm-up ticks run first and are not timed
+    steps = min(args.steps, 200)
+    warm = cpu_leg(n_streams, max(3, min(args.warmup, 20)))
+    leg = cpu_leg(n_streams, steps)
+    line = {"impl": "reference", "metric": "real-time 16 kHz streams per host, NS+VAD+AGC+mix, 10 ms tick",
+            "value": leg["value"], "unit": leg["unit"], "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": leg["ms_per_tick"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+i16 (reference C: float NS with double libm, integer AGC/VAD/mix)", "data": "synthetic",
+            "config": {"workload": "BASELINE config 3 chain on a bounded sample: %s" % leg["sample"],
+                       "note": "CPU arm: the unmodified reference (oracle/_ref) when it was built, else the C port"},
+            "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": leg["value"], "unit": leg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "warmup_value": warm["value"]}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import wmix_b200
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    S = args.streams
+    n_conf = S // CONF_SIZE
+    eng = wmix_b200.Engine(S, FREQ, device=local)
+    eng.set_conferences(np.arange(0, S + 1, CONF_SIZE, dtype=np.int32))
+    R = args.ring
+    pool = make_pool(S, R, seed=100 + rank)
+    h_pool = torch.from_numpy(pool).pin_memory()
+    d_pool = h_pool.to(dev)
+    d_pcm = torch.empty((S, FRAME), dtype=torch.int16, device=dev)
+    d_vad = torch.zeros((S,), dtype=torch.uint8, device=dev)
+    d_bus = torch.empty((n_conf, FRAME), dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream()
+    NS, AGC, VAD = wmix_b200.NS, wmix_b200.AGC, wmix_b200.VAD
+
+    def step(t, evs=None):
+        src = d_pool[t % R]
+        if evs is not None:
+            evs[0].record(stream)
+        eng.tick_device(src, d_pcm, None, NS, stream)
+        if evs is not None:
+            evs[1].record(stream)
+        eng.tick_device(d_pcm, d_pcm, d_vad, AGC | VAD, stream)
+        if evs is not None:
+            evs[2].record(stream)
+        eng.bus_sum(d_pcm, d_bus, stream)
+        if evs is not None:
+            evs[3].record(stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for t in range(args.warmup):
+        step(t)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = wmix_b200.kernel_launches()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
+    barrier()
+    t_begin = torch.cuda.Event(enable_timing=True)
+    t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record(stream)
+    for k in range(args.steps):
+        step(args.warmup + k, evs[k])
+    t_end.record(stream)
+    barrier()
+    launches = wmix_b200.kernel_launches() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    ms_total = t_begin.elapsed_time(t_end)
+    ns_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
+    post_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
+    mix_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
+
+    # ---- end to end through the host-buffer C-ABI: pinned H2D of the tick, kernels, D2H of PCM + flags + bus
+    h_out = torch.empty((S, FRAME), dtype=torch.int16).pin_memory()
+    h_vad = torch.empty((S,), dtype=torch.uint8).pin_memory()
+    h_bus = torch.empty((n_conf, FRAME), dtype=torch.int32).pin_memory()
+    e2e_steps = max(10, min(args.steps, 100))
+
+    def e2e_step(t):
+        eng.tick_host(h_pool[t % R].numpy(), h_out.numpy(), h_vad.numpy())        # H2D, NS, AGC+VAD, D2H, sync
+        d_pcm.copy_(h_out, non_blocking=True)                                       # (bus runs on the processed PCM)
+        eng.bus_sum(d_pcm, d_bus, stream)
+        h_bus.copy_(d_bus, non_blocking=True)
+        stream.synchronize()
+
+    for t in range(3):
+        e2e_step(t)
+    barrier()
+    t0 = time.perf_counter()
+    for t in range(e2e_steps):
+        e2e_step(args.warmup + args.steps + t)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+
+    ms_step = ms_total / args.steps
+    stats = torch.tensor([ms_step, e2e_ms, ns_ms, post_ms, mix_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms_step, e2e_ms, ns_ms, post_ms, mix_ms = [float(v) for v in stats.cpu()]
+    if rank == 0:
+        peak, peak_src = peaks()
+        total_streams = S * world
+        achieved = S * NS_BYTES_PER_STREAM_TICK / (ns_ms * 1e-3) / 1e9
+        line = {
+            "metric": "real-time 16 kHz streams per GPU, NS+VAD+AGC+mix, 10 ms tick; % HBM roofline",
+            "value": total_streams * 10.0 / ms_step, "unit": "real-time 16 kHz streams (10 ms tick), whole job",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+i16 (float NS with double transcendentals, integer AGC/VAD/mix)", "data": "synthetic",
+            "config": {"workload": "BASELINE config 3: NS->AGC(5 dB)->VAD(mode 3)->int32 conference bus, 16 kHz mono, "
+                                   "%d streams per GPU in conferences of %d" % (S, CONF_SIZE),
+                       "streams_per_gpu": S, "tick_ms": 10, "parallelism": "streams sharded, no collective",
+                       "l2_policy": "per-tick working set (state %.0f MB + PCM) exceeds the 126 MB L2; inputs rotate over %d ticks"
+                                    % (S * eng.state_bytes_per_stream() / 1e6, R)},
+            "realtime_headroom": 10.0 / ms_step,
+            "kernel_ms": {"ns_kernel": ns_ms, "post_kernel(agc+vad)": post_ms, "bus_sum_kernel": mix_ms},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "kernel": "ns_kernel<256>", "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": S * NS_BYTES_PER_STREAM_TICK,
+                         "whole_tick_frac": S * CHAIN_BYTES_PER_STREAM_TICK / (ms_step * 1e-3) / 1e9 / peak},
+            "e2e": {"value": total_streams * 10.0 / e2e_ms, "unit": "real-time 16 kHz streams (10 ms tick), whole job",
+                    "ms_per_step": e2e_ms, "h2d_bytes_per_step": S * FRAME * 2,
+                    "d2h_bytes_per_step": S * FRAME * 2 + S + n_conf * FRAME * 4, "steps": e2e_steps,
+                    "path": "wmixb_tick_host (pinned host PCM in/out + VAD flags) + bus D2H"},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            try:
+                leg = cpu_leg(2048, 40)
+                line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
+                line["cpu_baseline"]["us_per_stream_tick_per_core"] = leg["us_per_stream_tick_per_core"]
+            except Exception as ex:  # pragma: no cover
+                line["cpu_baseline"] = {"value": None, "unit": "", "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
+        print(json.dumps(line))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=250)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--streams", type=int, default=100_000, help="streams per GPU")
+    ap.add_argument("--ring", type=int, default=8, help="distinct input ticks kept resident")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
