@@ -78,6 +78,8 @@ ns_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Tables
     float* tile = smem + NsSmem<ANA>::kTableFloats + (size_t)warp * G::kShFloats;
     ns::Warp<ANA> W;
     W.lane_id = threadIdx.x & 31;
+    for (int i = W.lane_id; i < G::kShFloats; i += 32) tile[i] = 0.f;   // sum rows rely on +0.0f padding
+    __syncwarp();
     const int total_warps = gridDim.x * kNsWarps;
     for (int s = blockIdx.x * kNsWarps + warp; s < n_streams; s += total_warps) {
         float* r = rec + (size_t)s * G::kRecFloats;
