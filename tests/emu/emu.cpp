@@ -23,6 +23,7 @@ template <int ANA>
 static void fill_tables(ns::Tables<ANA>& T, int policy)
 {
     memset(&T, 0, sizeof(T));
+    host::dmath_tables(T.dm.log_invc, T.dm.log_logc, T.dm.exp_2jn);
     host::ns_window(ANA, ns::Geo<ANA>::kBlock, T.window);
     host::fft_w_table(ANA / 4, T.w);
     host::fft_c_table(ANA / 4, T.c);
@@ -118,4 +119,11 @@ int16_t emu_mix_step(int16_t bus, int16_t src, int rdce) { return mix_step(bus, 
 int emu_agc_gain_table(int32_t* t, int comp, int target, int lim, int at) { return host::agc_gain_table(t, (int16_t)comp, (int16_t)target, lim, (int16_t)at); }
 int emu_agc_analog_target(int comp) { return host::agc_analog_target((int16_t)comp); }
 void emu_ns_window(int ana, int block, float* w) { host::ns_window(ana, block, w); }
+void emu_logexp(const float* x, int n, float* lg, float* ex)
+{
+    static ns::DMath dm;
+    static bool init = false;
+    if (!init) { host::dmath_tables(dm.log_invc, dm.log_logc, dm.exp_2jn); init = true; }
+    for (int i = 0; i < n; ++i) { if (lg) lg[i] = ns::log_f(x[i], dm); if (ex) ex[i] = ns::exp_f(x[i], dm); }
+}
 }

@@ -90,6 +90,21 @@ void ns_log_table(int bins, float* log_i, float* sum, float* sum_sq)
     *sum_sq = s2;
 }
 
+// tables of ns.cuh's log_f / exp_f: sub-interval centres, their reciprocals and logs, and
+// 2^(j/128), evaluated in long double and rounded once to double
+void dmath_tables(double* invc, double* logc, double* exp2jn)
+{
+    for (int i = 0; i < 128; ++i) {
+        union { uint64_t u; double d; } lo, hi;
+        lo.u = 0x3fe6000000000000ull + ((uint64_t)i << 45);
+        hi.u = 0x3fe6000000000000ull + ((uint64_t)(i + 1) << 45);
+        const long double c = (i == 80) ? 1.0L : 0.5L * ((long double)lo.d + (long double)hi.d);
+        invc[i] = (double)(1.0L / c);
+        logc[i] = (i == 80) ? 0.0 : (double)(-logl((long double)invc[i]));
+        exp2jn[i] = (double)exp2l((long double)i / 128.0L);
+    }
+}
+
 // T:.../ns/ns_core.c:1012-1041
 int ns_policy(int mode, float* overdrive, float* floor_gain, int* gainmap)
 {

@@ -8,6 +8,7 @@ void ns_window(int ana, int block, float* w);
 void fft_w_table(int nw, float* w);
 void fft_c_table(int nc, float* c);
 void ns_log_table(int bins, float* log_i, float* sum, float* sum_sq);
+void dmath_tables(double* invc, double* logc, double* exp2jn);
 int ns_policy(int mode, float* overdrive, float* floor_gain, int* gainmap);
 int vad_thresholds(int mode, int frame_ms, int16_t out[4]);
 void vad_initial_words(int32_t* words);

@@ -295,6 +295,7 @@ static int upload_ns_tables(wmixb_engine* e)
 {
     ns::Tables<ANA> T;
     memset(&T, 0, sizeof T);
+    host::dmath_tables(T.dm.log_invc, T.dm.log_logc, T.dm.exp_2jn);
     host::ns_window(ANA, ns::Geo<ANA>::kBlock, T.window);
     host::fft_w_table(ANA / 4, T.w);
     host::fft_c_table(ANA / 4, T.c);
