@@ -52,6 +52,13 @@ static int fail_cuda(cudaError_t e, const char* what, int line)
 // ------------------------------------------------------------------------------------------
 constexpr int kNsWarps = 8;
 
+// bulk L2 prefetch (bytes a multiple of 16, address 16-byte aligned): one instruction, no
+// destination, no completion to wait for
+__device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 template <int ANA>
 struct NsSmem {
     static constexpr size_t kTableFloats = (sizeof(ns::Tables<ANA>) + 15) / 16 * 4;
@@ -86,8 +93,14 @@ ns_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Tables
         uint16_t* h = hist + (size_t)s * 3 * ns::kHistBins;
         const int16_t* pi = in + (size_t)s * n_frames * G::kBlock;
         int16_t* po = out + (size_t)s * n_frames * G::kBlock;
-        for (int f = 0; f < n_frames; ++f)
+        for (int f = 0; f < n_frames; ++f) {
+            if (f == n_frames - 1 && W.lane_id == 0 && s + total_warps < n_streams) {
+                // pull the next stream's record and first frame towards L2 while this one computes
+                l2_prefetch(rec + (size_t)(s + total_warps) * G::kRecFloats, G::kRecFloats * sizeof(float));
+                l2_prefetch(in + (size_t)(s + total_warps) * n_frames * G::kBlock, G::kBlock * sizeof(int16_t));
+            }
             ns::frame<ANA>(W, r, h, pi + (size_t)f * G::kBlock, po + (size_t)f * G::kBlock, tile, *T);
+        }
     }
 }
 
