@@ -131,6 +131,19 @@ void orc_ns_release(orc_ns *h);
 int orc_ns_block_index(const orc_ns *h);
 const float *orc_ns_prior_model(const orc_ns *h);
 
+/* ---- AEC float core as wmix drives it (T:webrtc/modules/audio_processing/aec; R:src/webrtc.c:217-500) ---- */
+typedef struct orc_aec orc_aec;
+orc_aec *orc_aec_init(int chn, int freq, int interval_ms);
+int orc_aec_set_frame_far(orc_aec *h, const int16_t *far, int frame_num);
+int orc_aec_process(orc_aec *h, const int16_t *near, int16_t *out, int frame_num, int delay_ms);
+int orc_aec_process2(orc_aec *h, const int16_t *far, const int16_t *near, int16_t *out, int frame_num, int delay_ms);
+void orc_aec_release(orc_aec *h);
+void orc_aec_rdft(float *a128, int inverse);                 /* aec_rdft_forward_128 / inverse_128 */
+void orc_aec_tables(float *w64, float *hann65, float *weight65, float *over65);
+int orc_aec_far_available(const orc_aec *h);
+int orc_aec_system_delay(const orc_aec *h);
+int orc_aec_startup(const orc_aec *h);
+
 #ifdef __cplusplus
 }
 #endif

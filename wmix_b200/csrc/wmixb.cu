@@ -67,8 +67,8 @@ struct NsSmem {
 template <int ANA>
 constexpr size_t ns_smem_bytes() { return NsSmem<ANA>::kBytes; }
 
-template <int ANA>
-__global__ void __launch_bounds__(kNsWarps * 32, 2)
+template <int ANA, int MINB>
+__global__ void __launch_bounds__(kNsWarps * 32, MINB)
 ns_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Tables<ANA>* __restrict__ tables,
           const int16_t* in, int16_t* out, int n_streams, int n_frames)
 {
@@ -299,9 +299,27 @@ struct wmixb_engine {
     int n_conf = 0, max_conf = 0;
     cudaStream_t stream = nullptr;
     int ns_grid = 0;
+    int ns_occ = 2;                         // CTAs per SM the NS kernel variant is compiled for
 };
 
 static int ns_rec_floats(const wmixb_engine* e) { return e->ana == 256 ? ns::Geo<256>::kRecFloats : ns::Geo<128>::kRecFloats; }
+
+template <int ANA>
+static const void* ns_fn(int occ)
+{
+    return occ == 4 ? (const void*)ns_kernel<ANA, 4> : occ == 3 ? (const void*)ns_kernel<ANA, 3> : (const void*)ns_kernel<ANA, 2>;
+}
+
+template <int ANA>
+static int launch_ns(wmixb_engine* e, int grid, cudaStream_t st, const int16_t* in, int16_t* out, int n, int n_frames)
+{
+    float* rec = e->ns_rec;
+    uint16_t* hist = e->ns_hist;
+    const ns::Tables<ANA>* T = (const ns::Tables<ANA>*)e->ns_tables;
+    void* args[] = {&rec, &hist, &T, &in, &out, &n, &n_frames};
+    CK(cudaLaunchKernel(ns_fn<ANA>(e->ns_occ), dim3(grid), dim3(kNsWarps * 32), args, ns_smem_bytes<ANA>(), st));
+    return WMIXB_OK;
+}
 
 template <int ANA>
 static int upload_ns_tables(wmixb_engine* e)
@@ -319,9 +337,13 @@ static int upload_ns_tables(wmixb_engine* e)
     }
     CK(cudaMalloc(&e->ns_tables, sizeof T));
     CK(cudaMemcpy(e->ns_tables, &T, sizeof T, cudaMemcpyHostToDevice));
-    CK(cudaFuncSetAttribute(ns_kernel<ANA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns_smem_bytes<ANA>()));
+    // register budget variant: 2 / 3 / 4 CTAs of 8 warps per SM (128 / 80 / 64 registers per lane)
+    if (const char* v = getenv("WMIXB_NS_OCC")) { const int o = atoi(v); if (o >= 2 && o <= 4) e->ns_occ = o; }
+    const void* fn = ns_fn<ANA>(e->ns_occ);
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns_smem_bytes<ANA>()));
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ns_kernel<ANA>, kNsWarps * 32, ns_smem_bytes<ANA>()));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kNsWarps * 32, ns_smem_bytes<ANA>()));
     if (per_sm < 1) per_sm = 1;
     e->ns_grid = e->sm_count * per_sm;
     return WMIXB_OK;
@@ -462,10 +484,8 @@ static int run_stages(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint
     if (stages & WMIXB_NS) {
         const int need = (n + kNsWarps - 1) / kNsWarps;
         const int grid = need < e->ns_grid ? need : e->ns_grid;
-        if (e->ana == 256)
-            ns_kernel<256><<<grid, kNsWarps * 32, ns_smem_bytes<256>(), st>>>(e->ns_rec, e->ns_hist, (const ns::Tables<256>*)e->ns_tables, cur, d_out, n, n_frames);
-        else
-            ns_kernel<128><<<grid, kNsWarps * 32, ns_smem_bytes<128>(), st>>>(e->ns_rec, e->ns_hist, (const ns::Tables<128>*)e->ns_tables, cur, d_out, n, n_frames);
+        const int rc = e->ana == 256 ? launch_ns<256>(e, grid, st, cur, d_out, n, n_frames) : launch_ns<128>(e, grid, st, cur, d_out, n, n_frames);
+        if (rc) return rc;
         CK_LAUNCH();
         cur = d_out;
     }

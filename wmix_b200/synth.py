@@ -67,3 +67,26 @@ def make_frames(n_streams, freq, tick0, n_ticks, seed=0, cohorts=True):
         x[np.ix_(late, early)] = 0.0
     x = np.clip(np.rint(x), -32768, 32767).astype(np.int16)
     return np.ascontiguousarray(x.reshape(n_streams, n_ticks, L).transpose(1, 0, 2))
+
+
+def make_aec_pairs(n_streams, freq, tick0, n_ticks, seed=0, delay_ms=5, echo_gain=0.5, cohorts=True):
+    """(far, near) int16 arrays [n_ticks, n_streams, freq//100] for BASELINE config 4 (SURVEY.md §8d):
+    near = far delayed by `delay_ms` and scaled by `echo_gain` + an independent local talker + noise.
+    Cohorts (s mod 64): 1 = far all-zero (zero far-end guard), 2 = far full-scale square (saturating echo)."""
+    L = freq // 100
+    d = freq * delay_ms // 1000
+    lead = (d + L - 1) // L
+    t0 = max(0, tick0 - lead)
+    far_all = make_frames(n_streams, freq, t0, n_ticks + (tick0 - t0), seed=seed, cohorts=cohorts)
+    far_flat = far_all.transpose(1, 0, 2).reshape(n_streams, -1).astype(np.float64)
+    pad = lead * L - (tick0 - t0) * L                       # zeros before the beginning of time
+    far_flat = np.concatenate([np.zeros((n_streams, pad)), far_flat], axis=1)
+    start = lead * L
+    echo = echo_gain * far_flat[:, start - d:start - d + n_ticks * L]
+    local = make_frames(n_streams, freq, tick0, n_ticks, seed=seed + 7919, cohorts=False).transpose(1, 0, 2)
+    local = local.reshape(n_streams, -1).astype(np.float64) * 0.6
+    near = np.clip(np.rint(echo + local), -32768, 32767).astype(np.int16)
+    far = far_flat[:, start:start + n_ticks * L].astype(np.int16)
+    shp = (n_streams, n_ticks, L)
+    return (np.ascontiguousarray(far.reshape(shp).transpose(1, 0, 2)),
+            np.ascontiguousarray(near.reshape(shp).transpose(1, 0, 2)))
