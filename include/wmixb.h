@@ -28,8 +28,8 @@ enum {
     WMIXB_ENOMEM = -4
 };
 
-/* stage bits, executed in the reference's order NS -> AGC -> VAD (R:src/wmix.c:613-710) */
-enum { WMIXB_NS = 1, WMIXB_AGC = 2, WMIXB_VAD = 4 };
+/* stage bits, executed in the reference's order NS -> AEC -> AGC -> VAD (R:src/wmix.c:613-710) */
+enum { WMIXB_NS = 1, WMIXB_AGC = 2, WMIXB_VAD = 4, WMIXB_AEC = 8 };
 
 typedef struct wmixb_config {
     int n_streams;      /* independent mono streams on this GPU                                  */
@@ -39,7 +39,9 @@ typedef struct wmixb_config {
     int agc_gain_db;    /* compressionGaindB = wmix's `value` (R:src/webrtc.c:707), e.g. 5        */
     int vad_mode;       /* 0..3; wmix uses 3   (R:src/webrtc.c:16 VAD_AGGRESSIVE)                */
     int device;         /* CUDA device ordinal                                                   */
-    int reserved[9];
+    int aec_far_depth;  /* far-end history kept per stream, in 64-sample partitions; 0 = 32.  The
+                           reference keeps 250 (T:.../aec/aec_core.c:37); the handle API uses 252.   */
+    int reserved[8];
 } wmixb_config;
 
 typedef struct wmixb_engine wmixb_engine;
@@ -60,6 +62,24 @@ int wmixb_tick_device(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint
                       void* stream);
 /* Same, host buffers: H2D copy, kernels, D2H copy on the engine's own stream, then waits. */
 int wmixb_tick_host(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int stages);
+
+/* Echo canceller (stage WMIXB_AEC), the arithmetic of aec_process2 (R:src/webrtc.c:410-483) for every
+ * stream: BufferFarend(d_far) then Process(d_near) -> d_out.  d_far == NULL is aec_process (near only),
+ * d_near == NULL is aec_setFrameFar (far only; d_out unused).  Buffers are int16 [n_streams][samples],
+ * samples = 80 or 160 per call (10 ms at the engine's rate, or wmix's 20 ms packets at 8 kHz);
+ * d_out may alias d_near.  delay_ms (0..500) is the reported sound-card delay, 0 in wmix
+ * (R:src/wmix.c:651-657). */
+int wmixb_aec_device(wmixb_engine* e, const int16_t* d_far, const int16_t* d_near, int16_t* d_out, int samples,
+                     int delay_ms, void* stream);
+/* Same with host buffers (pinned for full overlap): H2D, kernel, D2H on the engine's stream, then waits. */
+int wmixb_aec_host(wmixb_engine* e, const int16_t* h_far, const int16_t* h_near, int16_t* h_out, int samples, int delay_ms);
+/* The whole record chain NS -> AEC -> AGC -> VAD of one 10 ms tick (wmix's own order); d_far feeds the AEC. */
+int wmixb_tick_chain_device(wmixb_engine* e, const int16_t* d_far, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad,
+                            int stages, int delay_ms, void* stream);
+/* Sticky per-stream AEC flags OR-ed over all streams (0 = healthy): bit 0 = a far-end rewind/backlog needed
+ * more history than aec_far_depth holds, bit 1 = far-end underrun (the reference asserts it cannot happen).
+ * *h_flagged (nullable) receives the number of streams with any flag.  Synchronises the engine stream. */
+int wmixb_aec_status(wmixb_engine* e, int* h_flags, int* h_flagged);
 
 /* Persistent offline mode: every stream runs n_frames consecutive frames inside one launch per
  * stage.  d_in / d_out: int16 [n_streams][n_frames][frame].  d_vad (nullable): [n_streams][n_frames]. */

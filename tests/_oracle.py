@@ -34,7 +34,7 @@ def oracle():
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, so])
         L = C.CDLL(so)
-        for f in ("orc_vad_init", "orc_agc_init", "orc_ns_init"):
+        for f in ("orc_vad_init", "orc_agc_init", "orc_ns_init", "orc_aec_init"):
             getattr(L, f).restype = C.c_void_p
         L.orc_ns_prior_model.restype = C.POINTER(C.c_float)
         L.orc_mix_same_format.restype = C.c_uint32
@@ -102,3 +102,52 @@ class RefChain:
             self.g("agc_release")(self.agc)
         if self.vad:
             self.g("vad_release")(self.vad)
+
+
+class AecRef:
+    """aec_process2 / aec_setFrameFar / aec_process through a checker (oracle: prefix "orc_", reference: "")."""
+
+    def __init__(self, L, freq, interval_ms=10, prefix=""):
+        self.L, self.prefix = L, prefix
+        self.pkg = freq // 1000 * (20 if (freq <= 8000 and interval_ms % 20 == 0) else 10)
+        if prefix:
+            self.h = C.c_void_p(L.orc_aec_init(1, freq, interval_ms))
+        else:
+            self.h = C.c_void_p(L.aec_init(1, freq, interval_ms, None))
+        assert self.h
+
+    def process2(self, far, near, delay_ms=0):
+        far = np.ascontiguousarray(far, np.int16).copy()
+        near = np.ascontiguousarray(near, np.int16).copy()
+        out = np.zeros(len(near), np.int16)
+        f = self.L.orc_aec_process2 if self.prefix else self.L.aec_process2
+        rc = f(self.h, P(far), P(near), P(out), len(near), delay_ms)
+        return out, rc
+
+    def set_far(self, far):
+        far = np.ascontiguousarray(far, np.int16).copy()
+        f = self.L.orc_aec_set_frame_far if self.prefix else self.L.aec_setFrameFar
+        return f(self.h, P(far), len(far))
+
+    def process(self, near, delay_ms=0):
+        near = np.ascontiguousarray(near, np.int16).copy()
+        out = np.zeros(len(near), np.int16)
+        f = self.L.orc_aec_process if self.prefix else self.L.aec_process
+        rc = f(self.h, P(near), P(out), len(near), delay_ms)
+        return out, rc
+
+    def close(self):
+        (self.L.orc_aec_release if self.prefix else self.L.aec_release)(self.h)
+
+
+def aec_run_pairs(L, prefix, far, near, freq, interval_ms=10, delay_ms=0):
+    """far/near int16 [T, S, n] -> out [T, S, n] through one checker handle per stream."""
+    T, S, n = near.shape
+    out = np.empty_like(near)
+    for s in range(S):
+        h = AecRef(L, freq, interval_ms, prefix)
+        for t in range(T):
+            d = delay_ms(t) if callable(delay_ms) else delay_ms
+            out[t, s], _ = h.process2(far[t, s], near[t, s], d)
+        h.close()
+    return out

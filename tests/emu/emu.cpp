@@ -11,6 +11,7 @@
 #include <string.h>
 #include <vector>
 
+#include "../../wmix_b200/csrc/aec.cuh"
 #include "../../wmix_b200/csrc/agc.cuh"
 #include "../../wmix_b200/csrc/g711_mix.cuh"
 #include "../../wmix_b200/csrc/host_tables.h"
@@ -106,6 +107,45 @@ int emu_vad_frame(void* h, int16_t* x)
     return vad::process_packet<80, false>(st, x, e->vp);
 }
 void emu_int_destroy(void* h) { delete (EmuInt*)h; }
+
+struct EmuAec {
+    int mult, depth;
+    std::vector<float> rec, sh;
+    aec::Tables T;
+    aec::Warp W;
+};
+void* emu_aec_create(int freq, int depth)
+{
+    EmuAec* e = new EmuAec();
+    e->mult = freq / 8000;
+    e->depth = depth;
+    memset(&e->T, 0, sizeof e->T);
+    host::dmath_tables(e->T.dm.log_invc, e->T.dm.log_logc, e->T.dm.exp_2jn);
+    host::aec_tables(e->T.w, e->T.c, e->T.hann, e->T.weight, e->T.over, e->T.lcg_mul, e->T.lcg_add);
+    e->rec.assign(aec::rec_floats(depth), 0.f);
+    e->sh.assign(aec::Geo::kShFloats, 0.f);
+    for (int l = 0; l < 32; ++l) aec::init_record_values(e->rec.data(), l, 32);
+    return e;
+}
+// far / near may be NULL (aec_setFrameFar / aec_process); n = 80 or 160 samples
+void emu_aec_tick(void* h, const int16_t* far, const int16_t* near, int16_t* out, int n, int delay_ms)
+{
+    EmuAec* e = (EmuAec*)h;
+    aec::tick(e->W, e->rec.data(), e->depth, e->mult, n, far, near, out, delay_ms, e->sh.data(), e->T);
+}
+int emu_aec_error(void* h) { return ns::f2i(((EmuAec*)h)->rec[aec::Geo::kOffScal + aec::S_ERROR]); }
+int emu_aec_scalar(void* h, int id) { return ns::f2i(((EmuAec*)h)->rec[aec::Geo::kOffScal + id]); }
+void emu_aec_destroy(void* h) { delete (EmuAec*)h; }
+void emu_aec_rdft(float* a, int inverse)
+{
+    EmuAec* e = (EmuAec*)emu_aec_create(8000, 4);
+    float* sp = e->sh.data() + aec::Geo::kShSp;
+    memcpy(sp, a, 128 * sizeof(float));
+    if (inverse) aec::rdft_inv(e->W, sp, (float*)nullptr, e->sh.data() + aec::Geo::kShX, e->T, 1);
+    else aec::rdft_fwd(e->W, sp, (float*)nullptr, e->sh.data() + aec::Geo::kShX, e->T, 1);
+    memcpy(a, sp, 128 * sizeof(float));
+    delete e;
+}
 
 void emu_g711(const int16_t* pcm, int n, uint8_t* alaw, uint8_t* ulaw)
 {

@@ -53,6 +53,18 @@ def main():
             g["streams"]["%s_%d" % (stage, freq)] = dict(freq=freq, stage=stage, n_streams=S, n_ticks=T, seed=seed,
                                                          hash=fnv1a64(y.tobytes()),
                                                          head=y[:, :8].tolist(), tail=y[:, -8:].tolist())
+    # AEC: aec_process2 on near/far pairs (config 4's signal model)
+    from tests._oracle import aec_run_pairs
+    from wmix_b200.synth import make_aec_pairs
+
+    g["aec"] = {}
+    for freq, T, delay in ((8000, 900, 0), (16000, 500, 0), (8000, 500, 80)):
+        S, seed = 4, 29
+        far, near = make_aec_pairs(S, freq, 0, T, seed=seed)
+        y = aec_run_pairs(R, "", far, near, freq, 10, delay)
+        y = np.ascontiguousarray(y.transpose(1, 0, 2)).reshape(S, -1)
+        g["aec"]["aec_%d_d%d" % (freq, delay)] = dict(freq=freq, n_streams=S, n_ticks=T, seed=seed, delay_ms=delay,
+                                                     hash=fnv1a64(y.tobytes()), tail=y[:, -8:].tolist())
     json.dump(g, open(os.path.join(ROOT, "tests", "golden", "hashes.json"), "w"), indent=1)
     print("wrote hashes.json")
 

@@ -125,3 +125,97 @@ def test_synth_streams_are_reproducible_and_tick_addressable():
     b = make_frames(70, 16000, 10, 5, seed=3)
     assert np.array_equal(a[10:15], b)
     assert not a[:, 1].any() and np.abs(a[:, 2]).min() == 32767
+
+
+# ---------------------------------------------------------------- AEC (lane-loop emulation of aec.cuh)
+AEC_MAX_ABS = 1          # powf / cosf / sinf are evaluated in double and rounded: a last-bit difference of the
+AEC_MIN_EQUAL = 0.9999   # suppression gain or comfort noise can move an output sample by one LSB, never the state
+
+
+def _aec_emu_vs_oracle(freq, n, ims, T, S, depth, delay=0, bursts=False, seed=3):
+    from tests._oracle import AecRef
+    from wmix_b200.synth import make_aec_pairs
+
+    E, L = emu(), oracle()
+    E.emu_aec_create.restype = C.c_void_p
+    far, near = make_aec_pairs(S, freq, 0, T, seed=seed)
+    far = far.transpose(1, 0, 2).reshape(S, -1, n)
+    near = near.transpose(1, 0, 2).reshape(S, -1, n)
+    bad = tot = worst = flags = 0
+    for s in range(S):
+        a = AecRef(L, freq, ims, "orc_")
+        b = C.c_void_p(E.emu_aec_create(freq, depth))
+        t, nt = 0, far.shape[1]
+        while t < nt:
+            grp = min(nt - t, 1 + (t * 7 + s) % 3) if bursts else 1
+            outs = []
+            if bursts:
+                for g in range(grp):
+                    a.set_far(far[s, t + g])
+                    E.emu_aec_tick(b, P(np.ascontiguousarray(far[s, t + g])), None, None, n, 0)
+                for g in range(grp):
+                    ya, _ = a.process(near[s, t + g], delay)
+                    yb = np.zeros(n, np.int16)
+                    E.emu_aec_tick(b, None, P(np.ascontiguousarray(near[s, t + g])), P(yb), n, delay)
+                    outs.append((ya, yb))
+            else:
+                ya, _ = a.process2(far[s, t], near[s, t], delay)
+                yb = np.zeros(n, np.int16)
+                E.emu_aec_tick(b, P(np.ascontiguousarray(far[s, t])), P(np.ascontiguousarray(near[s, t])), P(yb), n, delay)
+                outs.append((ya, yb))
+            for ya, yb in outs:
+                d = np.abs(ya.astype(np.int32) - yb)
+                bad += int((d > 0).sum())
+                tot += n
+                worst = max(worst, int(d.max()))
+            t += grp
+        flags |= E.emu_aec_error(b)
+        a.close()
+        E.emu_aec_destroy(b)
+    return bad, tot, worst, flags
+
+
+@pytest.mark.parametrize("freq,n,ims,T,S,depth,delay,bursts", [
+    (8000, 80, 10, 700, 8, 32, 0, False),       # config 4's rate and cadence; includes the zero-far / square cohorts
+    (16000, 160, 10, 400, 4, 32, 0, False),
+    (8000, 160, 20, 300, 3, 32, 40, False),     # wmix's own 20 ms packets
+    (8000, 80, 10, 500, 3, 32, 120, True),      # far / near in bursts, non-zero reported delay
+    (16000, 160, 10, 300, 2, 252, 0, True),     # the handle API's full-depth ring
+])
+def test_emulated_aec_vs_oracle(freq, n, ims, T, S, depth, delay, bursts):
+    bad, tot, worst, flags = _aec_emu_vs_oracle(freq, n, ims, T, S, depth, delay, bursts)
+    print("[aec emu %d Hz n=%d] mismatching %d / %d, max |diff| %d, flags %d" % (freq, n, bad, tot, worst, flags))
+    assert flags == 0
+    assert worst <= AEC_MAX_ABS and bad <= (1.0 - AEC_MIN_EQUAL) * tot
+
+
+def test_emulated_aec_rdft_and_tables():
+    import wmix_b200
+
+    E, L = emu(), oracle()
+    rng = np.random.default_rng(2)
+    for k in range(100):
+        a = (rng.standard_normal(128) * 10 ** rng.uniform(-3, 4)).astype(np.float32)
+        for inv in (0, 1):
+            x, y = a.copy(), a.copy()
+            L.orc_aec_rdft(P(x), inv)
+            E.emu_aec_rdft(P(y), inv)
+            assert np.array_equal(x.view(np.int32), y.view(np.int32))
+    assert wmix_b200  # the product's tables are pinned through the GPU parity tests
+
+
+def test_aec_far_depth_flag_is_loud():
+    """A far-end backlog deeper than the configured history must raise the sticky flag, not corrupt silently."""
+    E = emu()
+    E.emu_aec_create.restype = C.c_void_p
+    h = C.c_void_p(E.emu_aec_create(8000, 8))
+    z = np.zeros(80, np.int16)
+    o = np.zeros(80, np.int16)
+    for t in range(40):                       # start-up: process normally
+        E.emu_aec_tick(h, P(z), P(z), P(o), 80, 0)
+    assert E.emu_aec_error(h) == 0
+    for t in range(30):                       # 30 far frames without a near frame: 37 partitions of backlog
+        E.emu_aec_tick(h, P(z), None, None, 80, 0)
+    E.emu_aec_tick(h, None, P(z), P(o), 80, 0)
+    assert E.emu_aec_error(h) & 1
+    E.emu_aec_destroy(h)

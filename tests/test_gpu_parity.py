@@ -19,8 +19,8 @@ torch = pytest.importorskip("torch")
 
 import wmix_b200  # noqa: E402
 from tests._oracle import P, RefChain, fnv1a64, oracle, ref  # noqa: E402
-from wmix_b200 import AGC, NS, VAD  # noqa: E402
-from wmix_b200.synth import make_frames  # noqa: E402
+from wmix_b200 import AEC, AGC, NS, VAD  # noqa: E402
+from wmix_b200.synth import make_aec_pairs, make_frames  # noqa: E402
 
 DEV = "cuda:0"
 NS_MAX_ABS = 2
@@ -357,6 +357,165 @@ def test_full_size_replication_property():
         y = d.view(-1)[: (S // base) * base * 160].view(S // base, base, 160)
         assert bool((y == y[0:1]).all())
         assert np.array_equal(y[0].cpu().numpy(), small[t])
+    eng.close()
+
+
+# ---------------------------------------------------------------- AEC (config 4)
+AEC_MAX_ABS = 1          # powf / cosf / sinf of the suppression gain and comfort noise are evaluated in double and
+AEC_MIN_EQUAL = 0.9995   # rounded; they shape the output only (never the adaptive state): <= 1 LSB, >= 99.95 % equal
+
+
+def _aec_compare(got, want, what):
+    diff = np.abs(got.astype(np.int32) - want.astype(np.int32))
+    per_stream_equal = (diff == 0).mean(axis=(0, 2))
+    info = dict(max_abs=int(diff.max()), mismatching=int((diff > 0).sum()), total=int(diff.size),
+                worst_stream_equal=float(per_stream_equal.min()))
+    print("[aec parity %s] %s" % (what, info))
+    assert diff.max() <= AEC_MAX_ABS, info
+    assert per_stream_equal.min() >= AEC_MIN_EQUAL, info
+    return info
+
+
+def run_gpu_aec(far, near, freq, delay=0, ns=False, depth=0):
+    T, S, n = near.shape
+    eng = wmix_b200.Engine(S, freq, stages=AEC | (NS if ns else 0), aec_far_depth=depth)
+    out = np.empty_like(near)
+    d_far = torch.empty((S, n), dtype=torch.int16, device=DEV)
+    d_near = torch.empty((S, n), dtype=torch.int16, device=DEV)
+    for t in range(T):
+        d_far.copy_(torch.from_numpy(far[t]))
+        d_near.copy_(torch.from_numpy(near[t]))
+        if ns:
+            eng.tick_chain_device(d_far, d_near, d_near, None, NS | AEC, delay)    # wmix's order: NS then AEC, in place
+        else:
+            eng.aec_device(d_far, d_near, d_near, n, delay)
+        out[t] = d_near.cpu().numpy()
+    status = eng.aec_status()
+    eng.close()
+    return out, status
+
+
+@pytest.mark.parametrize("freq,T,delay", [(8000, 900, 0), (16000, 500, 0), (8000, 500, 80)])
+def test_aec_vs_checkers(freq, T, delay):
+    from tests._oracle import aec_run_pairs
+
+    S = 70                                                   # cohorts: zero far end, full-scale square, DC, late start
+    far, near = make_aec_pairs(S, freq, 0, T, seed=29)
+    got, status = run_gpu_aec(far, near, freq, delay)
+    assert status == (0, 0)
+    for cname, L, prefix in checkers():
+        want = aec_run_pairs(L, prefix, far[:, :12], near[:, :12], freq, 10, delay)
+        info = _aec_compare(got[:, :12], want, "%s %d Hz delay %d" % (cname, freq, delay))
+        if info["mismatching"] == 0:
+            print("  -> bit-exact")
+    # committed fixture made from the reference (first 4 streams, same seed)
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "hashes.json")))
+    spec = g["aec"]["aec_%d_d%d" % (freq, delay)]
+    y = np.ascontiguousarray(got[:, :4].transpose(1, 0, 2)).reshape(4, -1)
+    tail = np.array(spec["tail"], np.int16)
+    assert np.abs(y[:, -8:].astype(int) - tail).max() <= AEC_MAX_ABS
+    print("[golden aec] %s" % ("bit-exact" if fnv1a64(y.tobytes()) == spec["hash"] else "within 1 LSB"))
+    # the canceller cancels: streams 4.. are echo + talker; the echo-only cohort must be strongly attenuated
+    assert np.abs(got[-50:, 2].astype(float)).mean() < 0.2 * np.abs(near[-50:, 2].astype(float)).mean()
+
+
+def test_config4_ns_then_aec_chain():
+    """BASELINE config 4: per tick ns_process(near) then aec_process2(far, near, out, 80, 0), 8 kHz."""
+    from tests._oracle import AecRef
+
+    S, T, freq = 20, 700, 8000
+    far, near = make_aec_pairs(S, freq, 0, T, seed=37)
+    got, status = run_gpu_aec(far, near, freq, 0, ns=True)
+    assert status == (0, 0)
+    L = oracle()
+    want = np.empty_like(near[:, :8])
+    for s in range(8):
+        nsr = RefChain(L, freq, agc=False, vad=False, prefix="orc_")
+        a = AecRef(L, freq, prefix="orc_")
+        for t in range(T):
+            want[t, s], _ = a.process2(far[t, s], nsr.frame(near[t, s]))
+        nsr.close()
+        a.close()
+    _aec_compare(got[:, :8], want, "NS->AEC chain 8 kHz")
+
+
+def test_aec_handle_api_and_20ms_packets():
+    from tests._oracle import AecRef
+
+    lib = wmix_b200.lib()
+    L = oracle()
+    far, near = make_aec_pairs(2, 8000, 0, 300, seed=43)
+    f = np.ascontiguousarray(far[:, 0]).reshape(-1)
+    n = np.ascontiguousarray(near[:, 0]).reshape(-1)
+    # wmix's own cadence: aec_init(chn, 8000, WMIX_INTERVAL_MS = 20) -> 160-sample packets, two per call
+    h = lib.aec_init(1, 8000, 20, None)
+    assert h
+    a = AecRef(L, 8000, 20, "orc_")
+    bad = 0
+    for c in range(len(f) // 320):
+        ff, nn = f[c * 320:(c + 1) * 320].copy(), n[c * 320:(c + 1) * 320].copy()
+        out = np.zeros(320, np.int16)
+        assert lib.aec_process2(h, ff.ctypes.data, nn.ctypes.data, out.ctypes.data, 320, 0) == 0
+        want, rc = a.process2(ff, nn, 0)
+        assert rc == 0
+        d = np.abs(out.astype(int) - want)
+        assert d.max() <= AEC_MAX_ABS
+        bad += int((d > 0).sum())
+    assert bad <= 0.0005 * len(f)
+    # split calls + out-of-range delay behave like the reference (processed, -1, output untouched)
+    out = np.full(160, 7, np.int16)
+    assert lib.aec_setFrameFar(h, f[:160].copy().ctypes.data, 160) == 0 and a.set_far(f[:160]) == 0
+    assert lib.aec_process(h, n[:160].copy().ctypes.data, out.ctypes.data, 160, 900) == -1
+    _, rc = a.process(n[:160], 900)
+    assert rc == -1 and (out == 7).all()
+    ff, nn = f[320:480].copy(), n[320:480].copy()
+    assert lib.aec_process2(h, ff.ctypes.data, nn.ctypes.data, out.ctypes.data, 160, 0) == 0
+    want, _ = a.process2(ff, nn, 0)
+    assert np.abs(out.astype(int) - want).max() <= AEC_MAX_ABS
+    lib.aec_release(h)
+    a.close()
+    # stereo: left channel in, result replicated (R:src/webrtc.c:428-476)
+    h2 = lib.aec_init(2, 16000, 10, None)
+    a2 = AecRef(L, 16000, 10, "orc_")
+    far16, near16 = make_aec_pairs(1, 16000, 0, 60, seed=47)
+    for t in range(60):
+        fs = np.repeat(far16[t, 0], 2).astype(np.int16)
+        fs[1::2] = 123
+        ns_ = np.repeat(near16[t, 0], 2).astype(np.int16)
+        ns_[1::2] = -77
+        out = np.zeros(320, np.int16)
+        assert lib.aec_process2(h2, fs.ctypes.data, ns_.ctypes.data, out.ctypes.data, 160, 0) == 0
+        want, _ = a2.process2(far16[t, 0], near16[t, 0], 0)
+        assert np.array_equal(out[0::2], out[1::2]) and np.abs(out[0::2].astype(int) - want).max() <= AEC_MAX_ABS
+    lib.aec_release(h2)
+    a2.close()
+    assert not lib.aec_init(1, 32000, 10, None) and not lib.aec_init(1, 44100, 10, None)
+
+
+def test_aec_full_size_replication_and_depth_flag():
+    """Config 4 size (16 384 pairs): stream s gets the input of stream s % 32 -> identical outputs per class;
+    a far-end backlog deeper than the configured history raises the sticky flag."""
+    S, base, T = 16384, 32, 90
+    far, near = make_aec_pairs(base, 8000, 0, T, seed=53)
+    small, _ = run_gpu_aec(far, near, 8000)
+    eng = wmix_b200.Engine(S, 8000, stages=AEC)
+    d_far = torch.empty((S, 80), dtype=torch.int16, device=DEV)
+    d_near = torch.empty((S, 80), dtype=torch.int16, device=DEV)
+    for t in range(T):
+        d_far.copy_(torch.from_numpy(far[t]).to(DEV).repeat(S // base, 1))
+        d_near.copy_(torch.from_numpy(near[t]).to(DEV).repeat(S // base, 1))
+        eng.aec_device(d_far, d_near, d_near)
+        y = d_near.view(S // base, base, 80)
+        assert bool((y == y[0:1]).all())
+        assert np.array_equal(y[0].cpu().numpy(), small[t])
+    assert eng.aec_status() == (0, 0)
+    for t in range(40):
+        eng.aec_device(d_far, None, None)
+    eng.aec_device(None, d_near, d_near)
+    flags, n = eng.aec_status()
+    assert flags & 1 and n == S
+    eng.reset()
+    assert eng.aec_status() == (0, 0)
     eng.close()
 
 

@@ -317,3 +317,109 @@ def test_golden_streams():
             c.close()
         y = np.stack(outs)
         assert fnv1a64(y.tobytes()) == spec["hash"], key
+
+
+# ---------------------------------------------------------------- AEC
+@need_ref
+def test_aec_tables_vs_reference_symbols():
+    """The oracle builds the AEC tables from formulas (+ eight one-ulp corrections of rdft_w); the reference
+    exports its literals (T:.../aec/aec_rdft.c:32-49, aec_core.c:49-96) — they must be identical."""
+    R, L = ref(), oracle()
+    w = np.zeros(64, np.float32)
+    h = np.zeros(65, np.float32)
+    wc = np.zeros(65, np.float32)
+    od = np.zeros(65, np.float32)
+    L.orc_aec_tables(P(w), P(h), P(wc), P(od))
+
+    def sym(name, n):
+        return np.array((C.c_float * n).in_dll(R, name), dtype=np.float32)
+
+    assert np.array_equal(w, sym("rdft_w", 64))
+    assert np.array_equal(h, sym("WebRtcAec_sqrtHanning", 65))
+    assert np.array_equal(wc, sym("WebRtcAec_weightCurve", 65))
+    assert np.array_equal(od, sym("WebRtcAec_overDriveCurve", 65))
+
+
+@need_ref
+def test_aec_rdft_vs_reference():
+    R, L = ref(), oracle()
+    R.aec_rdft_init()
+    rng = np.random.default_rng(5)
+    for k in range(300):
+        a = (rng.standard_normal(128) * 10 ** rng.uniform(-3, 4)).astype(np.float32)
+        for inv in (0, 1):
+            x, y = a.copy(), a.copy()
+            L.orc_aec_rdft(P(x), inv)
+            (R.aec_rdft_inverse_128 if inv else R.aec_rdft_forward_128)(P(y))
+            assert np.array_equal(x.view(np.int32), y.view(np.int32))
+
+
+@need_ref
+@pytest.mark.parametrize("freq,ims,T,delay", [(8000, 10, 1200, 0), (8000, 20, 500, 0), (16000, 10, 600, 0),
+                                              (8000, 10, 700, 60), (16000, 10, 500, 240)])
+def test_aec_vs_reference_pairs(freq, ims, T, delay):
+    """aec_process2 on echo + local talker + noise pairs (config 4's signal model), bit for bit; the streams
+    include the zero-far-end and full-scale cohorts."""
+    from tests._oracle import aec_run_pairs
+    from wmix_b200.synth import make_aec_pairs
+
+    S = 5
+    far, near = make_aec_pairs(S, freq, 0, T, seed=17)
+    n = freq // 1000 * (20 if (freq == 8000 and ims == 20) else 10)
+    far = far.transpose(1, 0, 2).reshape(S, -1, n).transpose(1, 0, 2)
+    near = near.transpose(1, 0, 2).reshape(S, -1, n).transpose(1, 0, 2)
+    a = aec_run_pairs(ref(), "", far, near, freq, ims, delay)
+    b = aec_run_pairs(oracle(), "orc_", far, near, freq, ims, delay)
+    assert np.array_equal(a, b)
+    # the canceller really cancels: the residual of the echo-only tail is far below the near-end level
+    assert np.abs(a[-100:].astype(float)).mean() < 0.5 * np.abs(near[-100:].astype(float)).mean()
+
+
+@need_ref
+def test_aec_vs_reference_irregular_cadence_and_errors():
+    """aec_setFrameFar / aec_process in bursts (exercises the stuffing / flush paths of the far ring), a
+    delay that changes mid-call, and the wrapper's error returns."""
+    from tests._oracle import AecRef
+    from wmix_b200.synth import make_aec_pairs
+
+    R, L = ref(), oracle()
+    for freq in (8000, 16000):
+        n = freq // 100
+        far, near = make_aec_pairs(2, freq, 0, 600, seed=23)
+        for s in range(2):
+            a, b = AecRef(R, freq), AecRef(L, freq, prefix="orc_")
+            t = 0
+            while t < 600:
+                grp = min(600 - t, 1 + (t * 7 + s) % 4)
+                for g in range(grp):
+                    assert a.set_far(far[t + g, s]) == b.set_far(far[t + g, s]) == 0
+                for g in range(grp):
+                    d = 0 if t < 200 else 100
+                    ya, ra = a.process(near[t + g, s], d)
+                    yb, rb = b.process(near[t + g, s], d)
+                    assert ra == rb == 0 and np.array_equal(ya, yb), (freq, s, t)
+                t += grp
+            # out-of-range delay: processed, then reported as an error, output untouched (R:src/webrtc.c:382-387)
+            ya, ra = a.process2(far[0, s], near[0, s], 600)
+            yb, rb = b.process2(far[0, s], near[0, s], 600)
+            assert ra == rb == -1 and not ya.any() and not yb.any()
+            ya, ra = a.process2(far[1, s], near[1, s], 0)
+            yb, rb = b.process2(far[1, s], near[1, s], 0)
+            assert ra == rb == 0 and np.array_equal(ya, yb)
+            a.close()
+            b.close()
+    assert not L.orc_aec_init(1, 32000, 10) and not R.aec_init(1, 32000, 10, None)
+
+
+def test_golden_aec_streams():
+    """Committed fixtures made from the reference's aec_process2 (tests/golden/make_golden.py)."""
+    from tests._oracle import aec_run_pairs
+    from wmix_b200.synth import make_aec_pairs
+
+    g = json.load(open(os.path.join(GOLDEN, "hashes.json")))
+    for key, spec in g["aec"].items():
+        far, near = make_aec_pairs(spec["n_streams"], spec["freq"], 0, spec["n_ticks"], seed=spec["seed"])
+        y = aec_run_pairs(oracle(), "orc_", far, near, spec["freq"], 10, spec["delay_ms"])
+        y = np.ascontiguousarray(y.transpose(1, 0, 2)).reshape(spec["n_streams"], -1)
+        assert fnv1a64(y.tobytes()) == spec["hash"], key
+        assert y[:, -8:].tolist() == spec["tail"]

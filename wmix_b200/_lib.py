@@ -7,12 +7,13 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libwmix_b200.so")
 
-NS, AGC, VAD = 1, 2, 4
+NS, AGC, VAD, AEC = 1, 2, 4, 8
 
 
 class Config(C.Structure):
     _fields_ = [("n_streams", C.c_int), ("freq", C.c_int), ("stages", C.c_int), ("ns_policy", C.c_int),
-                ("agc_gain_db", C.c_int), ("vad_mode", C.c_int), ("device", C.c_int), ("reserved", C.c_int * 9)]
+                ("agc_gain_db", C.c_int), ("vad_mode", C.c_int), ("device", C.c_int), ("aec_far_depth", C.c_int),
+                ("reserved", C.c_int * 8)]
 
 
 _lib = None
@@ -36,6 +37,10 @@ def lib():
         "wmixb_tick_device": (i, [vp, vp, vp, vp, i, vp]),
         "wmixb_tick_host": (i, [vp, vp, vp, vp, i]),
         "wmixb_offline_device": (i, [vp, vp, vp, vp, i, i, vp]),
+        "wmixb_aec_device": (i, [vp, vp, vp, vp, i, i, vp]),
+        "wmixb_aec_host": (i, [vp, vp, vp, vp, i, i]),
+        "wmixb_tick_chain_device": (i, [vp, vp, vp, vp, vp, i, i, vp]),
+        "wmixb_aec_status": (i, [vp, C.POINTER(i), C.POINTER(i)]),
         "wmixb_set_conferences": (i, [vp, vp, i]),
         "wmixb_bus_sum_device": (i, [vp, vp, vp, vp]),
         "wmixb_bus_nminus1_device": (i, [vp, vp, vp, vp, vp]),
@@ -60,7 +65,8 @@ def lib():
         "ns_init": (vp, [i, i, vp]), "ns_process": (None, [vp, vp, vp, i]), "ns_release": (None, [vp]),
         "agc_init": (vp, [i, i, i, i, vp]), "agc_process": (i, [vp, vp, vp, i]),
         "agc_addition": (None, [vp, C.c_uint8]), "agc_release": (None, [vp]),
-        "aec_init": (vp, [i, i, i, vp]),
+        "aec_init": (vp, [i, i, i, vp]), "aec_setFrameFar": (i, [vp, vp, i]), "aec_process": (i, [vp, vp, vp, i, i]),
+        "aec_process2": (i, [vp, vp, vp, vp, i, i]), "aec_release": (None, [vp]),
         # include/g711codec.h
         "PCM2G711a": (i, [vp, vp, i, i]), "PCM2G711u": (i, [vp, vp, i, i]),
         "G711a2PCM": (i, [vp, vp, i, i]), "G711u2PCM": (i, [vp, vp, i, i]),

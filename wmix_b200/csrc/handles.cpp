@@ -18,7 +18,7 @@ struct Handle {
     wmixb_engine* eng = nullptr;
     int chn = 1, freq = 0, pkg = 0, stage = 0;
     bool* debug = nullptr;
-    std::vector<int16_t> mono, res;
+    std::vector<int16_t> mono, res, far;
 };
 
 bool dbg(const bool* d) { return d && *d; }
@@ -184,18 +184,105 @@ void agc_addition(void* fp, uint8_t value)
 
 void agc_release(void* fp) { drop(fp, "agc_release"); }
 
-// ---------------------------------------------------------------- AEC (not on the GPU yet)
+// ---------------------------------------------------------------- AEC
+// R:src/webrtc.c:217-505.  The engine keeps the reference's full far-end history (250 partitions + the
+// two the block being read spans), so any cadence of aec_setFrameFar / aec_process calls the reference
+// accepts behaves the same here.
 void* aec_init(int chn, int freq, int intervalMs, bool* debug)
 {
-    (void)chn; (void)intervalMs;
     if (!rate_ok(freq, 16000)) return nullptr;                      // R:src/webrtc.c:220
-    if (dbg(debug)) printf("aec_init: the PBFDAF echo canceller is not implemented on the GPU path yet\r\n");
-    return nullptr;
+    wmixb_config c;
+    memset(&c, 0, sizeof c);
+    c.n_streams = 1;
+    c.freq = freq;
+    c.stages = WMIXB_AEC;
+    c.aec_far_depth = 252;
+    wmixb_engine* e = nullptr;
+    if (wmixb_create(&c, &e) != WMIXB_OK) {
+        if (dbg(debug)) printf("WebRtcAecX_Create failed !! (%s)\r\n", wmixb_last_error());
+        return nullptr;
+    }
+    Handle* h = new Handle();
+    h->eng = e;
+    h->chn = chn;
+    h->freq = freq;
+    h->stage = WMIXB_AEC;
+    h->debug = debug;
+    // 10 ms packets, or 20 ms at 8 kHz when the caller's interval is a multiple of 20 (R:src/webrtc.c:239-249)
+    const int interval = (freq <= 8000 && intervalMs % 20 == 0) ? 20 : 10;
+    h->pkg = freq / 1000 * interval;
+    h->mono.resize((size_t)h->pkg);
+    h->res.resize((size_t)h->pkg);
+    h->far.resize((size_t)h->pkg);
+    if (dbg(debug)) printf("aec_init: chn/%d freq/%d intervalMs/%d pkgFrame/%d x %d\r\n", chn, freq, interval, h->pkg, chn);
+    return h;
 }
-int aec_setFrameFar(void*, int16_t*, int) { return -1; }
-int aec_process(void*, int16_t*, int16_t*, int, int) { return -1; }
-int aec_process2(void*, int16_t*, int16_t*, int16_t*, int, int) { return -1; }
-void aec_release(void*) {}
+
+// one packet through the engine; mirrors WebRtcAec_Process's return code for an out-of-range delay
+// (it clamps, processes, and still reports -1: T:.../aec/echo_cancellation.c:366-376)
+static int aec_packet(Handle* h, const int16_t* far, const int16_t* near, int16_t* out, int delayms)
+{
+    int rc_ref = 0, d = (int16_t)delayms;
+    if (d < 0) { d = 0; rc_ref = -1; }
+    else if (d > 500) { d = 500; rc_ref = -1; }
+    if (wmixb_aec_host(h->eng, far, near, out, h->pkg, d) != WMIXB_OK) return -1;
+    return rc_ref;
+}
+
+int aec_setFrameFar(void* fp, int16_t* frameFar, int frameNum)
+{
+    Handle* h = (Handle*)fp;
+    const int total = frameNum * h->chn, step = h->pkg * h->chn;
+    for (int pos = 0; pos < total; pos += step) {                   // R:src/webrtc.c:298-321
+        for (int i = 0; i < h->pkg; ++i) { h->far[(size_t)i] = *frameFar; frameFar += h->chn; }
+        if (wmixb_aec_host(h->eng, h->far.data(), nullptr, nullptr, h->pkg, 0) != WMIXB_OK) {
+            if (dbg(h->debug)) printf("WebRtcAecX_BufferFarend failed !!, %s \r\n", wmixb_last_error());
+            return -1;
+        }
+    }
+    return 0;
+}
+
+int aec_process(void* fp, int16_t* frameNear, int16_t* frameOut, int frameNum, int delayms)
+{
+    Handle* h = (Handle*)fp;
+    const int total = frameNum * h->chn, step = h->pkg * h->chn;
+    for (int pos = 0; pos < total; pos += step) {                   // R:src/webrtc.c:349-403
+        for (int i = 0; i < h->pkg; ++i) { h->mono[(size_t)i] = *frameNear; frameNear += h->chn; }
+        const int ret = aec_packet(h, nullptr, h->mono.data(), h->res.data(), delayms);
+        if (ret != 0) {
+            if (dbg(h->debug)) printf("WebRtcAecX_Process failed !!, ret %d \r\n", ret);
+            return ret;
+        }
+        for (int i = 0; i < h->pkg; ++i)
+            for (int c = 0; c < h->chn; ++c) *frameOut++ = h->res[(size_t)i];
+    }
+    return 0;
+}
+
+int aec_process2(void* fp, int16_t* frameFar, int16_t* frameNear, int16_t* frameOut, int frameNum, int delayms)
+{
+    Handle* h = (Handle*)fp;
+    const int total = frameNum * h->chn, step = h->pkg * h->chn;
+    for (int pos = 0; pos < total; pos += step) {                   // R:src/webrtc.c:422-480
+        for (int i = 0; i < h->pkg; ++i) {
+            h->far[(size_t)i] = *frameFar;
+            h->mono[(size_t)i] = *frameNear;
+            frameFar += h->chn;
+            frameNear += h->chn;
+        }
+        const int ret = aec_packet(h, h->far.data(), h->mono.data(), h->res.data(), delayms);
+        if (ret != 0) {
+            if (dbg(h->debug)) printf("WebRtcAecX_Process failed !!, ret %d \r\n", ret);
+            return ret;
+        }
+        for (int i = 0; i < h->pkg; ++i)
+            for (int c = 0; c < h->chn; ++c) *frameOut++ = h->res[(size_t)i];
+    }
+    return 0;
+}
+
+void aec_release(void* fp) { drop(fp, "aec_release"); }
 
 // ---------------------------------------------------------------- G.711 host entry points
 static int g711_host(int law, bool encode, const void* in, void* out, int n)

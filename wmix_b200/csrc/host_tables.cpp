@@ -251,5 +251,41 @@ void agc_initial_words(int32_t* words /* agc::N_WORDS */)
     words[16] = 500 << 8;            // varianceShortTerm
 }
 
+
+// ---- AEC (T:webrtc/modules/audio_processing/aec) ------------------------------------------------
+// rdft_w (aec_rdft.c:32-49) is Ooura's makewt(32)/makect(32) table for a 128-point transform,
+// except that the shipped literal was generated by a cosf/sinf that was one ulp off in eight
+// entries.  The table below is therefore the correctly rounded one plus those eight one-ulp
+// corrections (pinned against the reference's exported symbol by tests/test_oracle_pin.py).
+// sqrtHanning (aec_core.c:49-66) is sin(pi i/128); weightCurve (:71-81) and overDriveCurve
+// (:86-96) are the 4-decimal Matlab prints 0.3 sqrt(linspace(0,1,64)) + 0.1 (with a leading 0)
+// and sqrt(linspace(0,1,65)) + 1.
+void aec_tables(float* w, float* c, float* hann, float* weight, float* over, uint32_t* lcg_mul, uint32_t* lcg_add)
+{
+    fft_w_table(32, w);
+    fft_c_table(32, c);
+    static const struct { int idx, ulps; } fix[8] = {{4, 1}, {7, 1}, {20, 1}, {27, 1}, {40, 1}, {41, -1}, {42, 1}, {47, 1}};
+    for (int k = 0; k < 8; ++k) {
+        float* p = fix[k].idx < 32 ? &w[fix[k].idx] : &c[fix[k].idx - 32];
+        int32_t bits;
+        memcpy(&bits, p, 4);
+        bits += fix[k].ulps;
+        memcpy(p, &bits, 4);
+    }
+    for (int i = 0; i <= 64; ++i) {
+        hann[i] = (float)sin(3.14159265358979323846 * i / 128.0);
+        weight[i] = i == 0 ? 0.f : (float)(floor((0.3 * sqrt((i - 1) / 63.0) + 0.1) * 1e4 + 0.5) / 1e4);
+        over[i] = (float)(floor((sqrt(i / 64.0) + 1.0) * 1e4 + 0.5) / 1e4);
+    }
+    // x_{k} = mul[k] * x_0 + add[k]  (mod 2^32; the generator keeps the low 31 bits)
+    uint32_t m = 1, a = 0;
+    for (int k = 0; k <= 64; ++k) {
+        lcg_mul[k] = m;
+        lcg_add[k] = a;
+        a = a * 69069u + 1u;
+        m = m * 69069u;
+    }
+}
+
 }  // namespace host
 }  // namespace wmx

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "../../include/wmixb.h"
+#include "aec.cuh"
 #include "agc.cuh"
 #include "g711_mix.cuh"
 #include "host_tables.h"
@@ -115,6 +116,60 @@ __global__ void ns_init_kernel(float* rec, uint16_t* hist, int first, int count)
     ns::init_record<ANA>(r, hist + (size_t)s * 3 * ns::kHistBins, lane, 32);
     __syncwarp();
     ns::init_record_values<ANA>(r, lane, 32);
+}
+
+// ------------------------------------------------------------------------------------------
+// AEC kernel: persistent grid, one warp per stream (aec.cuh)
+// ------------------------------------------------------------------------------------------
+constexpr int kAecWarps = 8;
+constexpr size_t kAecTableFloats = (sizeof(aec::Tables) + 15) / 16 * 4;
+constexpr size_t kAecSmemBytes = (kAecTableFloats + (size_t)kAecWarps * aec::Geo::kShFloats) * sizeof(float);
+
+__global__ void __launch_bounds__(kAecWarps * 32)
+aec_kernel(float* __restrict__ rec, size_t rec_floats, const aec::Tables* __restrict__ tables, const int16_t* far,
+           const int16_t* near, int16_t* out, int n_streams, int n, int mult, int depth, int delay_ms)
+{
+    extern __shared__ __align__(16) float smem[];
+    aec::Tables* T = reinterpret_cast<aec::Tables*>(smem);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+        for (int i = threadIdx.x; i < (int)(sizeof(aec::Tables) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    float* tile = smem + kAecTableFloats + (size_t)warp * aec::Geo::kShFloats;
+    aec::Warp W;
+    W.lane_id = threadIdx.x & 31;
+    const int total_warps = gridDim.x * kAecWarps;
+    for (int s = blockIdx.x * kAecWarps + warp; s < n_streams; s += total_warps) {
+        if (W.lane_id == 0 && s + total_warps < n_streams)
+            l2_prefetch(rec + (size_t)(s + total_warps) * rec_floats, (uint32_t)(rec_floats * sizeof(float)));
+        aec::tick(W, rec + (size_t)s * rec_floats, depth, mult, n, far ? far + (size_t)s * n : nullptr,
+                  near ? near + (size_t)s * n : nullptr, out ? out + (size_t)s * n : nullptr, delay_ms, tile, *T);
+        __syncwarp();
+    }
+}
+
+__global__ void aec_init_kernel(float* rec, size_t rec_floats, int depth, int first, int count)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= count) return;
+    float* r = rec + (size_t)(first + warp) * rec_floats;
+    aec::init_record(r, depth, lane, 32);
+    __syncwarp();
+    aec::init_record_values(r, lane, 32);
+}
+
+__global__ void aec_status_kernel(const float* rec, size_t rec_floats, int n_streams, int* result)
+{
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    const int f = __float_as_int(rec[(size_t)s * rec_floats + aec::Geo::kOffScal + aec::S_ERROR]);
+    if (f) {
+        atomicOr(&result[0], f);
+        atomicAdd(&result[1], 1);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -300,6 +355,12 @@ struct wmixb_engine {
     cudaStream_t stream = nullptr;
     int ns_grid = 0;
     int ns_occ = 2;                         // CTAs per SM the NS kernel variant is compiled for
+    float* aec_rec = nullptr;               // [n_streams][aec_rec_floats]
+    void* aec_tables = nullptr;
+    int* aec_result = nullptr;              // [2] flags OR, flagged count
+    int16_t* aec_stage = nullptr;           // far / near / out staging of the host-buffer entry point
+    int aec_depth = 0, aec_grid = 0;
+    size_t aec_rec_floats = 0;
 };
 
 static int ns_rec_floats(const wmixb_engine* e) { return e->ana == 256 ? ns::Geo<256>::kRecFloats : ns::Geo<128>::kRecFloats; }
@@ -372,6 +433,10 @@ extern "C" int wmixb_reset(wmixb_engine* e, int first, int count)
         else ns_init_kernel<128><<<blocks, 256, 0, e->stream>>>(e->ns_rec, e->ns_hist, first, count);
         CK_LAUNCH();
     }
+    if (e->aec_rec) {
+        aec_init_kernel<<<(count * 32 + 255) / 256, 256, 0, e->stream>>>(e->aec_rec, e->aec_rec_floats, e->aec_depth, first, count);
+        CK_LAUNCH();
+    }
     if (e->agc_words) {
         words_init_kernel<<<(count + 255) / 256, 256, 0, e->stream>>>(e->agc_words, e->agc_init, agc::N_WORDS, e->stride, first, count);
         CK_LAUNCH();
@@ -394,6 +459,7 @@ extern "C" void wmixb_destroy(wmixb_engine* e)
     cudaFree(e->agc_init); cudaFree(e->vad_init);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_vad);
     cudaFree(e->conf_start); cudaFree(e->conf_of);
+    cudaFree(e->aec_rec); cudaFree(e->aec_tables); cudaFree(e->aec_result); cudaFree(e->aec_stage);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -419,6 +485,26 @@ static int create_impl(const wmixb_config* cfg, wmixb_engine* e)
         CK(cudaMalloc(&e->ns_hist, n * 3 * ns::kHistBins * sizeof(uint16_t)));
         int rc = e->ana == 256 ? upload_ns_tables<256>(e) : upload_ns_tables<128>(e);
         if (rc) return rc;
+    }
+    if (cfg->stages & WMIXB_AEC) {
+        e->aec_depth = cfg->aec_far_depth > 0 ? cfg->aec_far_depth : 32;
+        if (e->aec_depth < 8 || e->aec_depth > 1024) { snprintf(g_err, sizeof g_err, "aec_far_depth %d outside 8..1024", e->aec_depth); return WMIXB_EINVAL; }
+        e->aec_rec_floats = (size_t)aec::rec_floats(e->aec_depth);
+        aec::Tables* T = new aec::Tables();
+        memset(T, 0, sizeof *T);
+        host::dmath_tables(T->dm.log_invc, T->dm.log_logc, T->dm.exp_2jn);
+        host::aec_tables(T->w, T->c, T->hann, T->weight, T->over, T->lcg_mul, T->lcg_add);
+        cudaError_t ce1 = cudaMalloc(&e->aec_tables, sizeof *T);
+        if (ce1 == cudaSuccess) ce1 = cudaMemcpy(e->aec_tables, T, sizeof *T, cudaMemcpyHostToDevice);
+        delete T;
+        CK(ce1);
+        CK(cudaMalloc(&e->aec_rec, n * e->aec_rec_floats * sizeof(float)));
+        CK(cudaMalloc(&e->aec_result, 2 * sizeof(int)));
+        CK(cudaFuncSetAttribute(aec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAecSmemBytes));
+        int per_sm = 0;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aec_kernel, kAecWarps * 32, kAecSmemBytes));
+        if (per_sm < 1) per_sm = 1;
+        e->aec_grid = e->sm_count * per_sm;
     }
     if (cfg->stages & WMIXB_AGC) {
         int32_t init[agc::N_WORDS];
@@ -455,7 +541,7 @@ extern "C" int wmixb_create(const wmixb_config* cfg, wmixb_engine** out)
     // the reference accepts freq <= 32000 && freq % 8000 == 0 (R:src/webrtc.c:43, :563, :711);
     // the batched engine covers the two rates BASELINE.json's configs use
     if (cfg->freq != 8000 && cfg->freq != 16000) { snprintf(g_err, sizeof g_err, "freq %d: batched engine supports 8000 and 16000", cfg->freq); return WMIXB_EINVAL; }
-    if ((cfg->stages & ~(WMIXB_NS | WMIXB_AGC | WMIXB_VAD)) != 0) { snprintf(g_err, sizeof g_err, "unknown stage bits"); return WMIXB_EINVAL; }
+    if ((cfg->stages & ~(WMIXB_NS | WMIXB_AGC | WMIXB_VAD | WMIXB_AEC)) != 0) { snprintf(g_err, sizeof g_err, "unknown stage bits"); return WMIXB_EINVAL; }
     wmixb_engine* e = new (std::nothrow) wmixb_engine();
     if (!e) return WMIXB_ENOMEM;
     e->cfg = *cfg;
@@ -474,8 +560,20 @@ extern "C" int wmixb_set_agc_gain(wmixb_engine* e, int gain_db)
     return upload_agc_table(e, gain_db);
 }
 
-static int run_stages(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int n_frames, int stages,
+static int launch_aec(wmixb_engine* e, const int16_t* d_far, const int16_t* d_near, int16_t* d_out, int samples, int delay_ms,
                       cudaStream_t st)
+{
+    const int n = e->cfg.n_streams;
+    const int need = (n + kAecWarps - 1) / kAecWarps;
+    const int grid = need < e->aec_grid ? need : e->aec_grid;
+    aec_kernel<<<grid, kAecWarps * 32, kAecSmemBytes, st>>>(e->aec_rec, e->aec_rec_floats, (const aec::Tables*)e->aec_tables, d_far,
+                                                             d_near, d_out, n, samples, e->cfg.freq / 8000, e->aec_depth, delay_ms);
+    CK_LAUNCH();
+    return WMIXB_OK;
+}
+
+static int run_stages(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int n_frames, int stages,
+                      cudaStream_t st, const int16_t* d_far = nullptr, int delay_ms = 0)
 {
     if (stages == 0) stages = e->cfg.stages;
     if (stages & ~e->cfg.stages) { snprintf(g_err, sizeof g_err, "stage mask 0x%x not configured (engine has 0x%x)", stages, e->cfg.stages); return WMIXB_EINVAL; }
@@ -487,6 +585,12 @@ static int run_stages(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint
         const int rc = e->ana == 256 ? launch_ns<256>(e, grid, st, cur, d_out, n, n_frames) : launch_ns<128>(e, grid, st, cur, d_out, n, n_frames);
         if (rc) return rc;
         CK_LAUNCH();
+        cur = d_out;
+    }
+    if (stages & WMIXB_AEC) {
+        if (n_frames != 1 || !d_far) { snprintf(g_err, sizeof g_err, "the AEC stage needs a far-end buffer and runs one tick per call"); return WMIXB_EINVAL; }
+        const int rc = launch_aec(e, d_far, cur, d_out, e->frame, delay_ms, st);
+        if (rc) return rc;
         cur = d_out;
     }
     if (stages & (WMIXB_AGC | WMIXB_VAD)) {
@@ -507,6 +611,62 @@ extern "C" int wmixb_tick_device(wmixb_engine* e, const int16_t* d_in, int16_t* 
     if (!e || !d_in || !d_out) return WMIXB_EINVAL;
     CK(cudaSetDevice(e->cfg.device));
     return run_stages(e, d_in, d_out, d_vad, 1, stages, (cudaStream_t)stream);
+}
+
+extern "C" int wmixb_tick_chain_device(wmixb_engine* e, const int16_t* d_far, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad,
+                                       int stages, int delay_ms, void* stream)
+{
+    if (!e || !d_in || !d_out) return WMIXB_EINVAL;
+    if (delay_ms < 0 || delay_ms > 500) { snprintf(g_err, sizeof g_err, "delay_ms %d outside 0..500 (the reference returns -1 for it)", delay_ms); return WMIXB_EINVAL; }
+    CK(cudaSetDevice(e->cfg.device));
+    return run_stages(e, d_in, d_out, d_vad, 1, stages, (cudaStream_t)stream, d_far, delay_ms);
+}
+
+extern "C" int wmixb_aec_device(wmixb_engine* e, const int16_t* d_far, const int16_t* d_near, int16_t* d_out, int samples,
+                                int delay_ms, void* stream)
+{
+    if (!e || !e->aec_rec || (!d_far && !d_near) || (d_near && !d_out)) return WMIXB_EINVAL;
+    // WebRtcAec_BufferFarend / _Process accept 80 or 160 samples (T:.../aec/echo_cancellation.c:297, :362)
+    if (samples != 80 && samples != 160) { snprintf(g_err, sizeof g_err, "aec: %d samples per call (80 or 160)", samples); return WMIXB_EINVAL; }
+    if (samples % (80 * (e->cfg.freq / 8000)) != 0) { snprintf(g_err, sizeof g_err, "aec: %d samples is not a whole 10 ms at %d Hz", samples, e->cfg.freq); return WMIXB_EINVAL; }
+    if (delay_ms < 0 || delay_ms > 500) { snprintf(g_err, sizeof g_err, "delay_ms %d outside 0..500 (the reference returns -1 for it)", delay_ms); return WMIXB_EINVAL; }
+    CK(cudaSetDevice(e->cfg.device));
+    return launch_aec(e, d_far, d_near, d_out, samples, delay_ms, (cudaStream_t)stream);
+}
+
+extern "C" int wmixb_aec_host(wmixb_engine* e, const int16_t* h_far, const int16_t* h_near, int16_t* h_out, int samples, int delay_ms)
+{
+    if (!e || !e->aec_rec || (!h_far && !h_near) || (h_near && !h_out)) return WMIXB_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t bytes = (size_t)e->cfg.n_streams * 160 * sizeof(int16_t);
+    if (!e->aec_stage) CK(cudaMalloc(&e->aec_stage, 3 * bytes));
+    int16_t* d_far = e->aec_stage;
+    int16_t* d_near = e->aec_stage + (size_t)e->cfg.n_streams * 160;
+    int16_t* d_out = d_near + (size_t)e->cfg.n_streams * 160;
+    const size_t used = (size_t)e->cfg.n_streams * samples * sizeof(int16_t);
+    if (h_far) CK(cudaMemcpyAsync(d_far, h_far, used, cudaMemcpyHostToDevice, e->stream));
+    if (h_near) CK(cudaMemcpyAsync(d_near, h_near, used, cudaMemcpyHostToDevice, e->stream));
+    const int rc = wmixb_aec_device(e, h_far ? d_far : nullptr, h_near ? d_near : nullptr, d_out, samples, delay_ms, e->stream);
+    if (rc) return rc;
+    if (h_near) CK(cudaMemcpyAsync(h_out, d_out, used, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_aec_status(wmixb_engine* e, int* h_flags, int* h_flagged)
+{
+    if (!e || !e->aec_rec) return WMIXB_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemsetAsync(e->aec_result, 0, 2 * sizeof(int), e->stream));
+    aec_status_kernel<<<(e->cfg.n_streams + 255) / 256, 256, 0, e->stream>>>(e->aec_rec, e->aec_rec_floats, e->cfg.n_streams, e->aec_result);
+    CK_LAUNCH();
+    int r[2] = {0, 0};
+    CK(cudaMemcpyAsync(r, e->aec_result, sizeof r, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    if (h_flags) *h_flags = r[0];
+    if (h_flagged) *h_flagged = r[1];
+    return WMIXB_OK;
 }
 
 extern "C" int wmixb_offline_device(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int n_frames,
@@ -665,6 +825,7 @@ extern "C" size_t wmixb_stream_state_bytes(const wmixb_engine* e)
     if (e->ns_rec) b += (size_t)ns_rec_floats(e) * 4 + 3 * ns::kHistBins * 2;
     if (e->agc_words) b += agc::N_WORDS * 4;
     if (e->vad_words) b += vad::N_WORDS * 4;
+    if (e->aec_rec) b += e->aec_rec_floats * 4;
     return b;
 }
 extern "C" size_t wmixb_state_bytes_per_stream(const wmixb_engine* e) { return wmixb_stream_state_bytes(e); }
@@ -692,6 +853,7 @@ static int state_xfer(wmixb_engine* e, int s, void* buf, bool get)
     }
     if (e->agc_words) CK(xfer2d(e->agc_words, agc::N_WORDS));
     if (e->vad_words) CK(xfer2d(e->vad_words, vad::N_WORDS));
+    if (e->aec_rec) CK(xfer(e->aec_rec + (size_t)s * e->aec_rec_floats, e->aec_rec_floats * 4));
     return WMIXB_OK;
 }
 extern "C" int wmixb_get_stream_state(wmixb_engine* e, int s, void* h_buf) { return state_xfer(e, s, h_buf, true); }

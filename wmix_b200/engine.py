@@ -6,7 +6,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import AGC, NS, VAD, Config, check, lib
+from ._lib import AEC, AGC, NS, VAD, Config, check, lib  # noqa: F401
 
 
 def _ptr(x):
@@ -28,10 +28,11 @@ def _stream_ptr(stream):
 class Engine:
     """N independent mono streams of wmix's record chain NS -> AGC -> VAD on one GPU."""
 
-    def __init__(self, n_streams, freq=16000, stages=NS | AGC | VAD, ns_policy=2, agc_gain_db=5, vad_mode=3, device=0):
+    def __init__(self, n_streams, freq=16000, stages=NS | AGC | VAD, ns_policy=2, agc_gain_db=5, vad_mode=3, device=0,
+                 aec_far_depth=0):
         self.L = lib()
         cfg = Config(n_streams=n_streams, freq=freq, stages=stages, ns_policy=ns_policy, agc_gain_db=agc_gain_db,
-                     vad_mode=vad_mode, device=device)
+                     vad_mode=vad_mode, device=device, aec_far_depth=aec_far_depth)
         h = C.c_void_p()
         check(self.L.wmixb_create(C.byref(cfg), C.byref(h)), "wmixb_create")
         self.h, self.n, self.freq, self.frame, self.stages, self.device = h, n_streams, freq, freq // 100, stages, device
@@ -58,6 +59,25 @@ class Engine:
     def offline_device(self, d_in, d_out, n_frames, d_vad=None, stages=0, stream=None):
         check(self.L.wmixb_offline_device(self.h, _ptr(d_in), _ptr(d_out), _ptr(d_vad), n_frames, stages,
                                           _stream_ptr(stream)), "wmixb_offline_device")
+
+    # --- echo canceller ---
+    def aec_device(self, d_far, d_near, d_out, samples=None, delay_ms=0, stream=None):
+        check(self.L.wmixb_aec_device(self.h, _ptr(d_far), _ptr(d_near), _ptr(d_out), samples or self.frame, delay_ms,
+                                      _stream_ptr(stream)), "wmixb_aec_device")
+
+    def aec_host(self, h_far, h_near, h_out, samples=None, delay_ms=0):
+        check(self.L.wmixb_aec_host(self.h, _ptr(h_far), _ptr(h_near), _ptr(h_out), samples or self.frame, delay_ms),
+              "wmixb_aec_host")
+
+    def tick_chain_device(self, d_far, d_in, d_out, d_vad=None, stages=0, delay_ms=0, stream=None):
+        check(self.L.wmixb_tick_chain_device(self.h, _ptr(d_far), _ptr(d_in), _ptr(d_out), _ptr(d_vad), stages, delay_ms,
+                                             _stream_ptr(stream)), "wmixb_tick_chain_device")
+
+    def aec_status(self):
+        """(OR of the sticky per-stream AEC flags, number of flagged streams)"""
+        flags, n = C.c_int(0), C.c_int(0)
+        check(self.L.wmixb_aec_status(self.h, C.byref(flags), C.byref(n)), "wmixb_aec_status")
+        return flags.value, n.value
 
     # --- conference bus ---
     def set_conferences(self, conf_start):
