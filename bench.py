@@ -216,11 +216,8 @@ def run_ours(args):
     e2e_steps = max(10, min(args.steps, 100))
 
     def e2e_step(t):
-        eng.tick_host(h_pool[t % R].numpy(), h_out.numpy(), h_vad.numpy())        # H2D, NS, AGC+VAD, D2H, sync
-        d_pcm.copy_(h_out, non_blocking=True)                                       # (bus runs on the processed PCM)
-        eng.bus_sum(d_pcm, d_bus, stream)
-        h_bus.copy_(d_bus, non_blocking=True)
-        stream.synchronize()
+        # one C-ABI call: chunk-pipelined H2D, NS, AGC+VAD, bus, D2H of PCM + flags + bus; returns when the host has them
+        eng.tick_host_bus(h_pool[t % R].numpy(), h_out.numpy(), h_vad.numpy(), h_bus.numpy())
 
     for t in range(3):
         e2e_step(t)
@@ -260,7 +257,8 @@ def run_ours(args):
             "e2e": {"value": total_streams * 10.0 / e2e_ms, "unit": "real-time 16 kHz streams (10 ms tick), whole job",
                     "ms_per_step": e2e_ms, "h2d_bytes_per_step": S * FRAME * 2,
                     "d2h_bytes_per_step": S * FRAME * 2 + S + n_conf * FRAME * 4, "steps": e2e_steps,
-                    "path": "wmixb_tick_host (pinned host PCM in/out + VAD flags) + bus D2H"},
+                    "path": "wmixb_tick_host_bus: pinned host PCM in -> NS -> AGC+VAD -> bus -> host PCM + VAD flags + bus, "
+                            "chunk-pipelined over 3 CUDA streams"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:

@@ -60,8 +60,13 @@ int wmixb_set_agc_gain(wmixb_engine* e, int gain_db);
  * stages (0 = all configured).  Asynchronous on `stream`. */
 int wmixb_tick_device(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int stages,
                       void* stream);
-/* Same, host buffers: H2D copy, kernels, D2H copy on the engine's own stream, then waits. */
+/* Same, host buffers (pinned for overlap): the streams are cut into chunks whose H2D copy, kernels and
+ * D2H copy are pipelined over the engine's own CUDA streams; returns when h_out / h_vad are complete. */
 int wmixb_tick_host(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int stages);
+/* wmixb_tick_host plus the conference bus of the processed tick (wmixb_set_conferences first):
+ * h_bus int32 [n_conf][frame] = what every producer adding its 10 ms into the mix ring through
+ * wmix_load_data yields while no partial sum clips (R:src/wmix.c:1678-1702). */
+int wmixb_tick_host_bus(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int32_t* h_bus, int stages);
 
 /* Echo canceller (stage WMIXB_AEC), the arithmetic of aec_process2 (R:src/webrtc.c:410-483) for every
  * stream: BufferFarend(d_far) then Process(d_near) -> d_out.  d_far == NULL is aec_process (near only),

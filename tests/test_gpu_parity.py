@@ -254,6 +254,39 @@ def test_full_chain_16k_and_vad_flags():
     assert vad[300:, 2].mean() > 0.9         # the full-scale square does
 
 
+@pytest.mark.parametrize("S", [300, 9000])
+def test_host_buffer_tick_equals_device_tick(S):
+    """wmixb_tick_host / wmixb_tick_host_bus (chunk-pipelined above 8192 streams, ragged last chunk) give exactly
+    what the device-resident tick gives, and the bus is the exact int32 sum of the processed PCM."""
+    T, freq, L = 12, 16000, 160
+    base = make_frames(64, freq, 300, T, seed=77)
+    x = np.ascontiguousarray(np.tile(base, (1, (S + 63) // 64, 1))[:, :S])
+    want, want_vad = run_gpu(x, freq, NS | AGC | VAD)
+    conf = np.unique(np.concatenate([np.arange(0, S, 7), [S]])).astype(np.int32)
+    eng = wmix_b200.Engine(S, freq)
+    eng.set_conferences(conf)
+    h_in = torch.empty((S, L), dtype=torch.int16).pin_memory()
+    h_out = torch.empty((S, L), dtype=torch.int16).pin_memory()
+    h_vad = torch.empty((S,), dtype=torch.uint8).pin_memory()
+    h_bus = torch.empty((len(conf) - 1, L), dtype=torch.int32).pin_memory()
+    for t in range(T):
+        h_in.copy_(torch.from_numpy(x[t]))
+        if t % 2:
+            eng.tick_host(h_in.numpy(), h_out.numpy(), h_vad.numpy())
+        else:
+            eng.tick_host_bus(h_in.numpy(), h_out.numpy(), h_vad.numpy(), h_bus.numpy())
+            bus = np.add.reduceat(h_out.numpy().astype(np.int32), conf[:-1], axis=0)
+            assert np.array_equal(h_bus.numpy(), bus)
+        assert np.array_equal(h_out.numpy(), want[t]), "tick %d" % t
+        assert np.array_equal(h_vad.numpy(), want_vad[t])
+    # pageable (not pinned) host memory is legal too
+    out2 = np.empty((S, L), np.int16)
+    eng.reset()
+    eng.tick_host(np.ascontiguousarray(x[0]), out2, None)
+    assert np.array_equal(out2, want[0])
+    eng.close()
+
+
 def test_config1_wav_fixture_hash():
     """BASELINE config 1 through the GPU: committed hash of the reference's output on audio/1x8000.wav
     is only checkable where the wav is; elsewhere the seeded-stream fixtures stand in."""

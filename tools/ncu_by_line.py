@@ -51,7 +51,13 @@ def main():
     hdr_i = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     hdr = rows[hdr_i]
     col = {h: i for i, h in enumerate(hdr)}
-    data = [r for r in rows[hdr_i + 1:] if len(r) == len(hdr)]
+    # the export repeats the table per captured launch: keep the first one
+    data = []
+    for r in rows[hdr_i + 1:]:
+        if r and r[0] in ("Address", "Kernel Name"):
+            break
+        if len(r) == len(hdr):
+            data.append(r)
     sass = sass_lines(a.sass, a.kernel)
     if len(sass) != len(data):
         print("warning: %d SASS instructions in the cubin vs %d rows in the export" % (len(sass), len(data)))

@@ -36,6 +36,7 @@ def lib():
         "wmixb_set_agc_gain": (i, [vp, i]),
         "wmixb_tick_device": (i, [vp, vp, vp, vp, i, vp]),
         "wmixb_tick_host": (i, [vp, vp, vp, vp, i]),
+        "wmixb_tick_host_bus": (i, [vp, vp, vp, vp, vp, i]),
         "wmixb_offline_device": (i, [vp, vp, vp, vp, i, i, vp]),
         "wmixb_aec_device": (i, [vp, vp, vp, vp, i, i, vp]),
         "wmixb_aec_host": (i, [vp, vp, vp, vp, i, i]),

@@ -353,6 +353,10 @@ struct wmixb_engine {
     int32_t* conf_of = nullptr;             // [n_streams]
     int n_conf = 0, max_conf = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};   // chunk pipeline of the host-buffer tick
+    cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};
+    int32_t* d_bus = nullptr;               // staging of the conference bus for the host-buffer tick
+    size_t d_bus_bytes = 0;
     int ns_grid = 0;
     int ns_occ = 2;                         // CTAs per SM the NS kernel variant is compiled for
     float* aec_rec = nullptr;               // [n_streams][aec_rec_floats]
@@ -372,10 +376,10 @@ static const void* ns_fn(int occ)
 }
 
 template <int ANA>
-static int launch_ns(wmixb_engine* e, int grid, cudaStream_t st, const int16_t* in, int16_t* out, int n, int n_frames)
+static int launch_ns(wmixb_engine* e, int grid, cudaStream_t st, const int16_t* in, int16_t* out, int first, int n, int n_frames)
 {
-    float* rec = e->ns_rec;
-    uint16_t* hist = e->ns_hist;
+    float* rec = e->ns_rec + (size_t)first * ns::Geo<ANA>::kRecFloats;
+    uint16_t* hist = e->ns_hist + (size_t)first * 3 * ns::kHistBins;
     const ns::Tables<ANA>* T = (const ns::Tables<ANA>*)e->ns_tables;
     void* args[] = {&rec, &hist, &T, &in, &out, &n, &n_frames};
     CK(cudaLaunchKernel(ns_fn<ANA>(e->ns_occ), dim3(grid), dim3(kNsWarps * 32), args, ns_smem_bytes<ANA>(), st));
@@ -460,6 +464,11 @@ extern "C" void wmixb_destroy(wmixb_engine* e)
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_vad);
     cudaFree(e->conf_start); cudaFree(e->conf_of);
     cudaFree(e->aec_rec); cudaFree(e->aec_tables); cudaFree(e->aec_result); cudaFree(e->aec_stage);
+    for (int k = 0; k < 3; ++k) {
+        if (e->pipe[k]) cudaStreamDestroy(e->pipe[k]);
+        if (e->pipe_ev[k]) cudaEventDestroy(e->pipe_ev[k]);
+    }
+    cudaFree(e->d_bus);
     if (e->stream) cudaStreamDestroy(e->stream);
     delete e;
 }
@@ -572,33 +581,37 @@ static int launch_aec(wmixb_engine* e, const int16_t* d_far, const int16_t* d_ne
     return WMIXB_OK;
 }
 
+// Streams [first, first+n) of the engine; d_in / d_out / d_vad / d_far point at stream `first`.
+// `first` must be a multiple of 32 (SoA rows stay line-aligned).
 static int run_stages(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int n_frames, int stages,
-                      cudaStream_t st, const int16_t* d_far = nullptr, int delay_ms = 0)
+                      cudaStream_t st, const int16_t* d_far = nullptr, int delay_ms = 0, int first = 0, int n = -1)
 {
     if (stages == 0) stages = e->cfg.stages;
     if (stages & ~e->cfg.stages) { snprintf(g_err, sizeof g_err, "stage mask 0x%x not configured (engine has 0x%x)", stages, e->cfg.stages); return WMIXB_EINVAL; }
-    const int n = e->cfg.n_streams;
+    if (n < 0) n = e->cfg.n_streams - first;
     const int16_t* cur = d_in;
     if (stages & WMIXB_NS) {
         const int need = (n + kNsWarps - 1) / kNsWarps;
         const int grid = need < e->ns_grid ? need : e->ns_grid;
-        const int rc = e->ana == 256 ? launch_ns<256>(e, grid, st, cur, d_out, n, n_frames) : launch_ns<128>(e, grid, st, cur, d_out, n, n_frames);
+        const int rc = e->ana == 256 ? launch_ns<256>(e, grid, st, cur, d_out, first, n, n_frames) : launch_ns<128>(e, grid, st, cur, d_out, first, n, n_frames);
         if (rc) return rc;
         CK_LAUNCH();
         cur = d_out;
     }
     if (stages & WMIXB_AEC) {
-        if (n_frames != 1 || !d_far) { snprintf(g_err, sizeof g_err, "the AEC stage needs a far-end buffer and runs one tick per call"); return WMIXB_EINVAL; }
+        if (n_frames != 1 || !d_far || first != 0 || n != e->cfg.n_streams) { snprintf(g_err, sizeof g_err, "the AEC stage needs a far-end buffer and runs one tick of the whole engine per call"); return WMIXB_EINVAL; }
         const int rc = launch_aec(e, d_far, cur, d_out, e->frame, delay_ms, st);
         if (rc) return rc;
         cur = d_out;
     }
     if (stages & (WMIXB_AGC | WMIXB_VAD)) {
         const int grid = (n + kPostThreads - 1) / kPostThreads;
+        int32_t* aw = e->agc_words ? e->agc_words + first : nullptr;
+        int32_t* vw = e->vad_words ? e->vad_words + first : nullptr;
         if (e->frame == 160)
-            post_kernel<true><<<grid, kPostThreads, 0, st>>>(e->agc_words, e->vad_words, e->agc_table, e->vp, cur, d_out, d_vad, n, e->stride, n_frames, stages);
+            post_kernel<true><<<grid, kPostThreads, 0, st>>>(aw, vw, e->agc_table, e->vp, cur, d_out, d_vad, n, e->stride, n_frames, stages);
         else
-            post_kernel<false><<<grid, kPostThreads, 0, st>>>(e->agc_words, e->vad_words, e->agc_table, e->vp, cur, d_out, d_vad, n, e->stride, n_frames, stages);
+            post_kernel<false><<<grid, kPostThreads, 0, st>>>(aw, vw, e->agc_table, e->vp, cur, d_out, d_vad, n, e->stride, n_frames, stages);
         CK_LAUNCH();
         cur = d_out;
     }
@@ -677,18 +690,70 @@ extern "C" int wmixb_offline_device(wmixb_engine* e, const int16_t* d_in, int16_
     return run_stages(e, d_in, d_out, d_vad, n_frames, stages, (cudaStream_t)stream);
 }
 
-extern "C" int wmixb_tick_host(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int stages)
+// Host-buffer tick.  The streams are cut into chunks that flow through three CUDA streams, so the
+// H2D copy of chunk k+1, the kernels of chunk k and the D2H copy of chunk k-1 overlap (the two copy
+// engines run full duplex); with h_bus the conference bus is summed on the device-resident result
+// and copied out last.
+static int tick_host_impl(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int32_t* h_bus, int stages)
 {
     if (!e || !h_in || !h_out) return WMIXB_EINVAL;
+    if (h_bus && e->n_conf < 1) { snprintf(g_err, sizeof g_err, "tick_host_bus: call wmixb_set_conferences first"); return WMIXB_EINVAL; }
     CK(cudaSetDevice(e->cfg.device));
-    const size_t bytes = (size_t)e->cfg.n_streams * e->frame * sizeof(int16_t);
-    CK(cudaMemcpyAsync(e->d_in, h_in, bytes, cudaMemcpyHostToDevice, e->stream));
-    const int rc = run_stages(e, e->d_in, e->d_out, e->d_vad, 1, stages, e->stream);
-    if (rc) return rc;
-    CK(cudaMemcpyAsync(h_out, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
-    if (h_vad) CK(cudaMemcpyAsync(h_vad, e->d_vad, (size_t)e->cfg.n_streams, cudaMemcpyDeviceToHost, e->stream));
+    const int n = e->cfg.n_streams;
+    int chunks = 4;
+    if (const char* v = getenv("WMIXB_HOST_CHUNKS")) { const int c = atoi(v); if (c >= 1 && c <= 64) chunks = c; }
+    if (n < 8192) chunks = 1;
+    int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;     // whole post_kernel CTAs, line-aligned SoA rows
+    if (chunks > 1 && !e->pipe[0]) {
+        for (int k = 0; k < 3; ++k) {
+            CK(cudaStreamCreateWithFlags(&e->pipe[k], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&e->pipe_ev[k], cudaEventDisableTiming));
+        }
+    }
+    int used = 0;
+    for (int first = 0, c = 0; first < n; first += per, ++c) {
+        const int cnt = n - first < per ? n - first : per;
+        cudaStream_t st = chunks > 1 ? e->pipe[c % 3] : e->stream;
+        const size_t off = (size_t)first * e->frame, bytes = (size_t)cnt * e->frame * sizeof(int16_t);
+        CK(cudaMemcpyAsync(e->d_in + off, h_in + off, bytes, cudaMemcpyHostToDevice, st));
+        const int rc = run_stages(e, e->d_in + off, e->d_out + off, e->d_vad + first, 1, stages, st, nullptr, 0, first, cnt);
+        if (rc) return rc;
+        if (chunks > 1 && h_bus) CK(cudaEventRecord(e->pipe_ev[c % 3], st));   // last record per stream covers its chunks
+        CK(cudaMemcpyAsync(h_out + off, e->d_out + off, bytes, cudaMemcpyDeviceToHost, st));
+        if (h_vad) CK(cudaMemcpyAsync(h_vad + first, e->d_vad + first, (size_t)cnt, cudaMemcpyDeviceToHost, st));
+        used = c + 1 < 3 ? c + 1 : 3;
+    }
+    if (h_bus) {
+        if (chunks > 1)
+            for (int k = 0; k < used; ++k) CK(cudaStreamWaitEvent(e->stream, e->pipe_ev[k], 0));
+        const size_t bus_bytes = (size_t)e->n_conf * e->frame * sizeof(int32_t);
+        if (e->d_bus_bytes < bus_bytes) {
+            CK(cudaStreamSynchronize(e->stream));
+            cudaFree(e->d_bus);
+            e->d_bus = nullptr;
+            e->d_bus_bytes = 0;
+            CK(cudaMalloc(&e->d_bus, bus_bytes));
+            e->d_bus_bytes = bus_bytes;
+        }
+        const int rc = wmixb_bus_sum_device(e, e->d_out, e->d_bus, e->stream);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h_bus, e->d_bus, bus_bytes, cudaMemcpyDeviceToHost, e->stream));
+    }
+    if (chunks > 1)
+        for (int k = 0; k < used; ++k) CK(cudaStreamSynchronize(e->pipe[k]));
     CK(cudaStreamSynchronize(e->stream));
     return WMIXB_OK;
+}
+
+extern "C" int wmixb_tick_host(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int stages)
+{
+    return tick_host_impl(e, h_in, h_out, h_vad, nullptr, stages);
+}
+
+extern "C" int wmixb_tick_host_bus(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int32_t* h_bus, int stages)
+{
+    if (!h_bus) return WMIXB_EINVAL;
+    return tick_host_impl(e, h_in, h_out, h_vad, h_bus, stages);
 }
 
 // ---- conference bus ----

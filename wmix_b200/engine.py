@@ -56,6 +56,10 @@ class Engine:
     def tick_host(self, h_in, h_out, h_vad=None, stages=0):
         check(self.L.wmixb_tick_host(self.h, _ptr(h_in), _ptr(h_out), _ptr(h_vad), stages), "wmixb_tick_host")
 
+    def tick_host_bus(self, h_in, h_out, h_vad, h_bus, stages=0):
+        check(self.L.wmixb_tick_host_bus(self.h, _ptr(h_in), _ptr(h_out), _ptr(h_vad), _ptr(h_bus), stages),
+              "wmixb_tick_host_bus")
+
     def offline_device(self, d_in, d_out, n_frames, d_vad=None, stages=0, stream=None):
         check(self.L.wmixb_offline_device(self.h, _ptr(d_in), _ptr(d_out), _ptr(d_vad), n_frames, stages,
                                           _stream_ptr(stream)), "wmixb_offline_device")
