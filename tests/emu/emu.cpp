@@ -159,6 +159,22 @@ int16_t emu_mix_step(int16_t bus, int16_t src, int rdce) { return mix_step(bus, 
 int emu_agc_gain_table(int32_t* t, int comp, int target, int lim, int at) { return host::agc_gain_table(t, (int16_t)comp, (int16_t)target, lim, (int16_t)at); }
 int emu_agc_analog_target(int comp) { return host::agc_analog_target((int16_t)comp); }
 void emu_ns_window(int ana, int block, float* w) { host::ns_window(ana, block, w); }
+// ns::div_by_counter against the IEEE division: every `stride`-th float significand at three binades,
+// divisors d_lo..d_hi; returns the number of disagreements
+long emu_div_by_counter_mismatches(int d_lo, int d_hi, int stride)
+{
+    long bad = 0;
+    const int exps[3] = {127 - 3, 127 + 2, 127 + 13};      // 0.125.., 4.., 8192..: the ranges the trackers produce
+    for (int d = d_lo; d <= d_hi; ++d) {
+        const float cf = (float)d, rc = 1.f / cf;
+        for (int e = 0; e < 3; ++e)
+            for (uint32_t m = 0; m < (1u << 23); m += (uint32_t)stride) {
+                const float x = ns::i2f((int32_t)(((uint32_t)exps[e] << 23) | m));
+                bad += (x / cf != ns::div_by_counter(x, cf, rc));
+            }
+    }
+    return bad;
+}
 void emu_logexp(const float* x, int n, float* lg, float* ex)
 {
     static ns::DMath dm;

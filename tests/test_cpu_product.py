@@ -120,6 +120,16 @@ def test_emulated_kernel_bodies_vs_reference(freq, stage):
         assert np.array_equal(ya, yb), (stage, freq, s)
 
 
+def test_ns_counter_division_is_exact():
+    """ns::div_by_counter (reciprocal + exact residual + one correction) replaces `x / (counter + 1)` in the NS quantile
+    trackers (T:.../ns/ns_core.c:233-249); it must BE the IEEE quotient: every divisor 1..201 on a significand grid, and
+    every one of the 2^23 significands for a handful of divisors."""
+    L = emu()
+    assert L.emu_div_by_counter_mismatches(1, 201, 16) == 0
+    for d in (3, 67, 134, 199, 200, 201):
+        assert L.emu_div_by_counter_mismatches(d, d, 1) == 0
+
+
 def test_synth_streams_are_reproducible_and_tick_addressable():
     a = make_frames(70, 16000, 0, 30, seed=3)
     b = make_frames(70, 16000, 10, 5, seed=3)

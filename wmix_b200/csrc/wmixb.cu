@@ -179,8 +179,8 @@ __global__ void aec_status_kernel(const float* rec, size_t rec_floats, int n_str
 // ------------------------------------------------------------------------------------------
 constexpr int kPostThreads = 128;
 
-template <bool FS16>
-__global__ void __launch_bounds__(kPostThreads)
+template <bool FS16, int MINB>
+__global__ void __launch_bounds__(kPostThreads, MINB)
 post_kernel(int32_t* __restrict__ agc_words, int32_t* __restrict__ vad_words, const int32_t* __restrict__ agc_table,
             vad::Params vp, const int16_t* in, int16_t* out, uint8_t* vad_out, int n_streams, size_t stride,
             int n_frames, int stages)
@@ -359,6 +359,7 @@ struct wmixb_engine {
     size_t d_bus_bytes = 0;
     int ns_grid = 0;
     int ns_occ = 2;                         // CTAs per SM the NS kernel variant is compiled for
+    int post_occ = 3;                       // same for post_kernel (3 CTAs of 128 threads, 168 registers per thread: measured best)
     float* aec_rec = nullptr;               // [n_streams][aec_rec_floats]
     void* aec_tables = nullptr;
     int* aec_result = nullptr;              // [2] flags OR, flagged count
@@ -535,6 +536,7 @@ static int create_impl(const wmixb_config* cfg, wmixb_engine* e)
         if (host::vad_thresholds(cfg->vad_mode, 10, th) != 0) { snprintf(g_err, sizeof g_err, "vad_mode %d out of range 0..3", cfg->vad_mode); return WMIXB_EINVAL; }
         e->vp = vad::Params{th[0], th[1], th[2], th[3]};
     }
+    if (const char* v = getenv("WMIXB_POST_OCC")) { const int o = atoi(v); if (o >= 2 && o <= 5) e->post_occ = o; }
     CK(cudaMalloc(&e->d_in, n * e->frame * sizeof(int16_t)));
     CK(cudaMalloc(&e->d_out, n * e->frame * sizeof(int16_t)));
     CK(cudaMalloc(&e->d_vad, n));
@@ -608,10 +610,11 @@ static int run_stages(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint
         const int grid = (n + kPostThreads - 1) / kPostThreads;
         int32_t* aw = e->agc_words ? e->agc_words + first : nullptr;
         int32_t* vw = e->vad_words ? e->vad_words + first : nullptr;
-        if (e->frame == 160)
-            post_kernel<true><<<grid, kPostThreads, 0, st>>>(aw, vw, e->agc_table, e->vp, cur, d_out, d_vad, n, e->stride, n_frames, stages);
-        else
-            post_kernel<false><<<grid, kPostThreads, 0, st>>>(aw, vw, e->agc_table, e->vp, cur, d_out, d_vad, n, e->stride, n_frames, stages);
+#define WMX_POST(FS, MB) post_kernel<FS, MB><<<grid, kPostThreads, 0, st>>>(aw, vw, e->agc_table, e->vp, cur, d_out, d_vad, n, e->stride, n_frames, stages)
+        const int occ = e->post_occ;
+        if (e->frame == 160) { if (occ == 2) WMX_POST(true, 2); else if (occ == 4) WMX_POST(true, 4); else if (occ == 5) WMX_POST(true, 5); else WMX_POST(true, 3); }
+        else { if (occ == 2) WMX_POST(false, 2); else if (occ == 4) WMX_POST(false, 4); else if (occ == 5) WMX_POST(false, 5); else WMX_POST(false, 3); }
+#undef WMX_POST
         CK_LAUNCH();
         cur = d_out;
     }
