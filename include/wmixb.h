@@ -102,6 +102,28 @@ int wmixb_bus_sum_device(wmixb_engine* e, const int16_t* d_pcm, int32_t* d_bus, 
 int wmixb_bus_nminus1_device(wmixb_engine* e, const int32_t* d_bus, const int16_t* d_pcm, int16_t* d_out,
                              void* stream);
 
+/* Conference bus across the GPUs of one node, fused with its exchange (one process or host thread per GPU).
+ * Every rank holds some members of each of the SAME n_conf conferences (its own wmixb_set_conferences table,
+ * empty ranges allowed).  One call = one kernel per rank: local partial sums (G.711 decoded in registers) are
+ * stored straight into every peer's mailbox over NVLink, row by row, then each rank adds the `world` partial
+ * rows (exact int32) and writes the N-minus-one read-out of its own members.  Equivalent to
+ * wmixb_*bus_sum_device -> int32 sum all-reduce (e.g. NCCL) -> wmixb_*bus_nminus1_device, bit for bit.
+ *   law: -1 = int16 PCM in/out, 0 = A-law, 1 = mu-law codes in/out.  d_out and d_bus are nullable.
+ * Ranks must call tick in lock-step (same number of calls), each on one stream of its own; a peer that never
+ * arrives trips a 2 s timeout (WMIXB_PEER_TIMEOUT_MS) reported by wmixb_peer_bus_status, not a hang.
+ * Wiring: create on every rank, then either exchange the WMIXB_PEER_HANDLE_BYTES blobs between processes
+ * (any transport) and call _connect with all `world` blobs in rank order, or, inside one process, call
+ * _connect_local with the `world` peer objects. */
+typedef struct wmixb_peer_bus wmixb_peer_bus;
+#define WMIXB_PEER_HANDLE_BYTES 80
+int wmixb_peer_bus_create(wmixb_engine* e, int rank, int world, wmixb_peer_bus** out);
+void wmixb_peer_bus_destroy(wmixb_peer_bus* pb);
+int wmixb_peer_bus_handle(const wmixb_peer_bus* pb, void* handle_out);
+int wmixb_peer_bus_connect(wmixb_peer_bus* pb, const void* handles);
+int wmixb_peer_bus_connect_local(wmixb_peer_bus* pb, wmixb_peer_bus* const* peers);
+int wmixb_peer_bus_tick_device(wmixb_peer_bus* pb, int law, const void* d_in, void* d_out, int32_t* d_bus, void* stream);
+int wmixb_peer_bus_status(wmixb_peer_bus* pb, int* h_error);
+
 /* G.711 on device buffers (R:src/g711codec.c).  law: 0 = A-law, 1 = mu-law.  n = samples. */
 int wmixb_g711_encode_device(int law, const int16_t* d_pcm, uint8_t* d_codes, size_t n, void* stream);
 int wmixb_g711_decode_device(int law, const uint8_t* d_codes, int16_t* d_pcm, size_t n, void* stream);

@@ -45,6 +45,13 @@ def lib():
         "wmixb_set_conferences": (i, [vp, vp, i]),
         "wmixb_bus_sum_device": (i, [vp, vp, vp, vp]),
         "wmixb_bus_nminus1_device": (i, [vp, vp, vp, vp, vp]),
+        "wmixb_peer_bus_create": (i, [vp, i, i, C.POINTER(vp)]),
+        "wmixb_peer_bus_destroy": (None, [vp]),
+        "wmixb_peer_bus_handle": (i, [vp, vp]),
+        "wmixb_peer_bus_connect": (i, [vp, vp]),
+        "wmixb_peer_bus_connect_local": (i, [vp, C.POINTER(vp)]),
+        "wmixb_peer_bus_tick_device": (i, [vp, i, vp, vp, vp, vp]),
+        "wmixb_peer_bus_status": (i, [vp, C.POINTER(i)]),
         "wmixb_g711_encode_device": (i, [i, vp, vp, sz, vp]),
         "wmixb_g711_decode_device": (i, [i, vp, vp, sz, vp]),
         "wmixb_g711_bus_sum_device": (i, [vp, i, vp, vp, vp]),

@@ -1,0 +1,162 @@
+// Cross-GPU conference bus in ONE persistent kernel: local partial sums, push over NVLink into every
+// peer's mailbox, flag, wait for the peers' rows, reduce, N-minus-one read-out (+ G.711 encode).
+//
+// The reference has a single mix bus inside one process (R:src/wmix.c:1639-1702: every producer adds
+// into the ring); here a conference's participants may live on several GPUs of one node.  Each rank
+// (one process per GPU) owns a MAILBOX that all peers can write through CUDA IPC peer mappings:
+//
+//     slots [2][world][n_conf * frame]  int32    partial bus rows, double-buffered by tick parity
+//     flags [2][world][n_conf * frame/16]   uint32   tick sequence number the 16-sample tile belongs to
+//
+// Phase 1 (per 16-sample tile of a conference row this CTA owns): sum the local members (decoding G.711
+//   in registers) and store the tile into slot [parity][my_rank] of EVERY rank's mailbox (16-byte stores;
+//   peer stores ride NVLink); then one fence at system scope and flags[parity][my_rank][tile] = seq on
+//   every rank for each of the CTA's tiles.
+// Phase 2 (same tiles): wait until all `world` flags of the tile carry `seq`, add the `world` partial
+//   tiles in rank order (int32: exact, so any order gives the same bits), and emit
+//   out = clamp16(bus - own) for the local members (re-encoded for the G.711 variants).
+// A CTA finishes phase 1 for all of its tiles before it waits for anything, and the grid never exceeds
+// what is co-resident, so no rank can block another: tiles stream across NVLink while later tiles are
+// still being summed.  Slot reuse is safe because a rank can only start tick t+2 after its tick t+1
+// kernel has seen every peer's t+1 rows, i.e. after every peer's tick-t kernel has retired.
+// A wait that exceeds `timeout_ns` (a peer that never ticks) sets *error and gives up instead of hanging.
+#pragma once
+#include "g711_mix.cuh"
+
+namespace wmx {
+namespace peer {
+
+constexpr int kMaxWorld = 16;
+constexpr int kThreads = 512;
+
+struct Ring {
+    int32_t* slots[kMaxWorld];     // mailbox of rank r (local pointer for r == rank, IPC mapping otherwise)
+    uint32_t* flags[kMaxWorld];
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+template <int LAW>
+__device__ __forceinline__ int load_sample(const void* src, size_t idx)
+{
+    if (LAW < 0) return static_cast<const int16_t*>(src)[idx];
+    const uint8_t c = static_cast<const uint8_t*>(src)[idx];
+    return LAW == 0 ? alaw2linear(c) : ulaw2linear(c);
+}
+
+// LAW < 0: int16 PCM in/out; 0 / 1: A-law / mu-law codes in/out.
+// Work unit = one TILE: kTile consecutive samples of one conference row, summed by a GROUP of kTile x S
+// threads (S member slices, a power of two chosen by the host from the largest local conference).  A CTA
+// holds G = blockDim / (kTile * S) groups working on G tiles at a time: big conferences get 32 slices
+// and one tile per CTA step, thousands of small ones run eight one-warp tiles per CTA step.
+constexpr int kTile = 16;
+
+template <int LAW>
+__global__ void __launch_bounds__(kThreads)
+peer_bus_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __restrict__ src, void* __restrict__ out,
+                int32_t* __restrict__ bus_out, const int32_t* __restrict__ conf_start, int n_conf, int frame, int S,
+                unsigned long long timeout_ns, int* __restrict__ error)
+{
+    extern __shared__ int32_t sh_all[];             // per group: [S][kTile] partials + [kTile] finished tile
+    const int gthreads = kTile * S;
+    const int G = blockDim.x / gthreads;
+    const int g = threadIdx.x / gthreads, gt = threadIdx.x - g * gthreads;
+    const int tx = gt % kTile, slice = gt / kTile;
+    int32_t* sh = sh_all + g * (S + 1) * kTile;
+    int32_t* done = sh + S * kTile;
+    const int tiles_per_row = frame / kTile;
+    const int n_tiles = n_conf * tiles_per_row;
+    const int par = (int)(seq & 1u);
+    const size_t row_words = (size_t)n_conf * frame;
+    const int steps = (n_tiles + gridDim.x * G - 1) / (gridDim.x * G);     // uniform trip count (CTA barriers inside)
+
+    // ---- phase 1: partial tiles out to every mailbox ----
+    for (int it = 0; it < steps; ++it) {
+        const int t = (it * gridDim.x + blockIdx.x) * G + g;
+        const bool valid = t < n_tiles;
+        const int c = valid ? t / tiles_per_row : 0, x0 = valid ? (t - c * tiles_per_row) * kTile : 0;
+        int32_t acc = 0;
+        if (valid) {
+            const int first = conf_start[c], last = conf_start[c + 1];
+            for (int p = first + slice; p < last; p += S) acc += load_sample<LAW>(src, (size_t)p * frame + x0 + tx);
+        }
+        __syncthreads();                            // the previous step's readers are done with sh
+        sh[slice * kTile + tx] = acc;
+        __syncthreads();
+        if (gt < kTile) {
+            int32_t v = 0;
+            for (int k = 0; k < S; ++k) v += sh[k * kTile + gt];
+            done[gt] = v;
+        }
+        __syncthreads();
+        // world x kTile/4 16-byte stores per tile
+        if (valid)
+            for (int j = gt; j < world * (kTile / 4); j += gthreads) {
+                const int r = j / (kTile / 4), v = j % (kTile / 4);
+                int4* dst = reinterpret_cast<int4*>(ring.slots[r] + ((size_t)par * world + rank) * row_words + (size_t)c * frame + x0);
+                dst[v] = reinterpret_cast<const int4*>(done)[v];
+            }
+    }
+    // one system-scope fence per CTA, then the flags of all of its tiles (a fence per tile would cost an
+    // NVLink round trip each)
+    __threadfence_system();
+    __syncthreads();
+    for (int j = threadIdx.x; j < steps * G * world; j += blockDim.x) {
+        const int r = j % world, k = j / world;                            // k = it * G + g
+        const int t = ((k / G) * gridDim.x + blockIdx.x) * G + (k % G);
+        if (t < n_tiles) st_release_sys(ring.flags[r] + ((size_t)par * world + rank) * n_tiles + t, seq);
+    }
+
+    // ---- phase 2: gather, reduce, N-minus-one ----
+    const int32_t* my_slots = ring.slots[rank] + (size_t)par * world * row_words;
+    const uint32_t* my_flags = ring.flags[rank] + (size_t)par * world * n_tiles;
+    for (int it = 0; it < steps; ++it) {
+        const int t = (it * gridDim.x + blockIdx.x) * G + g;
+        const bool valid = t < n_tiles;
+        const int c = valid ? t / tiles_per_row : 0, x0 = valid ? (t - c * tiles_per_row) * kTile : 0;
+        if (valid && gt < world) {
+            const uint32_t* f = my_flags + (size_t)gt * n_tiles + t;
+            const unsigned long long t0 = globaltimer_ns();
+            while (ld_acquire_sys(f) != seq) {
+                if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(error, 1 + gt); break; }
+                __nanosleep(32);
+            }
+        }
+        __syncthreads();
+        if (valid && gt < kTile) {
+            int32_t v = 0;
+            for (int r = 0; r < world; ++r) v += __ldcg(my_slots + (size_t)r * row_words + (size_t)c * frame + x0 + gt);
+            done[gt] = v;
+            if (bus_out) bus_out[(size_t)c * frame + x0 + gt] = v;
+        }
+        __syncthreads();
+        if (valid && out) {
+            const int32_t b = done[tx];
+            const int first = conf_start[c], last = conf_start[c + 1];
+            for (int p = first + slice; p < last; p += S) {
+                const size_t idx = (size_t)p * frame + x0 + tx;
+                const int16_t v = sat16(b - load_sample<LAW>(src, idx));
+                if (LAW < 0) static_cast<int16_t*>(out)[idx] = v;
+                else static_cast<uint8_t*>(out)[idx] = LAW == 0 ? linear2alaw(v) : linear2ulaw(v);
+            }
+        }
+    }
+}
+
+}  // namespace peer
+}  // namespace wmx

@@ -21,6 +21,7 @@
 #include "g711_mix.cuh"
 #include "host_tables.h"
 #include "ns.cuh"
+#include "peer_bus.cuh"
 #include "vad.cuh"
 
 using namespace wmx;
@@ -836,6 +837,167 @@ extern "C" int wmixb_g711_nminus1_device(wmixb_engine* e, int law, const int32_t
     if (law == 0) return nminus1_impl<0>(e, d_bus, d_codes, d_out_codes, (cudaStream_t)stream);
     if (law == 1) return nminus1_impl<1>(e, d_bus, d_codes, d_out_codes, (cudaStream_t)stream);
     return WMIXB_EINVAL;
+}
+
+// ---- cross-GPU conference bus over peer memory (peer_bus.cuh) ----
+struct wmixb_peer_bus {
+    wmixb_engine* e = nullptr;
+    int rank = 0, world = 1, n_conf = 0, frame = 0, grid = 0, threads = 0, slices = 0;
+    size_t smem = 0;
+    void* mailbox = nullptr;            // [slots | flags], cudaMalloc'ed on e's device
+    size_t slot_bytes = 0, flag_bytes = 0;
+    void* mapped[peer::kMaxWorld] = {}; // IPC mappings to close
+    peer::Ring ring{};
+    bool connected = false;
+    uint32_t seq = 0;
+    int* d_error = nullptr;
+    unsigned long long timeout_ns = 2000000000ull;
+};
+
+struct PeerMeta { int32_t magic, world, n_conf, frame; };   // rides behind the 64-byte IPC handle
+static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+static_assert(sizeof(cudaIpcMemHandle_t) + sizeof(PeerMeta) == WMIXB_PEER_HANDLE_BYTES, "handle blob size");
+
+static void peer_set_ring(wmixb_peer_bus* pb, int r, void* base)
+{
+    pb->ring.slots[r] = (int32_t*)base;
+    pb->ring.flags[r] = (uint32_t*)((char*)base + pb->slot_bytes);
+}
+
+extern "C" int wmixb_peer_bus_create(wmixb_engine* e, int rank, int world, wmixb_peer_bus** out)
+{
+    if (!e || !out || world < 1 || world > peer::kMaxWorld || rank < 0 || rank >= world) return WMIXB_EINVAL;
+    *out = nullptr;
+    if (e->n_conf < 1) { snprintf(g_err, sizeof g_err, "peer_bus: call wmixb_set_conferences first"); return WMIXB_EINVAL; }
+    CK(cudaSetDevice(e->cfg.device));
+    wmixb_peer_bus* pb = new (std::nothrow) wmixb_peer_bus();
+    if (!pb) return WMIXB_ENOMEM;
+    pb->e = e; pb->rank = rank; pb->world = world; pb->n_conf = e->n_conf; pb->frame = e->frame;
+    pb->slot_bytes = (size_t)2 * world * e->n_conf * e->frame * sizeof(int32_t);
+    pb->flag_bytes = (size_t)2 * world * e->n_conf * (e->frame / peer::kTile) * sizeof(uint32_t);
+    // member slices per tile: a quarter of the largest local conference, power of two, 2..32
+    int slices = 2;
+    while (slices < 32 && slices * 4 < e->max_conf) slices *= 2;
+    pb->slices = slices;
+    pb->threads = slices * peer::kTile < 256 ? 256 : slices * peer::kTile;
+    const int groups = pb->threads / (slices * peer::kTile);
+    pb->smem = (size_t)groups * (slices + 1) * peer::kTile * sizeof(int32_t);
+    if (const char* v = getenv("WMIXB_PEER_TIMEOUT_MS")) { const long ms = atol(v); if (ms > 0) pb->timeout_ns = (unsigned long long)ms * 1000000ull; }
+    cudaError_t ce = cudaMalloc(&pb->mailbox, pb->slot_bytes + pb->flag_bytes);
+    if (ce == cudaSuccess) ce = cudaMemset(pb->mailbox, 0, pb->slot_bytes + pb->flag_bytes);
+    if (ce == cudaSuccess) ce = cudaMalloc(&pb->d_error, sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMemset(pb->d_error, 0, sizeof(int));
+    int per_sm = 0;
+    if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer::peer_bus_kernel<0>, pb->threads, pb->smem);
+    if (ce != cudaSuccess) { cudaFree(pb->mailbox); cudaFree(pb->d_error); delete pb; return fail_cuda(ce, "peer_bus_create", __LINE__); }
+    // every CTA must be resident (phase 2 waits on other ranks): never more than one wave
+    // (half of it, so that a second rank living on the same device — tests — still fits beside this one)
+    const int cap = e->sm_count * (per_sm < 2 ? 1 : per_sm / 2);
+    const int n_steps = (e->n_conf * (e->frame / peer::kTile) + groups - 1) / groups;
+    pb->grid = n_steps < cap ? n_steps : cap;
+    peer_set_ring(pb, rank, pb->mailbox);
+    pb->connected = world == 1;
+    *out = pb;
+    return WMIXB_OK;
+}
+
+extern "C" void wmixb_peer_bus_destroy(wmixb_peer_bus* pb)
+{
+    if (!pb) return;
+    cudaSetDevice(pb->e->cfg.device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < pb->world; ++r)
+        if (pb->mapped[r]) cudaIpcCloseMemHandle(pb->mapped[r]);
+    cudaFree(pb->mailbox);
+    cudaFree(pb->d_error);
+    delete pb;
+}
+
+extern "C" int wmixb_peer_bus_handle(const wmixb_peer_bus* pb, void* handle_out)
+{
+    if (!pb || !handle_out) return WMIXB_EINVAL;
+    CK(cudaSetDevice(pb->e->cfg.device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, pb->mailbox));
+    const PeerMeta m{0x77425042, pb->world, pb->n_conf, pb->frame};
+    memcpy(handle_out, &h, sizeof h);
+    memcpy((char*)handle_out + sizeof h, &m, sizeof m);
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_peer_bus_connect(wmixb_peer_bus* pb, const void* handles)
+{
+    if (!pb || !handles) return WMIXB_EINVAL;
+    CK(cudaSetDevice(pb->e->cfg.device));
+    for (int r = 0; r < pb->world; ++r) {
+        const char* blob = (const char*)handles + (size_t)r * WMIXB_PEER_HANDLE_BYTES;
+        PeerMeta m;
+        memcpy(&m, blob + sizeof(cudaIpcMemHandle_t), sizeof m);
+        if (m.magic != 0x77425042 || m.world != pb->world || m.n_conf != pb->n_conf || m.frame != pb->frame) {
+            snprintf(g_err, sizeof g_err, "peer_bus_connect: rank %d announces world/n_conf/frame %d/%d/%d, this rank has %d/%d/%d",
+                     r, m.world, m.n_conf, m.frame, pb->world, pb->n_conf, pb->frame);
+            return WMIXB_EINVAL;
+        }
+        if (r == pb->rank || pb->mapped[r]) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, blob, sizeof h);
+        void* base = nullptr;
+        CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+        pb->mapped[r] = base;
+        peer_set_ring(pb, r, base);
+    }
+    pb->connected = true;
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_peer_bus_connect_local(wmixb_peer_bus* pb, wmixb_peer_bus* const* peers)
+{
+    if (!pb || !peers) return WMIXB_EINVAL;
+    CK(cudaSetDevice(pb->e->cfg.device));
+    for (int r = 0; r < pb->world; ++r) {
+        const wmixb_peer_bus* q = peers[r];
+        if (!q || q->rank != r || q->world != pb->world || q->n_conf != pb->n_conf || q->frame != pb->frame) {
+            snprintf(g_err, sizeof g_err, "peer_bus_connect_local: peers[%d] does not match (rank/world/n_conf/frame)", r);
+            return WMIXB_EINVAL;
+        }
+        if (r == pb->rank) continue;
+        if (q->e->cfg.device != pb->e->cfg.device) {
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, pb->e->cfg.device, q->e->cfg.device));
+            if (!can) { snprintf(g_err, sizeof g_err, "peer_bus: device %d cannot access device %d", pb->e->cfg.device, q->e->cfg.device); return WMIXB_ECUDA; }
+            const cudaError_t ce = cudaDeviceEnablePeerAccess(q->e->cfg.device, 0);
+            if (ce != cudaSuccess && ce != cudaErrorPeerAccessAlreadyEnabled) return fail_cuda(ce, "cudaDeviceEnablePeerAccess", __LINE__);
+            (void)cudaGetLastError();
+        }
+        peer_set_ring(pb, r, q->mailbox);
+    }
+    pb->connected = true;
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_peer_bus_tick_device(wmixb_peer_bus* pb, int law, const void* d_in, void* d_out, int32_t* d_bus, void* stream)
+{
+    if (!pb || !d_in || law < -1 || law > 1) return WMIXB_EINVAL;
+    if (!pb->connected) { snprintf(g_err, sizeof g_err, "peer_bus: not connected to its %d peers yet", pb->world - 1); return WMIXB_EINVAL; }
+    wmixb_engine* e = pb->e;
+    if (e->n_conf != pb->n_conf) { snprintf(g_err, sizeof g_err, "peer_bus: the conference table changed after create"); return WMIXB_EINVAL; }
+    CK(cudaSetDevice(e->cfg.device));
+    if (++pb->seq == 0) pb->seq = 2;     // 0 is the "never written" flag value; keep the parity sequence alternating
+    cudaStream_t st = (cudaStream_t)stream;
+#define WMX_PEER(LAW) peer::peer_bus_kernel<LAW><<<pb->grid, pb->threads, pb->smem, st>>>(pb->ring, pb->rank, pb->world, pb->seq, d_in, d_out, d_bus, e->conf_start, pb->n_conf, e->frame, pb->slices, pb->timeout_ns, pb->d_error)
+    if (law < 0) WMX_PEER(-1); else if (law == 0) WMX_PEER(0); else WMX_PEER(1);
+#undef WMX_PEER
+    CK_LAUNCH();
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_peer_bus_status(wmixb_peer_bus* pb, int* h_error)
+{
+    if (!pb || !h_error) return WMIXB_EINVAL;
+    CK(cudaSetDevice(pb->e->cfg.device));
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h_error, pb->d_error, sizeof(int), cudaMemcpyDeviceToHost));
+    return WMIXB_OK;
 }
 
 // ---- G.711 / mix ring ----
