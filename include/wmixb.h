@@ -68,6 +68,13 @@ int wmixb_tick_host(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_
  * wmix_load_data yields while no partial sum clips (R:src/wmix.c:1678-1702). */
 int wmixb_tick_host_bus(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int32_t* h_bus, int stages);
 
+/* VAD on 20 ms packets, in place: what wmix itself configures (vad_init(.., WMIX_INTERVAL_MS = 20, ..),
+ * R:src/wmix.c:703; 20 ms thresholds of T:.../vad/vad_core.c:149-164).  d_pcm: int16 [n_streams][2*frame],
+ * attenuated by the wrapper's mute ramp (R:src/webrtc.c:127-141); d_vad (nullable): uint8 [n_streams].
+ * Shares the per-stream VAD state with the 10 ms stage — use one packet size per engine. */
+int wmixb_vad20_device(wmixb_engine* e, int16_t* d_pcm, uint8_t* d_vad, void* stream);
+int wmixb_vad20_host(wmixb_engine* e, int16_t* h_pcm, uint8_t* h_vad);
+
 /* Echo canceller (stage WMIXB_AEC), the arithmetic of aec_process2 (R:src/webrtc.c:410-483) for every
  * stream: BufferFarend(d_far) then Process(d_near) -> d_out.  d_far == NULL is aec_process (near only),
  * d_near == NULL is aec_setFrameFar (far only; d_out unused).  Buffers are int16 [n_streams][samples],
@@ -149,6 +156,10 @@ const char* wmixb_last_error(void);
 long long wmixb_kernel_launches(void);          /* kernels this library has launched so far */
 size_t wmixb_state_bytes_per_stream(const wmixb_engine* e);
 int wmixb_frame_len(const wmixb_engine* e);
+/* device self-test: the NS kernel's range-restricted float division against the IEEE one on n random operand
+ * pairs, |a| in [2^a_lo, 2^a_hi) (and exact zeros), b in [2^b_lo, 2^b_hi); *h_mismatches must come back 0 */
+int wmixb_selftest_fdiv(unsigned long long n, unsigned seed, float a_lo_log2, float a_hi_log2, float b_lo_log2,
+                        float b_hi_log2, unsigned long long* h_mismatches);
 /* init-time tables, exported so tests can pin them against the reference's literals */
 void wmixb_ns_window(int ana, int block, float* out);
 int wmixb_agc_gain_table(int32_t table[32], int comp_db, int target_dbfs, int limiter, int analog_target);

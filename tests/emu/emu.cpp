@@ -106,6 +106,17 @@ int emu_vad_frame(void* h, int16_t* x)
     if (e->freq == 16000) return vad::process_packet<80, true>(st, x, e->vp);
     return vad::process_packet<80, false>(st, x, e->vp);
 }
+// 20 ms packets (thresholds of the 20 ms column): x holds 160 (8 kHz) / 320 (16 kHz) samples
+int emu_vad_frame20(void* h, int16_t* x, int vad_mode)
+{
+    EmuInt* e = (EmuInt*)h;
+    SoaWords st{e->vad.data(), 1};
+    int16_t th[4];
+    host::vad_thresholds(vad_mode, 20, th);
+    const vad::Params vp{th[0], th[1], th[2], th[3]};
+    if (e->freq == 16000) return vad::process_packet<160, true>(st, x, vp);
+    return vad::process_packet<160, false>(st, x, vp);
+}
 void emu_int_destroy(void* h) { delete (EmuInt*)h; }
 
 struct EmuAec {

@@ -120,6 +120,36 @@ def test_emulated_kernel_bodies_vs_reference(freq, stage):
         assert np.array_equal(ya, yb), (stage, freq, s)
 
 
+@pytest.mark.parametrize("freq", [16000, 8000])
+def test_emulated_vad_20ms_packets_vs_reference(freq):
+    """wmix itself creates its VAD with intervalMs = 20 (R:src/wmix.c:703): 20 ms packets and the 20 ms threshold
+    column (T:.../vad/vad_core.c:149-164).  Kernel body (lane-loop emulation) against the reference handle."""
+    import ctypes as C
+
+    chk = ref() or oracle()
+    n = freq // 50
+    x = make_frames(6, freq, 0, 400, seed=17)                      # 400 ticks = 200 packets per stream
+    E = emu()
+    E.emu_int_create.restype = C.c_void_p
+    for s in range(6):
+        pcm = np.ascontiguousarray(x[:, s, :]).reshape(-1, n)
+        if ref() is not None:
+            chk.vad_init.restype = C.c_void_p
+            h = C.c_void_p(chk.vad_init(1, freq, 20, None))
+            proc, rel = chk.vad_process, chk.vad_release
+        else:
+            h = C.c_void_p(chk.orc_vad_init(1, freq, 20))
+            proc, rel = chk.orc_vad_process, chk.orc_vad_release
+        e = C.c_void_p(E.emu_int_create(freq, 5, 3))
+        for k in range(len(pcm)):
+            a, b = pcm[k].copy(), pcm[k].copy()
+            proc(h, P(a), n)
+            E.emu_vad_frame20(e, P(b), 3)
+            assert np.array_equal(a, b), (freq, s, k)
+        rel(h)
+        E.emu_int_destroy(e)
+
+
 def test_ns_counter_division_is_exact():
     """ns::div_by_counter (reciprocal + exact residual + one correction) replaces `x / (counter + 1)` in the NS quantile
     trackers (T:.../ns/ns_core.c:233-249); it must BE the IEEE quotient: every divisor 1..201 on a significand grid, and

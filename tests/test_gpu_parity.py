@@ -376,6 +376,58 @@ def test_dropin_handle_api():
     assert not lib.agc_init(1, 12000, 10, 5, None) and not lib.aec_init(1, 32000, 10, None)
 
 
+@pytest.mark.parametrize("freq", [8000, 16000])
+def test_vad_20ms_packets_handle_and_batched(freq):
+    """vad_init(.., 20, ..) as wmix calls it (R:src/wmix.c:703): drop-in handle and wmixb_vad20_device, bit-exact"""
+    lib = wmix_b200.lib()
+    n = freq // 50
+    S, K = 40, 150
+    x = make_frames(S, freq, 0, 2 * K, seed=83)                    # [2K, S, L]
+    pk = np.ascontiguousarray(x.transpose(1, 0, 2)).reshape(S, K, n)  # [S, K, 20 ms]
+    want = np.empty_like(pk)
+    for cname, L, prefix in checkers():
+        for s in range(S):
+            if prefix:
+                h = C.c_void_p(L.orc_vad_init(1, freq, 20))
+                proc, rel = L.orc_vad_process, L.orc_vad_release
+            else:
+                h = C.c_void_p(L.vad_init(1, freq, 20, None))
+                proc, rel = L.vad_process, L.vad_release
+            for k in range(K):
+                f = pk[s, k].copy()
+                proc(h, P(f), n)
+                want[s, k] = f
+            rel(h)
+        # batched
+        eng = wmix_b200.Engine(S, freq, stages=VAD)
+        d = torch.empty((S, n), dtype=torch.int16, device=DEV)
+        flags = torch.zeros((S,), dtype=torch.uint8, device=DEV)
+        for k in range(K):
+            d.copy_(torch.from_numpy(np.ascontiguousarray(pk[:, k])))
+            eng.vad20_device(d, flags)
+            assert np.array_equal(d.cpu().numpy(), want[:, k]), (cname, k)
+        eng.close()
+        # handle
+        vad = lib.vad_init(1, freq, 20, None)
+        assert vad
+        for k in range(K):
+            f = pk[3, k].copy()
+            lib.vad_process(vad, f.ctypes.data, n)
+            assert np.array_equal(f, want[3, k]), (cname, "handle", k)
+        lib.vad_release(vad)
+
+
+def test_ns_range_restricted_division_is_ieee_on_device():
+    """ns::fdiv (no FCHK probe / slow path) == __fdiv_rn over 2^31 random operand pairs spanning far more than the
+    magnitudes the NS kernel divides (|a| in [2^-60, 2^60) and zeros, b in [2^-20, 2^50))"""
+    bad = C.c_ulonglong(1)
+    lib = wmix_b200.lib()
+    assert lib.wmixb_selftest_fdiv(1 << 31, 12345, -60.0, 60.0, -20.0, 50.0, C.byref(bad)) == 0
+    assert bad.value == 0
+    assert lib.wmixb_selftest_fdiv(1 << 28, 777, -10.0, 30.0, -14.0, 26.0, C.byref(bad)) == 0
+    assert bad.value == 0
+
+
 def test_full_size_replication_property():
     """Config 3 size (100k streams): stream s is fed the input of stream s % 64, so its output
     must equal that of stream s % 64 at every tick — checks indexing/occupancy paths at scale."""

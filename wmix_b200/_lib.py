@@ -37,6 +37,8 @@ def lib():
         "wmixb_tick_device": (i, [vp, vp, vp, vp, i, vp]),
         "wmixb_tick_host": (i, [vp, vp, vp, vp, i]),
         "wmixb_tick_host_bus": (i, [vp, vp, vp, vp, vp, i]),
+        "wmixb_vad20_device": (i, [vp, vp, vp, vp]),
+        "wmixb_vad20_host": (i, [vp, vp, vp]),
         "wmixb_offline_device": (i, [vp, vp, vp, vp, i, i, vp]),
         "wmixb_aec_device": (i, [vp, vp, vp, vp, i, i, vp]),
         "wmixb_aec_host": (i, [vp, vp, vp, vp, i, i]),
@@ -65,6 +67,7 @@ def lib():
         "wmixb_kernel_launches": (C.c_longlong, []),
         "wmixb_state_bytes_per_stream": (sz, [vp]),
         "wmixb_frame_len": (i, [vp]),
+        "wmixb_selftest_fdiv": (i, [C.c_ulonglong, C.c_uint, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(C.c_ulonglong)]),
         "wmixb_ns_window": (None, [i, i, vp]),
         "wmixb_agc_gain_table": (i, [vp, i, i, i, i]),
         "wmixb_agc_analog_target": (i, [i]),

@@ -68,13 +68,18 @@ extern "C" {
 void* vad_init(int chn, int freq, int intervalMs, bool* debug)
 {
     if (!rate_ok(freq, 32000)) return nullptr;                      // R:src/webrtc.c:43
-    if (freq == 32000 || (freq <= 16000 && intervalMs % 20 == 0)) {
-        // 32 kHz and the 20 ms packet (R:src/webrtc.c:56-65) are not wired up yet — INTEGRATION.md
-        if (dbg(debug)) printf("vad_init: only 8/16 kHz with 10 ms packets on the GPU path so far\r\n");
+    if (freq == 32000) {
+        // the 32 kHz path (CalcVad32khz) is not on the GPU — INTEGRATION.md
+        if (dbg(debug)) printf("vad_init: only 8/16 kHz on the GPU path so far\r\n");
         return nullptr;
     }
     Handle* h = make(WMIXB_VAD, chn, freq, 0, debug, "vad_init");
-    if (h && dbg(debug)) printf("vad_init: chn/%d freq/%d intervalMs/%d pkgFrame/%d\r\n", chn, freq, 10, h->pkg);
+    if (!h) return nullptr;
+    const int ms = intervalMs % 20 == 0 ? 20 : 10;                  // R:src/webrtc.c:56-65
+    h->pkg = freq / 1000 * ms;
+    h->mono.resize((size_t)h->pkg);
+    h->res.resize((size_t)h->pkg);
+    if (dbg(debug)) printf("vad_init: chn/%d freq/%d intervalMs/%d pkgFrame/%d\r\n", chn, freq, ms, h->pkg);
     return h;
 }
 
@@ -96,7 +101,14 @@ void vad_process(void* fp, int16_t* frame, int frameNum)
     for (int pos = 0; pos < mono; pos += h->pkg) {
         memcpy(h->mono.data(), frame, (size_t)h->pkg * 2);
         uint8_t flag = 0;
-        if (wmixb_tick_host(h->eng, h->mono.data(), h->res.data(), &flag, WMIXB_VAD) != WMIXB_OK) {
+        int rc;
+        if (h->pkg == h->freq / 100) {
+            rc = wmixb_tick_host(h->eng, h->mono.data(), h->res.data(), &flag, WMIXB_VAD);
+        } else {                                                    // 20 ms packet
+            memcpy(h->res.data(), h->mono.data(), (size_t)h->pkg * 2);
+            rc = wmixb_vad20_host(h->eng, h->res.data(), &flag);
+        }
+        if (rc != WMIXB_OK) {
             if (dbg(h->debug)) printf("WebRtcVad_Process failed !!, %s \r\n", wmixb_last_error());
             return;
         }

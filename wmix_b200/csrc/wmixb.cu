@@ -52,7 +52,6 @@ static int fail_cuda(cudaError_t e, const char* what, int line)
 // ------------------------------------------------------------------------------------------
 // NS kernel: persistent grid, one warp per stream, K frames per stream per launch
 // ------------------------------------------------------------------------------------------
-constexpr int kNsWarps = 8;
 
 // bulk L2 prefetch (bytes a multiple of 16, address 16-byte aligned): one instruction, no
 // destination, no completion to wait for
@@ -64,15 +63,14 @@ __device__ __forceinline__ void l2_prefetch(const void* p, uint32_t bytes)
 template <int ANA>
 struct NsSmem {
     static constexpr size_t kTableFloats = (sizeof(ns::Tables<ANA>) + 15) / 16 * 4;
-    static constexpr size_t kBytes = (kTableFloats + (size_t)kNsWarps * ns::Geo<ANA>::kShFloats) * sizeof(float);
 };
 template <int ANA>
-constexpr size_t ns_smem_bytes() { return NsSmem<ANA>::kBytes; }
+constexpr size_t ns_smem_bytes(int warps) { return (NsSmem<ANA>::kTableFloats + (size_t)warps * ns::Geo<ANA>::kShFloats) * sizeof(float); }
 
-template <int ANA, int MINB>
-__global__ void __launch_bounds__(kNsWarps * 32, MINB)
+template <int ANA, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 ns_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Tables<ANA>* __restrict__ tables,
-          const int16_t* in, int16_t* out, int n_streams, int n_frames)
+          const int16_t* in, int16_t* out, int n_streams, int n_frames, int align)
 {
     typedef ns::Geo<ANA> G;
     extern __shared__ __align__(16) float smem[];
@@ -89,13 +87,21 @@ ns_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Tables
     W.lane_id = threadIdx.x & 31;
     for (int i = W.lane_id; i < G::kShFloats; i += 32) tile[i] = 0.f;   // sum rows rely on +0.0f padding
     __syncwarp();
-    const int total_warps = gridDim.x * kNsWarps;
-    for (int s = blockIdx.x * kNsWarps + warp; s < n_streams; s += total_warps) {
+    const int total_warps = gridDim.x * WARPS;
+    // The loop body is ~110 KB of code against a 32 KB instruction cache: warps that drift apart each stream
+    // their own copy of it from L2.  With `align` the warps of a CTA start every frame together, so they run
+    // the same phases at the same time and share the fetched lines (uniform trip count: barriers inside).
+    const int iters = (n_streams - blockIdx.x * WARPS + total_warps - 1) / total_warps;   // of warp 0; >= every other warp's
+    for (int it = 0; it < iters; ++it) {
+        const int s = blockIdx.x * WARPS + warp + it * total_warps;
+        const bool live = s < n_streams;
         float* r = rec + (size_t)s * G::kRecFloats;
         uint16_t* h = hist + (size_t)s * 3 * ns::kHistBins;
         const int16_t* pi = in + (size_t)s * n_frames * G::kBlock;
         int16_t* po = out + (size_t)s * n_frames * G::kBlock;
         for (int f = 0; f < n_frames; ++f) {
+            if (align) __syncthreads();
+            if (!live) continue;
             if (f == n_frames - 1 && W.lane_id == 0 && s + total_warps < n_streams) {
                 // pull the next stream's record and first frame towards L2 while this one computes
                 l2_prefetch(rec + (size_t)(s + total_warps) * G::kRecFloats, G::kRecFloats * sizeof(float));
@@ -220,6 +226,25 @@ post_kernel(int32_t* __restrict__ agc_words, int32_t* __restrict__ vad_words, co
             out32[((size_t)(s0 + r) * n_frames + f) * (L / 2) + w] = tile[r * ROWW + w];
         }
     }
+}
+
+// VAD on 20 ms packets (what wmix itself asks for: vad_init(.., WMIX_INTERVAL_MS = 20, ..), R:src/wmix.c:703,
+// R:src/webrtc.c:56-65; the 20 ms threshold column of T:.../vad/vad_core.c:149-164).  One stream per thread,
+// the packet staged in local memory: a correctness path for the drop-in handle, not a throughput path.
+template <bool FS16>
+__global__ void __launch_bounds__(64)
+vad_packet20_kernel(int32_t* __restrict__ vad_words, vad::Params vp, int16_t* pcm, uint8_t* vad_out, int n_streams, size_t stride)
+{
+    constexpr int L = FS16 ? 320 : 160;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    int16_t x[L];
+    int16_t* row = pcm + (size_t)s * L;
+    for (int i = 0; i < L; ++i) x[i] = row[i];
+    SoaWords st{vad_words + s, stride};
+    const int flag = vad::process_packet<160, FS16>(st, x, vp);
+    for (int i = 0; i < L; ++i) row[i] = x[i];
+    if (vad_out) vad_out[s] = (uint8_t)flag;
 }
 
 __global__ void words_init_kernel(int32_t* words, const int32_t* init, int n_words, size_t stride, int first, int count)
@@ -347,8 +372,9 @@ struct wmixb_engine {
     int32_t* agc_table = nullptr;
     int32_t* agc_init = nullptr;
     int32_t* vad_init = nullptr;
-    vad::Params vp{};
+    vad::Params vp{}, vp20{};
     int16_t *d_in = nullptr, *d_out = nullptr;   // staging for the host-buffer entry point
+    int16_t* d_pkt20 = nullptr;             // staging of wmixb_vad20_host
     uint8_t* d_vad = nullptr;
     int32_t* conf_start = nullptr;          // [n_conf+1]
     int32_t* conf_of = nullptr;             // [n_streams]
@@ -359,7 +385,8 @@ struct wmixb_engine {
     int32_t* d_bus = nullptr;               // staging of the conference bus for the host-buffer tick
     size_t d_bus_bytes = 0;
     int ns_grid = 0;
-    int ns_occ = 2;                         // CTAs per SM the NS kernel variant is compiled for
+    int ns_cfg = 0;                         // index into kNsCfgs
+    int ns_align = 1;                       // CTA barrier at the top of every frame (instruction-cache sharing)
     int post_occ = 3;                       // same for post_kernel (3 CTAs of 128 threads, 168 registers per thread: measured best)
     float* aec_rec = nullptr;               // [n_streams][aec_rec_floats]
     void* aec_tables = nullptr;
@@ -371,10 +398,22 @@ struct wmixb_engine {
 
 static int ns_rec_floats(const wmixb_engine* e) { return e->ana == 256 ? ns::Geo<256>::kRecFloats : ns::Geo<128>::kRecFloats; }
 
+// compiled (warps per CTA, CTAs per SM) shapes of the NS kernel; WMIXB_NS_CFG=<index> picks one (default 0)
+struct NsCfg { int warps, minb; };
+static const NsCfg kNsCfgs[] = {{8, 2}, {8, 3}, {10, 2}, {6, 3}, {12, 1}, {4, 5}, {9, 2}, {4, 4}};
 template <int ANA>
-static const void* ns_fn(int occ)
+static const void* ns_fn(int cfg)
 {
-    return occ == 4 ? (const void*)ns_kernel<ANA, 4> : occ == 3 ? (const void*)ns_kernel<ANA, 3> : (const void*)ns_kernel<ANA, 2>;
+    switch (cfg) {
+    case 1: return (const void*)ns_kernel<ANA, 8, 3>;
+    case 2: return (const void*)ns_kernel<ANA, 10, 2>;
+    case 3: return (const void*)ns_kernel<ANA, 6, 3>;
+    case 4: return (const void*)ns_kernel<ANA, 12, 1>;
+    case 5: return (const void*)ns_kernel<ANA, 4, 5>;
+    case 6: return (const void*)ns_kernel<ANA, 9, 2>;
+    case 7: return (const void*)ns_kernel<ANA, 4, 4>;
+    default: return (const void*)ns_kernel<ANA, 8, 2>;
+    }
 }
 
 template <int ANA>
@@ -383,8 +422,10 @@ static int launch_ns(wmixb_engine* e, int grid, cudaStream_t st, const int16_t* 
     float* rec = e->ns_rec + (size_t)first * ns::Geo<ANA>::kRecFloats;
     uint16_t* hist = e->ns_hist + (size_t)first * 3 * ns::kHistBins;
     const ns::Tables<ANA>* T = (const ns::Tables<ANA>*)e->ns_tables;
-    void* args[] = {&rec, &hist, &T, &in, &out, &n, &n_frames};
-    CK(cudaLaunchKernel(ns_fn<ANA>(e->ns_occ), dim3(grid), dim3(kNsWarps * 32), args, ns_smem_bytes<ANA>(), st));
+    int align = e->ns_align;
+    void* args[] = {&rec, &hist, &T, &in, &out, &n, &n_frames, &align};
+    const int warps = kNsCfgs[e->ns_cfg].warps;
+    CK(cudaLaunchKernel(ns_fn<ANA>(e->ns_cfg), dim3(grid), dim3(warps * 32), args, ns_smem_bytes<ANA>(warps), st));
     return WMIXB_OK;
 }
 
@@ -405,12 +446,14 @@ static int upload_ns_tables(wmixb_engine* e)
     CK(cudaMalloc(&e->ns_tables, sizeof T));
     CK(cudaMemcpy(e->ns_tables, &T, sizeof T, cudaMemcpyHostToDevice));
     // register budget variant: 2 / 3 / 4 CTAs of 8 warps per SM (128 / 80 / 64 registers per lane)
-    if (const char* v = getenv("WMIXB_NS_OCC")) { const int o = atoi(v); if (o >= 2 && o <= 4) e->ns_occ = o; }
-    const void* fn = ns_fn<ANA>(e->ns_occ);
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns_smem_bytes<ANA>()));
+    if (const char* v = getenv("WMIXB_NS_CFG")) { const int o = atoi(v); if (o >= 0 && o < (int)(sizeof kNsCfgs / sizeof kNsCfgs[0])) e->ns_cfg = o; }
+    if (const char* v = getenv("WMIXB_NS_ALIGN")) e->ns_align = atoi(v) != 0;
+    const void* fn = ns_fn<ANA>(e->ns_cfg);
+    const int warps = kNsCfgs[e->ns_cfg].warps;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns_smem_bytes<ANA>(warps)));
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kNsWarps * 32, ns_smem_bytes<ANA>()));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, ns_smem_bytes<ANA>(warps)));
     if (per_sm < 1) per_sm = 1;
     e->ns_grid = e->sm_count * per_sm;
     return WMIXB_OK;
@@ -463,7 +506,7 @@ extern "C" void wmixb_destroy(wmixb_engine* e)
     cudaFree(e->ns_rec); cudaFree(e->ns_hist); cudaFree(e->ns_tables);
     cudaFree(e->agc_words); cudaFree(e->vad_words); cudaFree(e->agc_table);
     cudaFree(e->agc_init); cudaFree(e->vad_init);
-    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_vad);
+    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_vad); cudaFree(e->d_pkt20);
     cudaFree(e->conf_start); cudaFree(e->conf_of);
     cudaFree(e->aec_rec); cudaFree(e->aec_tables); cudaFree(e->aec_result); cudaFree(e->aec_stage);
     for (int k = 0; k < 3; ++k) {
@@ -536,6 +579,8 @@ static int create_impl(const wmixb_config* cfg, wmixb_engine* e)
         int16_t th[4];
         if (host::vad_thresholds(cfg->vad_mode, 10, th) != 0) { snprintf(g_err, sizeof g_err, "vad_mode %d out of range 0..3", cfg->vad_mode); return WMIXB_EINVAL; }
         e->vp = vad::Params{th[0], th[1], th[2], th[3]};
+        host::vad_thresholds(cfg->vad_mode, 20, th);
+        e->vp20 = vad::Params{th[0], th[1], th[2], th[3]};
     }
     if (const char* v = getenv("WMIXB_POST_OCC")) { const int o = atoi(v); if (o >= 2 && o <= 5) e->post_occ = o; }
     CK(cudaMalloc(&e->d_in, n * e->frame * sizeof(int16_t)));
@@ -594,7 +639,8 @@ static int run_stages(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint
     if (n < 0) n = e->cfg.n_streams - first;
     const int16_t* cur = d_in;
     if (stages & WMIXB_NS) {
-        const int need = (n + kNsWarps - 1) / kNsWarps;
+        const int nw = kNsCfgs[e->ns_cfg].warps;
+        const int need = (n + nw - 1) / nw;
         const int grid = need < e->ns_grid ? need : e->ns_grid;
         const int rc = e->ana == 256 ? launch_ns<256>(e, grid, st, cur, d_out, first, n, n_frames) : launch_ns<128>(e, grid, st, cur, d_out, first, n, n_frames);
         if (rc) return rc;
@@ -628,6 +674,33 @@ extern "C" int wmixb_tick_device(wmixb_engine* e, const int16_t* d_in, int16_t* 
     if (!e || !d_in || !d_out) return WMIXB_EINVAL;
     CK(cudaSetDevice(e->cfg.device));
     return run_stages(e, d_in, d_out, d_vad, 1, stages, (cudaStream_t)stream);
+}
+
+extern "C" int wmixb_vad20_device(wmixb_engine* e, int16_t* d_pcm, uint8_t* d_vad, void* stream)
+{
+    if (!e || !d_pcm) return WMIXB_EINVAL;
+    if (!e->vad_words) { snprintf(g_err, sizeof g_err, "vad20: the engine was created without WMIXB_VAD"); return WMIXB_EINVAL; }
+    CK(cudaSetDevice(e->cfg.device));
+    const int n = e->cfg.n_streams, grid = (n + 63) / 64;
+    if (e->frame == 160) vad_packet20_kernel<true><<<grid, 64, 0, (cudaStream_t)stream>>>(e->vad_words, e->vp20, d_pcm, d_vad, n, e->stride);
+    else vad_packet20_kernel<false><<<grid, 64, 0, (cudaStream_t)stream>>>(e->vad_words, e->vp20, d_pcm, d_vad, n, e->stride);
+    CK_LAUNCH();
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_vad20_host(wmixb_engine* e, int16_t* h_pcm, uint8_t* h_vad)
+{
+    if (!e || !h_pcm) return WMIXB_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    if (!e->d_pkt20) CK(cudaMalloc(&e->d_pkt20, (size_t)e->cfg.n_streams * 2 * e->frame * sizeof(int16_t)));
+    const size_t bytes = (size_t)e->cfg.n_streams * 2 * e->frame * sizeof(int16_t);
+    CK(cudaMemcpyAsync(e->d_pkt20, h_pcm, bytes, cudaMemcpyHostToDevice, e->stream));
+    const int rc = wmixb_vad20_device(e, e->d_pkt20, e->d_vad, e->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_pcm, e->d_pkt20, bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (h_vad) CK(cudaMemcpyAsync(h_vad, e->d_vad, (size_t)e->cfg.n_streams, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return WMIXB_OK;
 }
 
 extern "C" int wmixb_tick_chain_device(wmixb_engine* e, const int16_t* d_far, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad,
@@ -1088,6 +1161,42 @@ static int state_xfer(wmixb_engine* e, int s, void* buf, bool get)
 }
 extern "C" int wmixb_get_stream_state(wmixb_engine* e, int s, void* h_buf) { return state_xfer(e, s, h_buf, true); }
 extern "C" int wmixb_set_stream_state(wmixb_engine* e, int s, const void* h_buf) { return state_xfer(e, s, (void*)h_buf, false); }
+
+// ---- device self-test of ns::fdiv against the IEEE division ----
+__global__ void fdiv_selftest_kernel(unsigned long long n, uint32_t seed, float a_lo_log2, float a_hi_log2, float b_lo_log2,
+                                     float b_hi_log2, unsigned long long* mismatches)
+{
+    unsigned long long bad = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (unsigned long long)gridDim.x * blockDim.x) {
+        // counter-based hash -> two floats with log-uniform magnitude and full random mantissas
+        uint64_t z = (i + 1) * 0x9E3779B97F4A7C15ull + seed;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        const uint32_t ma = (uint32_t)z & 0x7FFFFF, mb = (uint32_t)(z >> 23) & 0x7FFFFF;
+        const float ua = (float)((z >> 46) & 0x1FF) / 512.f, ub = (float)((z >> 55) & 0x1FF) / 512.f;
+        const int ea = (int)floorf(a_lo_log2 + ua * (a_hi_log2 - a_lo_log2)), eb = (int)floorf(b_lo_log2 + ub * (b_hi_log2 - b_lo_log2));
+        float a = __int_as_float(((ea + 127) << 23) | ma), b = __int_as_float(((eb + 127) << 23) | mb);
+        if (z & (1ull << 63)) a = -a;
+        if ((i & 1023) == 0) a = 0.f;
+        bad += (__float_as_int(ns::fdiv(a, b)) != __float_as_int(__fdiv_rn(a, b)));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+extern "C" int wmixb_selftest_fdiv(unsigned long long n, unsigned seed, float a_lo_log2, float a_hi_log2, float b_lo_log2,
+                                   float b_hi_log2, unsigned long long* h_mismatches)
+{
+    if (!h_mismatches) return WMIXB_EINVAL;
+    unsigned long long* d = nullptr;
+    CK(cudaMalloc(&d, sizeof *d));
+    CK(cudaMemset(d, 0, sizeof *d));
+    fdiv_selftest_kernel<<<148 * 8, 256>>>(n, seed, a_lo_log2, a_hi_log2, b_lo_log2, b_hi_log2, d);
+    CK_LAUNCH();
+    CK(cudaMemcpy(h_mismatches, d, sizeof *d, cudaMemcpyDeviceToHost));
+    CK(cudaFree(d));
+    return WMIXB_OK;
+}
 
 // ---- bookkeeping ----
 extern "C" int wmixb_sync(wmixb_engine* e)

@@ -60,6 +60,12 @@ class Engine:
         check(self.L.wmixb_tick_host_bus(self.h, _ptr(h_in), _ptr(h_out), _ptr(h_vad), _ptr(h_bus), stages),
               "wmixb_tick_host_bus")
 
+    def vad20_device(self, d_pcm, d_vad=None, stream=None):
+        check(self.L.wmixb_vad20_device(self.h, _ptr(d_pcm), _ptr(d_vad), _stream_ptr(stream)), "wmixb_vad20_device")
+
+    def vad20_host(self, h_pcm, h_vad=None):
+        check(self.L.wmixb_vad20_host(self.h, _ptr(h_pcm), _ptr(h_vad)), "wmixb_vad20_host")
+
     def offline_device(self, d_in, d_out, n_frames, d_vad=None, stages=0, stream=None):
         check(self.L.wmixb_offline_device(self.h, _ptr(d_in), _ptr(d_out), _ptr(d_vad), n_frames, stages,
                                           _stream_ptr(stream)), "wmixb_offline_device")
