@@ -42,6 +42,19 @@ uint32_t orc_mix_same_format(int16_t *ring, uint32_t ring_len, uint32_t pos,
 void orc_bus_sum(int32_t *bus, const int16_t *pcm, int n_part, int frame);
 void orc_bus_nminus1(int16_t *out, const int32_t *bus, const int16_t *own, int frame);
 
+/* nearest-sample rate / channel conversion (R:src/wmix.c:49-222) */
+uint32_t orc_len_of_out(uint8_t in_chn, uint16_t in_freq, uint32_t in_len, uint8_t out_chn, uint16_t out_freq);
+uint32_t orc_len_of_in(uint8_t in_chn, uint16_t in_freq, uint8_t out_chn, uint16_t out_freq, uint32_t out_len);
+uint32_t orc_pcm_zoom(uint8_t in_chn, uint16_t in_freq, const uint8_t *in, uint32_t in_len, uint8_t out_chn,
+                      uint16_t out_freq, uint8_t *out);
+
+/* ---- RTP framing of the G.711 legs (R:src/rtp.h:51-70, R:src/rtp.c:20-99, R:src/wmixTask.c:1139-1143) ---- */
+void orc_rtp_header_bytes(uint8_t out[12], uint8_t cc, uint8_t x, uint8_t p, uint8_t v, uint8_t pt, uint8_t m,
+                          uint16_t seq, uint32_t timestamp, uint32_t ssrc);
+void orc_rtp_send_step(uint32_t *timestamp, uint32_t ssrc, uint16_t *seq, uint8_t pt, uint8_t marker, int chn,
+                       const uint8_t *codes, int n_codes, uint8_t *packet);
+int orc_rtp_parse(const uint8_t *packet, uint16_t *seq, uint32_t *timestamp, uint32_t *ssrc, uint8_t *pt, uint8_t *marker);
+
 /* ---- signal-processing primitives (T:webrtc/common_audio/signal_processing) ---- */
 int16_t orc_norm_w32(int32_t a);
 int16_t orc_norm_u32(uint32_t a);

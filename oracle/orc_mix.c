@@ -1,5 +1,6 @@
 /* ORACLE (test infrastructure) — the int16 mix bus, restating R:src/wmix.c:1617-1702. */
 #include "oracle.h"
+#include <string.h>
 
 /* R:src/wmix.c:1617-1636.  The zero short-circuits are value-neutral (x+0 never clips) but
  * are kept so the statement reads like the reference. */
@@ -53,4 +54,113 @@ void orc_bus_nminus1(int16_t *out, const int32_t *bus, const int16_t *own, int f
         int32_t v = bus[i] - own[i];
         out[i] = (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v));
     }
+}
+
+/* ---- nearest-sample rate / channel conversion, restating R:src/wmix.c:49-222 ----
+ * All three reference functions walk the same float phase accumulator: the slower side advances when
+ * (int)acc > 0, after which 1.0 is subtracted in DOUBLE and stored back to float.  Lengths are whatever
+ * unit the caller uses for wmix_len_of_* (the reference adds the channel count per step) and bytes for
+ * wmix_pcm_zoom.  Quirk kept: the stereo->stereo copy is dead code there (its test repeats 0x12,
+ * R:src/wmix.c:178, :212), so a 2ch->2ch rate change writes nothing and returns 0. */
+static float orc_zoom_ratio(uint16_t in_freq, uint16_t out_freq, int *up)
+{
+    *up = in_freq < out_freq;
+    return *up ? (float)in_freq / out_freq : (float)out_freq / in_freq;   /* smaller over larger */
+}
+
+static int orc_zoom_tick(float *acc, float div)
+{
+    *acc += div;
+    if ((int)*acc > 0) {
+        *acc -= 1.0;
+        return 1;
+    }
+    return 0;
+}
+
+/* R:src/wmix.c:49-91 */
+uint32_t orc_len_of_out(uint8_t in_chn, uint16_t in_freq, uint32_t in_len, uint8_t out_chn, uint16_t out_freq)
+{
+    uint32_t in_n = 0, out_n = 0;
+    float acc = 0;
+    int up;
+    float div;
+    if (in_freq == out_freq && in_chn == out_chn)
+        return in_len;
+    div = orc_zoom_ratio(in_freq, out_freq, &up);
+    while (in_n < in_len) {
+        if (up) {
+            out_n += out_chn;
+            if (orc_zoom_tick(&acc, div))
+                in_n += in_chn;
+        } else {
+            if (orc_zoom_tick(&acc, div))
+                out_n += out_chn;
+            in_n += in_chn;
+        }
+    }
+    return out_n;
+}
+
+/* R:src/wmix.c:94-136 */
+uint32_t orc_len_of_in(uint8_t in_chn, uint16_t in_freq, uint8_t out_chn, uint16_t out_freq, uint32_t out_len)
+{
+    uint32_t in_n = 0, out_n = 0;
+    float acc = 0;
+    int up;
+    float div;
+    if (in_freq == out_freq && in_chn == out_chn)
+        return out_len;
+    div = orc_zoom_ratio(in_freq, out_freq, &up);
+    while (out_n < out_len) {
+        if (up) {
+            out_n += out_chn;
+            if (orc_zoom_tick(&acc, div))
+                in_n += in_chn;
+        } else {
+            if (orc_zoom_tick(&acc, div))
+                out_n += out_chn;
+            in_n += in_chn;
+        }
+    }
+    return in_n;
+}
+
+/* one output "frame" for the channel pairing (R:src/wmix.c:160-176 / :194-210); returns samples written */
+static int orc_zoom_emit(int mode, const int16_t *src, int16_t *dst)
+{
+    switch (mode) {
+    case 0x11: dst[0] = src[0]; return 1;
+    case 0x12: dst[0] = src[0]; dst[1] = src[0]; return 2;
+    case 0x21: dst[0] = src[0]; return 1;           /* left channel only */
+    default: return 0;                               /* 0x22: never reached in the reference */
+    }
+}
+
+/* R:src/wmix.c:139-222.  in_len and the return value are bytes. */
+uint32_t orc_pcm_zoom(uint8_t in_chn, uint16_t in_freq, const uint8_t *in, uint32_t in_len, uint8_t out_chn,
+                      uint16_t out_freq, uint8_t *out)
+{
+    const int16_t *p = (const int16_t *)in, *end = (const int16_t *)(in + in_len);
+    int16_t *q = (int16_t *)out;
+    const int mode = (in_chn << 4) | (out_chn & 0x0F);
+    float acc = 0, div;
+    int up;
+    if (in_freq == out_freq && in_chn == out_chn) {
+        memcpy(out, in, in_len);
+        return in_len;
+    }
+    div = orc_zoom_ratio(in_freq, out_freq, &up);
+    while (p < end) {
+        if (up) {
+            q += orc_zoom_emit(mode, p, q);
+            if (orc_zoom_tick(&acc, div))
+                p += in_chn;
+        } else {
+            if (orc_zoom_tick(&acc, div))
+                q += orc_zoom_emit(mode, p, q);
+            p += in_chn;
+        }
+    }
+    return (uint32_t)((uint8_t *)q - out);
 }

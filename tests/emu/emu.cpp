@@ -186,6 +186,9 @@ long emu_div_by_counter_mismatches(int d_lo, int d_hi, int stride)
     }
     return bad;
 }
+uint32_t emu_zoom_map(int ic, int ifr, uint32_t in_bytes, int oc, int ofr, int32_t* map) { return host::zoom_map(ic, ifr, in_bytes, oc, ofr, map); }
+uint32_t emu_len_of_out(int ic, int ifr, uint32_t n, int oc, int ofr) { return host::zoom_len_of_out(ic, ifr, n, oc, ofr); }
+uint32_t emu_len_of_in(int ic, int ifr, int oc, int ofr, uint32_t n) { return host::zoom_len_of_in(ic, ifr, oc, ofr, n); }
 void emu_logexp(const float* x, int n, float* lg, float* ex)
 {
     static ns::DMath dm;

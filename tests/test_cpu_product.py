@@ -24,7 +24,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
     L = C.CDLL(wmix_b200.LIB_PATH)
     declared = set()
-    for h in ("wmixb.h", "webrtc.h", "g711codec.h"):
+    for h in sorted(os.listdir(os.path.join(ROOT, "include"))):
         src = open(os.path.join(ROOT, "include", h)).read()
         src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
         declared |= set(re.findall(r"\b(\w+)\s*\([^;{]*\)\s*;", src))
@@ -259,3 +259,52 @@ def test_aec_far_depth_flag_is_loud():
     E.emu_aec_tick(h, None, P(z), P(o), 80, 0)
     assert E.emu_aec_error(h) & 1
     E.emu_aec_destroy(h)
+
+
+def test_zoom_host_routing_table_vs_oracle():
+    """wmix_len_of_in / wmix_len_of_out (host arithmetic of the drop-in) and the gather table that the CUDA kernel
+    applies, against the oracle's sample-moving walk: routing known samples through the table must give the oracle's
+    output.  (Needs no GPU: the table is init-time host logic, exported for exactly this check.)"""
+    import ctypes as C
+
+    from tests.test_oracle_pin import ZOOM_CASES
+
+    E, L = emu(), oracle()
+    for f in (E.emu_zoom_map, E.emu_len_of_out, E.emu_len_of_in, L.orc_pcm_zoom, L.orc_len_of_out, L.orc_len_of_in):
+        f.restype = C.c_uint32
+    rng = np.random.default_rng(3)
+    for ic, ifr, oc, ofr in ZOOM_CASES:
+        for in_bytes in (2 * ic, 320 * ic, 640, 3528, 2 * ic * 777):
+            x = rng.integers(-32768, 32768, in_bytes // 2).astype(np.int16)
+            cap = 16 * in_bytes * max(1, ofr // ifr + 1) + 64
+            want = np.zeros(cap, np.int16)
+            nb = L.orc_pcm_zoom(ic, ifr, P(x.copy()), in_bytes, oc, ofr, P(want))
+            m = np.zeros(cap, np.int32)
+            n = E.emu_zoom_map(ic, ifr, in_bytes, oc, ofr, P(m))
+            assert 2 * n == nb, (ic, ifr, oc, ofr, in_bytes)
+            assert np.array_equal(x[m[:n]], want[:n])
+            assert E.emu_len_of_out(ic, ifr, in_bytes, oc, ofr) == L.orc_len_of_out(ic, ifr, in_bytes, oc, ofr)
+            assert E.emu_len_of_in(ic, ifr, oc, ofr, in_bytes) == L.orc_len_of_in(ic, ifr, oc, ofr, in_bytes)
+
+
+def test_rtp_host_header_helpers_vs_oracle():
+    """wmixb_rtp_write_header / wmixb_rtp_read_header (host byte shuffling of the C-ABI) against the oracle"""
+    import ctypes as C
+
+    import wmix_b200
+
+    lib, L = wmix_b200.lib(), oracle()
+    rng = np.random.default_rng(9)
+    for _ in range(500):
+        cc, x, p, v = int(rng.integers(0, 16)), int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(0, 4))
+        pt, m = int(rng.integers(0, 128)), int(rng.integers(0, 2))
+        seq, ts, ssrc = int(rng.integers(0, 65536)), int(rng.integers(0, 2**32)), int(rng.integers(0, 2**32))
+        a, b = np.zeros(12, np.uint8), np.zeros(12, np.uint8)
+        L.orc_rtp_header_bytes(P(a), cc, x, p, v, pt, m, seq, ts, ssrc)
+        lib.wmixb_rtp_write_header(b.ctypes.data, cc | (x << 4) | (p << 5) | (v << 6), m, pt, seq, ts, ssrc)
+        assert np.array_equal(a, b)
+        meta = np.zeros(16, np.uint8)
+        lib.wmixb_rtp_read_header(a.ctypes.data, meta.ctypes.data)
+        f = meta.view(np.uint32)
+        assert f[0] == ts and f[1] == ssrc and meta[8:10].view(np.uint16)[0] == seq
+        assert meta[10] == pt and meta[11] == m and meta[12] == a[0] and meta[13] == int(v == 2 and pt in (0, 8))

@@ -604,6 +604,108 @@ def test_aec_full_size_replication_and_depth_flag():
     eng.close()
 
 
+def test_pcm_zoom_batched_and_dropin():
+    """wmix_pcm_zoom (R:src/wmix.c:139-222): the gather kernel over a batch of streams and the drop-in symbol,
+    bit-exact against the oracle (and the reference when it travelled)"""
+    from tests.test_oracle_pin import ZOOM_CASES
+
+    lib = wmix_b200.lib()
+    L = oracle()
+    L.orc_pcm_zoom.restype = C.c_uint32
+    rng = np.random.default_rng(8)
+    S = 257
+    for ic, ifr, oc, ofr in ZOOM_CASES:
+        for in_bytes in (320 * ic, 2 * ic * 777):
+            x = rng.integers(-32768, 32768, (S, in_bytes // 2)).astype(np.int16)
+            cap = 16 * in_bytes * max(1, ofr // ifr + 1) + 64
+            want = np.zeros((S, cap), np.int16)
+            nb = 0
+            for s in range(S):
+                nb = L.orc_pcm_zoom(ic, ifr, P(x[s].copy()), in_bytes, oc, ofr, P(want[s]))
+            # drop-in, one buffer
+            got1 = np.zeros(cap, np.int16)
+            n1 = lib.wmix_pcm_zoom(ic, ifr, x[5].ctypes.data, in_bytes, oc, ofr, got1.ctypes.data)
+            assert n1 == nb and np.array_equal(got1[:nb // 2], want[5, :nb // 2]), (ic, ifr, oc, ofr, in_bytes)
+            if ifr == ofr and ic == oc:
+                continue
+            z = C.c_void_p()
+            assert lib.wmixb_zoom_create(ic, ifr, in_bytes, oc, ofr, 0, C.byref(z)) == 0
+            assert lib.wmixb_zoom_out_bytes(z) == nb
+            if nb:
+                d_in = torch.from_numpy(x).to(DEV)
+                d_out = torch.zeros((S, nb // 2), dtype=torch.int16, device=DEV)
+                assert lib.wmixb_zoom_device(z, d_in.data_ptr(), d_out.data_ptr(), S, None) == 0
+                assert np.array_equal(d_out.cpu().numpy(), want[:, :nb // 2])
+            lib.wmixb_zoom_destroy(z)
+    if ref() is not None:
+        R = ref()
+        R.wmix_pcm_zoom.restype = C.c_uint32
+        x = rng.integers(-32768, 32768, 1600).astype(np.int16)
+        a, b = np.zeros(8000, np.int16), np.zeros(8000, np.int16)
+        na = R.wmix_pcm_zoom(1, 16000, P(x.copy()), 3200, 1, 8000, P(a))
+        nb = lib.wmix_pcm_zoom(1, 16000, x.ctypes.data, 3200, 1, 8000, b.ctypes.data)
+        assert na == nb and np.array_equal(a, b)
+    assert lib.wmix_len_of_out(1, 16000, 3200, 1, 8000) == 1600 and lib.wmix_len_of_in(1, 16000, 1, 8000, 1600) == 3200
+
+
+def test_rtp_pack_unpack_batched():
+    """egress: codes -> packets with the reference's timestamp / sequence rule, 300 ticks of 3000 legs incl. a 16-bit
+    sequence wrap; ingress: packets -> codes + parsed headers, bad packets (wrong version / payload type / short
+    datagram) replaced by codec silence.  Checker: the oracle's per-leg statement."""
+    lib, L = wmix_b200.lib(), oracle()
+    n, stride, T = 3000, 176, 300
+    rng = np.random.default_rng(12)
+    st = np.zeros(n, dtype=[("ts", "<u4"), ("ssrc", "<u4"), ("seq", "<u2"), ("pt", "u1"), ("m", "u1")])
+    st["ts"] = rng.integers(0, 2**32, n)
+    st["ssrc"] = rng.integers(0, 2**32, n)
+    st["seq"] = rng.integers(65536 - T // 2, 65536, n) % 65536
+    st["pt"] = np.where(np.arange(n) % 3 == 0, 0, 8)
+    st["m"] = np.arange(n) % 2
+    assert st.itemsize == 12
+    d_state = torch.from_numpy(st.view(np.uint8).reshape(n, 12).copy()).to(DEV)
+    d_slab = torch.zeros((n, stride), dtype=torch.uint8, device=DEV)
+    d_back = torch.zeros((n, 160), dtype=torch.uint8, device=DEV)
+    d_meta = torch.zeros((n, 16), dtype=torch.uint8, device=DEV)
+    ts = [C.c_uint32(int(v)) for v in st["ts"][:8]]
+    seq = [C.c_uint16(int(v)) for v in st["seq"][:8]]
+    want = np.zeros(172, np.uint8)
+    for t in range(T):
+        codes = rng.integers(0, 256, (n, 160)).astype(np.uint8)
+        d_codes = torch.from_numpy(codes).to(DEV)
+        assert lib.wmixb_rtp_pack_device(d_codes.data_ptr(), n, 1, d_state.data_ptr(), d_slab.data_ptr(), stride, None) == 0
+        slab = d_slab.cpu().numpy()
+        for leg in range(8):
+            L.orc_rtp_send_step(C.byref(ts[leg]), int(st["ssrc"][leg]), C.byref(seq[leg]), int(st["pt"][leg]), int(st["m"][leg]), 1,
+                                P(codes[leg]), 160, P(want))
+            assert np.array_equal(slab[leg, :172], want), (t, leg)
+        assert np.array_equal(slab[:, 12:172], codes)
+        # ingress of what was just framed, with a few legs damaged
+        bad = slab.copy()
+        bad[1, 0] = 0x40          # version 1
+        bad[2, 1] = 96            # H.264 payload type
+        sizes = np.full(n, 172, np.int32)
+        sizes[4] = 100            # truncated datagram
+        d_bad = torch.from_numpy(bad).to(DEV)
+        d_sizes = torch.from_numpy(sizes).to(DEV)
+        assert lib.wmixb_rtp_unpack_device(d_bad.data_ptr(), d_sizes.data_ptr(), n, stride, 0, d_back.data_ptr(), d_meta.data_ptr(), None) == 0
+        back, meta = d_back.cpu().numpy(), d_meta.cpu().numpy()
+        good = np.ones(n, bool)
+        good[[1, 2, 4]] = False
+        assert np.array_equal(back[good], codes[good]) and (back[~good] == 0xD5).all()
+        assert np.array_equal(meta[:, 13] == 1, good)
+        for leg in (0, 3, 5, 7):
+            s2, t2, c2, pt, m = C.c_uint16(), C.c_uint32(), C.c_uint32(), C.c_uint8(), C.c_uint8()
+            assert L.orc_rtp_parse(P(slab[leg].copy()), C.byref(s2), C.byref(t2), C.byref(c2), C.byref(pt), C.byref(m)) == 160
+            f = meta[leg].view(np.uint32)
+            assert (f[0], f[1], meta[leg, 8:10].view(np.uint16)[0], meta[leg, 10], meta[leg, 11]) == (t2.value, c2.value, s2.value, pt.value, m.value)
+        if t > 3 and t < T - 3:
+            continue
+    # end state: every leg advanced T packets
+    end = d_state.cpu().numpy().view(st.dtype).reshape(n)
+    assert np.array_equal(end["seq"], (st["seq"].astype(np.int64) + T) % 65536)
+    assert np.array_equal(end["ts"], (st["ts"].astype(np.int64) + 160 * T) % 2**32)
+
+
 def test_errors_are_loud():
     with pytest.raises(wmix_b200.WmixError):
         wmix_b200.Engine(16, 44100)

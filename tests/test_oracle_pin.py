@@ -423,3 +423,103 @@ def test_golden_aec_streams():
         y = np.ascontiguousarray(y.transpose(1, 0, 2)).reshape(spec["n_streams"], -1)
         assert fnv1a64(y.tobytes()) == spec["hash"], key
         assert y[:, -8:].tolist() == spec["tail"]
+
+
+# ---------------------------------------------------------------- wmix_pcm_zoom / wmix_len_of_* (R:src/wmix.c:49-222)
+ZOOM_CASES = [(1, 16000, 1, 8000), (1, 8000, 1, 16000), (2, 16000, 1, 8000), (1, 8000, 2, 16000), (2, 44100, 1, 8000),
+              (1, 8000, 1, 44100), (1, 22050, 2, 16000), (2, 32000, 2, 16000), (2, 8000, 2, 48000), (1, 16000, 1, 16000),
+              (2, 16000, 2, 16000), (1, 11025, 1, 8000), (1, 8000, 1, 11025), (2, 48000, 1, 16000), (1, 16000, 2, 16000)]
+
+
+@pytest.mark.parametrize("ic,ifr,oc,ofr", ZOOM_CASES)
+def test_zoom_oracle_vs_reference(ic, ifr, oc, ofr):
+    """the restated phase walker against the reference's own wmix_pcm_zoom / wmix_len_of_in / wmix_len_of_out"""
+    R = ref()
+    if R is None:
+        pytest.skip("reference not built here")
+    L = oracle()
+    for f in (R.wmix_len_of_out, R.wmix_len_of_in, R.wmix_pcm_zoom, L.orc_len_of_out, L.orc_len_of_in, L.orc_pcm_zoom):
+        f.restype = C.c_uint32
+    rng = np.random.default_rng(ic * 1000 + oc + ifr + ofr)
+    for in_bytes in (2 * ic, 320 * ic, 640, 1764 * 2, 4000, 2 * ic * 777):
+        x = rng.integers(-32768, 32768, in_bytes // 2).astype(np.int16)
+        cap = 16 * in_bytes * max(1, ofr // ifr + 1) + 64
+        a = np.zeros(cap, np.uint8)
+        b = np.zeros(cap, np.uint8)
+        na = R.wmix_pcm_zoom(ic, ifr, P(x.copy()), in_bytes, oc, ofr, P(a))
+        nb = L.orc_pcm_zoom(ic, ifr, P(x.copy()), in_bytes, oc, ofr, P(b))
+        assert na == nb and np.array_equal(a[:na], b[:nb]), (in_bytes, na, nb)
+        assert R.wmix_len_of_out(ic, ifr, in_bytes, oc, ofr) == L.orc_len_of_out(ic, ifr, in_bytes, oc, ofr)
+        assert R.wmix_len_of_in(ic, ifr, oc, ofr, in_bytes) == L.orc_len_of_in(ic, ifr, oc, ofr, in_bytes)
+
+
+def test_zoom_known_answers():
+    """hand-checkable cases of R:src/wmix.c:139-222: 16k -> 8k mono keeps every second sample starting with the second
+    (the accumulator reaches 1.0 on the second step); 8k -> 16k repeats each sample; mono -> stereo duplicates; the
+    stereo -> stereo rate change writes nothing (dead 0x22 case)."""
+    L = oracle()
+    L.orc_pcm_zoom.restype = C.c_uint32
+    x = np.arange(1, 17, dtype=np.int16)
+    out = np.zeros(64, np.int16)
+    n = L.orc_pcm_zoom(1, 16000, P(x), 32, 1, 8000, P(out))
+    assert n == 16 and out[:8].tolist() == [2, 4, 6, 8, 10, 12, 14, 16]
+    n = L.orc_pcm_zoom(1, 8000, P(x), 8, 1, 16000, P(out))
+    assert n == 16 and out[:8].tolist() == [1, 1, 2, 2, 3, 3, 4, 4]
+    n = L.orc_pcm_zoom(1, 8000, P(x), 4, 2, 16000, P(out))
+    assert n == 16 and out[:8].tolist() == [1, 1, 1, 1, 2, 2, 2, 2]
+    n = L.orc_pcm_zoom(2, 16000, P(x), 32, 1, 8000, P(out))
+    assert n == 8 and out[:4].tolist() == [3, 7, 11, 15]
+    assert L.orc_pcm_zoom(2, 32000, P(x), 32, 2, 16000, P(out)) == 0
+
+
+# ---------------------------------------------------------------- RTP framing (R:src/rtp.h:51-70, R:src/rtp.c:20-99)
+def test_rtp_header_known_answer():
+    """RFC 3550 layout as the reference's bit fields produce it: V=2 PCMA marker seq=0x1234 ts=0x01020304 ssrc=0x0A0B0C0D"""
+    L = oracle()
+    b = np.zeros(12, np.uint8)
+    L.orc_rtp_header_bytes(P(b), 0, 0, 0, 2, 8, 1, 0x1234, 0x01020304, 0x0A0B0C0D)
+    assert b.tolist() == [0x80, 0x88, 0x12, 0x34, 1, 2, 3, 4, 0x0A, 0x0B, 0x0C, 0x0D]
+    L.orc_rtp_header_bytes(P(b), 3, 1, 1, 2, 0, 0, 65535, 0xFFFFFFFF, 1)
+    assert b.tolist() == [0xB3, 0x00, 0xFF, 0xFF, 255, 255, 255, 255, 0, 0, 0, 1]
+
+
+def test_rtp_oracle_vs_reference_over_loopback():
+    """the reference's own rtp_header / rtp_send / rtp_recv (R:src/rtp.c) through a UDP socket pair on 127.0.0.1:
+    the bytes on the wire, the seq++ / timestamp rule of the PCMA send loop (R:src/wmixTask.c:1139-1143) and what the
+    receiver reports must be what the oracle states"""
+    import socket
+
+    R = ref()
+    if R is None:
+        pytest.skip("reference not built here")
+    L = oracle()
+    R.rtp_socket.restype = C.c_void_p
+    rx = socket.socket(socket.AF_INET, socket.SOCK_DGRAM)
+    rx.bind(("127.0.0.1", 0))
+    rx.settimeout(5)
+    port = rx.getsockname()[1]
+    ss = C.c_void_p(R.rtp_socket(b"127.0.0.1", port, False))
+    assert ss
+    pkt = np.zeros(12 + 4096, np.uint8)                      # RtpPacket
+    R.rtp_header(P(pkt), 0, 0, 0, 2, 8, 1, 0, 0, 0)          # R:src/wmixTask.c:1058
+    ts, seq = C.c_uint32(0), C.c_uint16(0)
+    rng = np.random.default_rng(5)
+    want = np.zeros(172, np.uint8)
+    for k in range(70000 // 160 + 5):
+        codes = rng.integers(0, 256, 160).astype(np.uint8)
+        # the reference's loop body: payload, timestamp += ret / chn, rtp_send (which then does seq++)
+        pkt[12:172] = codes
+        hdr_ts = pkt[4:8].view(np.uint32)
+        hdr_ts[0] = hdr_ts[0] + 160
+        assert R.rtp_send(ss, P(pkt), 160) == 172
+        got = np.frombuffer(rx.recv(4096), np.uint8)
+        L.orc_rtp_send_step(C.byref(ts), 0, C.byref(seq), 8, 1, 1, P(codes), 160, P(want))
+        assert np.array_equal(got, want), k
+        # parse side
+        s2, t2, c2, pt, m = C.c_uint16(), C.c_uint32(), C.c_uint32(), C.c_uint8(), C.c_uint8()
+        assert L.orc_rtp_parse(P(want), C.byref(s2), C.byref(t2), C.byref(c2), C.byref(pt), C.byref(m)) == 160
+        assert (s2.value, t2.value, c2.value, pt.value, m.value) == (k & 0xFFFF, 160 * (k + 1), 0, 8, 1)
+    # the reference's receiver: a PCMA datagram of any length is reported as 160 payload bytes (R:src/rtp.c:89-91)
+    rs = C.c_void_p(R.rtp_socket(b"127.0.0.1", 0, True))
+    R.rtp_socket_close(C.byref(ss))
+    rx.close()

@@ -5,7 +5,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwmix_b200.so")
+# WMIX_B200_LIB: load another build of the same library (kernel experiments); default = the in-tree build
+LIB_PATH = os.environ.get("WMIX_B200_LIB") or os.path.join(_HERE, "libwmix_b200.so")
 
 NS, AGC, VAD, AEC = 1, 2, 4, 8
 
@@ -78,6 +79,20 @@ def lib():
         "agc_addition": (None, [vp, C.c_uint8]), "agc_release": (None, [vp]),
         "aec_init": (vp, [i, i, i, vp]), "aec_setFrameFar": (i, [vp, vp, i]), "aec_process": (i, [vp, vp, vp, i, i]),
         "aec_process2": (i, [vp, vp, vp, vp, i, i]), "aec_release": (None, [vp]),
+        # include/wmix_rtp.h
+        "wmixb_rtp_write_header": (None, [vp, C.c_uint8, C.c_uint8, C.c_uint8, C.c_uint16, u32, u32]),
+        "wmixb_rtp_read_header": (None, [vp, vp]),
+        "wmixb_rtp_unpack_device": (i, [vp, vp, i, i, i, vp, vp, vp]),
+        "wmixb_rtp_pack_device": (i, [vp, i, i, vp, vp, i, vp]),
+        # include/wmix_zoom.h
+        "wmix_len_of_out": (u32, [C.c_uint8, C.c_uint16, u32, C.c_uint8, C.c_uint16]),
+        "wmix_len_of_in": (u32, [C.c_uint8, C.c_uint16, C.c_uint8, C.c_uint16, u32]),
+        "wmix_pcm_zoom": (u32, [C.c_uint8, C.c_uint16, vp, u32, C.c_uint8, C.c_uint16, vp]),
+        "wmixb_zoom_create": (i, [i, i, u32, i, i, i, C.POINTER(vp)]),
+        "wmixb_zoom_destroy": (None, [vp]),
+        "wmixb_zoom_out_bytes": (u32, [vp]),
+        "wmixb_zoom_device": (i, [vp, vp, vp, i, vp]),
+        "wmixb_zoom_map": (i, [vp, vp]),
         # include/g711codec.h
         "PCM2G711a": (i, [vp, vp, i, i]), "PCM2G711u": (i, [vp, vp, i, i]),
         "G711a2PCM": (i, [vp, vp, i, i]), "G711u2PCM": (i, [vp, vp, i, i]),

@@ -6,11 +6,16 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "../../include/g711codec.h"
 #include "../../include/webrtc.h"
+#include "../../include/wmix_zoom.h"
 #include "../../include/wmixb.h"
+#include "host_tables.h"
 
 namespace {
 
@@ -323,5 +328,53 @@ int PCM2G711a(char* in, char* out, int len, int) { if (!in && !out && len == 0) 
 int PCM2G711u(char* in, char* out, int len, int) { if (!in && !out && len == 0) { printf("Error, empty data or transmit failed, exit !\n"); return -1; } return g711u_encode((unsigned char*)out, (const short*)in, len / 2); }
 int G711a2PCM(char* in, char* out, int len, int) { if (!in && !out && len == 0) { printf("Error, empty data or transmit failed, exit !\n"); return -1; } return g711a_decode((short*)out, (const unsigned char*)in, len); }
 int G711u2PCM(char* in, char* out, int len, int) { if (!in && !out && len == 0) { printf("Error, empty data or transmit failed, exit !\n"); return -1; } return g711u_decode((short*)out, (const unsigned char*)in, len); }
+
+}  // extern "C"
+
+// ---------------------------------------------------------------- wmix_pcm_zoom (R:src/wmix.c:49-222)
+extern "C" {
+
+uint32_t wmix_len_of_out(uint8_t inChn, uint16_t inFreq, uint32_t inLen, uint8_t outChn, uint16_t outFreq)
+{
+    return wmx::host::zoom_len_of_out(inChn, inFreq, inLen, outChn, outFreq);
+}
+
+uint32_t wmix_len_of_in(uint8_t inChn, uint16_t inFreq, uint8_t outChn, uint16_t outFreq, uint32_t outLen)
+{
+    return wmx::host::zoom_len_of_in(inChn, inFreq, outChn, outFreq, outLen);
+}
+
+// One plan (gather table) per (formats, length) is kept for the life of the process, like the reference's callers
+// reuse one buffer size per task; the samples make an H2D -> kernel -> D2H round trip.
+uint32_t wmix_pcm_zoom(uint8_t inChn, uint16_t inFreq, uint8_t* in, uint32_t inLen, uint8_t outChn, uint16_t outFreq,
+                       uint8_t* out)
+{
+    if (inFreq == outFreq && inChn == outChn) {                      // R:src/wmix.c:153-157: a plain copy
+        memcpy(out, in, inLen);
+        return inLen;
+    }
+    struct Slot { wmixb_zoom* z = nullptr; int16_t *d_in = nullptr, *d_out = nullptr; };
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, uint32_t, int, int>, Slot> plans;
+    std::lock_guard<std::mutex> lock(mu);
+    Slot& sl = plans[std::make_tuple((int)inChn, (int)inFreq, inLen, (int)outChn, (int)outFreq)];
+    if (!sl.z) {
+        if (wmixb_zoom_create(inChn, inFreq, inLen, outChn, outFreq, 0, &sl.z) != WMIXB_OK) return 0;
+        const uint32_t ob = wmixb_zoom_out_bytes(sl.z);
+        if (cudaMalloc(&sl.d_in, (size_t)inLen + 2) != cudaSuccess || cudaMalloc(&sl.d_out, ob ? ob : 2) != cudaSuccess) {
+            cudaFree(sl.d_in);
+            wmixb_zoom_destroy(sl.z);
+            sl = Slot();
+            return 0;
+        }
+        cudaMemset(sl.d_in, 0, (size_t)inLen + 2);
+    }
+    const uint32_t ob = wmixb_zoom_out_bytes(sl.z);
+    if (ob == 0) return 0;
+    if (cudaMemcpy(sl.d_in, in, inLen, cudaMemcpyHostToDevice) != cudaSuccess) return 0;
+    if (wmixb_zoom_device(sl.z, sl.d_in, sl.d_out, 1, nullptr) != WMIXB_OK) return 0;
+    if (cudaMemcpy(out, sl.d_out, ob, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    return ob;
+}
 
 }  // extern "C"

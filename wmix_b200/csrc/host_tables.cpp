@@ -287,5 +287,80 @@ void aec_tables(float* w, float* c, float* hann, float* weight, float* over, uin
     }
 }
 
+// ---- wmix_pcm_zoom / wmix_len_of_* (R:src/wmix.c:49-222) ----
+// One phase accumulator drives all three: a float that gains `div` (the smaller rate over the larger) per
+// step; when its integer part turns positive the slower side moves and 1.0 is taken off — in double,
+// stored back to float, which is what `divStep -= 1.0` does to a float in C.
+namespace {
+struct ZoomPhase {
+    float div, acc = 0.f;
+    bool up;
+    ZoomPhase(int in_freq, int out_freq) : up(in_freq < out_freq)
+    {
+        div = up ? (float)in_freq / (float)out_freq : (float)out_freq / (float)in_freq;
+    }
+    bool step()
+    {
+        acc += div;
+        if ((int)acc > 0) {
+            acc = (float)((double)acc - 1.0);
+            return true;
+        }
+        return false;
+    }
+};
+}  // namespace
+
+uint32_t zoom_len_of_out(int in_chn, int in_freq, uint32_t in_len, int out_chn, int out_freq)
+{
+    if (in_freq == out_freq && in_chn == out_chn) return in_len;
+    ZoomPhase ph(in_freq, out_freq);
+    uint32_t in_n = 0, out_n = 0;
+    while (in_n < in_len) {
+        if (ph.up) { out_n += out_chn; if (ph.step()) in_n += in_chn; }
+        else { if (ph.step()) out_n += out_chn; in_n += in_chn; }
+    }
+    return out_n;
+}
+
+uint32_t zoom_len_of_in(int in_chn, int in_freq, int out_chn, int out_freq, uint32_t out_len)
+{
+    if (in_freq == out_freq && in_chn == out_chn) return out_len;
+    ZoomPhase ph(in_freq, out_freq);
+    uint32_t in_n = 0, out_n = 0;
+    while (out_n < out_len) {
+        if (ph.up) { out_n += out_chn; if (ph.step()) in_n += in_chn; }
+        else { if (ph.step()) out_n += out_chn; in_n += in_chn; }
+    }
+    return in_n;
+}
+
+uint32_t zoom_map(int in_chn, int in_freq, uint32_t in_bytes, int out_chn, int out_freq, int32_t* map)
+{
+    const uint32_t in_samples = in_bytes / 2;
+    if (in_freq == out_freq && in_chn == out_chn) {                     // memcpy branch
+        if (map) for (uint32_t i = 0; i < in_samples; ++i) map[i] = (int32_t)i;
+        return in_samples;
+    }
+    // samples one output frame takes from the input frame at `pos`: 1->1 and 2->1 copy the first (left)
+    // sample, 1->2 writes it twice, 2->2 is unreachable in the reference and writes nothing
+    const int mode = (in_chn << 4) | (out_chn & 0x0F);
+    const int emit = mode == 0x11 || mode == 0x21 ? 1 : (mode == 0x12 ? 2 : 0);
+    ZoomPhase ph(in_freq, out_freq);
+    uint32_t pos = 0, n = 0;
+    // the reference compares int16 pointers, so an odd trailing byte still counts as a readable sample
+    const uint32_t end = (in_bytes + 1) / 2;
+    while (pos < end) {
+        bool write = ph.up;
+        bool advance = !ph.up;
+        if (ph.step()) { if (ph.up) advance = true; else write = true; }
+        if (write) {
+            for (int k = 0; k < emit; ++k) { if (map) map[n] = (int32_t)pos; ++n; }
+        }
+        if (advance) pos += in_chn;
+    }
+    return n;
+}
+
 }  // namespace host
 }  // namespace wmx

@@ -18,5 +18,10 @@ void agc_initial_words(int32_t* words);
 // AEC: rdft-128 twiddles (w[32], c[32]), sqrt-Hann window, NLP weight / overdrive curves (65 each) and
 // the k-step jump constants of the comfort-noise generator (65 each)
 void aec_tables(float* w, float* c, float* hann, float* weight, float* over, uint32_t* lcg_mul, uint32_t* lcg_add);
+// wmix_pcm_zoom's sample routing (R:src/wmix.c:139-222): map[k] = input sample feeding output sample k.
+// Returns the output length in samples; map may be nullptr to only count.
+uint32_t zoom_map(int in_chn, int in_freq, uint32_t in_bytes, int out_chn, int out_freq, int32_t* map);
+uint32_t zoom_len_of_out(int in_chn, int in_freq, uint32_t in_len, int out_chn, int out_freq);
+uint32_t zoom_len_of_in(int in_chn, int in_freq, int out_chn, int out_freq, uint32_t out_len);
 }  // namespace host
 }  // namespace wmx

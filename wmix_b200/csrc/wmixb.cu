@@ -15,6 +15,8 @@
 #include <atomic>
 #include <vector>
 
+#include "../../include/wmix_rtp.h"
+#include "../../include/wmix_zoom.h"
 #include "../../include/wmixb.h"
 #include "aec.cuh"
 #include "agc.cuh"
@@ -1161,6 +1163,186 @@ static int state_xfer(wmixb_engine* e, int s, void* buf, bool get)
 }
 extern "C" int wmixb_get_stream_state(wmixb_engine* e, int s, void* h_buf) { return state_xfer(e, s, h_buf, true); }
 extern "C" int wmixb_set_stream_state(wmixb_engine* e, int s, const void* h_buf) { return state_xfer(e, s, (void*)h_buf, false); }
+
+// ---- RTP / G.711 wire framing for batches of legs (include/wmix_rtp.h) ----
+static_assert(sizeof(wmixb_rtp_meta) == 16 && sizeof(wmixb_rtp_state) == 12, "wire-framing structs are part of the ABI");
+constexpr int kRtpWords = WMIXB_RTP_PCMA_PAYLOAD / 4;       // 40 payload words per packet
+__host__ __device__ inline uint32_t bswap32(uint32_t v) { return (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24); }
+
+extern "C" void wmixb_rtp_write_header(uint8_t out[12], uint8_t vpxcc, uint8_t marker, uint8_t pt, uint16_t seq, uint32_t timestamp,
+                                       uint32_t ssrc)
+{
+    out[0] = vpxcc;
+    out[1] = (uint8_t)((pt & 127) | ((marker & 1) << 7));
+    out[2] = (uint8_t)(seq >> 8);
+    out[3] = (uint8_t)seq;
+    for (int k = 0; k < 4; ++k) { out[4 + k] = (uint8_t)(timestamp >> (24 - 8 * k)); out[8 + k] = (uint8_t)(ssrc >> (24 - 8 * k)); }
+}
+
+extern "C" void wmixb_rtp_read_header(const uint8_t in[12], wmixb_rtp_meta* m)
+{
+    memset(m, 0, sizeof *m);
+    m->vpxcc = in[0];
+    m->pt = in[1] & 127;
+    m->marker = in[1] >> 7;
+    m->seq = (uint16_t)((in[2] << 8) | in[3]);
+    m->timestamp = ((uint32_t)in[4] << 24) | ((uint32_t)in[5] << 16) | ((uint32_t)in[6] << 8) | in[7];
+    m->ssrc = ((uint32_t)in[8] << 24) | ((uint32_t)in[9] << 16) | ((uint32_t)in[10] << 8) | in[11];
+    m->ok = (uint8_t)((in[0] >> 6) == 2 && (m->pt == WMIXB_RTP_PT_PCMA || m->pt == WMIXB_RTP_PT_PCMU));
+}
+
+// thread per payload word: word w of leg l moves from slab[l*stride + 12 + 4w] to codes[l*160 + 4w]
+__global__ void rtp_unpack_kernel(const uint32_t* __restrict__ slab, const int32_t* __restrict__ sizes, int n, int stride_words,
+                                  uint32_t fill, uint32_t* __restrict__ codes, wmixb_rtp_meta* __restrict__ meta)
+{
+    const size_t total = (size_t)n * kRtpWords;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int leg = (int)(idx / kRtpWords), w = (int)(idx - (size_t)leg * kRtpWords);
+        const uint32_t* pkt = slab + (size_t)leg * stride_words;
+        const uint32_t h0 = pkt[0];                                   // bytes 0..3 (little-endian load)
+        const uint32_t b0 = h0 & 0xFF, pt = (h0 >> 8) & 127;
+        bool ok = (b0 >> 6) == 2 && (pt == WMIXB_RTP_PT_PCMA || pt == WMIXB_RTP_PT_PCMU);
+        if (sizes) ok = ok && sizes[leg] >= WMIXB_RTP_HEADER + WMIXB_RTP_PCMA_PAYLOAD;
+        codes[idx] = ok ? pkt[WMIXB_RTP_HEADER / 4 + w] : fill;
+        if (w == 0 && meta) {
+            wmixb_rtp_meta m;
+            m.timestamp = bswap32(pkt[1]);
+            m.ssrc = bswap32(pkt[2]);
+            m.seq = (uint16_t)((((h0 >> 16) & 0xFF) << 8) | (h0 >> 24));
+            m.pt = (uint8_t)pt;
+            m.marker = (uint8_t)((h0 >> 15) & 1);
+            m.vpxcc = (uint8_t)b0;
+            m.ok = (uint8_t)ok;
+            m.reserved = 0;
+            meta[leg] = m;
+        }
+    }
+}
+
+__global__ void rtp_pack_kernel(const uint32_t* __restrict__ codes, int n, int chn, wmixb_rtp_state* __restrict__ state,
+                                uint32_t* __restrict__ slab, int stride_words)
+{
+    const size_t total = (size_t)n * kRtpWords;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int leg = (int)(idx / kRtpWords), w = (int)(idx - (size_t)leg * kRtpWords);
+        uint32_t* pkt = slab + (size_t)leg * stride_words;
+        pkt[WMIXB_RTP_HEADER / 4 + w] = codes[idx];
+        if (w == 0) {
+            wmixb_rtp_state st = state[leg];
+            st.timestamp += (uint32_t)(WMIXB_RTP_PCMA_PAYLOAD / chn);            // R:src/wmixTask.c:1141
+            // V=2, P=X=CC=0 (R:src/wmixTask.c:1058); seq big-endian in bytes 2..3
+            pkt[0] = 0x80u | ((uint32_t)((st.pt & 127) | ((st.marker & 1) << 7)) << 8) | ((uint32_t)(st.seq >> 8) << 16) | ((uint32_t)(st.seq & 0xFF) << 24);
+            pkt[1] = bswap32(st.timestamp);
+            pkt[2] = bswap32(st.ssrc);
+            st.seq = (uint16_t)(st.seq + 1);                                      // R:src/rtp.c:68
+            state[leg] = st;
+        }
+    }
+}
+
+extern "C" int wmixb_rtp_unpack_device(const uint8_t* d_slab, const int32_t* d_sizes, int n, int stride, int law_fill, uint8_t* d_codes,
+                                       wmixb_rtp_meta* d_meta, void* stream)
+{
+    if (n < 0 || (n && (!d_slab || !d_codes)) || (law_fill != 0 && law_fill != 1)) return WMIXB_EINVAL;
+    if (stride < WMIXB_RTP_HEADER + WMIXB_RTP_PCMA_PAYLOAD || (stride & 3) || ((uintptr_t)d_slab & 3) || ((uintptr_t)d_codes & 3)) {
+        snprintf(g_err, sizeof g_err, "rtp_unpack: stride must be >= 172 and a multiple of 4, buffers 4-byte aligned");
+        return WMIXB_EINVAL;
+    }
+    if (n == 0) return WMIXB_OK;
+    const uint32_t fill = law_fill == 0 ? 0xD5D5D5D5u : 0xFFFFFFFFu;      // linear 0 in A-law / mu-law
+    rtp_unpack_kernel<<<ew_blocks((size_t)n * kRtpWords), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)d_slab, d_sizes, n, stride / 4, fill,
+                                                                                           (uint32_t*)d_codes, d_meta);
+    CK_LAUNCH();
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_rtp_pack_device(const uint8_t* d_codes, int n, int chn, wmixb_rtp_state* d_state, uint8_t* d_slab, int stride,
+                                     void* stream)
+{
+    if (n < 0 || (n && (!d_slab || !d_codes || !d_state)) || chn < 1 || chn > 2) return WMIXB_EINVAL;
+    if (stride < WMIXB_RTP_HEADER + WMIXB_RTP_PCMA_PAYLOAD || (stride & 3) || ((uintptr_t)d_slab & 3) || ((uintptr_t)d_codes & 3)) {
+        snprintf(g_err, sizeof g_err, "rtp_pack: stride must be >= 172 and a multiple of 4, buffers 4-byte aligned");
+        return WMIXB_EINVAL;
+    }
+    if (n == 0) return WMIXB_OK;
+    rtp_pack_kernel<<<ew_blocks((size_t)n * kRtpWords), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)d_codes, n, chn, d_state, (uint32_t*)d_slab, stride / 4);
+    CK_LAUNCH();
+    return WMIXB_OK;
+}
+
+// ---- wmix_pcm_zoom as a gather (include/wmix_zoom.h) ----
+// out[s][k] = in[s][map[k]]: thread per output sample pair where possible; the table is shared by all streams
+__global__ void zoom_gather_kernel(const int16_t* __restrict__ in, int16_t* __restrict__ out, const int32_t* __restrict__ map,
+                                   uint32_t in_samples, uint32_t out_samples, int n_streams)
+{
+    const size_t total = (size_t)n_streams * out_samples;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t s = idx / out_samples;
+        const uint32_t k = (uint32_t)(idx - s * out_samples);
+        out[idx] = in[s * in_samples + map[k]];
+    }
+}
+
+struct wmixb_zoom {
+    int device = 0;
+    uint32_t in_bytes = 0, in_samples = 0, out_samples = 0;
+    int32_t* d_map = nullptr;
+    std::vector<int32_t> h_map;
+};
+
+extern "C" int wmixb_zoom_create(int in_chn, int in_freq, uint32_t in_bytes, int out_chn, int out_freq, int device, wmixb_zoom** out)
+{
+    if (!out) return WMIXB_EINVAL;
+    *out = nullptr;
+    if (in_chn < 1 || in_chn > 2 || out_chn < 1 || out_chn > 2 || in_freq < 1 || out_freq < 1 || in_freq > 65535 || out_freq > 65535) {
+        snprintf(g_err, sizeof g_err, "zoom: channels must be 1 or 2 and rates 1..65535 Hz");
+        return WMIXB_EINVAL;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { snprintf(g_err, sizeof g_err, "no CUDA device — wmix_b200 has no CPU path"); return WMIXB_ENODEV; }
+    if (device < 0 || device >= ndev) return WMIXB_EINVAL;
+    wmixb_zoom* z = new (std::nothrow) wmixb_zoom();
+    if (!z) return WMIXB_ENOMEM;
+    z->device = device;
+    z->in_bytes = in_bytes;
+    z->in_samples = (in_bytes + 1) / 2;
+    z->out_samples = host::zoom_map(in_chn, in_freq, in_bytes, out_chn, out_freq, nullptr);
+    z->h_map.resize(z->out_samples ? z->out_samples : 1);
+    host::zoom_map(in_chn, in_freq, in_bytes, out_chn, out_freq, z->h_map.data());
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce == cudaSuccess) ce = cudaMalloc(&z->d_map, z->h_map.size() * sizeof(int32_t));
+    if (ce == cudaSuccess) ce = cudaMemcpy(z->d_map, z->h_map.data(), z->h_map.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { cudaFree(z->d_map); delete z; return fail_cuda(ce, "zoom_create", __LINE__); }
+    *out = z;
+    return WMIXB_OK;
+}
+
+extern "C" void wmixb_zoom_destroy(wmixb_zoom* z)
+{
+    if (!z) return;
+    cudaSetDevice(z->device);
+    cudaFree(z->d_map);
+    delete z;
+}
+
+extern "C" uint32_t wmixb_zoom_out_bytes(const wmixb_zoom* z) { return z ? z->out_samples * 2u : 0u; }
+
+extern "C" int wmixb_zoom_map(const wmixb_zoom* z, int32_t* h_map)
+{
+    if (!z || !h_map) return WMIXB_EINVAL;
+    memcpy(h_map, z->h_map.data(), (size_t)z->out_samples * sizeof(int32_t));
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_zoom_device(const wmixb_zoom* z, const int16_t* d_in, int16_t* d_out, int n_streams, void* stream)
+{
+    if (!z || n_streams < 0 || (n_streams && z->out_samples && (!d_in || !d_out))) return WMIXB_EINVAL;
+    if (n_streams == 0 || z->out_samples == 0) return WMIXB_OK;
+    CK(cudaSetDevice(z->device));
+    zoom_gather_kernel<<<ew_blocks((size_t)n_streams * z->out_samples), 256, 0, (cudaStream_t)stream>>>(d_in, d_out, z->d_map, z->in_samples, z->out_samples, n_streams);
+    CK_LAUNCH();
+    return WMIXB_OK;
+}
 
 // ---- device self-test of ns::fdiv against the IEEE division ----
 __global__ void fdiv_selftest_kernel(unsigned long long n, uint32_t seed, float a_lo_log2, float a_hi_log2, float b_lo_log2,
