@@ -145,6 +145,23 @@ int wmixb_g711_nminus1_device(wmixb_engine* e, int law, const int32_t* d_bus, co
 int wmixb_mix_load_device(int16_t* d_ring, uint32_t ring_len, uint32_t pos, const int16_t* d_src, uint32_t n,
                           int rdce, uint32_t* new_pos, void* stream);
 
+/* Different-format branches of wmix_load_data on a device-resident MONO ring (R:src/wmix.c:1704-1939): a 16-bit
+ * source whose rate or channel count differs from the bus is dropped / linearly filled into it under the
+ * reference's float phase accumulator (faster source: frames skipped; slower source: n-step float ramps between
+ * neighbouring frames; stereo: left sample only).  The accumulator never depends on the audio, so a plan per
+ * (format, chunk length) is walked once on the host and the kernel evaluates it for n_src sources at once:
+ * d_src int16 [n_src][src_bytes/2] are added IN ORDER, source s divided by d_rdce[s] (device, nullable = 1) —
+ * the same bits as n_src consecutive wmix_load_data calls starting at the same head.  src_bytes must be whole
+ * frames; a rate ratio that would overrun the reference's 64-entry ramp buffer is refused (WMIXB_EINVAL), as is a
+ * chunk longer than the ring.  *new_pos = position after the chunk. */
+typedef struct wmixb_mixplan wmixb_mixplan;
+int wmixb_mixplan_create(int src_chn, int src_freq, uint32_t src_bytes, int mix_freq, int device, wmixb_mixplan** out);
+void wmixb_mixplan_destroy(wmixb_mixplan* m);
+uint32_t wmixb_mixplan_out_samples(const wmixb_mixplan* m);     /* bus samples one chunk adds (tickAdd / 2) */
+int wmixb_mixplan_tables(const wmixb_mixplan* m, int32_t* h_map, uint16_t* h_ramp);   /* host copies, for tests */
+int wmixb_mix_load_plan_device(const wmixb_mixplan* m, int16_t* d_ring, uint32_t ring_len, uint32_t pos, const int16_t* d_src,
+                               int n_src, const uint8_t* d_rdce, uint32_t* new_pos, void* stream);
+
 /* state snapshot / restore of one stream (checkpointing; byte layout is engine-internal) */
 size_t wmixb_stream_state_bytes(const wmixb_engine* e);
 int wmixb_get_stream_state(wmixb_engine* e, int stream_index, void* h_buf);

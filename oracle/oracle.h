@@ -42,6 +42,11 @@ uint32_t orc_mix_same_format(int16_t *ring, uint32_t ring_len, uint32_t pos,
 void orc_bus_sum(int32_t *bus, const int16_t *pcm, int n_part, int frame);
 void orc_bus_nminus1(int16_t *out, const int32_t *bus, const int16_t *own, int frame);
 
+/* different-format branches of wmix_load_data for a mono bus (R:src/wmix.c:1704-1939): drop / linear-fill
+ * resampling driven by a float phase accumulator; returns the new position, *written = samples added */
+uint32_t orc_mix_resample(int16_t *ring, uint32_t ring_len, uint32_t pos, const int16_t *src, uint32_t src_bytes,
+                          uint16_t freq, uint8_t channels, uint16_t mix_freq, uint8_t rdce, uint32_t *written);
+
 /* nearest-sample rate / channel conversion (R:src/wmix.c:49-222) */
 uint32_t orc_len_of_out(uint8_t in_chn, uint16_t in_freq, uint32_t in_len, uint8_t out_chn, uint16_t out_freq);
 uint32_t orc_len_of_in(uint8_t in_chn, uint16_t in_freq, uint8_t out_chn, uint16_t out_freq, uint32_t out_len);

@@ -164,3 +164,79 @@ uint32_t orc_pcm_zoom(uint8_t in_chn, uint16_t in_freq, const uint8_t *in, uint3
     }
     return (uint32_t)((uint8_t *)q - out);
 }
+
+/* ---- different-format branches of wmix_load_data, MONO mix bus (R:src/wmix.c:1704-1939) ----
+ * Only 16-bit sources do anything there (the 8- and 32-bit cases are empty).  One float phase accumulator:
+ *   source faster than the bus (R:src/wmix.c:1707-1789): gains (freq - bus)/bus per copied frame; while it is
+ *     >= 1.0 the next source frame is skipped and 1.0 is taken off (in double, stored to float);
+ *   source slower or only the channel count differs (R:src/wmix.c:1791-1925): gains (bus - freq)/freq per
+ *     copied frame; while it is >= 1.0 the bus is fed from a linear ramp between the frame just copied and
+ *     the next one: n = (int)acc + 1 steps of (float)(next - last) / n, accumulated in float and added to
+ *     the int16 `last` (float arithmetic, truncated on the store to int16).
+ * A stereo source contributes its left sample only (bus is mono).  Every written sample goes through
+ * volumeAdd(bus, value / rdce) like the same-format branch.  The reference computes a ramp after the very
+ * last source frame too (reading one sample past the buffer) but its loop ends before using it; that read is
+ * skipped here.  Returns the new position; *written = samples added to the bus. */
+uint32_t orc_mix_resample(int16_t *ring, uint32_t ring_len, uint32_t pos, const int16_t *src, uint32_t src_bytes,
+                          uint16_t freq, uint8_t channels, uint16_t mix_freq, uint8_t rdce, uint32_t *written)
+{
+    const int d = rdce ? rdce : 1;
+    const uint32_t frame_bytes = 2u * channels;
+    uint32_t used = 0, n_out = 0;
+    const int16_t *p = src;
+    float acc = 0, pow_;
+    int16_t ramp[64];
+    int ramp_i = 0;
+    if (written)
+        *written = 0;
+    if (channels != 1 && channels != 2)
+        return pos;
+    if (freq > mix_freq) {
+        pow_ = (float)(freq - mix_freq) / mix_freq;
+        while (used < src_bytes) {
+            if (acc >= 1.0) {
+                acc -= 1.0;
+            } else {
+                ring[pos] = orc_volume_add(ring[pos], (int16_t)(p[0] / d));
+                if (++pos >= ring_len)
+                    pos = 0;
+                ++n_out;
+                acc += pow_;
+            }
+            p += channels;
+            used += frame_bytes;
+        }
+    } else {
+        pow_ = (float)(mix_freq - freq) / freq;
+        while (used < src_bytes) {
+            if (acc >= 1.0) {
+                ring[pos] = orc_volume_add(ring[pos], (int16_t)(ramp[ramp_i] / d));
+                ++ramp_i;
+                acc -= 1.0;
+            } else {
+                ring[pos] = orc_volume_add(ring[pos], (int16_t)(p[0] / d));
+                p += channels;
+                used += frame_bytes;
+                acc += pow_;
+                if (acc >= 1.0 && used < src_bytes) {
+                    const int n = (int)acc + 1;
+                    const int16_t last = p[-(int)channels];
+                    const float step = (float)(p[0] - last) / n;
+                    float run = step;
+                    int k;
+                    for (k = 0; k < n && k < 64; ++k) {
+                        ramp[k] = (int16_t)(last + run);
+                        run += step;
+                    }
+                    ramp_i = 0;
+                }
+            }
+            if (++pos >= ring_len)
+                pos = 0;
+            ++n_out;
+        }
+    }
+    if (written)
+        *written = n_out;
+    return pos;
+}

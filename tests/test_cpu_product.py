@@ -287,6 +287,66 @@ def test_zoom_host_routing_table_vs_oracle():
             assert E.emu_len_of_in(ic, ifr, oc, ofr, in_bytes) == L.orc_len_of_in(ic, ifr, oc, ofr, in_bytes)
 
 
+MIX_RESAMPLE_CASES = [(8000, 1), (8000, 2), (11025, 1), (12000, 2), (16000, 2), (22050, 1), (32000, 2), (44100, 2),
+                      (48000, 1), (15999, 1), (16001, 2), (300, 1), (65535, 1)]
+
+
+def apply_mix_plan(ring, pos, src, chn, m, ramp, d):
+    """numpy model of mix_plan_kernel for ONE source (float32 arithmetic step by step, like the kernel)"""
+    f32 = np.float32
+    for i in range(len(m)):
+        v = int(src[m[i]])
+        if ramp[i]:
+            n, k = int(ramp[i]) >> 8, int(ramp[i]) & 0xFF
+            step = f32(int(src[m[i] + chn]) - v) / f32(n)
+            run = step
+            for _ in range(1, k):
+                run = f32(run + step)
+            v = int(np.trunc(f32(f32(v) + run)))
+        q = -(-v // d) if v < 0 else v // d      # C division truncates toward zero
+        p = (pos + i) % len(ring)
+        ring[p] = max(-32768, min(32767, int(ring[p]) + q))
+
+
+def test_mix_resample_host_plan_vs_oracle():
+    """the host-built plan of wmixb_mix_load_plan_device (which source sample / which ramp step feeds every bus
+    sample) against the oracle's sequential walk of wmix_load_data's resampling branches (R:src/wmix.c:1704-1939)"""
+    import ctypes as C
+
+    E, L = emu(), oracle()
+    E.emu_mix_plan.restype = C.c_uint32
+    L.orc_mix_resample.restype = C.c_uint32
+    L.orc_mix_resample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint8,
+                                   C.c_uint16, C.c_uint8, C.POINTER(C.c_uint32)]
+    rng = np.random.default_rng(21)
+    for mix_freq in (16000, 8000):
+        for k, (freq, chn) in enumerate(MIX_RESAMPLE_CASES):
+            if freq == mix_freq and chn == 1:
+                continue
+            frames = 257 if freq >= 1000 else 30
+            src = rng.integers(-32768, 32768, frames * chn).astype(np.int16)
+            if k % 3 == 0:
+                src[:] = np.where(rng.random(src.size) < 0.5, 32767, -32768)
+            nbytes = src.nbytes
+            cap = frames * (mix_freq // freq + 2) + 8
+            m, ramp = np.zeros(cap, np.int32), np.zeros(cap, np.uint16)
+            n = E.emu_mix_plan(chn, freq, nbytes, mix_freq, P(m), P(ramp))
+            if n == 0xFFFFFFFF:
+                assert mix_freq // freq >= 63
+                continue
+            d = (1, 3, 16)[k % 3]
+            ring_len = n + 37
+            ring0 = rng.integers(-32768, 32768, ring_len).astype(np.int16)
+            want, got = ring0.copy(), ring0.copy()
+            wr = C.c_uint32(0)
+            pos = L.orc_mix_resample(P(want), ring_len, ring_len - 20, P(src), nbytes, freq, chn, mix_freq, d, C.byref(wr))
+            assert wr.value == n and pos == (ring_len - 20 + n) % ring_len, (freq, chn)
+            apply_mix_plan(got, ring_len - 20, src, chn, m[:n], ramp[:n], d)
+            assert np.array_equal(want, got), (mix_freq, freq, chn)
+    # a ratio the reference's 64-entry ramp buffer cannot hold is refused
+    assert E.emu_mix_plan(1, 200, 200, 16000, None, None) == 0xFFFFFFFF
+
+
 def test_rtp_host_header_helpers_vs_oracle():
     """wmixb_rtp_write_header / wmixb_rtp_read_header (host byte shuffling of the C-ABI) against the oracle"""
     import ctypes as C

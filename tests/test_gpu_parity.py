@@ -155,6 +155,62 @@ def test_mix_load_ring_vs_oracle():
     assert d_r.cpu().tolist() == [13758, -26991]
 
 
+def test_mix_load_resample_vs_oracle():
+    """different-format branches of wmix_load_data (R:src/wmix.c:1704-1939): the host plan + mix_plan_kernel, for
+    several producers chained in one launch, against the oracle run once per producer (the oracle itself is pinned
+    to the real wmix_load_data in tests/test_oracle_pin.py)"""
+    from tests.test_cpu_product import MIX_RESAMPLE_CASES
+
+    lib, L = wmix_b200.lib(), oracle()
+    L.orc_mix_resample.restype = C.c_uint32
+    L.orc_mix_resample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint8,
+                                   C.c_uint16, C.c_uint8, C.POINTER(C.c_uint32)]
+    rng = np.random.default_rng(23)
+    for mix_freq in (16000, 8000):
+        for k, (freq, chn) in enumerate(MIX_RESAMPLE_CASES):
+            if freq == mix_freq and chn == 1:
+                continue
+            frames, n_src = (1601 if freq >= 1000 else 25), (1, 5, 32)[k % 3]
+            src = rng.integers(-32768, 32768, (n_src, frames * chn)).astype(np.int16)
+            src[:, ::5] = 0
+            if k % 4 == 0:
+                src[0] = np.where(rng.random(frames * chn) < 0.5, 32767, -32768)
+            if n_src > 1:
+                src[1] = src[0]                      # identical loud producers drive the bus into saturation
+            rd = rng.choice(np.array([1, 1, 3, 16], np.uint8), n_src)
+            plan = C.c_void_p()
+            rc = lib.wmixb_mixplan_create(chn, freq, src[0].nbytes, mix_freq, 0, C.byref(plan))
+            if mix_freq // freq >= 63:
+                assert rc != 0                       # the reference's 64-entry ramp buffer would overflow
+                continue
+            assert rc == 0, lib.wmixb_last_error()
+            n = lib.wmixb_mixplan_out_samples(plan)
+            ring_len = n + 53
+            ring = rng.integers(-32768, 32768, ring_len).astype(np.int16)
+            ring[::7] = 0
+            d_ring = torch.from_numpy(ring.copy()).to(DEV)
+            d_src, d_rd = torch.from_numpy(src).to(DEV), torch.from_numpy(rd).to(DEV)
+            new_pos = C.c_uint32(0)
+            start = ring_len - 29
+            assert lib.wmixb_mix_load_plan_device(plan, d_ring.data_ptr(), ring_len, start, d_src.data_ptr(), n_src,
+                                                  d_rd.data_ptr(), C.byref(new_pos), None) == 0
+            for s in range(n_src):
+                wr = C.c_uint32(0)
+                pos = L.orc_mix_resample(P(ring), ring_len, start, P(src[s]), src[s].nbytes, freq, chn, mix_freq, int(rd[s]),
+                                         C.byref(wr))
+                assert wr.value == n
+            assert new_pos.value == pos
+            assert np.array_equal(d_ring.cpu().numpy(), ring), (mix_freq, freq, chn, n_src)
+            # a chunk longer than the ring is refused (two threads would own one bus sample)
+            assert lib.wmixb_mix_load_plan_device(plan, d_ring.data_ptr(), n - 1, 0, d_src.data_ptr(), n_src, None, None, None) != 0
+            lib.wmixb_mixplan_destroy(plan)
+    # formats the reference routes to its same-format branch, or cannot express, are refused
+    plan = C.c_void_p()
+    assert lib.wmixb_mixplan_create(1, 16000, 320, 16000, 0, C.byref(plan)) != 0
+    assert lib.wmixb_mixplan_create(3, 8000, 320, 16000, 0, C.byref(plan)) != 0
+    assert lib.wmixb_mixplan_create(2, 8000, 322, 16000, 0, C.byref(plan)) != 0
+
+
 @pytest.mark.parametrize("sizes", [[1, 2, 3, 58], [1024] * 3, [16] * 40, [5000]])
 def test_conference_bus(sizes):
     rng = np.random.default_rng(3)

@@ -107,6 +107,52 @@ def test_mix_vs_reference_wmix_load_data():
         assert out.U8 - ring_ref.ctypes.data == pos * 2
 
 
+@need_ref
+def test_mix_resample_vs_reference_wmix_load_data():
+    """different-format branches (R:src/wmix.c:1704-1939) of the real wmix_load_data, mono 16 kHz bus"""
+    R, L = ref(), oracle()
+    rng = np.random.default_rng(11)
+    ring_bytes = R.oracle_ref_wmix_buff_size()
+    n = ring_bytes // 2
+    mix_freq = R.oracle_ref_wmix_freq()
+
+    class WPoint(C.Union):
+        _fields_ = [("U8", C.c_void_p)]
+
+    R.wmix_load_data.restype = WPoint
+    R.wmix_load_data.argtypes = [C.c_void_p, WPoint, C.c_uint32, C.c_uint16, C.c_uint8, C.c_uint8, WPoint,
+                                 C.c_uint8, C.POINTER(C.c_uint32)]
+    L.orc_mix_resample.restype = C.c_uint32
+    L.orc_mix_resample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint8,
+                                   C.c_uint16, C.c_uint8, C.POINTER(C.c_uint32)]
+    wm = (C.c_uint8 * R.oracle_ref_sizeof_wmix())()
+    cases = [(8000, 1), (8000, 2), (11025, 1), (12000, 2), (16000, 2), (22050, 1), (32000, 2), (44100, 2), (48000, 1),
+             (15999, 1), (16001, 2), (300, 1), (65535, 1)]
+    for k, (freq, chn) in enumerate(cases):
+        rdce_mode, reduce = ((1, 1), (3, 0), (16, 2))[k % 3]
+        frames = 331 if freq >= 1000 else 40
+        ring_ref = rng.integers(-32768, 32768, n).astype(np.int16)
+        ring_ref[::7] = 0
+        ring_orc = ring_ref.copy()
+        head_off = (n - 150) * 2
+        R.oracle_ref_wmix_seat(wm, P(ring_ref), ring_bytes, rdce_mode, 0, 0)
+        # the reference reads one frame past the source when it prepares the ramp after the last frame
+        src = rng.integers(-32768, 32768, frames * chn + 2).astype(np.int16)
+        src[::5] = 0
+        if k % 4 == 0:
+            src[:] = np.where(rng.random(src.size) < 0.5, 32767, -32768)
+        nbytes = frames * chn * 2
+        tick = C.c_uint32(0)
+        head = WPoint(ring_ref.ctypes.data + head_off)
+        out = R.wmix_load_data(wm, WPoint(src.ctypes.data), nbytes, freq, chn, 16, head, reduce, C.byref(tick))
+        d = 1 if reduce == rdce_mode else rdce_mode
+        wr = C.c_uint32(0)
+        pos = L.orc_mix_resample(P(ring_orc), n, head_off // 2, P(src), nbytes, freq, chn, mix_freq, d, C.byref(wr))
+        assert np.array_equal(ring_ref, ring_orc), (freq, chn)
+        assert out.U8 - ring_ref.ctypes.data == pos * 2, (freq, chn)
+        assert tick.value == wr.value * 2, (freq, chn)
+
+
 # ---------------------------------------------------------------- SPL primitives (reference unit-test KATs)
 def test_spl_kats():
     L = oracle()

@@ -84,6 +84,11 @@ def lib():
         "wmixb_rtp_read_header": (None, [vp, vp]),
         "wmixb_rtp_unpack_device": (i, [vp, vp, i, i, i, vp, vp, vp]),
         "wmixb_rtp_pack_device": (i, [vp, i, i, vp, vp, i, vp]),
+        "wmixb_mixplan_create": (i, [i, i, u32, i, i, C.POINTER(vp)]),
+        "wmixb_mixplan_destroy": (None, [vp]),
+        "wmixb_mixplan_out_samples": (u32, [vp]),
+        "wmixb_mixplan_tables": (i, [vp, vp, vp]),
+        "wmixb_mix_load_plan_device": (i, [vp, vp, u32, u32, vp, i, vp, C.POINTER(u32), vp]),
         # include/wmix_zoom.h
         "wmix_len_of_out": (u32, [C.c_uint8, C.c_uint16, u32, C.c_uint8, C.c_uint16]),
         "wmix_len_of_in": (u32, [C.c_uint8, C.c_uint16, C.c_uint8, C.c_uint16, u32]),

@@ -362,5 +362,58 @@ uint32_t zoom_map(int in_chn, int in_freq, uint32_t in_bytes, int out_chn, int o
     return n;
 }
 
+
+// ---- resampling branches of wmix_load_data for a mono bus (R:src/wmix.c:1704-1939) ----
+// The float phase accumulator decides, per bus sample, whether it is a copied source frame or the k-th of n ramp
+// values between the frame just copied and the next one.  None of that depends on the audio, so it is walked once
+// here, exactly as the reference walks it, and the kernel only evaluates the ramps.
+//   map[i]  = int16 index of the (left) source sample feeding bus sample i
+//   ramp[i] = 0 for a copied frame, else (n << 8) | (k + 1): value = (int16)(src[map] + (k+1 accumulated steps of
+//             (float)(src[map + chn] - src[map]) / n))
+// Returns the number of bus samples, or UINT32_MAX where the reference would overrun its 64-entry ramp buffer.
+uint32_t mix_plan(int src_chn, int src_freq, uint32_t src_bytes, int mix_freq, int32_t* map, uint16_t* ramp)
+{
+    const uint32_t frame_bytes = 2u * (uint32_t)src_chn;
+    uint32_t used = 0, n_out = 0;
+    int32_t pos = 0;
+    float acc = 0.f;
+    if (src_freq > mix_freq) {
+        const float gain = (float)(src_freq - mix_freq) / (float)mix_freq;
+        while (used < src_bytes) {
+            if (acc >= 1.0) {
+                acc = (float)((double)acc - 1.0);
+            } else {
+                if (map) { map[n_out] = pos; ramp[n_out] = 0; }
+                ++n_out;
+                acc += gain;
+            }
+            pos += src_chn;
+            used += frame_bytes;
+        }
+    } else {
+        const float gain = (float)(mix_freq - src_freq) / (float)src_freq;
+        int n = 0, k = 0;
+        while (used < src_bytes) {
+            if (acc >= 1.0) {
+                if (map) { map[n_out] = pos - src_chn; ramp[n_out] = (uint16_t)((n << 8) | (k + 1)); }
+                ++k;
+                acc = (float)((double)acc - 1.0);
+            } else {
+                if (map) { map[n_out] = pos; ramp[n_out] = 0; }
+                pos += src_chn;
+                used += frame_bytes;
+                acc += gain;
+                if (acc >= 1.0) {
+                    n = (int)acc + 1;
+                    k = 0;
+                    if (n > 64) return 0xFFFFFFFFu;
+                }
+            }
+            ++n_out;
+        }
+    }
+    return n_out;
+}
+
 }  // namespace host
 }  // namespace wmx

@@ -23,5 +23,9 @@ void aec_tables(float* w, float* c, float* hann, float* weight, float* over, uin
 uint32_t zoom_map(int in_chn, int in_freq, uint32_t in_bytes, int out_chn, int out_freq, int32_t* map);
 uint32_t zoom_len_of_out(int in_chn, int in_freq, uint32_t in_len, int out_chn, int out_freq);
 uint32_t zoom_len_of_in(int in_chn, int in_freq, int out_chn, int out_freq, uint32_t out_len);
+// resampling branches of wmix_load_data, mono bus (R:src/wmix.c:1704-1939): per bus sample the source index and the
+// ramp code (0 = copied frame, else (n << 8) | (k + 1)).  Returns the bus samples written (map/ramp may be nullptr to
+// only count) or UINT32_MAX if the reference's 64-entry ramp buffer would overflow.
+uint32_t mix_plan(int src_chn, int src_freq, uint32_t src_bytes, int mix_freq, int32_t* map, uint16_t* ramp);
 }  // namespace host
 }  // namespace wmx

@@ -1122,6 +1122,117 @@ extern "C" int wmixb_mix_load_device(int16_t* d_ring, uint32_t ring_len, uint32_
     return WMIXB_OK;
 }
 
+// ---- resampling branches of wmix_load_data on a device ring (R:src/wmix.c:1704-1939, mono bus) ----
+// Thread i owns bus sample i of the chunk: it evaluates, for every source IN ORDER, the copied or ramped sample
+// the host plan names and chains the reference's saturating add, so n_src producers that the reference would
+// mix one after another land in one launch with the same bits.
+__global__ void mix_plan_kernel(int16_t* ring, uint32_t ring_len, uint32_t pos, const int16_t* __restrict__ src, uint32_t src_stride,
+                                int src_chn, const int32_t* __restrict__ map, const uint16_t* __restrict__ ramp, uint32_t n_out,
+                                int n_src, const uint8_t* __restrict__ rdce)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += gridDim.x * blockDim.x) {
+        const uint32_t p = (uint32_t)(((uint64_t)pos + i) % ring_len);
+        const int32_t m = map[i];
+        const uint32_t code = ramp[i];
+        const int n = (int)(code >> 8), k = (int)(code & 0xffu);
+        int16_t bus = ring[p];
+        for (int s = 0; s < n_src; ++s) {
+            const int16_t* row = src + (size_t)s * src_stride;
+            int16_t v = row[m];
+            if (code) {
+                // repairStep = (float)(next - last) / n; the k-th ramp value adds k accumulated steps (R:src/wmix.c:1911-1920)
+                const float step = __fdiv_rn((float)((int)row[m + src_chn] - (int)v), (float)n);
+                float run = step;
+                for (int j = 1; j < k; ++j) run = __fadd_rn(run, step);
+                v = (int16_t)(int)__fadd_rn((float)v, run);
+            }
+            int d = rdce ? rdce[s] : 1;
+            if (d == 0) d = 1;
+            bus = wmx::mix_step(bus, v, d);
+        }
+        ring[p] = bus;
+    }
+}
+
+struct wmixb_mixplan {
+    int device = 0, src_chn = 1;
+    uint32_t src_bytes = 0, out_samples = 0;
+    int32_t* d_map = nullptr;
+    uint16_t* d_ramp = nullptr;
+    std::vector<int32_t> h_map;
+    std::vector<uint16_t> h_ramp;
+};
+
+extern "C" int wmixb_mixplan_create(int src_chn, int src_freq, uint32_t src_bytes, int mix_freq, int device, wmixb_mixplan** out)
+{
+    if (!out) return WMIXB_EINVAL;
+    *out = nullptr;
+    if (src_chn < 1 || src_chn > 2 || src_freq < 1 || src_freq > 65535 || mix_freq < 1 || mix_freq > 65535 ||
+        src_bytes % (2u * (uint32_t)src_chn) != 0 || (src_freq == mix_freq && src_chn == 1)) {
+        snprintf(g_err, sizeof g_err, "mixplan: 1 or 2 channels of whole 16-bit frames, rates 1..65535 Hz, and a format that differs from the bus");
+        return WMIXB_EINVAL;
+    }
+    const uint32_t n = host::mix_plan(src_chn, src_freq, src_bytes, mix_freq, nullptr, nullptr);
+    if (n == 0xFFFFFFFFu) {
+        snprintf(g_err, sizeof g_err, "mixplan: %d Hz into %d Hz needs a ramp longer than the reference's 64-entry buffer", src_freq, mix_freq);
+        return WMIXB_EINVAL;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { snprintf(g_err, sizeof g_err, "no CUDA device — wmix_b200 has no CPU path"); return WMIXB_ENODEV; }
+    if (device < 0 || device >= ndev) return WMIXB_EINVAL;
+    wmixb_mixplan* m = new (std::nothrow) wmixb_mixplan();
+    if (!m) return WMIXB_ENOMEM;
+    m->device = device;
+    m->src_chn = src_chn;
+    m->src_bytes = src_bytes;
+    m->out_samples = n;
+    m->h_map.resize(n ? n : 1);
+    m->h_ramp.resize(n ? n : 1);
+    host::mix_plan(src_chn, src_freq, src_bytes, mix_freq, m->h_map.data(), m->h_ramp.data());
+    cudaError_t ce = cudaSetDevice(device);
+    if (ce == cudaSuccess) ce = cudaMalloc(&m->d_map, m->h_map.size() * sizeof(int32_t));
+    if (ce == cudaSuccess) ce = cudaMalloc(&m->d_ramp, m->h_ramp.size() * sizeof(uint16_t));
+    if (ce == cudaSuccess) ce = cudaMemcpy(m->d_map, m->h_map.data(), m->h_map.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+    if (ce == cudaSuccess) ce = cudaMemcpy(m->d_ramp, m->h_ramp.data(), m->h_ramp.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+    if (ce != cudaSuccess) { cudaFree(m->d_map); cudaFree(m->d_ramp); delete m; return fail_cuda(ce, "mixplan_create", __LINE__); }
+    *out = m;
+    return WMIXB_OK;
+}
+
+extern "C" void wmixb_mixplan_destroy(wmixb_mixplan* m)
+{
+    if (!m) return;
+    cudaSetDevice(m->device);
+    cudaFree(m->d_map);
+    cudaFree(m->d_ramp);
+    delete m;
+}
+
+extern "C" uint32_t wmixb_mixplan_out_samples(const wmixb_mixplan* m) { return m ? m->out_samples : 0u; }
+
+extern "C" int wmixb_mixplan_tables(const wmixb_mixplan* m, int32_t* h_map, uint16_t* h_ramp)
+{
+    if (!m) return WMIXB_EINVAL;
+    if (h_map) memcpy(h_map, m->h_map.data(), (size_t)m->out_samples * sizeof(int32_t));
+    if (h_ramp) memcpy(h_ramp, m->h_ramp.data(), (size_t)m->out_samples * sizeof(uint16_t));
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_mix_load_plan_device(const wmixb_mixplan* m, int16_t* d_ring, uint32_t ring_len, uint32_t pos, const int16_t* d_src,
+                                          int n_src, const uint8_t* d_rdce, uint32_t* new_pos, void* stream)
+{
+    if (!m || !d_ring || ring_len == 0 || pos >= ring_len || n_src < 0 || (n_src && m->out_samples && !d_src) || m->out_samples > ring_len)
+        return WMIXB_EINVAL;
+    if (n_src && m->out_samples) {
+        CK(cudaSetDevice(m->device));
+        mix_plan_kernel<<<ew_blocks(m->out_samples), 256, 0, (cudaStream_t)stream>>>(d_ring, ring_len, pos, d_src, m->src_bytes / 2, m->src_chn,
+                                                                                     m->d_map, m->d_ramp, m->out_samples, n_src, d_rdce);
+        CK_LAUNCH();
+    }
+    if (new_pos) *new_pos = (uint32_t)(((uint64_t)pos + m->out_samples) % ring_len);
+    return WMIXB_OK;
+}
+
 // ---- state snapshot ----
 extern "C" size_t wmixb_stream_state_bytes(const wmixb_engine* e)
 {
