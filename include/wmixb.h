@@ -75,6 +75,13 @@ int wmixb_tick_host_bus(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, ui
 int wmixb_vad20_device(wmixb_engine* e, int16_t* d_pcm, uint8_t* d_vad, void* stream);
 int wmixb_vad20_host(wmixb_engine* e, int16_t* h_pcm, uint8_t* h_vad);
 
+/* VAD on 32 kHz packets of 10 ms (320 samples), in place: the handle API's 32 kHz case (R:src/webrtc.c:43, :66-67;
+ * CalcVad32khz, T:.../vad/vad_core.c:623-643: 32k -> 16k -> 8k, then the 8 kHz detector with the 10 ms thresholds).
+ * Runs on an engine created with freq = 16000 and WMIXB_VAD; d_pcm: int16 [n_streams][320].  Use one packet kind
+ * per engine. */
+int wmixb_vad32_device(wmixb_engine* e, int16_t* d_pcm, uint8_t* d_vad, void* stream);
+int wmixb_vad32_host(wmixb_engine* e, int16_t* h_pcm, uint8_t* h_vad);
+
 /* Echo canceller (stage WMIXB_AEC), the arithmetic of aec_process2 (R:src/webrtc.c:410-483) for every
  * stream: BufferFarend(d_far) then Process(d_near) -> d_out.  d_far == NULL is aec_process (near only),
  * d_near == NULL is aec_setFrameFar (far only; d_out unused).  Buffers are int16 [n_streams][samples],

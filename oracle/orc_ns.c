@@ -639,14 +639,17 @@ void orc_ns_process(orc_ns *h, const int16_t *in, int16_t *out, int frame_num)
     float fin[160], fo[160];
     int pos, i;
     orc_ns_core *s = h->core;
+    /* At 32 kHz the packet is 320 samples but the core still works on 160-sample blocks and wmix passes ONE band
+     * (R:src/webrtc.c:633), so only the first 160 samples of a packet are analysed and written; the rest of the
+     * reference's calloc'ed out[0] is never touched and reads back as zero. */
     for (pos = 0; pos + h->pkg <= frame_num; pos += h->pkg) {
-        for (i = 0; i < h->pkg; ++i)
+        for (i = 0; i < s->block; ++i)
             fin[i] = (float)in[pos + i];
         orc_slide_in(s->inbuf, s->ana, s->block, fin);
         orc_ns_analyze(s, fin);
         orc_ns_synthesize(s, fo);
         for (i = 0; i < h->pkg; ++i)
-            out[pos + i] = (int16_t)fo[i];
+            out[pos + i] = i < s->block ? (int16_t)fo[i] : 0;
     }
 }
 

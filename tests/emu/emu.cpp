@@ -117,6 +117,13 @@ int emu_vad_frame20(void* h, int16_t* x, int vad_mode)
     if (e->freq == 16000) return vad::process_packet<160, true>(st, x, vp);
     return vad::process_packet<160, false>(st, x, vp);
 }
+// 32 kHz packets of 10 ms: x holds 320 samples (the emulated engine must have been created at 16 kHz)
+int emu_vad_frame32(void* h, int16_t* x)
+{
+    EmuInt* e = (EmuInt*)h;
+    SoaWords st{e->vad.data(), 1};
+    return vad::process_packet32<80>(st, x, e->vp);
+}
 void emu_int_destroy(void* h) { delete (EmuInt*)h; }
 
 struct EmuAec {

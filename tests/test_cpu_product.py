@@ -150,6 +150,26 @@ def test_emulated_vad_20ms_packets_vs_reference(freq):
         E.emu_int_destroy(e)
 
 
+def test_vad_32khz_packets_match_oracle():
+    """vad_init(chn, 32000, ..): 320-sample packets through CalcVad32khz (T:.../vad/vad_core.c:623-643) — the kernel body of
+    wmixb_vad32_device against the oracle (pinned to the reference at 32 kHz in tests/test_oracle_pin.py)"""
+    import ctypes as C
+
+    E, chk = emu(), oracle()
+    x = make_frames(3, 16000, 0, 240, seed=29)                       # 160-sample rows; pairs of rows = one 320-sample packet
+    for s in range(3):
+        pcm = np.ascontiguousarray(x[:, s]).reshape(-1, 320)
+        h = C.c_void_p(chk.orc_vad_init(1, 32000, 10))
+        e = C.c_void_p(E.emu_int_create(16000, 5, 3))
+        for k in range(len(pcm)):
+            a, b = pcm[k].copy(), pcm[k].copy()
+            chk.orc_vad_process(h, P(a), 320)
+            E.emu_vad_frame32(e, P(b))
+            assert np.array_equal(a, b), (s, k)
+        chk.orc_vad_release(h)
+        E.emu_int_destroy(e)
+
+
 def test_ns_counter_division_is_exact():
     """ns::div_by_counter (reciprocal + exact residual + one correction) replaces `x / (counter + 1)` in the NS quantile
     trackers (T:.../ns/ns_core.c:233-249); it must BE the IEEE quotient: every divisor 1..201 on a significand grid, and

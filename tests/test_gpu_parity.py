@@ -432,6 +432,41 @@ def test_dropin_handle_api():
     assert not lib.agc_init(1, 12000, 10, 5, None) and not lib.aec_init(1, 32000, 10, None)
 
 
+def test_dropin_handle_api_32khz():
+    """the reference accepts 32 kHz handles (R:src/webrtc.c:43, :563, :711): NS analyses the first 160 samples of every
+    320-sample packet and leaves zeros behind, AGC runs 5 ms packets through its 16 kHz path, VAD decimates 32k -> 16k
+    -> 8k.  Drop-in handles vs the oracle and the compiled reference, stage by stage and chained."""
+    lib = wmix_b200.lib()
+    x = make_frames(3, 16000, 0, 400, seed=91)
+    for cname, L, prefix in checkers():
+        for kw in (dict(ns=True, agc=False, vad=False), dict(ns=False, agc=True, vad=False), dict(ns=False, agc=False, vad=True),
+                   dict(ns=True, agc=True, vad=True)):
+            pcm = np.ascontiguousarray(x[:, 1 if kw["ns"] else 0]).reshape(-1)       # 200 packets of 320 samples
+            a, b = RefChain(L, 32000, prefix=prefix, **kw), RefChain(lib, 32000, **kw)
+            ya, yb = a.run(pcm), b.run(pcm)
+            a.close()
+            b.close()
+            assert np.array_equal(ya, yb), (cname, kw)
+    # batched form of the 32 kHz VAD
+    S, K = 24, 100
+    xs = make_frames(S, 16000, 0, 2 * K, seed=93)
+    pk = np.ascontiguousarray(xs.transpose(1, 0, 2)).reshape(S, K, 320)
+    L = oracle()
+    eng = wmix_b200.Engine(S, 16000, stages=VAD)
+    d = torch.empty((S, 320), dtype=torch.int16, device=DEV)
+    hs = [C.c_void_p(L.orc_vad_init(1, 32000, 10)) for _ in range(S)]
+    for k in range(K):
+        want = pk[:, k].copy()
+        for s in range(S):
+            L.orc_vad_process(hs[s], P(want[s]), 320)
+        d.copy_(torch.from_numpy(np.ascontiguousarray(pk[:, k])))
+        assert lib.wmixb_vad32_device(eng.h, d.data_ptr(), None, torch.cuda.current_stream().cuda_stream) == 0
+        assert np.array_equal(d.cpu().numpy(), want), k
+    for h in hs:
+        L.orc_vad_release(h)
+    eng.close()
+
+
 @pytest.mark.parametrize("freq", [8000, 16000])
 def test_vad_20ms_packets_handle_and_batched(freq):
     """vad_init(.., 20, ..) as wmix calls it (R:src/wmix.c:703): drop-in handle and wmixb_vad20_device, bit-exact"""

@@ -316,11 +316,15 @@ def _streams(freq, n_streams, n_ticks, seed):
 
 
 @need_ref
-@pytest.mark.parametrize("freq", [8000, 16000])
+@pytest.mark.parametrize("freq", [8000, 16000, 32000])
 @pytest.mark.parametrize("stage", ["vad", "agc", "ns", "chain"])
 def test_stage_vs_reference(freq, stage):
+    """32000: the handle API's 32 kHz quirks — NS touches only the first 160 samples of each 320-sample packet and
+    leaves zeros behind (R:src/webrtc.c:633), AGC runs 5 ms packets (R:src/webrtc.c:727), VAD decimates twice"""
     R, L = ref(), oracle()
     S, T = (6, 700) if stage in ("ns", "chain") else (8, 400)
+    if freq == 32000:
+        S, T = 3, 300
     x = _streams(freq, S, T, seed=11)
     kw = dict(ns=stage in ("ns", "chain"), agc=stage in ("agc", "chain"), vad=stage in ("vad", "chain"))
     for s in range(S):

@@ -40,6 +40,8 @@ def lib():
         "wmixb_tick_host_bus": (i, [vp, vp, vp, vp, vp, i]),
         "wmixb_vad20_device": (i, [vp, vp, vp, vp]),
         "wmixb_vad20_host": (i, [vp, vp, vp]),
+        "wmixb_vad32_device": (i, [vp, vp, vp, vp]),
+        "wmixb_vad32_host": (i, [vp, vp, vp]),
         "wmixb_offline_device": (i, [vp, vp, vp, vp, i, i, vp]),
         "wmixb_aec_device": (i, [vp, vp, vp, vp, i, i, vp]),
         "wmixb_aec_host": (i, [vp, vp, vp, vp, i, i]),

@@ -28,12 +28,14 @@ struct Handle {
 
 bool dbg(const bool* d) { return d && *d; }
 
+// 32 kHz handles run on a 16 kHz engine: at that rate the reference's AGC and NS see 160-sample packets and take
+// exactly their 16 kHz paths, and the VAD only adds a 32k -> 16k decimator in front (wmixb_vad32_*).
 Handle* make(int stage, int chn, int freq, int gain, bool* debug, const char* who)
 {
     wmixb_config c;
     memset(&c, 0, sizeof c);
     c.n_streams = 1;
-    c.freq = freq;
+    c.freq = freq == 32000 ? 16000 : freq;
     c.stages = stage;
     c.ns_policy = 2;      // NS_AGGRESSIVE, R:src/webrtc.c:532
     c.agc_gain_db = gain; // compressionGaindB, R:src/webrtc.c:707
@@ -47,7 +49,7 @@ Handle* make(int stage, int chn, int freq, int gain, bool* debug, const char* wh
     h->eng = e;
     h->chn = chn;
     h->freq = freq;
-    h->pkg = freq / 100;
+    h->pkg = c.freq / 100;
     h->stage = stage;
     h->debug = debug;
     h->mono.resize((size_t)h->pkg);
@@ -73,14 +75,9 @@ extern "C" {
 void* vad_init(int chn, int freq, int intervalMs, bool* debug)
 {
     if (!rate_ok(freq, 32000)) return nullptr;                      // R:src/webrtc.c:43
-    if (freq == 32000) {
-        // the 32 kHz path (CalcVad32khz) is not on the GPU — INTEGRATION.md
-        if (dbg(debug)) printf("vad_init: only 8/16 kHz on the GPU path so far\r\n");
-        return nullptr;
-    }
     Handle* h = make(WMIXB_VAD, chn, freq, 0, debug, "vad_init");
     if (!h) return nullptr;
-    const int ms = intervalMs % 20 == 0 ? 20 : 10;                  // R:src/webrtc.c:56-65
+    const int ms = (freq <= 16000 && intervalMs % 20 == 0) ? 20 : 10;   // R:src/webrtc.c:56-67
     h->pkg = freq / 1000 * ms;
     h->mono.resize((size_t)h->pkg);
     h->res.resize((size_t)h->pkg);
@@ -107,7 +104,10 @@ void vad_process(void* fp, int16_t* frame, int frameNum)
         memcpy(h->mono.data(), frame, (size_t)h->pkg * 2);
         uint8_t flag = 0;
         int rc;
-        if (h->pkg == h->freq / 100) {
+        if (h->freq == 32000) {                                     // 320-sample packet, CalcVad32khz
+            memcpy(h->res.data(), h->mono.data(), (size_t)h->pkg * 2);
+            rc = wmixb_vad32_host(h->eng, h->res.data(), &flag);
+        } else if (h->pkg == h->freq / 100) {
             rc = wmixb_tick_host(h->eng, h->mono.data(), h->res.data(), &flag, WMIXB_VAD);
         } else {                                                    // 20 ms packet
             memcpy(h->res.data(), h->mono.data(), (size_t)h->pkg * 2);
@@ -132,13 +132,20 @@ void vad_release(void* fp) { drop(fp, "vad_release"); }
 void* ns_init(int chn, int freq, bool* debug)
 {
     if (!rate_ok(freq, 32000)) return nullptr;                      // R:src/webrtc.c:563
-    if (freq == 32000 || chn != 1) {
-        // stereo is fed to WebRtcNs as low band + "high band" (R:src/webrtc.c:624-636); 32 kHz
-        // mono would need the 160-sample 32k path — neither is on the GPU yet
-        if (dbg(debug)) printf("ns_init: only mono 8/16 kHz on the GPU path so far\r\n");
+    if (chn != 1) {
+        // stereo is fed to WebRtcNs as low band + "high band" (R:src/webrtc.c:624-636): not on the GPU yet
+        if (dbg(debug)) printf("ns_init: only mono on the GPU path so far\r\n");
         return nullptr;
     }
     Handle* h = make(WMIXB_NS, chn, freq, 0, debug, "ns_init");
+    if (h && freq == 32000) {
+        // WebRtcNs at 32 kHz still works on 160-sample blocks with the 16 kHz window (T:.../ns/ns_core.c:89-98) and
+        // wmix hands it ONE band (R:src/webrtc.c:633: num_bands = chn), so of each 320-sample packet only the first 160
+        // samples are analysed and written; the rest of the reference's calloc'ed out buffer stays zero.
+        h->pkg = 320;
+        h->mono.resize(320);
+        h->res.assign(320, 0);
+    }
     if (h && dbg(debug)) printf("ns_init: chn/%d freq/%d intervalMs/%d pkgFrame/%d x %d\r\n", chn, freq, 10, h->pkg, chn);
     return h;
 }
@@ -148,6 +155,7 @@ void ns_process(void* fp, int16_t* frame, int16_t* frameOut, int frameNum)
     Handle* h = (Handle*)fp;
     for (int pos = 0; pos < frameNum; pos += h->pkg) {              // R:src/webrtc.c:624-643
         memcpy(h->mono.data(), frame + pos, (size_t)h->pkg * 2);
+        // (a 32 kHz packet: the engine's frame is the first 160 samples, res[160..319] stays zero)
         if (wmixb_tick_host(h->eng, h->mono.data(), h->res.data(), nullptr, WMIXB_NS) != WMIXB_OK) {
             if (dbg(h->debug)) printf("ns_process failed !!, %s \r\n", wmixb_last_error());
             return;
@@ -163,12 +171,10 @@ void* agc_init(int chn, int freq, int intervalMs, int value, bool* debug)
 {
     (void)intervalMs;
     if (!rate_ok(freq, 32000)) return nullptr;                      // R:src/webrtc.c:711
-    if (freq == 32000) {
-        if (dbg(debug)) printf("agc_init: only 8/16 kHz on the GPU path so far\r\n");
-        return nullptr;
-    }
+    // 32 kHz: 5 ms packets of 160 samples through the 16 kHz path (R:src/webrtc.c:724-728; WebRtcAgc_Process accepts 160
+    // samples at 16 / 32 / 48 kHz alike, T:.../agc/legacy/analog_agc.c:1152-1163, and nothing else reads fs in wmix's use)
     Handle* h = make(WMIXB_AGC, chn, freq, value, debug, "agc_init");
-    if (h && dbg(debug)) printf("agc_init: chn/%d freq/%d intervalMs/%d pkgFrame/%d x %d\r\n", chn, freq, 10, h->pkg, chn);
+    if (h && dbg(debug)) printf("agc_init: chn/%d freq/%d intervalMs/%d pkgFrame/%d x %d\r\n", chn, freq, freq <= 16000 ? 10 : 5, h->pkg, chn);
     return h;
 }
 

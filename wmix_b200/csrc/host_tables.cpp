@@ -143,7 +143,7 @@ void vad_initial_words(int32_t* words /* vad::N_WORDS */)
     static const int16_t nstd[12] = {378, 1064, 493, 582, 688, 593, 474, 697, 475, 688, 421, 455};
     static const int16_t sstd[12] = {555, 505, 567, 524, 585, 1231, 509, 828, 492, 1540, 1079, 850};
     auto pk = [](int16_t lo, int16_t hi) { return (int32_t)(((uint32_t)(uint16_t)hi << 16) | (uint16_t)lo); };
-    memset(words, 0, sizeof(int32_t) * 136);
+    memset(words, 0, sizeof(int32_t) * 138);
     for (int ch = 0; ch < 6; ++ch) {
         words[2 + ch] = pk(nmean[ch], nmean[ch + 6]);
         words[8 + ch] = pk(smean[ch], smean[ch + 6]);

@@ -27,7 +27,8 @@ enum {
     W_LOWER = 130,   // 3 words : split-filter lower states [5] (+pad)
     W_HP = 133,      // 2 words : 80 Hz high-pass state [4]
     W_REDUCE = 135,  // 1 word  : wmix wrapper's attenuation shift 0..4
-    N_WORDS = 136
+    W_DS32 = 136,    // 2 words : 32k->16k decimator all-pass states (int32), T:.../vad/vad_core.c:632
+    N_WORDS = 138
 };
 
 struct Params {            // mode-dependent thresholds for the frame length in use
@@ -445,6 +446,31 @@ WMX_HD int process_packet(const SoaWords& st, int16_t* x, const Params& P)
     st.set(W_REDUCE, reduce);
     const int n = LEN8 * (FS16 ? 2 : 1);
     for (int i = 0; i < n; ++i) x[i] = (int16_t)(x[i] >> reduce);
+    return flag > 0 ? 1 : 0;
+}
+
+// 32 kHz packet (T:.../vad/vad_core.c:623-643): 32k -> 16k -> 8k through the same decimator with two state pairs,
+// then the 8 kHz detector; the wrapper attenuates all 4*LEN8 samples.
+template <int LEN8>
+WMX_HD int process_packet32(const SoaWords& st, int16_t* x, const Params& P)
+{
+    int16_t feat[6], wb[2 * LEN8], nb[LEN8];
+    int32_t s0 = st.get(W_DS32), s1 = st.get(W_DS32 + 1);
+    decimate<2 * LEN8>(x, wb, s0, s1);
+    st.set(W_DS32, s0);
+    st.set(W_DS32 + 1, s1);
+    s0 = st.get(W_DS);
+    s1 = st.get(W_DS + 1);
+    decimate<LEN8>(wb, nb, s0, s1);
+    st.set(W_DS, s0);
+    st.set(W_DS + 1, s1);
+    const int16_t power = features<LEN8>(st, nb, feat);
+    int flag = gmm(st, feat, power, P);
+    int reduce = st.get(W_REDUCE);
+    if (flag == 0) { if (reduce < 4) reduce++; }
+    else if (reduce > 0) reduce--;
+    st.set(W_REDUCE, reduce);
+    for (int i = 0; i < 4 * LEN8; ++i) x[i] = (int16_t)(x[i] >> reduce);
     return flag > 0 ? 1 : 0;
 }
 

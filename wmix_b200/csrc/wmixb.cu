@@ -249,6 +249,22 @@ vad_packet20_kernel(int32_t* __restrict__ vad_words, vad::Params vp, int16_t* pc
     if (vad_out) vad_out[s] = (uint8_t)flag;
 }
 
+// VAD on 32 kHz packets of 10 ms (CalcVad32khz, T:.../vad/vad_core.c:623-643): the handle API's 32 kHz case.
+__global__ void __launch_bounds__(64)
+vad_packet32_kernel(int32_t* __restrict__ vad_words, vad::Params vp, int16_t* pcm, uint8_t* vad_out, int n_streams, size_t stride)
+{
+    constexpr int L = 320;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_streams) return;
+    int16_t x[L];
+    int16_t* row = pcm + (size_t)s * L;
+    for (int i = 0; i < L; ++i) x[i] = row[i];
+    SoaWords st{vad_words + s, stride};
+    const int flag = vad::process_packet32<80>(st, x, vp);
+    for (int i = 0; i < L; ++i) row[i] = x[i];
+    if (vad_out) vad_out[s] = (uint8_t)flag;
+}
+
 __global__ void words_init_kernel(int32_t* words, const int32_t* init, int n_words, size_t stride, int first, int count)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -698,6 +714,33 @@ extern "C" int wmixb_vad20_host(wmixb_engine* e, int16_t* h_pcm, uint8_t* h_vad)
     const size_t bytes = (size_t)e->cfg.n_streams * 2 * e->frame * sizeof(int16_t);
     CK(cudaMemcpyAsync(e->d_pkt20, h_pcm, bytes, cudaMemcpyHostToDevice, e->stream));
     const int rc = wmixb_vad20_device(e, e->d_pkt20, e->d_vad, e->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_pcm, e->d_pkt20, bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (h_vad) CK(cudaMemcpyAsync(h_vad, e->d_vad, (size_t)e->cfg.n_streams, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_vad32_device(wmixb_engine* e, int16_t* d_pcm, uint8_t* d_vad, void* stream)
+{
+    if (!e || !d_pcm) return WMIXB_EINVAL;
+    if (!e->vad_words || e->frame != 160) { snprintf(g_err, sizeof g_err, "vad32: needs a 16 kHz engine created with WMIXB_VAD"); return WMIXB_EINVAL; }
+    CK(cudaSetDevice(e->cfg.device));
+    const int n = e->cfg.n_streams, grid = (n + 63) / 64;
+    vad_packet32_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>(e->vad_words, e->vp, d_pcm, d_vad, n, e->stride);
+    CK_LAUNCH();
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_vad32_host(wmixb_engine* e, int16_t* h_pcm, uint8_t* h_vad)
+{
+    if (!e || !h_pcm) return WMIXB_EINVAL;
+    if (!e->vad_words || e->frame != 160) { snprintf(g_err, sizeof g_err, "vad32: needs a 16 kHz engine created with WMIXB_VAD"); return WMIXB_EINVAL; }
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t bytes = (size_t)e->cfg.n_streams * 320 * sizeof(int16_t);      // same size as a 20 ms packet at 16 kHz
+    if (!e->d_pkt20) CK(cudaMalloc(&e->d_pkt20, bytes));
+    CK(cudaMemcpyAsync(e->d_pkt20, h_pcm, bytes, cudaMemcpyHostToDevice, e->stream));
+    const int rc = wmixb_vad32_device(e, e->d_pkt20, e->d_vad, e->stream);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h_pcm, e->d_pkt20, bytes, cudaMemcpyDeviceToHost, e->stream));
     if (h_vad) CK(cudaMemcpyAsync(h_vad, e->d_vad, (size_t)e->cfg.n_streams, cudaMemcpyDeviceToHost, e->stream));
