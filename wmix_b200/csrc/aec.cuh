@@ -116,8 +116,11 @@ using ns::i2f;
 
 struct Lane {
     Cpx f[4];
+    Cpx px[4], pw[4];   // NLMS update: far spectrum of the next round / filter taps of this round, fetched ahead of the FFTs
 };
 struct Warp {
+    const float* pf_next = nullptr;   // record the warp will work on next: pulled towards L2 late in the tick (see block())
+    uint32_t pf_bytes = 0;
 #if defined(__CUDA_ARCH__)
     Lane lane_regs;
     int lane_id;
@@ -474,21 +477,32 @@ WMX_HD void block(WarpT& W, float* rec, int depth, int mult, const float* d_new,
     {
         const int pos = f2i(sc[S_XF_POS]);
         float yr[2] = {0.f, 0.f}, yi[2] = {0.f, 0.f};
-        for (int p = 0; p < kNPart; ++p) {
-            int xp = p + pos;
-            if (xp >= kNPart) xp -= kNPart;
-            const float* X = rec + Geo::kOffXf + xp * kPart2;
-            const float* Wf = rec + Geo::kOffWf + p * kPart2;
+        // the 12 partitions in two batches of 6: all 24 eight-byte loads of a batch are in flight before the first
+        // multiply, so the warp pays two memory round trips for the whole filter instead of twelve
+        for (int p0 = 0; p0 < kNPart; p0 += kNPart / 2) {
+            Cpx xa[kNPart / 2][2], wa[kNPart / 2][2];
 #pragma unroll
-            for (int s = 0; s < 2; ++s) {
-                const int c = lane + 32 * s;
-                const float a0 = X[2 * c], a1 = X[2 * c + 1], b0 = Wf[2 * c], b1 = Wf[2 * c + 1];
-                if (c == 0) {            // bins 0 and 64: purely real operands (imaginary parts are +0)
-                    yr[s] += a0 * b0 - 0.f * 0.f;
-                    yi[s] += a1 * b1 - 0.f * 0.f;
-                } else {
-                    yr[s] += a0 * b0 - a1 * b1;
-                    yi[s] += a0 * b1 + a1 * b0;
+            for (int q = 0; q < kNPart / 2; ++q) {
+                int xp = p0 + q + pos;
+                if (xp >= kNPart) xp -= kNPart;
+                const Cpx* X = reinterpret_cast<const Cpx*>(rec + Geo::kOffXf + xp * kPart2);
+                const Cpx* Wf = reinterpret_cast<const Cpx*>(rec + Geo::kOffWf + (p0 + q) * kPart2);
+#pragma unroll
+                for (int s = 0; s < 2; ++s) { xa[q][s] = X[lane + 32 * s]; wa[q][s] = Wf[lane + 32 * s]; }
+            }
+#pragma unroll
+            for (int q = 0; q < kNPart / 2; ++q) {
+#pragma unroll
+                for (int s = 0; s < 2; ++s) {
+                    const int c = lane + 32 * s;
+                    const float a0 = xa[q][s].r, a1 = xa[q][s].i, b0 = wa[q][s].r, b1 = wa[q][s].i;
+                    if (c == 0) {            // bins 0 and 64: purely real operands (imaginary parts are +0)
+                        yr[s] += a0 * b0 - 0.f * 0.f;
+                        yi[s] += a1 * b1 - 0.f * 0.f;
+                    } else {
+                        yr[s] += a0 * b0 - a1 * b1;
+                        yi[s] += a0 * b1 + a1 * b0;
+                    }
                 }
             }
         }
@@ -559,6 +573,19 @@ WMX_HD void block(WarpT& W, float* rec, int depth, int mult, const float* d_new,
     WMX_AEC_PHASE_END
 
     // ---- B7: constrained NLMS update of the 12 partitions, two per round (FilterAdaptation :222-270) ----
+    // Global operands are fetched a stage ahead: the far spectrum of round r+1 and the filter taps of round r are
+    // requested before round r's two transforms, so their latency hides behind the FFTs instead of stalling the warp
+    // twice per round.
+    WMX_AEC_PHASE_BEGIN
+    {
+        const int h = lane >> 4, l = lane & 15;
+        int xp = h + f2i(sc[S_XF_POS]);
+        if (xp >= kNPart) xp -= kNPart;
+        const Cpx* X = reinterpret_cast<const Cpx*>(rec + Geo::kOffXf + xp * kPart2);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) R.px[r] = X[l + 16 * r];
+    }
+    WMX_AEC_PHASE_END
     for (int rnd = 0; rnd < kNPart / 2; ++rnd) {
         float* g0 = sp + SP_XF * kPart2;
         float* g1 = sp + SP_DF * kPart2;
@@ -566,15 +593,12 @@ WMX_HD void block(WarpT& W, float* rec, int depth, int mult, const float* d_new,
         {
             const int h = lane >> 4, l = lane & 15;
             const int p = 2 * rnd + h;
-            int xp = p + f2i(sc[S_XF_POS]);
-            if (xp >= kNPart) xp -= kNPart;
-            const float* X = rec + Geo::kOffXf + xp * kPart2;
             const float* E = sp + SP_EF * kPart2;
             float* G = h ? g1 : g0;
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const int c = l + 16 * r;
-                const float xr = X[2 * c], x1 = X[2 * c + 1], er = E[2 * c], e1 = E[2 * c + 1];
+                const float xr = R.px[r].r, x1 = R.px[r].i, er = E[2 * c], e1 = E[2 * c + 1];
                 if (c == 0) {
                     // bin 0 and bin 64: conj(x) e with x = (xr, +0), e = (er, +0): xr*er - (-0)*(+0)
                     G[0] = xr * er - (-0.f) * 0.f;
@@ -584,6 +608,16 @@ WMX_HD void block(WarpT& W, float* rec, int depth, int mult, const float* d_new,
                     G[2 * c] = xr * er - xi * e1;
                     G[2 * c + 1] = xr * e1 + xi * er;
                 }
+            }
+            const Cpx* Wf = reinterpret_cast<const Cpx*>(rec + Geo::kOffWf + p * kPart2);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) R.pw[r] = Wf[l + 16 * r];
+            if (rnd + 1 < kNPart / 2) {
+                int xp = p + 2 + f2i(sc[S_XF_POS]);
+                if (xp >= kNPart) xp -= kNPart;
+                const Cpx* X = reinterpret_cast<const Cpx*>(rec + Geo::kOffXf + xp * kPart2);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) R.px[r] = X[l + 16 * r];
             }
         }
         WMX_AEC_PHASE_END
@@ -606,15 +640,24 @@ WMX_HD void block(WarpT& W, float* rec, int depth, int mult, const float* d_new,
             const int h = lane >> 4, l = lane & 15;
             const int p = 2 * rnd + h;
             const float* G = h ? g1 : g0;
-            float* Wf = rec + Geo::kOffWf + p * kPart2;
+            Cpx* Wf = reinterpret_cast<Cpx*>(rec + Geo::kOffWf + p * kPart2);
 #pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                const int i = l + 16 * r;
-                Wf[i] += G[i];
+            for (int r = 0; r < 4; ++r) {
+                const int c = l + 16 * r;
+                Cpx w = R.pw[r];
+                w.r += G[2 * c];
+                w.i += G[2 * c + 1];
+                Wf[c] = w;
             }
         }
         WMX_AEC_PHASE_END
     }
+
+    // The NLMS half of the block is done: ask for the record this warp turns to next.  Requested earlier (a whole tick
+    // ahead) the in-flight records of all resident warps outgrow the L2 and are evicted before they are used.
+    WMX_AEC_PHASE_BEGIN
+    if (lane == 0 && W.pf_next) l2_prefetch_bulk(W.pf_next, W.pf_bytes);
+    WMX_AEC_PHASE_END
 
     // ======================= NonLinearProcessing (:911-1141) =======================
     // ---- N0 (lane 0): delay-estimation counter ----

@@ -51,6 +51,18 @@ WMX_HD int32_t wshl(int32_t a, int s) { return (int32_t)((uint32_t)a << s); }
 // WEBRTC_SPL_SHIFT_W32
 WMX_HD int32_t shift_w32(int32_t x, int c) { return c >= 0 ? wshl(x, c) : (x >> (-c)); }
 
+// Bulk L2 prefetch (bytes a multiple of 16, address 16-byte aligned): one instruction, no destination, nothing to
+// wait for.  A no-op in the host emulation build.
+WMX_HD void l2_prefetch_bulk(const void* p, uint32_t bytes)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#else
+    (void)p;
+    (void)bytes;
+#endif
+}
+
 // packed int16 pair <-> 32-bit state word (lo = first field, hi = second field)
 WMX_HD int16_t lo16(int32_t w) { return (int16_t)(w & 0xFFFF); }
 WMX_HD int16_t hi16(int32_t w) { return (int16_t)(w >> 16); }

@@ -136,7 +136,7 @@ constexpr size_t kAecSmemBytes = (kAecTableFloats + (size_t)kAecWarps * aec::Geo
 
 __global__ void __launch_bounds__(kAecWarps * 32)
 aec_kernel(float* __restrict__ rec, size_t rec_floats, const aec::Tables* __restrict__ tables, const int16_t* far,
-           const int16_t* near, int16_t* out, int n_streams, int n, int mult, int depth, int delay_ms)
+           const int16_t* near, int16_t* out, int n_streams, int n, int mult, int depth, int delay_ms, int pf_mode)
 {
     extern __shared__ __align__(16) float smem[];
     aec::Tables* T = reinterpret_cast<aec::Tables*>(smem);
@@ -152,8 +152,17 @@ aec_kernel(float* __restrict__ rec, size_t rec_floats, const aec::Tables* __rest
     W.lane_id = threadIdx.x & 31;
     const int total_warps = gridDim.x * kAecWarps;
     for (int s = blockIdx.x * kAecWarps + warp; s < n_streams; s += total_warps) {
-        if (W.lane_id == 0 && s + total_warps < n_streams)
-            l2_prefetch(rec + (size_t)(s + total_warps) * rec_floats, (uint32_t)(rec_floats * sizeof(float)));
+        // L2 staging of the record (WMIXB_AEC_PF): 2 (default) = this stream's fixed part as ONE bulk request when the tick
+        // starts — the first loads wait for DRAM once, the rest of the tick hits L2; 1 = the next stream's record a whole
+        // tick ahead (measured slower: 2368 resident warps x two 23-31 KB records outgrow the L2 and the lines are evicted
+        // before use); 5 = 2 plus the next record requested mid-tick (also slower); 0 = none.
+        if (W.lane_id == 0) {
+            if (pf_mode == 1 && s + total_warps < n_streams)
+                l2_prefetch(rec + (size_t)(s + total_warps) * rec_floats, (uint32_t)(rec_floats * sizeof(float)));
+            if (pf_mode == 2 || pf_mode == 5) l2_prefetch(rec + (size_t)s * rec_floats, (uint32_t)(aec::Geo::kFixedFloats * sizeof(float)));
+        }
+        W.pf_next = (pf_mode == 5 && s + total_warps < n_streams) ? rec + (size_t)(s + total_warps) * rec_floats : nullptr;
+        W.pf_bytes = (uint32_t)(aec::Geo::kFixedFloats * sizeof(float));
         aec::tick(W, rec + (size_t)s * rec_floats, depth, mult, n, far ? far + (size_t)s * n : nullptr,
                   near ? near + (size_t)s * n : nullptr, out ? out + (size_t)s * n : nullptr, delay_ms, tile, *T);
         __syncwarp();
@@ -410,7 +419,7 @@ struct wmixb_engine {
     void* aec_tables = nullptr;
     int* aec_result = nullptr;              // [2] flags OR, flagged count
     int16_t* aec_stage = nullptr;           // far / near / out staging of the host-buffer entry point
-    int aec_depth = 0, aec_grid = 0;
+    int aec_depth = 0, aec_grid = 0, aec_pf = 2;
     size_t aec_rec_floats = 0;
 };
 
@@ -577,6 +586,8 @@ static int create_impl(const wmixb_config* cfg, wmixb_engine* e)
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aec_kernel, kAecWarps * 32, kAecSmemBytes));
         if (per_sm < 1) per_sm = 1;
         e->aec_grid = e->sm_count * per_sm;
+        if (const char* v = getenv("WMIXB_AEC_PF")) e->aec_pf = atoi(v);
+        if (const char* v = getenv("WMIXB_AEC_GRID")) { const int g = atoi(v); if (g > 0 && g < e->aec_grid) e->aec_grid = g; }
     }
     if (cfg->stages & WMIXB_AGC) {
         int32_t init[agc::N_WORDS];
@@ -642,7 +653,7 @@ static int launch_aec(wmixb_engine* e, const int16_t* d_far, const int16_t* d_ne
     const int need = (n + kAecWarps - 1) / kAecWarps;
     const int grid = need < e->aec_grid ? need : e->aec_grid;
     aec_kernel<<<grid, kAecWarps * 32, kAecSmemBytes, st>>>(e->aec_rec, e->aec_rec_floats, (const aec::Tables*)e->aec_tables, d_far,
-                                                             d_near, d_out, n, samples, e->cfg.freq / 8000, e->aec_depth, delay_ms);
+                                                             d_near, d_out, n, samples, e->cfg.freq / 8000, e->aec_depth, delay_ms, e->aec_pf);
     CK_LAUNCH();
     return WMIXB_OK;
 }
