@@ -41,7 +41,8 @@ typedef struct wmixb_config {
     int device;         /* CUDA device ordinal                                                   */
     int aec_far_depth;  /* far-end history kept per stream, in 64-sample partitions; 0 = 32.  The
                            reference keeps 250 (T:.../aec/aec_core.c:37); the handle API uses 252.   */
-    int reserved[8];
+    int ns_high_band;   /* 1: allocate the high-band history wmixb_ns2_* needs (wmix's stereo NS, see below)      */
+    int reserved[7];
 } wmixb_config;
 
 typedef struct wmixb_engine wmixb_engine;
@@ -74,6 +75,14 @@ int wmixb_tick_host_bus(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, ui
  * Shares the per-stream VAD state with the 10 ms stage — use one packet size per engine. */
 int wmixb_vad20_device(wmixb_engine* e, int16_t* d_pcm, uint8_t* d_vad, void* stream);
 int wmixb_vad20_host(wmixb_engine* e, int16_t* h_pcm, uint8_t* h_vad);
+
+/* wmix's stereo noise suppression: ns_process hands WebRtcNs the RIGHT channel as a second band (num_bands = chn,
+ * R:src/webrtc.c:624-636), which ProcessCore delays by its analysis overlap and scales with one time-domain gain per
+ * frame taken from the left channel's speech probability and filter (T:.../ns/ns_core.c:1214-1261, :1361-1414).
+ * d_in / d_out = left (the normal NS path), d_in_hb / d_out_hb = right; all int16 [n_streams][frame], in and out may
+ * alias pairwise.  Needs WMIXB_NS and ns_high_band = 1 at creation. */
+int wmixb_ns2_device(wmixb_engine* e, const int16_t* d_in, const int16_t* d_in_hb, int16_t* d_out, int16_t* d_out_hb, void* stream);
+int wmixb_ns2_host(wmixb_engine* e, const int16_t* h_in, const int16_t* h_in_hb, int16_t* h_out, int16_t* h_out_hb);
 
 /* VAD on 32 kHz packets of 10 ms (320 samples), in place: the handle API's 32 kHz case (R:src/webrtc.c:43, :66-67;
  * CalcVad32khz, T:.../vad/vad_core.c:623-643: 32k -> 16k -> 8k, then the 8 kHz detector with the 10 ms thresholds).

@@ -23,6 +23,7 @@ struct orc_ns_core {
     int fs, block, ana, bins;
     float window[ANA_MAX];
     float inbuf[ANA_MAX];      /* analyzeBuf and dataBuf: always fed the same frames */
+    float inbuf_hb[ANA_MAX];   /* dataBufHB[0]: wmix's right channel when chn == 2 (R:src/webrtc.c:633) */
     float synth[ANA_MAX];
     float density[3 * BINS_MAX], lquant[3 * BINS_MAX], quant[BINS_MAX];
     int counter[3], updates;
@@ -518,13 +519,18 @@ static void orc_ns_analyze(orc_ns_core *s, const float *frame)
 }
 
 /* T:.../ns/ns_core.c:1183-1415 (single band) */
-static void orc_ns_synthesize(orc_ns_core *s, float *out)
+/* out_hb != NULL: ProcessCore with num_bands = 2 (ns_core.c:1214-1234, :1252-1261, :1361-1414).  The "high band" only
+ * gets a time-domain gain derived from the low band's speech probability and filter over the upper quarter of the
+ * spectrum; its samples come out of dataBufHB, i.e. delayed by ana - block. */
+static void orc_ns_synthesize(orc_ns_core *s, float *out, const float *in_hb, float *out_hb)
 {
     int i, nb = s->bins;
     float t[ANA_MAX], re[ANA_MAX], im[BINS_MAX], mag[BINS_MAX], h[BINS_MAX], h0[BINS_MAX];
     float fout[160];
     float e1, e2, gain, factor, f1, f2;
 
+    if (out_hb)
+        orc_slide_in(s->inbuf_hb, s->ana, s->block, in_hb);
     for (i = 0; i < s->ana; ++i)
         t[i] = s->window[i] * s->inbuf[i];
     e1 = orc_energy_f(t, s->ana);
@@ -534,6 +540,9 @@ static void orc_ns_synthesize(orc_ns_core *s, float *out)
         orc_slide_in(s->synth, s->ana, s->block, NULL);
         for (i = 0; i < s->block; ++i)
             out[i] = fout[i] > 32767 ? 32767 : (fout[i] < -32768 ? -32768 : fout[i]);
+        if (out_hb)
+            for (i = 0; i < s->block; ++i)
+                out_hb[i] = s->inbuf_hb[i] > 32767 ? 32767 : (s->inbuf_hb[i] < -32768 ? -32768 : s->inbuf_hb[i]);
         return;
     }
     orc_ns_spectrum(s, t, re, im, mag);
@@ -610,6 +619,34 @@ static void orc_ns_synthesize(orc_ns_core *s, float *out)
     orc_slide_in(s->synth, s->ana, s->block, NULL);
     for (i = 0; i < s->block; ++i)
         out[i] = fout[i] > 32767 ? 32767 : (fout[i] < -32768 ? -32768 : fout[i]);
+    if (out_hb) {
+        const int delta = nb / 4;
+        float p_hb = 0.f, g_hb = 0.f, sa = 0.f, sp = 0.f, mod, g;
+        for (i = nb - delta - 1; i < nb - 1; ++i)
+            p_hb += s->speech_prob[i];
+        p_hb = p_hb / ((float)delta);
+        for (i = 0; i < nb; ++i) {
+            sa += s->magn_prev_an[i];
+            sp += s->magn_prev_pr[i];
+        }
+        p_hb *= sp / sa;
+        for (i = nb - delta - 1; i < nb - 1; ++i)
+            g_hb += s->smooth[i];
+        g_hb = g_hb / ((float)delta);
+        mod = 0.5f * (1.f + (float)tanh(1.0f * (2.f * p_hb - 1.f)));
+        g = 0.5f * mod + 0.5f * g_hb;
+        if (p_hb >= 0.5f)
+            g = 0.25f * mod + 0.75f * g_hb;
+        g = g * 1.0f;
+        if (g < s->floor_gain)
+            g = s->floor_gain;
+        if (g > 1.f)
+            g = 1.f;
+        for (i = 0; i < s->block; ++i) {
+            float v = g * s->inbuf_hb[i];
+            out_hb[i] = v > 32767 ? 32767 : (v < -32768 ? -32768 : v);
+        }
+    }
 }
 
 /* ---- wmix handle layer: R:src/webrtc.c:560-660 ---- */
@@ -619,8 +656,8 @@ orc_ns *orc_ns_init(int chn, int freq)
     orc_ns *h;
     if (freq > 32000 || freq % 8000 != 0)
         return NULL;
-    if (chn != 1)
-        return NULL; /* oracle restates the mono path only */
+    if (chn != 1 && chn != 2)
+        return NULL;
     h = (orc_ns *)calloc(1, sizeof(*h));
     h->core = (orc_ns_core *)malloc(sizeof(orc_ns_core));
     if (orc_ns_core_init(h->core, freq, 2) != 0) {
@@ -636,20 +673,28 @@ orc_ns *orc_ns_init(int chn, int freq)
 
 void orc_ns_process(orc_ns *h, const int16_t *in, int16_t *out, int frame_num)
 {
-    float fin[160], fo[160];
+    float fin[160], fo[160], fin_hb[160], fo_hb[160];
     int pos, i;
+    const int chn = h->chn;
     orc_ns_core *s = h->core;
     /* At 32 kHz the packet is 320 samples but the core still works on 160-sample blocks and wmix passes ONE band
      * (R:src/webrtc.c:633), so only the first 160 samples of a packet are analysed and written; the rest of the
-     * reference's calloc'ed out[0] is never touched and reads back as zero. */
+     * reference's calloc'ed out[0] is never touched and reads back as zero.  With two channels the interleaved
+     * right channel is handed over as a SECOND BAND (num_bands = chn, R:src/webrtc.c:624-636). */
     for (pos = 0; pos + h->pkg <= frame_num; pos += h->pkg) {
-        for (i = 0; i < s->block; ++i)
-            fin[i] = (float)in[pos + i];
+        for (i = 0; i < s->block; ++i) {
+            fin[i] = (float)in[(pos + i) * chn];
+            if (chn == 2)
+                fin_hb[i] = (float)in[(pos + i) * chn + 1];
+        }
         orc_slide_in(s->inbuf, s->ana, s->block, fin);
         orc_ns_analyze(s, fin);
-        orc_ns_synthesize(s, fo);
-        for (i = 0; i < h->pkg; ++i)
-            out[pos + i] = i < s->block ? (int16_t)fo[i] : 0;
+        orc_ns_synthesize(s, fo, chn == 2 ? fin_hb : NULL, chn == 2 ? fo_hb : NULL);
+        for (i = 0; i < h->pkg; ++i) {
+            out[(pos + i) * chn] = i < s->block ? (int16_t)fo[i] : 0;
+            if (chn == 2)
+                out[(pos + i) * chn + 1] = i < s->block ? (int16_t)fo_hb[i] : 0;
+        }
     }
 }
 

@@ -34,7 +34,7 @@ static void fill_tables(ns::Tables<ANA>& T, int policy)
 
 struct EmuNs {
     int ana;
-    std::vector<float> rec, sh;
+    std::vector<float> rec, sh, hb;
     std::vector<uint16_t> hist;
     ns::Tables<256> t256;
     ns::Tables<128> t128;
@@ -52,12 +52,14 @@ void* emu_ns_create(int freq)
     if (e->ana == 256) {
         fill_tables(e->t256, 2);
         e->rec.assign(ns::Geo<256>::kRecFloats, 0.f);
-        e->sh.assign(ns::Geo<256>::kShFloats, 0.f);
+        e->sh.assign(ns::Geo<256>::kShFloats + ns::Geo<256>::kBlock, 0.f);
+        e->hb.assign(ns::Geo<256>::kOverlap, 0.f);
         for (int l = 0; l < 32; ++l) ns::init_record_values<256>(e->rec.data(), l, 32);
     } else {
         fill_tables(e->t128, 2);
         e->rec.assign(ns::Geo<128>::kRecFloats, 0.f);
-        e->sh.assign(ns::Geo<128>::kShFloats, 0.f);
+        e->sh.assign(ns::Geo<128>::kShFloats + ns::Geo<128>::kBlock, 0.f);
+        e->hb.assign(ns::Geo<128>::kOverlap, 0.f);
         for (int l = 0; l < 32; ++l) ns::init_record_values<128>(e->rec.data(), l, 32);
     }
     return e;
@@ -67,6 +69,13 @@ void emu_ns_frame(void* h, const int16_t* in, int16_t* out)
     EmuNs* e = (EmuNs*)h;
     if (e->ana == 256) ns::frame<256>(e->w256, e->rec.data(), e->hist.data(), in, out, e->sh.data(), e->t256);
     else ns::frame<128>(e->w128, e->rec.data(), e->hist.data(), in, out, e->sh.data(), e->t128);
+}
+// wmix's stereo NS: the right channel as a second band (ns.cuh, frame<ANA, true>)
+void emu_ns_frame_hb(void* h, const int16_t* in, int16_t* out, const int16_t* in_hb, int16_t* out_hb)
+{
+    EmuNs* e = (EmuNs*)h;
+    if (e->ana == 256) ns::frame<256, true>(e->w256, e->rec.data(), e->hist.data(), in, out, e->sh.data(), e->t256, e->hb.data(), in_hb, out_hb);
+    else ns::frame<128, true>(e->w128, e->rec.data(), e->hist.data(), in, out, e->sh.data(), e->t128, e->hb.data(), in_hb, out_hb);
 }
 void emu_ns_destroy(void* h) { delete (EmuNs*)h; }
 const float* emu_ns_record(void* h) { return ((EmuNs*)h)->rec.data(); }

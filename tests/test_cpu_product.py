@@ -150,6 +150,33 @@ def test_emulated_vad_20ms_packets_vs_reference(freq):
         E.emu_int_destroy(e)
 
 
+@pytest.mark.parametrize("freq", [16000, 8000])
+def test_emulated_ns_stereo_high_band_vs_oracle(freq):
+    """ns_init(2, ..): the right channel rides through WebRtcNs as a second band (R:src/webrtc.c:624-636;
+    T:.../ns/ns_core.c:1214-1261, :1361-1414).  Kernel body frame<ANA, true> (lane-loop emulation) against the
+    oracle, which tests/test_oracle_pin.py pins to the reference for this case; pair (1, 2) has an all-zero left
+    channel (the energy == 0 early-out also flushes the high band)."""
+    import ctypes as C
+
+    E, L = emu(), oracle()
+    n = freq // 100
+    T = 300
+    x = make_frames(4, freq, 0, T, seed=31)
+    for a, b in ((0, 3), (1, 2), (2, 2)):
+        h = C.c_void_p(L.orc_ns_init(2, freq))
+        e = C.c_void_p(E.emu_ns_create(freq))
+        for t in range(T):
+            st = np.empty(2 * n, np.int16)
+            st[0::2], st[1::2] = x[t, a], x[t, b]
+            want = np.zeros(2 * n, np.int16)
+            L.orc_ns_process(h, P(st), P(want), n)
+            lo, hi = x[t, a].copy(), x[t, b].copy()
+            E.emu_ns_frame_hb(e, P(lo), P(lo), P(hi), P(hi))          # in place, as wmix calls it
+            assert np.array_equal(lo, want[0::2]) and np.array_equal(hi, want[1::2]), (freq, a, b, t)
+        L.orc_ns_release(h)
+        E.emu_ns_destroy(e)
+
+
 def test_vad_32khz_packets_match_oracle():
     """vad_init(chn, 32000, ..): 320-sample packets through CalcVad32khz (T:.../vad/vad_core.c:623-643) — the kernel body of
     wmixb_vad32_device against the oracle (pinned to the reference at 32 kHz in tests/test_oracle_pin.py)"""

@@ -432,6 +432,58 @@ def test_dropin_handle_api():
     assert not lib.agc_init(1, 12000, 10, 5, None) and not lib.aec_init(1, 32000, 10, None)
 
 
+@pytest.mark.parametrize("freq", [8000, 16000, 32000])
+def test_ns_stereo_handle_and_batched(freq):
+    """ns_init(2, ..): wmix passes the right channel to WebRtcNs as a second band (R:src/webrtc.c:624-636).  Drop-in
+    handle (interleaved stereo, in place) against the oracle and the compiled reference; wmixb_ns2_device for a batch."""
+    lib = wmix_b200.lib()
+    n = freq // 100
+    core = min(freq, 16000)
+    T = 260
+    x = make_frames(6, core, 0, T * (2 if freq == 32000 else 1), seed=97)
+    pcm = np.ascontiguousarray(x.transpose(1, 0, 2)).reshape(6, -1)
+    pairs = ((0, 3), (1, 2), (2, 2), (4, 5))
+    for cname, L, prefix in checkers():
+        for a, b in pairs:
+            st = np.empty(2 * pcm.shape[1], np.int16)
+            st[0::2], st[1::2] = pcm[a], pcm[b]
+            hc = C.c_void_p(L.orc_ns_init(2, freq) if prefix else L.ns_init(2, freq, None))
+            hg = lib.ns_init(2, freq, None)
+            assert hc and hg
+            for t in range(len(st) // (2 * n)):
+                f = st[t * 2 * n:(t + 1) * 2 * n]
+                want, got = np.zeros(2 * n, np.int16), f.copy()
+                (L.orc_ns_process if prefix else L.ns_process)(hc, P(f.copy()), P(want), n)
+                lib.ns_process(hg, got.ctypes.data, got.ctypes.data, n)
+                assert np.array_equal(got, want), (cname, freq, a, b, t)
+            (L.orc_ns_release if prefix else L.ns_release)(hc)
+            lib.ns_release(hg)
+    if freq == 32000:
+        return
+    # batched: S stereo streams per launch
+    S = 64
+    xs = make_frames(2 * S, freq, 0, 120, seed=99)
+    L = oracle()
+    eng = wmix_b200.Engine(S, freq, stages=NS, ns_high_band=1)
+    hs = [C.c_void_p(L.orc_ns_init(2, freq)) for _ in range(S)]
+    dl = torch.empty((S, n), dtype=torch.int16, device=DEV)
+    dr = torch.empty_like(dl)
+    st_ptr = torch.cuda.current_stream().cuda_stream
+    for t in range(120):
+        want = np.zeros((S, 2 * n), np.int16)
+        for s in range(S):
+            f = np.empty(2 * n, np.int16)
+            f[0::2], f[1::2] = xs[t, s], xs[t, S + s]
+            L.orc_ns_process(hs[s], P(f), P(want[s]), n)
+        dl.copy_(torch.from_numpy(np.ascontiguousarray(xs[t, :S])))
+        dr.copy_(torch.from_numpy(np.ascontiguousarray(xs[t, S:])))
+        assert lib.wmixb_ns2_device(eng.h, dl.data_ptr(), dr.data_ptr(), dl.data_ptr(), dr.data_ptr(), st_ptr) == 0
+        assert np.array_equal(dl.cpu().numpy(), want[:, 0::2]) and np.array_equal(dr.cpu().numpy(), want[:, 1::2]), t
+    for h in hs:
+        L.orc_ns_release(h)
+    eng.close()
+
+
 def test_dropin_handle_api_32khz():
     """the reference accepts 32 kHz handles (R:src/webrtc.c:43, :563, :711): NS analyses the first 160 samples of every
     320-sample packet and leaves zeros behind, AGC runs 5 ms packets through its 16 kHz path, VAD decimates 32k -> 16k

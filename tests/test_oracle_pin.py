@@ -338,6 +338,32 @@ def test_stage_vs_reference(freq, stage):
 
 
 @need_ref
+@pytest.mark.parametrize("freq", [8000, 16000, 32000])
+def test_ns_stereo_right_channel_as_high_band_vs_reference(freq):
+    """ns_init(2, ..): wmix hands the right channel to WebRtcNs as a second band (R:src/webrtc.c:624-636), which only
+    gets the time-domain high-band gain (T:.../ns/ns_core.c:1361-1414) and the analysis-buffer delay"""
+    R, L = ref(), oracle()
+    n = freq // 100
+    T = 320
+    x = _streams(min(freq, 16000), 4, T * (2 if freq == 32000 else 1), seed=19)
+    pcm = np.ascontiguousarray(x.transpose(1, 0, 2)).reshape(4, -1)       # 4 mono streams
+    for a, b in ((0, 1), (2, 3), (3, 3)):
+        st = np.empty(2 * pcm.shape[1], np.int16)
+        st[0::2], st[1::2] = pcm[a], pcm[b]
+        hr = C.c_void_p(R.ns_init(2, freq, None))
+        ho = C.c_void_p(L.orc_ns_init(2, freq))
+        assert hr and ho
+        for t in range(len(st) // (2 * n)):
+            f = st[t * 2 * n:(t + 1) * 2 * n]
+            ya, yb = np.zeros(2 * n, np.int16), np.zeros(2 * n, np.int16)
+            R.ns_process(hr, P(f.copy()), P(ya), n)
+            L.orc_ns_process(ho, P(f.copy()), P(yb), n)
+            assert np.array_equal(ya, yb), (freq, a, b, t)
+        R.ns_release(hr)
+        L.orc_ns_release(ho)
+
+
+@need_ref
 def test_config1_wav_vs_reference():
     """BASELINE config 1: NS on audio/1x8000.wav through src/webrtc.c, then AGC(5) and VAD(10 ms) in place."""
     wav = "/root/reference/audio/1x8000.wav"

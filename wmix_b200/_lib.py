@@ -14,7 +14,7 @@ NS, AGC, VAD, AEC = 1, 2, 4, 8
 class Config(C.Structure):
     _fields_ = [("n_streams", C.c_int), ("freq", C.c_int), ("stages", C.c_int), ("ns_policy", C.c_int),
                 ("agc_gain_db", C.c_int), ("vad_mode", C.c_int), ("device", C.c_int), ("aec_far_depth", C.c_int),
-                ("reserved", C.c_int * 8)]
+                ("ns_high_band", C.c_int), ("reserved", C.c_int * 7)]
 
 
 _lib = None
@@ -40,6 +40,8 @@ def lib():
         "wmixb_tick_host_bus": (i, [vp, vp, vp, vp, vp, i]),
         "wmixb_vad20_device": (i, [vp, vp, vp, vp]),
         "wmixb_vad20_host": (i, [vp, vp, vp]),
+        "wmixb_ns2_device": (i, [vp, vp, vp, vp, vp, vp]),
+        "wmixb_ns2_host": (i, [vp, vp, vp, vp, vp]),
         "wmixb_vad32_device": (i, [vp, vp, vp, vp]),
         "wmixb_vad32_host": (i, [vp, vp, vp]),
         "wmixb_offline_device": (i, [vp, vp, vp, vp, i, i, vp]),

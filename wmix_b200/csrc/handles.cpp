@@ -23,14 +23,14 @@ struct Handle {
     wmixb_engine* eng = nullptr;
     int chn = 1, freq = 0, pkg = 0, stage = 0;
     bool* debug = nullptr;
-    std::vector<int16_t> mono, res, far;
+    std::vector<int16_t> mono, res, far, hb, hb_res;   // hb: right channel of a stereo NS handle
 };
 
 bool dbg(const bool* d) { return d && *d; }
 
 // 32 kHz handles run on a 16 kHz engine: at that rate the reference's AGC and NS see 160-sample packets and take
 // exactly their 16 kHz paths, and the VAD only adds a 32k -> 16k decimator in front (wmixb_vad32_*).
-Handle* make(int stage, int chn, int freq, int gain, bool* debug, const char* who)
+Handle* make(int stage, int chn, int freq, int gain, bool* debug, const char* who, bool ns_high_band = false)
 {
     wmixb_config c;
     memset(&c, 0, sizeof c);
@@ -40,6 +40,7 @@ Handle* make(int stage, int chn, int freq, int gain, bool* debug, const char* wh
     c.ns_policy = 2;      // NS_AGGRESSIVE, R:src/webrtc.c:532
     c.agc_gain_db = gain; // compressionGaindB, R:src/webrtc.c:707
     c.vad_mode = 3;       // VAD_AGGRESSIVE, R:src/webrtc.c:16
+    c.ns_high_band = ns_high_band ? 1 : 0;
     wmixb_engine* e = nullptr;
     if (wmixb_create(&c, &e) != WMIXB_OK) {
         if (dbg(debug)) printf("%s failed !! (%s)\r\n", who, wmixb_last_error());
@@ -132,21 +133,21 @@ void vad_release(void* fp) { drop(fp, "vad_release"); }
 void* ns_init(int chn, int freq, bool* debug)
 {
     if (!rate_ok(freq, 32000)) return nullptr;                      // R:src/webrtc.c:563
-    if (chn != 1) {
-        // stereo is fed to WebRtcNs as low band + "high band" (R:src/webrtc.c:624-636): not on the GPU yet
-        if (dbg(debug)) printf("ns_init: only mono on the GPU path so far\r\n");
-        return nullptr;
-    }
-    Handle* h = make(WMIXB_NS, chn, freq, 0, debug, "ns_init");
-    if (h && freq == 32000) {
+    if (chn != 1 && chn != 2) return nullptr;                        // the reference only has in[2] / out[2]
+    // two channels: the right one is WebRtcNs's "high band" (num_bands = chn, R:src/webrtc.c:624-636) -> wmixb_ns2_host
+    Handle* h = make(WMIXB_NS, chn, freq, 0, debug, "ns_init", chn == 2);
+    if (!h) return nullptr;
+    if (freq == 32000) {
         // WebRtcNs at 32 kHz still works on 160-sample blocks with the 16 kHz window (T:.../ns/ns_core.c:89-98) and
-        // wmix hands it ONE band (R:src/webrtc.c:633: num_bands = chn), so of each 320-sample packet only the first 160
-        // samples are analysed and written; the rest of the reference's calloc'ed out buffer stays zero.
+        // wmix hands it the channels as bands, so of each 320-sample packet only the first 160 samples are analysed
+        // and written; the rest of the reference's calloc'ed out buffers stays zero.
         h->pkg = 320;
-        h->mono.resize(320);
-        h->res.assign(320, 0);
     }
-    if (h && dbg(debug)) printf("ns_init: chn/%d freq/%d intervalMs/%d pkgFrame/%d x %d\r\n", chn, freq, 10, h->pkg, chn);
+    h->mono.assign((size_t)h->pkg, 0);
+    h->res.assign((size_t)h->pkg, 0);
+    h->hb.assign((size_t)h->pkg, 0);
+    h->hb_res.assign((size_t)h->pkg, 0);
+    if (dbg(debug)) printf("ns_init: chn/%d freq/%d intervalMs/%d pkgFrame/%d x %d\r\n", chn, freq, 10, h->pkg, chn);
     return h;
 }
 
@@ -154,13 +155,21 @@ void ns_process(void* fp, int16_t* frame, int16_t* frameOut, int frameNum)
 {
     Handle* h = (Handle*)fp;
     for (int pos = 0; pos < frameNum; pos += h->pkg) {              // R:src/webrtc.c:624-643
-        memcpy(h->mono.data(), frame + pos, (size_t)h->pkg * 2);
+        int rc;
         // (a 32 kHz packet: the engine's frame is the first 160 samples, res[160..319] stays zero)
-        if (wmixb_tick_host(h->eng, h->mono.data(), h->res.data(), nullptr, WMIXB_NS) != WMIXB_OK) {
+        if (h->chn == 1) {
+            memcpy(h->mono.data(), frame + pos, (size_t)h->pkg * 2);
+            rc = wmixb_tick_host(h->eng, h->mono.data(), h->res.data(), nullptr, WMIXB_NS);
+        } else {
+            for (int i = 0; i < h->pkg; ++i) { h->mono[(size_t)i] = frame[2 * (pos + i)]; h->hb[(size_t)i] = frame[2 * (pos + i) + 1]; }
+            rc = wmixb_ns2_host(h->eng, h->mono.data(), h->hb.data(), h->res.data(), h->hb_res.data());
+        }
+        if (rc != WMIXB_OK) {
             if (dbg(h->debug)) printf("ns_process failed !!, %s \r\n", wmixb_last_error());
             return;
         }
-        memcpy(frameOut + pos, h->res.data(), (size_t)h->pkg * 2);
+        if (h->chn == 1) memcpy(frameOut + pos, h->res.data(), (size_t)h->pkg * 2);
+        else for (int i = 0; i < h->pkg; ++i) { frameOut[2 * (pos + i)] = h->res[(size_t)i]; frameOut[2 * (pos + i) + 1] = h->hb_res[(size_t)i]; }
     }
 }
 

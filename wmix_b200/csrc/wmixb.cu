@@ -114,6 +114,41 @@ ns_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Tables
     }
 }
 
+// wmix's stereo case (ns_init(2, ..)): the right channel rides through WebRtcNs as a "high band" (ns.cuh, frame<ANA, true>).
+// Same warp-per-stream shape as ns_kernel, one frame per launch; kept apart so the mono kernel's code and registers
+// are untouched.  The drop-in handle's path, not a throughput path.
+template <int ANA>
+__global__ void __launch_bounds__(256, 2)
+ns_hb_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, float* __restrict__ hb_hist, const ns::Tables<ANA>* __restrict__ tables,
+             const int16_t* in, int16_t* out, const int16_t* in_hb, int16_t* out_hb, int n_streams)
+{
+    typedef ns::Geo<ANA> G;
+    constexpr int kTile = G::kShFloats + G::kBlock;
+    extern __shared__ __align__(16) float smem[];
+    ns::Tables<ANA>* T = reinterpret_cast<ns::Tables<ANA>*>(smem);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+        for (int i = threadIdx.x; i < (int)(sizeof(ns::Tables<ANA>) / 4); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    float* tile = smem + NsSmem<ANA>::kTableFloats + (size_t)warp * kTile;
+    ns::Warp<ANA> W;
+    W.lane_id = threadIdx.x & 31;
+    for (int i = W.lane_id; i < kTile; i += 32) tile[i] = 0.f;
+    __syncwarp();
+    const int total_warps = gridDim.x * 8;
+    for (int s = blockIdx.x * 8 + warp; s < n_streams; s += total_warps) {
+        ns::frame<ANA, true>(W, rec + (size_t)s * G::kRecFloats, hist + (size_t)s * 3 * ns::kHistBins, in + (size_t)s * G::kBlock,
+                             out + (size_t)s * G::kBlock, tile, *T, hb_hist + (size_t)s * G::kOverlap, in_hb + (size_t)s * G::kBlock,
+                             out_hb + (size_t)s * G::kBlock);
+        __syncwarp();
+    }
+}
+template <int ANA>
+constexpr size_t ns_hb_smem_bytes() { return (NsSmem<ANA>::kTableFloats + (size_t)8 * (ns::Geo<ANA>::kShFloats + ns::Geo<ANA>::kBlock)) * sizeof(float); }
+
 template <int ANA>
 __global__ void ns_init_kernel(float* rec, uint16_t* hist, int first, int count)
 {
@@ -392,6 +427,8 @@ struct wmixb_engine {
     int frame = 0, ana = 0, sm_count = 0;
     size_t stride = 0;                      // SoA row pitch (streams rounded up to 32)
     float* ns_rec = nullptr;
+    float* ns_hb = nullptr;                 // [n][OVERLAP] high-band history (cfg.ns_high_band: wmix's stereo NS)
+    int16_t* ns_stage = nullptr;            // 4 x [n][frame] staging of wmixb_ns2_host
     uint16_t* ns_hist = nullptr;
     void* ns_tables = nullptr;
     int32_t* agc_words = nullptr;
@@ -508,6 +545,10 @@ extern "C" int wmixb_reset(wmixb_engine* e, int first, int count)
         if (e->ana == 256) ns_init_kernel<256><<<blocks, 256, 0, e->stream>>>(e->ns_rec, e->ns_hist, first, count);
         else ns_init_kernel<128><<<blocks, 256, 0, e->stream>>>(e->ns_rec, e->ns_hist, first, count);
         CK_LAUNCH();
+        if (e->ns_hb) {
+            const size_t ov = e->ana == 256 ? ns::Geo<256>::kOverlap : ns::Geo<128>::kOverlap;
+            CK(cudaMemsetAsync(e->ns_hb + (size_t)first * ov, 0, (size_t)count * ov * sizeof(float), e->stream));
+        }
     }
     if (e->aec_rec) {
         aec_init_kernel<<<(count * 32 + 255) / 256, 256, 0, e->stream>>>(e->aec_rec, e->aec_rec_floats, e->aec_depth, first, count);
@@ -530,7 +571,7 @@ extern "C" void wmixb_destroy(wmixb_engine* e)
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->ns_rec); cudaFree(e->ns_hist); cudaFree(e->ns_tables);
+    cudaFree(e->ns_rec); cudaFree(e->ns_hist); cudaFree(e->ns_tables); cudaFree(e->ns_hb); cudaFree(e->ns_stage);
     cudaFree(e->agc_words); cudaFree(e->vad_words); cudaFree(e->agc_table);
     cudaFree(e->agc_init); cudaFree(e->vad_init);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_vad); cudaFree(e->d_pkt20);
@@ -566,6 +607,12 @@ static int create_impl(const wmixb_config* cfg, wmixb_engine* e)
         CK(cudaMalloc(&e->ns_hist, n * 3 * ns::kHistBins * sizeof(uint16_t)));
         int rc = e->ana == 256 ? upload_ns_tables<256>(e) : upload_ns_tables<128>(e);
         if (rc) return rc;
+        if (cfg->ns_high_band) {
+            const size_t ov = e->ana == 256 ? ns::Geo<256>::kOverlap : ns::Geo<128>::kOverlap;
+            CK(cudaMalloc(&e->ns_hb, n * ov * sizeof(float)));
+            if (e->ana == 256) CK(cudaFuncSetAttribute(ns_hb_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns_hb_smem_bytes<256>()));
+            else CK(cudaFuncSetAttribute(ns_hb_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns_hb_smem_bytes<128>()));
+        }
     }
     if (cfg->stages & WMIXB_AEC) {
         e->aec_depth = cfg->aec_far_depth > 0 ? cfg->aec_far_depth : 32;
@@ -728,6 +775,40 @@ extern "C" int wmixb_vad20_host(wmixb_engine* e, int16_t* h_pcm, uint8_t* h_vad)
     if (rc) return rc;
     CK(cudaMemcpyAsync(h_pcm, e->d_pkt20, bytes, cudaMemcpyDeviceToHost, e->stream));
     if (h_vad) CK(cudaMemcpyAsync(h_vad, e->d_vad, (size_t)e->cfg.n_streams, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_ns2_device(wmixb_engine* e, const int16_t* d_in, const int16_t* d_in_hb, int16_t* d_out, int16_t* d_out_hb, void* stream)
+{
+    if (!e || !d_in || !d_in_hb || !d_out || !d_out_hb) return WMIXB_EINVAL;
+    if (!e->ns_hb) { snprintf(g_err, sizeof g_err, "ns2: the engine was created without WMIXB_NS + ns_high_band"); return WMIXB_EINVAL; }
+    CK(cudaSetDevice(e->cfg.device));
+    const int n = e->cfg.n_streams;
+    const int need = (n + 7) / 8, cap = e->sm_count * 2, grid = need < cap ? need : cap;
+    if (e->ana == 256)
+        ns_hb_kernel<256><<<grid, 256, ns_hb_smem_bytes<256>(), (cudaStream_t)stream>>>(e->ns_rec, e->ns_hist, e->ns_hb, (const ns::Tables<256>*)e->ns_tables,
+                                                                                      d_in, d_out, d_in_hb, d_out_hb, n);
+    else
+        ns_hb_kernel<128><<<grid, 256, ns_hb_smem_bytes<128>(), (cudaStream_t)stream>>>(e->ns_rec, e->ns_hist, e->ns_hb, (const ns::Tables<128>*)e->ns_tables,
+                                                                                      d_in, d_out, d_in_hb, d_out_hb, n);
+    CK_LAUNCH();
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_ns2_host(wmixb_engine* e, const int16_t* h_in, const int16_t* h_in_hb, int16_t* h_out, int16_t* h_out_hb)
+{
+    if (!e || !h_in || !h_in_hb || !h_out || !h_out_hb) return WMIXB_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t cnt = (size_t)e->cfg.n_streams * e->frame, bytes = cnt * sizeof(int16_t);
+    if (!e->ns_stage) CK(cudaMalloc(&e->ns_stage, 4 * bytes));
+    int16_t *a = e->ns_stage, *b = a + cnt, *c = b + cnt, *d = c + cnt;
+    CK(cudaMemcpyAsync(a, h_in, bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(b, h_in_hb, bytes, cudaMemcpyHostToDevice, e->stream));
+    const int rc = wmixb_ns2_device(e, a, b, c, d, e->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_out, c, bytes, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaMemcpyAsync(h_out_hb, d, bytes, cudaMemcpyDeviceToHost, e->stream));
     CK(cudaStreamSynchronize(e->stream));
     return WMIXB_OK;
 }
@@ -1293,6 +1374,7 @@ extern "C" size_t wmixb_stream_state_bytes(const wmixb_engine* e)
     if (!e) return 0;
     size_t b = 0;
     if (e->ns_rec) b += (size_t)ns_rec_floats(e) * 4 + 3 * ns::kHistBins * 2;
+    if (e->ns_hb) b += (size_t)(e->ana - e->frame) * 4;
     if (e->agc_words) b += agc::N_WORDS * 4;
     if (e->vad_words) b += vad::N_WORDS * 4;
     if (e->aec_rec) b += e->aec_rec_floats * 4;
@@ -1320,6 +1402,7 @@ static int state_xfer(wmixb_engine* e, int s, void* buf, bool get)
     if (e->ns_rec) {
         CK(xfer(e->ns_rec + (size_t)s * ns_rec_floats(e), (size_t)ns_rec_floats(e) * 4));
         CK(xfer(e->ns_hist + (size_t)s * 3 * ns::kHistBins, 3 * ns::kHistBins * 2));
+        if (e->ns_hb) CK(xfer(e->ns_hb + (size_t)s * (e->ana - e->frame), (size_t)(e->ana - e->frame) * 4));
     }
     if (e->agc_words) CK(xfer2d(e->agc_words, agc::N_WORDS));
     if (e->vad_words) CK(xfer2d(e->vad_words, vad::N_WORDS));
