@@ -109,6 +109,22 @@ int wmixb_tick_chain_device(wmixb_engine* e, const int16_t* d_far, const int16_t
  * *h_flagged (nullable) receives the number of streams with any flag.  Synchronises the engine stream. */
 int wmixb_aec_status(wmixb_engine* e, int* h_flags, int* h_flagged);
 
+/* The daemon's record tick at ITS cadence, for every stream (R:src/wmix.c:528-760; WMIX_INTERVAL_MS = 20): per 20 ms
+ * package  playPkgBuff_add(play)  (R:src/wmix.c:1419)  then  ns_process -> aec_process2(playPkgBuff_get(AEC_INTERVALMS),
+ * mic, mic, ..., 0) -> agc_process -> vad_process  with the handle geometries wmix itself creates: NS and AGC on two
+ * 10 ms packets, the AEC on one 160-sample packet at 8 kHz / two at 16 kHz (aec_init(.., 20, ..)), the VAD on ONE
+ * 20 ms packet (vad_init(.., 20, ..)).  The play FIFO (AEC_INTERVALMS / 20 + 2 packages, R:src/wmixConf.h:141) lives on
+ * the device, slot-major, and the reference's slot arithmetic is reproduced as written (R:src/wmix.c:496-509) — it
+ * reads the oldest package, not the one AEC_INTERVALMS back, on most ticks.  aec_interval_ms must be a whole number of
+ * packages.  Buffers: int16 [n_streams][freq/50]; d_out may alias d_mic; d_vad and d_far_used (the far end the AEC
+ * was given, for inspection) are nullable.  One tick = 1 copy + 4..6 launches. */
+typedef struct wmixb_record wmixb_record;
+int wmixb_record_create(wmixb_engine* e, int aec_interval_ms, wmixb_record** out);
+void wmixb_record_destroy(wmixb_record* r);
+int wmixb_record_far_slot(const wmixb_record* r);   /* slot the NEXT get would read (tests) */
+int wmixb_record_tick_device(wmixb_record* r, const int16_t* d_play, const int16_t* d_mic, int16_t* d_out, uint8_t* d_vad,
+                             int16_t* d_far_used, int stages, void* stream);
+
 /* Persistent offline mode: every stream runs n_frames consecutive frames inside one launch per
  * stage.  d_in / d_out: int16 [n_streams][n_frames][frame].  d_vad (nullable): [n_streams][n_frames]. */
 int wmixb_offline_device(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int n_frames,

@@ -47,6 +47,18 @@ void orc_bus_nminus1(int16_t *out, const int32_t *bus, const int16_t *own, int f
 uint32_t orc_mix_resample(int16_t *ring, uint32_t ring_len, uint32_t pos, const int16_t *src, uint32_t src_bytes,
                           uint16_t freq, uint8_t channels, uint16_t mix_freq, uint8_t rdce, uint32_t *written);
 
+/* play-package FIFO feeding the AEC its far end (R:src/wmix.c:482-526), whole-package delays */
+#define ORC_FIFO_MAX_PKG 64
+#define ORC_FIFO_MAX_BYTES 1280
+typedef struct {
+    int n_pkg, pkg_bytes, count;
+    uint8_t buf[ORC_FIFO_MAX_PKG][ORC_FIFO_MAX_BYTES];
+} orc_play_fifo;
+void orc_play_fifo_init(orc_play_fifo *f, int n_pkg, int pkg_bytes);
+void orc_play_fifo_add(orc_play_fifo *f, const uint8_t *pkg);
+int orc_play_fifo_slot(int count, int n_pkg, int delay_pkgs);
+void orc_play_fifo_get(const orc_play_fifo *f, uint8_t *out, int delay_pkgs);
+
 /* nearest-sample rate / channel conversion (R:src/wmix.c:49-222) */
 uint32_t orc_len_of_out(uint8_t in_chn, uint16_t in_freq, uint32_t in_len, uint8_t out_chn, uint16_t out_freq);
 uint32_t orc_len_of_in(uint8_t in_chn, uint16_t in_freq, uint8_t out_chn, uint16_t out_freq, uint32_t out_len);

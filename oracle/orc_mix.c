@@ -240,3 +240,45 @@ uint32_t orc_mix_resample(int16_t *ring, uint32_t ring_len, uint32_t pos, const 
         *written = n_out;
     return pos;
 }
+
+/* ---- play-package FIFO that feeds the echo canceller its far end (R:src/wmix.c:482-526) ----
+ * playPkgBuff_add stores the package the play thread just wrote to the sound card (R:src/wmix.c:1419) in a ring of
+ * n_pkg = AEC_INTERVALMS / WMIX_INTERVAL_MS + 2 packages (R:src/wmixConf.h:141); playPkgBuff_get(AEC_INTERVALMS)
+ * then hands aec_process2 its far end (R:src/wmix.c:653).  Restated for delays that are whole packages (the only
+ * case wmix uses: 400 ms / 20 ms); with a remainder the reference copies from before the ring row (R:src/wmix.c:510-516).
+ * The index arithmetic is kept as written, including its effect: `count - clamp(count - d)` is d while count >= d
+ * and count itself otherwise, so the slot read is the OLDEST package (the one the next add overwrites) except on
+ * the ticks where count has just passed d. */
+void orc_play_fifo_init(orc_play_fifo *f, int n_pkg, int pkg_bytes)
+{
+    memset(f, 0, sizeof(*f));
+    f->n_pkg = n_pkg > ORC_FIFO_MAX_PKG ? ORC_FIFO_MAX_PKG : n_pkg;
+    f->pkg_bytes = pkg_bytes > ORC_FIFO_MAX_BYTES ? ORC_FIFO_MAX_BYTES : pkg_bytes;
+}
+
+void orc_play_fifo_add(orc_play_fifo *f, const uint8_t *pkg)
+{
+    memcpy(f->buf[f->count++], pkg, (size_t)f->pkg_bytes);
+    if (f->count >= f->n_pkg)
+        f->count = 0;
+}
+
+int orc_play_fifo_slot(int count, int n_pkg, int delay_pkgs)
+{
+    int k = count - delay_pkgs;
+    if (k >= n_pkg)
+        k = n_pkg;
+    else if (k < 0)
+        k = 0;
+    k = count - k;
+    if (k >= n_pkg)
+        k -= n_pkg;
+    else if (k < 0)
+        k += n_pkg;
+    return k;
+}
+
+void orc_play_fifo_get(const orc_play_fifo *f, uint8_t *out, int delay_pkgs)
+{
+    memcpy(out, f->buf[orc_play_fifo_slot(f->count, f->n_pkg, delay_pkgs)], (size_t)f->pkg_bytes);
+}

@@ -34,3 +34,7 @@ void oracle_ref_wmix_seat(WMix_Struct *w, uint8_t *ring, uint32_t ring_bytes, ui
 int oracle_ref_wmix_freq(void) { return WMIX_FREQ; }
 int oracle_ref_wmix_buff_size(void) { return WMIX_BUFF_SIZE; }
 int oracle_ref_wmix_play_correct(void) { return VIEW_PLAY_CORRECT; }
+int oracle_ref_wmix_pkg_size(void) { return WMIX_PKG_SIZE; }
+int oracle_ref_wmix_aec_fifo_pkgs(void) { return AEC_FIFO_PKG_NUM; }
+int oracle_ref_wmix_aec_interval_ms(void) { return AEC_INTERVALMS; }
+int oracle_ref_wmix_interval_ms(void) { return WMIX_INTERVAL_MS; }

@@ -204,6 +204,7 @@ long emu_div_by_counter_mismatches(int d_lo, int d_hi, int stride)
 }
 uint32_t emu_zoom_map(int ic, int ifr, uint32_t in_bytes, int oc, int ofr, int32_t* map) { return host::zoom_map(ic, ifr, in_bytes, oc, ofr, map); }
 uint32_t emu_mix_plan(int chn, int freq, uint32_t src_bytes, int mix_freq, int32_t* map, uint16_t* ramp) { return host::mix_plan(chn, freq, src_bytes, mix_freq, map, ramp); }
+int emu_play_fifo_slot(int count, int n_pkg, int delay_pkgs) { return host::play_fifo_slot(count, n_pkg, delay_pkgs); }
 uint32_t emu_len_of_out(int ic, int ifr, uint32_t n, int oc, int ofr) { return host::zoom_len_of_out(ic, ifr, n, oc, ofr); }
 uint32_t emu_len_of_in(int ic, int ifr, int oc, int ofr, uint32_t n) { return host::zoom_len_of_in(ic, ifr, oc, ofr, n); }
 void emu_logexp(const float* x, int n, float* lg, float* ex)

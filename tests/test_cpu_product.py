@@ -394,6 +394,16 @@ def test_mix_resample_host_plan_vs_oracle():
     assert E.emu_mix_plan(1, 200, 200, 16000, None, None) == 0xFFFFFFFF
 
 
+def test_play_fifo_slot_arithmetic_vs_oracle():
+    """playPkgBuff_get's slot choice (R:src/wmix.c:496-509) as the record tick computes it on the host, against the oracle
+    (itself pinned to the reference's playPkgBuff_add / _get) for every ring size, write index and delay"""
+    E, L = emu(), oracle()
+    for n_pkg in range(2, 40):
+        for count in range(n_pkg):
+            for d in range(0, n_pkg + 6):
+                assert E.emu_play_fifo_slot(count, n_pkg, d) == L.orc_play_fifo_slot(count, n_pkg, d), (n_pkg, count, d)
+
+
 def test_rtp_host_header_helpers_vs_oracle():
     """wmixb_rtp_write_header / wmixb_rtp_read_header (host byte shuffling of the C-ABI) against the oracle"""
     import ctypes as C

@@ -720,6 +720,72 @@ def test_aec_handle_api_and_20ms_packets():
     assert not lib.aec_init(1, 32000, 10, None) and not lib.aec_init(1, 44100, 10, None)
 
 
+@pytest.mark.parametrize("freq,stages", [(8000, NS | AEC | AGC | VAD), (16000, NS | AEC | AGC | VAD), (16000, NS | AGC | VAD)])
+def test_record_tick_at_wmix_cadence(freq, stages):
+    """The daemon's record tick (R:src/wmix.c:528-760) for a batch: play FIFO -> NS -> aec_process2(FIFO far) -> AGC -> VAD on
+    20 ms packages with wmix's own handle geometries, against one set of checker handles + the FIFO oracle per stream.
+    The far end the AEC is given must be identical; the chain is bit-exact without the AEC and within the AEC's stated
+    tolerance (<= 1 LSB before the AGC, so a handful of samples / VAD decisions may differ after it) with it."""
+    lib, L = wmix_b200.lib(), oracle()
+    pkg, S, K = freq // 50, 24, 130
+    far10, near10 = make_aec_pairs(S, freq, 0, 2 * (K + 21), seed=53)              # [2(K+21), S, n10]
+    F = np.ascontiguousarray(far10.transpose(1, 0, 2)).reshape(S, K + 21, pkg)
+    N = np.ascontiguousarray(near10.transpose(1, 0, 2)).reshape(S, K + 21, pkg)
+    # the FIFO hands the AEC the package added 21 ticks earlier on 20 ticks out of 22 (see include/wmixb.h)
+    play, mic = F[:, 21:], N[:, :K]
+    delay_ms = 400
+    eng = wmix_b200.Engine(S, freq, stages=stages, aec_far_depth=64)
+    rec = C.c_void_p()
+    assert lib.wmixb_record_create(eng.h, delay_ms, C.byref(rec)) == 0
+    bad = C.c_void_p()
+    assert lib.wmixb_record_create(eng.h, 410, C.byref(bad)) != 0
+    d_play = torch.empty((S, pkg), dtype=torch.int16, device=DEV)
+    d_mic, d_out, d_far = torch.empty_like(d_play), torch.empty_like(d_play), torch.empty_like(d_play)
+    d_vad = torch.zeros((S,), dtype=torch.uint8, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    got, got_far = np.empty((K, S, pkg), np.int16), np.empty((K, S, pkg), np.int16)
+    for t in range(K):
+        d_play.copy_(torch.from_numpy(np.ascontiguousarray(play[:, t])))
+        d_mic.copy_(torch.from_numpy(np.ascontiguousarray(mic[:, t])))
+        assert lib.wmixb_record_tick_device(rec, d_play.data_ptr(), d_mic.data_ptr(), d_out.data_ptr(), d_vad.data_ptr(),
+                                            d_far.data_ptr(), stages, st) == 0, lib.wmixb_last_error()
+        got[t], got_far[t] = d_out.cpu().numpy(), d_far.cpu().numpy()
+    lib.wmixb_record_destroy(rec)
+    eng.close()
+    want, want_far = np.empty_like(got), np.empty_like(got)
+    fifo = (C.c_uint8 * (16 + 64 * 1280))()
+    for s in range(S):
+        L.orc_play_fifo_init(fifo, delay_ms // 20 + 2, pkg * 2)
+        ns = C.c_void_p(L.orc_ns_init(1, freq))
+        aec = C.c_void_p(L.orc_aec_init(1, freq, 20)) if stages & AEC else None
+        agc = C.c_void_p(L.orc_agc_init(1, freq, 20, 5))
+        vad = C.c_void_p(L.orc_vad_init(1, freq, 20))
+        for t in range(K):
+            L.orc_play_fifo_add(fifo, P(np.ascontiguousarray(play[s, t])))
+            far = np.zeros(pkg, np.int16)
+            L.orc_play_fifo_get(fifo, P(far), delay_ms // 20)
+            x = mic[s, t].copy()
+            L.orc_ns_process(ns, P(x), P(x), pkg)
+            if aec:
+                assert L.orc_aec_process2(aec, P(far), P(x), P(x), pkg, 0) == 0
+            assert L.orc_agc_process(agc, P(x), P(x), pkg) == 0
+            L.orc_vad_process(vad, P(x), pkg)
+            want[t, s], want_far[t, s] = x, far
+        L.orc_ns_release(ns)
+        L.orc_agc_release(agc)
+        L.orc_vad_release(vad)
+        if aec:
+            L.orc_aec_release(aec)
+    assert np.array_equal(got_far, want_far)
+    if not stages & AEC:
+        assert np.array_equal(got, want)
+    else:
+        diff = got.astype(np.int32) - want
+        assert (diff != 0).mean() <= 0.005, float((diff != 0).mean())
+        # streams that never differ by more than the AEC's 1 LSB before the AGC stay within the AGC's gain of it
+        assert np.percentile(np.abs(diff), 99.9) <= 8
+
+
 def test_aec_full_size_replication_and_depth_flag():
     """Config 4 size (16 384 pairs): stream s gets the input of stream s % 32 -> identical outputs per class;
     a far-end backlog deeper than the configured history raises the sticky flag."""

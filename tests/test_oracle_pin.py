@@ -153,6 +153,35 @@ def test_mix_resample_vs_reference_wmix_load_data():
         assert tick.value == wr.value * 2, (freq, chn)
 
 
+@need_ref
+def test_play_fifo_vs_reference():
+    """playPkgBuff_add / playPkgBuff_get (R:src/wmix.c:482-526): the far-end alignment of the daemon's record tick.
+    The reference keeps ONE static ring, so the walk below runs a whole number of ring turns past the start."""
+    R, L = ref(), oracle()
+    pkg, num = R.oracle_ref_wmix_pkg_size(), R.oracle_ref_wmix_aec_fifo_pkgs()
+    delay, interval = R.oracle_ref_wmix_aec_interval_ms(), R.oracle_ref_wmix_interval_ms()
+    assert num == delay // interval + 2
+    R.playPkgBuff_get.restype = C.c_void_p
+    R.playPkgBuff_get.argtypes = [C.c_void_p, C.c_int]
+    rng = np.random.default_rng(5)
+    fifo = (C.c_uint8 * (16 + 64 * 1280))()
+    L.orc_play_fifo_init(fifo, num, pkg)
+    zero = np.zeros(pkg, np.uint8)
+    for _ in range(num):                      # flush whatever an earlier test left in the static ring
+        R.playPkgBuff_add(P(zero))
+    for t in range(5 * num):
+        x = rng.integers(0, 256, pkg).astype(np.uint8)
+        R.playPkgBuff_add(P(x))
+        L.orc_play_fifo_add(fifo, P(x))
+        for d in (delay, 0, interval, 5 * interval, delay + interval, delay + 5 * interval):
+            a, b = np.zeros(pkg, np.uint8), np.zeros(pkg, np.uint8)
+            R.playPkgBuff_get(a.ctypes.data, d)
+            L.orc_play_fifo_get(fifo, P(b), d // interval)
+            assert np.array_equal(a, b), (t, d)
+    for _ in range(num):
+        R.playPkgBuff_add(P(zero))
+
+
 # ---------------------------------------------------------------- SPL primitives (reference unit-test KATs)
 def test_spl_kats():
     L = oracle()

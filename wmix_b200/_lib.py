@@ -40,6 +40,10 @@ def lib():
         "wmixb_tick_host_bus": (i, [vp, vp, vp, vp, vp, i]),
         "wmixb_vad20_device": (i, [vp, vp, vp, vp]),
         "wmixb_vad20_host": (i, [vp, vp, vp]),
+        "wmixb_record_create": (i, [vp, i, C.POINTER(vp)]),
+        "wmixb_record_destroy": (None, [vp]),
+        "wmixb_record_far_slot": (i, [vp]),
+        "wmixb_record_tick_device": (i, [vp, vp, vp, vp, vp, vp, i, vp]),
         "wmixb_ns2_device": (i, [vp, vp, vp, vp, vp, vp]),
         "wmixb_ns2_host": (i, [vp, vp, vp, vp, vp]),
         "wmixb_vad32_device": (i, [vp, vp, vp, vp]),

@@ -415,5 +415,18 @@ uint32_t mix_plan(int src_chn, int src_freq, uint32_t src_bytes, int mix_freq, i
     return n_out;
 }
 
+// ---- playPkgBuff_get's slot choice (R:src/wmix.c:496-509) for a delay of whole packages ----
+// count = the ring's next write index.  The clamp-then-subtract of the reference makes the result `delay` while
+// count >= delay and `count` (the oldest package) otherwise; reproduced literally.
+int play_fifo_slot(int count, int n_pkg, int delay_pkgs)
+{
+    int k = count - delay_pkgs;
+    k = k >= n_pkg ? n_pkg : (k < 0 ? 0 : k);
+    k = count - k;
+    if (k >= n_pkg) k -= n_pkg;
+    else if (k < 0) k += n_pkg;
+    return k;
+}
+
 }  // namespace host
 }  // namespace wmx

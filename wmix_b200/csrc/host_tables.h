@@ -27,5 +27,7 @@ uint32_t zoom_len_of_in(int in_chn, int in_freq, int out_chn, int out_freq, uint
 // ramp code (0 = copied frame, else (n << 8) | (k + 1)).  Returns the bus samples written (map/ramp may be nullptr to
 // only count) or UINT32_MAX if the reference's 64-entry ramp buffer would overflow.
 uint32_t mix_plan(int src_chn, int src_freq, uint32_t src_bytes, int mix_freq, int32_t* map, uint16_t* ramp);
+// slot playPkgBuff_get(delay) reads (R:src/wmix.c:496-509), delay in whole packages, count = next write index
+int play_fifo_slot(int count, int n_pkg, int delay_pkgs);
 }  // namespace host
 }  // namespace wmx

@@ -171,7 +171,7 @@ constexpr size_t kAecSmemBytes = (kAecTableFloats + (size_t)kAecWarps * aec::Geo
 
 __global__ void __launch_bounds__(kAecWarps * 32)
 aec_kernel(float* __restrict__ rec, size_t rec_floats, const aec::Tables* __restrict__ tables, const int16_t* far,
-           const int16_t* near, int16_t* out, int n_streams, int n, int mult, int depth, int delay_ms, int pf_mode)
+           const int16_t* near, int16_t* out, int n_streams, int n, int mult, int depth, int delay_ms, int pf_mode, int row_stride)
 {
     extern __shared__ __align__(16) float smem[];
     aec::Tables* T = reinterpret_cast<aec::Tables*>(smem);
@@ -198,8 +198,8 @@ aec_kernel(float* __restrict__ rec, size_t rec_floats, const aec::Tables* __rest
         }
         W.pf_next = (pf_mode == 5 && s + total_warps < n_streams) ? rec + (size_t)(s + total_warps) * rec_floats : nullptr;
         W.pf_bytes = (uint32_t)(aec::Geo::kFixedFloats * sizeof(float));
-        aec::tick(W, rec + (size_t)s * rec_floats, depth, mult, n, far ? far + (size_t)s * n : nullptr,
-                  near ? near + (size_t)s * n : nullptr, out ? out + (size_t)s * n : nullptr, delay_ms, tile, *T);
+        aec::tick(W, rec + (size_t)s * rec_floats, depth, mult, n, far ? far + (size_t)s * row_stride : nullptr,
+                  near ? near + (size_t)s * row_stride : nullptr, out ? out + (size_t)s * row_stride : nullptr, delay_ms, tile, *T);
         __syncwarp();
     }
 }
@@ -693,14 +693,16 @@ extern "C" int wmixb_set_agc_gain(wmixb_engine* e, int gain_db)
     return upload_agc_table(e, gain_db);
 }
 
+// row_stride: samples between consecutive streams' rows (0 = packed rows of `samples`)
 static int launch_aec(wmixb_engine* e, const int16_t* d_far, const int16_t* d_near, int16_t* d_out, int samples, int delay_ms,
-                      cudaStream_t st)
+                      cudaStream_t st, int row_stride = 0)
 {
+    if (row_stride == 0) row_stride = samples;
     const int n = e->cfg.n_streams;
     const int need = (n + kAecWarps - 1) / kAecWarps;
     const int grid = need < e->aec_grid ? need : e->aec_grid;
     aec_kernel<<<grid, kAecWarps * 32, kAecSmemBytes, st>>>(e->aec_rec, e->aec_rec_floats, (const aec::Tables*)e->aec_tables, d_far,
-                                                             d_near, d_out, n, samples, e->cfg.freq / 8000, e->aec_depth, delay_ms, e->aec_pf);
+                                                             d_near, d_out, n, samples, e->cfg.freq / 8000, e->aec_depth, delay_ms, e->aec_pf, row_stride);
     CK_LAUNCH();
     return WMIXB_OK;
 }
@@ -893,6 +895,87 @@ extern "C" int wmixb_aec_status(wmixb_engine* e, int* h_flags, int* h_flagged)
     CK(cudaStreamSynchronize(e->stream));
     if (h_flags) *h_flags = r[0];
     if (h_flagged) *h_flagged = r[1];
+    return WMIXB_OK;
+}
+
+// ---- the daemon's record tick at its own 20 ms cadence (R:src/wmix.c:528-760), for every stream ----
+struct wmixb_record {
+    wmixb_engine* e = nullptr;
+    int pkg = 0, n_pkg = 0, count = 0, delay_pkgs = 0;
+    int16_t* fifo = nullptr;                // [n_pkg][n_streams][pkg]: slot-major, so a slot is a ready [n_streams][pkg] far-end batch
+};
+
+extern "C" int wmixb_record_create(wmixb_engine* e, int aec_interval_ms, wmixb_record** out)
+{
+    if (!e || !out) return WMIXB_EINVAL;
+    *out = nullptr;
+    const int interval = 20;                                         // WMIX_INTERVAL_MS, R:src/wmixConf.h:112
+    if (aec_interval_ms < 0 || aec_interval_ms % interval != 0 || aec_interval_ms > 2000) {
+        snprintf(g_err, sizeof g_err, "record: AEC_INTERVALMS %d must be a whole number of 20 ms packages (with a remainder the reference reads before its ring row)", aec_interval_ms);
+        return WMIXB_EINVAL;
+    }
+    wmixb_record* r = new (std::nothrow) wmixb_record();
+    if (!r) return WMIXB_ENOMEM;
+    r->e = e;
+    r->pkg = 2 * e->frame;
+    r->delay_pkgs = aec_interval_ms / interval;
+    r->n_pkg = r->delay_pkgs + 2;                                    // AEC_FIFO_PKG_NUM, R:src/wmixConf.h:141
+    const size_t bytes = (size_t)r->n_pkg * e->cfg.n_streams * r->pkg * sizeof(int16_t);
+    cudaError_t ce = cudaSetDevice(e->cfg.device);
+    if (ce == cudaSuccess) ce = cudaMalloc(&r->fifo, bytes);
+    if (ce == cudaSuccess) ce = cudaMemset(r->fifo, 0, bytes);       // the reference's ring is a zero-initialised static
+    if (ce != cudaSuccess) { cudaFree(r->fifo); delete r; return fail_cuda(ce, "record_create", __LINE__); }
+    *out = r;
+    return WMIXB_OK;
+}
+
+extern "C" void wmixb_record_destroy(wmixb_record* r)
+{
+    if (!r) return;
+    cudaSetDevice(r->e->cfg.device);
+    cudaFree(r->fifo);
+    delete r;
+}
+
+extern "C" int wmixb_record_far_slot(const wmixb_record* r) { return r ? host::play_fifo_slot(r->count, r->n_pkg, r->delay_pkgs) : -1; }
+
+extern "C" int wmixb_record_tick_device(wmixb_record* r, const int16_t* d_play, const int16_t* d_mic, int16_t* d_out, uint8_t* d_vad,
+                                        int16_t* d_far_used, int stages, void* stream)
+{
+    if (!r || !d_play || !d_mic || !d_out) return WMIXB_EINVAL;
+    wmixb_engine* e = r->e;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (stages == 0) stages = e->cfg.stages;
+    if (stages & ~e->cfg.stages) { snprintf(g_err, sizeof g_err, "record: stages 0x%x not all configured (0x%x)", stages, e->cfg.stages); return WMIXB_EINVAL; }
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t slot_elems = (size_t)e->cfg.n_streams * r->pkg, slot_bytes = slot_elems * sizeof(int16_t);
+    // playPkgBuff_add(playBuff) — R:src/wmix.c:1419, right before the record tick under WMIX_RECORD_PLAY_SYNC (:1438)
+    CK(cudaMemcpyAsync(r->fifo + (size_t)r->count * slot_elems, d_play, slot_bytes, cudaMemcpyDeviceToDevice, st));
+    r->count = (r->count + 1) % r->n_pkg;
+    // playPkgBuff_get(playPkgBuff, AEC_INTERVALMS) — R:src/wmix.c:653
+    const int16_t* far = r->fifo + (size_t)host::play_fifo_slot(r->count, r->n_pkg, r->delay_pkgs) * slot_elems;
+    if (d_far_used) CK(cudaMemcpyAsync(d_far_used, far, slot_bytes, cudaMemcpyDeviceToDevice, st));
+    const int16_t* cur = d_mic;
+    int rc;
+    if (stages & WMIXB_NS) {                                         // ns_process(buffSrc, WMIX_FRAME_NUM): two 10 ms packets
+        if ((rc = run_stages(e, cur, d_out, nullptr, 2, WMIXB_NS, st)) != WMIXB_OK) return rc;
+        cur = d_out;
+    }
+    if (stages & WMIXB_AEC) {                                        // aec_process2(far, buffSrc, buffSrc, WMIX_FRAME_NUM, 0)
+        if (e->frame == 80) {                                        // aec_init(.., 20, ..) at 8 kHz: ONE 160-sample packet
+            if ((rc = launch_aec(e, far, cur, d_out, 160, 0, st)) != WMIXB_OK) return rc;
+        } else {                                                     // 16 kHz: 10 ms packets, two per package
+            for (int k = 0; k < 2; ++k)
+                if ((rc = launch_aec(e, far + 160 * k, cur + 160 * k, d_out + 160 * k, 160, 0, st, 320)) != WMIXB_OK) return rc;
+        }
+        cur = d_out;
+    }
+    if (stages & WMIXB_AGC) {                                        // agc_process: 10 ms packets
+        if ((rc = run_stages(e, cur, d_out, nullptr, 2, WMIXB_AGC, st)) != WMIXB_OK) return rc;
+        cur = d_out;
+    }
+    if (cur != d_out) CK(cudaMemcpyAsync(d_out, cur, slot_bytes, cudaMemcpyDeviceToDevice, st));
+    if (stages & WMIXB_VAD) return wmixb_vad20_device(e, d_out, d_vad, st);     // vad_init(.., WMIX_INTERVAL_MS = 20, ..)
     return WMIXB_OK;
 }
 
