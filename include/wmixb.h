@@ -69,6 +69,15 @@ int wmixb_tick_host(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_
  * wmix_load_data yields while no partial sum clips (R:src/wmix.c:1678-1702). */
 int wmixb_tick_host_bus(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int32_t* h_bus, int stages);
 
+/* Pipelined form of the two calls above for a host that feeds ticks back to back (a media server's steady state):
+ * _submit queues the tick's H2D copies, kernels, bus sum and D2H copies and returns; _wait returns when the OLDEST
+ * submitted tick's h_out / h_vad / h_bus (nullable) are complete.  At most two ticks are in flight, so tick t+1's
+ * input copy and first kernels overlap tick t's last kernels and output copy instead of the pipeline draining at every
+ * tick boundary; results are identical to wmixb_tick_host_bus.  The buffers of a tick must stay valid (and should be
+ * pinned) until its _wait returns.  Do not mix with the synchronous calls while a tick is in flight. */
+int wmixb_tick_host_submit(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int32_t* h_bus, int stages);
+int wmixb_tick_host_wait(wmixb_engine* e);
+
 /* VAD on 20 ms packets, in place: what wmix itself configures (vad_init(.., WMIX_INTERVAL_MS = 20, ..),
  * R:src/wmix.c:703; 20 ms thresholds of T:.../vad/vad_core.c:149-164).  d_pcm: int16 [n_streams][2*frame],
  * attenuated by the wrapper's mute ramp (R:src/webrtc.c:127-141); d_vad (nullable): uint8 [n_streams].

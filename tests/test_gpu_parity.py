@@ -343,6 +343,54 @@ def test_host_buffer_tick_equals_device_tick(S):
     eng.close()
 
 
+def test_pipelined_host_ticks_equal_blocking_ticks():
+    """wmixb_tick_host_submit / _wait (two ticks in flight) must return exactly what the blocking wmixb_tick_host_bus
+    returns tick after tick: per-stream state order survives the overlap of consecutive ticks"""
+    S, T = 9000, 40
+    x = make_frames(256, 16000, 0, T, seed=61)
+    x = np.ascontiguousarray(np.tile(x, (1, S // 256 + 1, 1))[:, :S])
+    conf = np.arange(0, S + 1, 8, dtype=np.int32)
+    a, b = wmix_b200.Engine(S, 16000), wmix_b200.Engine(S, 16000)
+    a.set_conferences(conf)
+    b.set_conferences(conf)
+    n_conf = len(conf) - 1
+    pin = lambda shape, dt: torch.empty(shape, dtype=dt).pin_memory()
+    ins = [pin((S, 160), torch.int16) for _ in range(2)]
+    outs = [pin((S, 160), torch.int16) for _ in range(2)]
+    vads = [pin((S,), torch.uint8) for _ in range(2)]
+    buses = [pin((n_conf, 160), torch.int32) for _ in range(2)]
+    ref_out, ref_vad, ref_bus = np.empty((S, 160), np.int16), np.empty(S, np.uint8), np.empty((n_conf, 160), np.int32)
+    want = []
+    for t in range(T):
+        a.tick_host_bus(x[t], ref_out, ref_vad, ref_bus)
+        want.append((ref_out.copy(), ref_vad.copy(), ref_bus.copy()))
+
+    def check_tick(t):
+        k = t & 1
+        assert np.array_equal(outs[k].numpy(), want[t][0]), t
+        assert np.array_equal(vads[k].numpy(), want[t][1]), t
+        assert np.array_equal(buses[k].numpy(), want[t][2]), t
+
+    for t in range(T):
+        k = t & 1
+        ins[k].copy_(torch.from_numpy(x[t]))
+        b.tick_host_submit(ins[k].numpy(), outs[k].numpy(), vads[k].numpy(), buses[k].numpy())
+        if t >= 1:
+            b.tick_host_wait()
+            check_tick(t - 1)
+    b.tick_host_wait()
+    check_tick(T - 1)
+    # a third tick in flight is refused
+    b.tick_host_submit(ins[0].numpy(), outs[0].numpy(), vads[0].numpy(), buses[0].numpy())
+    b.tick_host_submit(ins[1].numpy(), outs[1].numpy(), vads[1].numpy(), buses[1].numpy())
+    with pytest.raises(wmix_b200.WmixError):
+        b.tick_host_submit(ins[0].numpy(), outs[0].numpy(), vads[0].numpy(), buses[0].numpy())
+    b.tick_host_wait()
+    b.tick_host_wait()
+    a.close()
+    b.close()
+
+
 def test_config1_wav_fixture_hash():
     """BASELINE config 1 through the GPU: committed hash of the reference's output on audio/1x8000.wav
     is only checkable where the wav is; elsewhere the seeded-stream fixtures stand in."""

@@ -38,6 +38,8 @@ def lib():
         "wmixb_tick_device": (i, [vp, vp, vp, vp, i, vp]),
         "wmixb_tick_host": (i, [vp, vp, vp, vp, i]),
         "wmixb_tick_host_bus": (i, [vp, vp, vp, vp, vp, i]),
+        "wmixb_tick_host_submit": (i, [vp, vp, vp, vp, vp, i]),
+        "wmixb_tick_host_wait": (i, [vp]),
         "wmixb_vad20_device": (i, [vp, vp, vp, vp]),
         "wmixb_vad20_host": (i, [vp, vp, vp]),
         "wmixb_record_create": (i, [vp, i, C.POINTER(vp)]),

@@ -56,6 +56,14 @@ class Engine:
     def tick_host(self, h_in, h_out, h_vad=None, stages=0):
         check(self.L.wmixb_tick_host(self.h, _ptr(h_in), _ptr(h_out), _ptr(h_vad), stages), "wmixb_tick_host")
 
+    def tick_host_submit(self, h_in, h_out, h_vad=None, h_bus=None, stages=0):
+        """queue one tick (see wmixb_tick_host_submit); keep the buffers alive until tick_host_wait() returns for it"""
+        check(self.L.wmixb_tick_host_submit(self.h, _ptr(h_in), _ptr(h_out), _ptr(h_vad), _ptr(h_bus), stages),
+              "wmixb_tick_host_submit")
+
+    def tick_host_wait(self):
+        check(self.L.wmixb_tick_host_wait(self.h), "wmixb_tick_host_wait")
+
     def tick_host_bus(self, h_in, h_out, h_vad, h_bus, stages=0):
         check(self.L.wmixb_tick_host_bus(self.h, _ptr(h_in), _ptr(h_out), _ptr(h_vad), _ptr(h_bus), stages),
               "wmixb_tick_host_bus")
