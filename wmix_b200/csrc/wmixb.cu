@@ -453,7 +453,7 @@ struct wmixb_engine {
     int32_t* d_bus = nullptr;               // staging of the conference bus for the host-buffer tick
     size_t d_bus_bytes = 0;
     int ns_grid = 0;
-    int ns_cfg = 0;                         // index into kNsCfgs
+    int ns_cfg = 2;                         // index into kNsCfgs: 2 CTAs of 10 warps at 96 registers per lane (measured best)
     int ns_align = 1;                       // CTA barrier at the top of every frame (instruction-cache sharing)
     int post_occ = 3;                       // same for post_kernel (3 CTAs of 128 threads, 168 registers per thread: measured best)
     float* aec_rec = nullptr;               // [n_streams][aec_rec_floats]
@@ -468,7 +468,7 @@ static int ns_rec_floats(const wmixb_engine* e) { return e->ana == 256 ? ns::Geo
 
 // compiled (warps per CTA, CTAs per SM) shapes of the NS kernel; WMIXB_NS_CFG=<index> picks one (default 0)
 struct NsCfg { int warps, minb; };
-static const NsCfg kNsCfgs[] = {{8, 2}, {8, 3}, {10, 2}, {6, 3}, {12, 1}, {4, 5}, {9, 2}, {4, 4}};
+static const NsCfg kNsCfgs[] = {{8, 2}, {8, 3}, {10, 2}, {6, 3}, {12, 1}, {4, 5}, {9, 2}, {4, 4}, {7, 4}, {6, 4}};
 template <int ANA>
 static const void* ns_fn(int cfg)
 {
@@ -480,6 +480,8 @@ static const void* ns_fn(int cfg)
     case 5: return (const void*)ns_kernel<ANA, 4, 5>;
     case 6: return (const void*)ns_kernel<ANA, 9, 2>;
     case 7: return (const void*)ns_kernel<ANA, 4, 4>;
+    case 8: return (const void*)ns_kernel<ANA, 7, 4>;
+    case 9: return (const void*)ns_kernel<ANA, 6, 4>;
     default: return (const void*)ns_kernel<ANA, 8, 2>;
     }
 }
