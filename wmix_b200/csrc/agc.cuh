@@ -212,7 +212,8 @@ WMX_HD void process_packet(const SoaWords& st, int16_t* x, const int32_t* table)
     int32_t env[10], gains[11];
     for (int k = 0; k < 10; ++k) {
         int32_t peak = 0;
-        for (int i = 0; i < L; ++i) {
+#pragma unroll 4
+        for (int i = 0; i < L; ++i) {                 // (sample loops stay rolled: post_kernel is bound by instruction fetch)
             int32_t v = x[k * L + i];
             int32_t e = v * v;
             if (e > peak) peak = e;
@@ -300,6 +301,7 @@ WMX_HD void process_packet(const SoaWords& st, int16_t* x, const int32_t* table)
     for (int k = 1; k < 10; ++k) {
         delta = wshl(gains[k + 1] - gains[k], 4 - L2);
         g32 = wshl(gains[k], 4);
+#pragma unroll 4
         for (int i = 0; i < L; ++i) {
             int32_t v = x[k * L + i];
             x[k * L + i] = (int16_t)(wmul(v, g32 >> 4) >> 16);

@@ -176,7 +176,7 @@ WMX_HD int16_t features(const SoaWords& st, const int16_t* in, int16_t* feat)
 }
 
 // T:.../vad/vad_gmm.c:30-83
-WMX_HD int32_t gaussian(int16_t input, int16_t mean, int16_t sd, int16_t& delta)
+WMX_HD int32_t gaussian_body(int16_t input, int16_t mean, int16_t sd, int16_t& delta)
 {
     int16_t inv_std = (int16_t)div_w32_w16(131072 + (int32_t)(sd >> 1), sd);
     int16_t t16 = (int16_t)(inv_std >> 2);
@@ -196,6 +196,27 @@ WMX_HD int32_t gaussian(int16_t input, int16_t mean, int16_t sd, int16_t& delta)
         expv >>= t16;
     }
     return inv_std * expv;
+}
+
+// 24 calls per frame: one out-of-line copy on the device (post_kernel is bound by instruction fetch, see common.cuh);
+// probability and delta come back packed in one 64-bit value
+#if defined(__CUDACC__)
+static __device__ __noinline__ long long gaussian_device(int input, int mean, int sd)
+{
+    int16_t d;
+    const int32_t p = gaussian_body((int16_t)input, (int16_t)mean, (int16_t)sd, d);
+    return (long long)(((unsigned long long)(uint32_t)p << 16) | (uint16_t)d);
+}
+#endif
+WMX_HD int32_t gaussian(int16_t input, int16_t mean, int16_t sd, int16_t& delta)
+{
+#if defined(__CUDA_ARCH__)
+    const unsigned long long r = (unsigned long long)gaussian_device(input, mean, sd);
+    delta = (int16_t)(r & 0xFFFFu);
+    return (int32_t)(uint32_t)(r >> 16);
+#else
+    return gaussian_body(input, mean, sd, delta);
+#endif
 }
 
 // 16 smallest feature values of the last 100 frames + smoothed "median"
@@ -421,6 +442,14 @@ WMX_HD int gmm(const SoaWords& st, const int16_t* feat, int16_t total_power, con
     return vadflag;
 }
 
+// the wrapper's mute ramp (R:src/webrtc.c:138-141): every sample >> reduce, arithmetic.  A rolled loop: unrolled it was
+// 570 instructions of a kernel that is bound by instruction fetch.
+WMX_HD void attenuate(int16_t* x, int n, int reduce)
+{
+#pragma unroll 4
+    for (int i = 0; i < n; ++i) x[i] = (int16_t)(x[i] >> reduce);
+}
+
 // One packet of one stream: WebRtcVad_Process (T:.../vad/webrtc_vad.c:71-105) + the wmix
 // wrapper's mute ramp (R:src/webrtc.c:127-141).  `x` holds LEN8*(FS16?2:1) samples and is
 // attenuated in place.  Returns the 0/1 decision.
@@ -445,7 +474,7 @@ WMX_HD int process_packet(const SoaWords& st, int16_t* x, const Params& P)
     else if (reduce > 0) reduce--;
     st.set(W_REDUCE, reduce);
     const int n = LEN8 * (FS16 ? 2 : 1);
-    for (int i = 0; i < n; ++i) x[i] = (int16_t)(x[i] >> reduce);
+    attenuate(x, n, reduce);
     return flag > 0 ? 1 : 0;
 }
 
@@ -470,7 +499,7 @@ WMX_HD int process_packet32(const SoaWords& st, int16_t* x, const Params& P)
     if (flag == 0) { if (reduce < 4) reduce++; }
     else if (reduce > 0) reduce--;
     st.set(W_REDUCE, reduce);
-    for (int i = 0; i < 4 * LEN8; ++i) x[i] = (int16_t)(x[i] >> reduce);
+    attenuate(x, 4 * LEN8, reduce);
     return flag > 0 ? 1 : 0;
 }
 
