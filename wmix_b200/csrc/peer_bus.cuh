@@ -32,6 +32,8 @@ constexpr int kThreads = 512;
 struct Ring {
     int32_t* slots[kMaxWorld];     // mailbox of rank r (local pointer for r == rank, IPC mapping otherwise)
     uint32_t* flags[kMaxWorld];
+    int32_t* result[kMaxWorld];    // reduce-scatter mode: [2][n_conf * frame] finished bus rows pushed by their owners
+    uint32_t* rflags[kMaxWorld];   //                      [2][n_conf] tick sequence number of a finished row
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
@@ -64,22 +66,28 @@ __device__ __forceinline__ int load_sample(const void* src, size_t idx)
 // threads (S member slices, a power of two chosen by the host from the largest local conference).  A CTA
 // holds G = blockDim / (kTile * S) groups working on G tiles at a time: big conferences get 32 slices
 // and one tile per CTA step, thousands of small ones run eight one-warp tiles per CTA step.
+//
+// TILE is 16 samples, or the whole frame (80 / 160) when there are many conferences: a tile costs `world` release
+// stores for its flags whatever its size, so thousands of small conferences are better served by one tile per bus row
+// (5 / 10 times fewer flags, and 320 / 640-byte bursts per peer instead of 64-byte ones).  The choice must be the same on
+// every rank (it fixes the flag indexing) and is therefore made from n_conf alone (tile_for()).
 constexpr int kTile = 16;
+__host__ __device__ inline int tile_for(int n_conf, int frame) { return n_conf >= 256 ? frame : kTile; }
 
-template <int LAW>
+template <int LAW, int TILE>
 __global__ void __launch_bounds__(kThreads)
 peer_bus_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __restrict__ src, void* __restrict__ out,
                 int32_t* __restrict__ bus_out, const int32_t* __restrict__ conf_start, int n_conf, int frame, int S,
                 unsigned long long timeout_ns, int* __restrict__ error)
 {
-    extern __shared__ int32_t sh_all[];             // per group: [S][kTile] partials + [kTile] finished tile
-    const int gthreads = kTile * S;
+    extern __shared__ int32_t sh_all[];             // per group: [S][TILE] partials + [TILE] finished tile
+    const int gthreads = TILE * S;
     const int G = blockDim.x / gthreads;
     const int g = threadIdx.x / gthreads, gt = threadIdx.x - g * gthreads;
-    const int tx = gt % kTile, slice = gt / kTile;
-    int32_t* sh = sh_all + g * (S + 1) * kTile;
-    int32_t* done = sh + S * kTile;
-    const int tiles_per_row = frame / kTile;
+    const int tx = gt % TILE, slice = gt / TILE;
+    int32_t* sh = sh_all + g * (S + 1) * TILE;
+    int32_t* done = sh + S * TILE;
+    const int tiles_per_row = frame / TILE;
     const int n_tiles = n_conf * tiles_per_row;
     const int par = (int)(seq & 1u);
     const size_t row_words = (size_t)n_conf * frame;
@@ -89,25 +97,25 @@ peer_bus_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __rest
     for (int it = 0; it < steps; ++it) {
         const int t = (it * gridDim.x + blockIdx.x) * G + g;
         const bool valid = t < n_tiles;
-        const int c = valid ? t / tiles_per_row : 0, x0 = valid ? (t - c * tiles_per_row) * kTile : 0;
+        const int c = valid ? t / tiles_per_row : 0, x0 = valid ? (t - c * tiles_per_row) * TILE : 0;
         int32_t acc = 0;
         if (valid) {
             const int first = conf_start[c], last = conf_start[c + 1];
             for (int p = first + slice; p < last; p += S) acc += load_sample<LAW>(src, (size_t)p * frame + x0 + tx);
         }
         __syncthreads();                            // the previous step's readers are done with sh
-        sh[slice * kTile + tx] = acc;
+        sh[slice * TILE + tx] = acc;
         __syncthreads();
-        if (gt < kTile) {
+        if (gt < TILE) {
             int32_t v = 0;
-            for (int k = 0; k < S; ++k) v += sh[k * kTile + gt];
+            for (int k = 0; k < S; ++k) v += sh[k * TILE + gt];
             done[gt] = v;
         }
         __syncthreads();
-        // world x kTile/4 16-byte stores per tile
+        // world x TILE/4 16-byte stores per tile
         if (valid)
-            for (int j = gt; j < world * (kTile / 4); j += gthreads) {
-                const int r = j / (kTile / 4), v = j % (kTile / 4);
+            for (int j = gt; j < world * (TILE / 4); j += gthreads) {
+                const int r = j / (TILE / 4), v = j % (TILE / 4);
                 int4* dst = reinterpret_cast<int4*>(ring.slots[r] + ((size_t)par * world + rank) * row_words + (size_t)c * frame + x0);
                 dst[v] = reinterpret_cast<const int4*>(done)[v];
             }
@@ -128,7 +136,7 @@ peer_bus_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __rest
     for (int it = 0; it < steps; ++it) {
         const int t = (it * gridDim.x + blockIdx.x) * G + g;
         const bool valid = t < n_tiles;
-        const int c = valid ? t / tiles_per_row : 0, x0 = valid ? (t - c * tiles_per_row) * kTile : 0;
+        const int c = valid ? t / tiles_per_row : 0, x0 = valid ? (t - c * tiles_per_row) * TILE : 0;
         if (valid && gt < world) {
             const uint32_t* f = my_flags + (size_t)gt * n_tiles + t;
             const unsigned long long t0 = globaltimer_ns();
@@ -138,7 +146,7 @@ peer_bus_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __rest
             }
         }
         __syncthreads();
-        if (valid && gt < kTile) {
+        if (valid && gt < TILE) {
             int32_t v = 0;
             for (int r = 0; r < world; ++r) v += __ldcg(my_slots + (size_t)r * row_words + (size_t)c * frame + x0 + gt);
             done[gt] = v;
@@ -157,6 +165,141 @@ peer_bus_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __rest
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Reduce-scatter / all-gather form, for MANY conferences on MANY ranks.  Pushing every partial row to every rank costs
+// world^2 row transfers and world^2 flags per row across the node; here row c has an OWNER (rank c % world):
+//   phase 1  every rank pushes its partial row to the owner only (+ one flag),
+//   phase 2a the owner waits for the `world` partials of its rows, adds them (int32: exact) and pushes the finished row
+//            to every rank's result area (+ one flag per rank),
+//   phase 2b every rank waits for the finished rows and writes the N-minus-one read-out of its own members.
+// 2 * world row transfers per row instead of world^2, two NVLink hops of latency instead of one.  TILE == frame (one
+// tile per row).  No CTA waits before it has finished phase 1 for all of its rows, phase 2a only waits for phase-1
+// flags and phase 2b only for phase-2a flags, and the grid is one resident wave: ranks cannot block each other.
+// Slot reuse by tick parity is safe for the same reason as above: a rank that has seen all finished rows of tick t+1
+// knows every rank has started tick t+1, i.e. retired tick t.
+template <int LAW, int TILE>
+__global__ void __launch_bounds__(kThreads)
+peer_bus_rs_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __restrict__ src, void* __restrict__ out,
+                   int32_t* __restrict__ bus_out, const int32_t* __restrict__ conf_start, int n_conf, int S,
+                   unsigned long long timeout_ns, int* __restrict__ error)
+{
+    extern __shared__ int32_t sh_all[];             // per group: [S][TILE] partials + [TILE] finished row
+    const int gthreads = TILE * S;
+    const int G = blockDim.x / gthreads;
+    const int g = threadIdx.x / gthreads, gt = threadIdx.x - g * gthreads;
+    const int tx = gt % TILE, slice = gt / TILE;
+    int32_t* sh = sh_all + g * (S + 1) * TILE;
+    int32_t* done = sh + S * TILE;
+    const int par = (int)(seq & 1u);
+    const size_t row_words = (size_t)n_conf * TILE;
+    const int steps = (n_conf + gridDim.x * G - 1) / (gridDim.x * G);
+    const int n_owned = rank < n_conf ? (n_conf - rank + world - 1) / world : 0;      // rows c = k * world + rank
+    const int osteps = (n_owned + gridDim.x * G - 1) / (gridDim.x * G);
+
+    // ---- phase 1: partial rows to their owners ----
+    for (int it = 0; it < steps; ++it) {
+        const int c = (it * gridDim.x + blockIdx.x) * G + g;
+        const bool valid = c < n_conf;
+        int32_t acc = 0;
+        if (valid) {
+            const int first = conf_start[c], last = conf_start[c + 1];
+            for (int p = first + slice; p < last; p += S) acc += load_sample<LAW>(src, (size_t)p * TILE + tx);
+        }
+        __syncthreads();
+        sh[slice * TILE + tx] = acc;
+        __syncthreads();
+        if (gt < TILE) {
+            int32_t v = 0;
+            for (int k = 0; k < S; ++k) v += sh[k * TILE + gt];
+            done[gt] = v;
+        }
+        __syncthreads();
+        if (valid) {
+            int4* dst = reinterpret_cast<int4*>(ring.slots[c % world] + ((size_t)par * world + rank) * row_words + (size_t)c * TILE);
+            for (int j = gt; j < TILE / 4; j += gthreads) dst[j] = reinterpret_cast<const int4*>(done)[j];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int j = threadIdx.x; j < steps * G; j += blockDim.x) {
+        const int c = ((j / G) * gridDim.x + blockIdx.x) * G + (j % G);
+        if (c < n_conf) st_release_sys(ring.flags[c % world] + ((size_t)par * world + rank) * n_conf + c, seq);
+    }
+
+    // ---- phase 2a: the rows this rank owns: wait for the partials, reduce, push the finished row to everybody ----
+    const int32_t* my_slots = ring.slots[rank] + (size_t)par * world * row_words;
+    const uint32_t* my_flags = ring.flags[rank] + (size_t)par * world * n_conf;
+    for (int it = 0; it < osteps; ++it) {
+        const int k = (it * gridDim.x + blockIdx.x) * G + g;
+        const bool valid = k < n_owned;
+        const int c = valid ? k * world + rank : 0;
+        if (valid && gt < world) {
+            const uint32_t* f = my_flags + (size_t)gt * n_conf + c;
+            const unsigned long long t0 = globaltimer_ns();
+            while (ld_acquire_sys(f) != seq) {
+                if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(error, 1 + gt); break; }
+                __nanosleep(32);
+            }
+        }
+        __syncthreads();
+        if (valid && gt < TILE) {
+            int32_t v = 0;
+            for (int r = 0; r < world; ++r) v += __ldcg(my_slots + (size_t)r * row_words + (size_t)c * TILE + gt);
+            done[gt] = v;
+        }
+        __syncthreads();
+        if (valid)
+            for (int j = gt; j < world * (TILE / 4); j += gthreads) {
+                const int r = j / (TILE / 4), v = j % (TILE / 4);
+                int4* dst = reinterpret_cast<int4*>(ring.result[r] + (size_t)par * row_words + (size_t)c * TILE);
+                dst[v] = reinterpret_cast<const int4*>(done)[v];
+            }
+        __syncthreads();                            // done is rewritten by the next step
+    }
+    __threadfence_system();
+    __syncthreads();
+    for (int j = threadIdx.x; j < osteps * G * world; j += blockDim.x) {
+        const int r = j % world, kk = j / world;
+        const int k = ((kk / G) * gridDim.x + blockIdx.x) * G + (kk % G);
+        if (k < n_owned) st_release_sys(ring.rflags[r] + (size_t)par * n_conf + (size_t)k * world + rank, seq);
+    }
+
+    // ---- phase 2b: finished rows in, N-minus-one out ----
+    const int32_t* my_result = ring.result[rank] + (size_t)par * row_words;
+    const uint32_t* my_rflags = ring.rflags[rank] + (size_t)par * n_conf;
+    for (int it = 0; it < steps; ++it) {
+        const int c = (it * gridDim.x + blockIdx.x) * G + g;
+        const bool valid = c < n_conf;
+        if (valid && gt == 0) {
+            const unsigned long long t0 = globaltimer_ns();
+            while (ld_acquire_sys(my_rflags + c) != seq) {
+                if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(error, 1 + c % world); break; }
+                __nanosleep(32);
+            }
+        }
+        __syncthreads();
+        if (valid && gt < TILE) {
+            const int32_t v = __ldcg(my_result + (size_t)c * TILE + gt);
+            done[gt] = v;
+            if (bus_out) bus_out[(size_t)c * TILE + gt] = v;
+        }
+        __syncthreads();
+        if (valid && out) {
+            const int32_t b = done[tx];
+            const int first = conf_start[c], last = conf_start[c + 1];
+            for (int p = first + slice; p < last; p += S) {
+                const size_t idx = (size_t)p * TILE + tx;
+                const int16_t v = sat16(b - load_sample<LAW>(src, idx));
+                if (LAW < 0) static_cast<int16_t*>(out)[idx] = v;
+                else static_cast<uint8_t*>(out)[idx] = LAW == 0 ? linear2alaw(v) : linear2ulaw(v);
+            }
+        }
+    }
+}
+
+// the exchange pattern, like the tile, must be the same on every rank: a function of (n_conf, frame, world) only
+__host__ __device__ inline bool reduce_scatter_for(int n_conf, int frame, int world) { return tile_for(n_conf, frame) == frame && world >= 4; }
 
 }  // namespace peer
 }  // namespace wmx

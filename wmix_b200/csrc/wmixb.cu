@@ -1191,10 +1191,11 @@ extern "C" int wmixb_g711_nminus1_device(wmixb_engine* e, int law, const int32_t
 // ---- cross-GPU conference bus over peer memory (peer_bus.cuh) ----
 struct wmixb_peer_bus {
     wmixb_engine* e = nullptr;
-    int rank = 0, world = 1, n_conf = 0, frame = 0, grid = 0, threads = 0, slices = 0;
+    int rank = 0, world = 1, n_conf = 0, frame = 0, grid = 0, threads = 0, slices = 0, tile = 16;
     size_t smem = 0;
     void* mailbox = nullptr;            // [slots | flags], cudaMalloc'ed on e's device
-    size_t slot_bytes = 0, flag_bytes = 0;
+    size_t slot_bytes = 0, flag_bytes = 0, result_bytes = 0, rflag_bytes = 0;
+    bool rs = false;                    // reduce-scatter / all-gather exchange (peer::reduce_scatter_for)
     void* mapped[peer::kMaxWorld] = {}; // IPC mappings to close
     peer::Ring ring{};
     bool connected = false;
@@ -1211,6 +1212,8 @@ static void peer_set_ring(wmixb_peer_bus* pb, int r, void* base)
 {
     pb->ring.slots[r] = (int32_t*)base;
     pb->ring.flags[r] = (uint32_t*)((char*)base + pb->slot_bytes);
+    pb->ring.result[r] = (int32_t*)((char*)base + pb->slot_bytes + pb->flag_bytes);
+    pb->ring.rflags[r] = (uint32_t*)((char*)base + pb->slot_bytes + pb->flag_bytes + pb->result_bytes);
 }
 
 extern "C" int wmixb_peer_bus_create(wmixb_engine* e, int rank, int world, wmixb_peer_bus** out)
@@ -1224,25 +1227,47 @@ extern "C" int wmixb_peer_bus_create(wmixb_engine* e, int rank, int world, wmixb
     pb->e = e; pb->rank = rank; pb->world = world; pb->n_conf = e->n_conf; pb->frame = e->frame;
     pb->slot_bytes = (size_t)2 * world * e->n_conf * e->frame * sizeof(int32_t);
     pb->flag_bytes = (size_t)2 * world * e->n_conf * (e->frame / peer::kTile) * sizeof(uint32_t);
-    // member slices per tile: a quarter of the largest local conference, power of two, 2..32
-    int slices = 2;
-    while (slices < 32 && slices * 4 < e->max_conf) slices *= 2;
+    pb->result_bytes = (size_t)2 * e->n_conf * e->frame * sizeof(int32_t);
+    pb->rflag_bytes = ((size_t)2 * e->n_conf * sizeof(uint32_t) + 15) / 16 * 16;
+    // tile = 16 samples or the whole bus row (the same on every rank: a function of n_conf only, peer::tile_for)
+    pb->tile = peer::tile_for(e->n_conf, e->frame);
+    if (const char* v = getenv("WMIXB_PEER_TILE")) { const int t = strcmp(v, "row") == 0 ? e->frame : atoi(v); if (t == 16 || t == e->frame) pb->tile = t; }   // experiments / tests: set on ALL ranks
+    pb->rs = peer::reduce_scatter_for(e->n_conf, e->frame, world) && pb->tile == e->frame;
+    if (const char* v = getenv("WMIXB_PEER_RS")) pb->rs = atoi(v) != 0 && pb->tile == e->frame;                                 // experiments: set on ALL ranks
+    // member slices per tile: a quarter of the largest local conference, power of two, 2..32 (1.. for row tiles),
+    // as many as fit one CTA
+    int slices = pb->tile == peer::kTile ? 2 : 1;
+    while (slices < 32 && slices * 4 < e->max_conf && slices * 2 * pb->tile <= peer::kThreads) slices *= 2;
     pb->slices = slices;
-    pb->threads = slices * peer::kTile < 256 ? 256 : slices * peer::kTile;
-    const int groups = pb->threads / (slices * peer::kTile);
-    pb->smem = (size_t)groups * (slices + 1) * peer::kTile * sizeof(int32_t);
+    {
+        const int gthreads = slices * pb->tile;
+        int groups = (gthreads >= 256 ? gthreads : 256) / gthreads;
+        if (pb->tile != peer::kTile) groups = peer::kThreads / gthreads;          // row tiles: fill the CTA
+        if (groups < 1) groups = 1;
+        pb->threads = groups * gthreads;
+        if (pb->threads < 256 && pb->tile == peer::kTile) pb->threads = 256;
+    }
+    const int groups = pb->threads / (slices * pb->tile);
+    pb->smem = (size_t)groups * (slices + 1) * pb->tile * sizeof(int32_t);
     if (const char* v = getenv("WMIXB_PEER_TIMEOUT_MS")) { const long ms = atol(v); if (ms > 0) pb->timeout_ns = (unsigned long long)ms * 1000000ull; }
-    cudaError_t ce = cudaMalloc(&pb->mailbox, pb->slot_bytes + pb->flag_bytes);
-    if (ce == cudaSuccess) ce = cudaMemset(pb->mailbox, 0, pb->slot_bytes + pb->flag_bytes);
+    const size_t mailbox_bytes = pb->slot_bytes + pb->flag_bytes + pb->result_bytes + pb->rflag_bytes;
+    cudaError_t ce = cudaMalloc(&pb->mailbox, mailbox_bytes);
+    if (ce == cudaSuccess) ce = cudaMemset(pb->mailbox, 0, mailbox_bytes);
     if (ce == cudaSuccess) ce = cudaMalloc(&pb->d_error, sizeof(int));
     if (ce == cudaSuccess) ce = cudaMemset(pb->d_error, 0, sizeof(int));
     int per_sm = 0;
-    if (ce == cudaSuccess) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer::peer_bus_kernel<0>, pb->threads, pb->smem);
+    if (ce == cudaSuccess) {
+        if (pb->rs && pb->tile == 80) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer::peer_bus_rs_kernel<0, 80>, pb->threads, pb->smem);
+        else if (pb->rs) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer::peer_bus_rs_kernel<0, 160>, pb->threads, pb->smem);
+        else if (pb->tile == 16) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer::peer_bus_kernel<0, 16>, pb->threads, pb->smem);
+        else if (pb->tile == 80) ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer::peer_bus_kernel<0, 80>, pb->threads, pb->smem);
+        else ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer::peer_bus_kernel<0, 160>, pb->threads, pb->smem);
+    }
     if (ce != cudaSuccess) { cudaFree(pb->mailbox); cudaFree(pb->d_error); delete pb; return fail_cuda(ce, "peer_bus_create", __LINE__); }
     // every CTA must be resident (phase 2 waits on other ranks): never more than one wave
     // (half of it, so that a second rank living on the same device — tests — still fits beside this one)
     const int cap = e->sm_count * (per_sm < 2 ? 1 : per_sm / 2);
-    const int n_steps = (e->n_conf * (e->frame / peer::kTile) + groups - 1) / groups;
+    const int n_steps = (e->n_conf * (e->frame / pb->tile) + groups - 1) / groups;
     pb->grid = n_steps < cap ? n_steps : cap;
     peer_set_ring(pb, rank, pb->mailbox);
     pb->connected = world == 1;
@@ -1333,8 +1358,15 @@ extern "C" int wmixb_peer_bus_tick_device(wmixb_peer_bus* pb, int law, const voi
     CK(cudaSetDevice(e->cfg.device));
     if (++pb->seq == 0) pb->seq = 2;     // 0 is the "never written" flag value; keep the parity sequence alternating
     cudaStream_t st = (cudaStream_t)stream;
-#define WMX_PEER(LAW) peer::peer_bus_kernel<LAW><<<pb->grid, pb->threads, pb->smem, st>>>(pb->ring, pb->rank, pb->world, pb->seq, d_in, d_out, d_bus, e->conf_start, pb->n_conf, e->frame, pb->slices, pb->timeout_ns, pb->d_error)
-    if (law < 0) WMX_PEER(-1); else if (law == 0) WMX_PEER(0); else WMX_PEER(1);
+#define WMX_PEER(LAW, TILE) peer::peer_bus_kernel<LAW, TILE><<<pb->grid, pb->threads, pb->smem, st>>>(pb->ring, pb->rank, pb->world, pb->seq, d_in, d_out, d_bus, e->conf_start, pb->n_conf, e->frame, pb->slices, pb->timeout_ns, pb->d_error)
+#define WMX_PEER_T(TILE) do { if (law < 0) WMX_PEER(-1, TILE); else if (law == 0) WMX_PEER(0, TILE); else WMX_PEER(1, TILE); } while (0)
+#define WMX_PEER_RS(LAW, TILE) peer::peer_bus_rs_kernel<LAW, TILE><<<pb->grid, pb->threads, pb->smem, st>>>(pb->ring, pb->rank, pb->world, pb->seq, d_in, d_out, d_bus, e->conf_start, pb->n_conf, pb->slices, pb->timeout_ns, pb->d_error)
+#define WMX_PEER_RS_T(TILE) do { if (law < 0) WMX_PEER_RS(-1, TILE); else if (law == 0) WMX_PEER_RS(0, TILE); else WMX_PEER_RS(1, TILE); } while (0)
+    if (pb->rs) { if (pb->tile == 80) WMX_PEER_RS_T(80); else WMX_PEER_RS_T(160); }
+    else if (pb->tile == 16) WMX_PEER_T(16); else if (pb->tile == 80) WMX_PEER_T(80); else WMX_PEER_T(160);
+#undef WMX_PEER_RS_T
+#undef WMX_PEER_RS
+#undef WMX_PEER_T
 #undef WMX_PEER
     CK_LAUNCH();
     return WMIXB_OK;
