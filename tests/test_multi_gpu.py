@@ -90,6 +90,18 @@ def test_peer_bus_two_ranks_on_one_device():
     _run_local_ranks([0, 0, 0], 1, [33] * 10)
 
 
+@pytest.mark.parametrize("env", [{"WMIXB_PEER_TILE": "row"}, {"WMIXB_PEER_TILE": "row", "WMIXB_PEER_RS": "1"}])
+def test_peer_bus_exchange_variants_on_one_device(env, monkeypatch):
+    """the shapes the fused kernel takes for MANY conferences — one tile per bus row, and the reduce-scatter / all-gather
+    exchange it uses from 4 ranks up — forced here on 2, 3 and 4 ranks sharing cuda:0 (the library reads the knobs when
+    the peer bus is created; normally they follow from n_conf and world alone)"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    _run_local_ranks([0, 0], 0, [40, 7, 64, 1, 9, 200])
+    _run_local_ranks([0, 0, 0], 1, [33] * 10)
+    _run_local_ranks([0, 0, 0, 0], -1, [5, 0, 17, 3, 1, 1, 2])
+
+
 def test_peer_bus_missing_peer_times_out_instead_of_hanging():
     os.environ["WMIXB_PEER_TIMEOUT_MS"] = "30"
     try:
@@ -129,7 +141,8 @@ def _free_port():
     return p
 
 
-def _nccl_worker(rank, world, port, sizes, law, q):
+def _nccl_worker(rank, world, port, sizes, law, q, env=None):
+    os.environ.update(env or {})
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -170,14 +183,16 @@ def _nccl_worker(rank, world, port, sizes, law, q):
 
 
 @needs2
-@pytest.mark.parametrize("law,sizes", [(0, [1024] * 8), (1, [16] * 512), (-1, [1, 2, 3, 58, 7, 0, 5])])
-def test_two_processes_peer_and_nccl_modes_agree_with_oracle(law, sizes):
+@pytest.mark.parametrize("law,sizes,env", [(0, [1024] * 8, None), (1, [16] * 512, None), (-1, [1, 2, 3, 58, 7, 0, 5], None),
+                                           (1, [16] * 512, {"WMIXB_PEER_RS": "1"}),
+                                           (0, [3, 40, 1, 0, 9], {"WMIXB_PEER_TILE": "row", "WMIXB_PEER_RS": "1"})])
+def test_two_processes_peer_and_nccl_modes_agree_with_oracle(law, sizes, env):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, sizes, law, q)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, sizes, law, q, env)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]
