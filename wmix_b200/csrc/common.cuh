@@ -90,6 +90,16 @@ struct SoaWords {
     size_t stride;   // streams per word row
     WMX_HD int32_t get(int w) const { return p[(size_t)w * stride]; }
     WMX_HD void set(int w, int32_t v) const { p[(size_t)w * stride] = v; }
+    // hint: words [w, w + n) will be read soon (a warp's 32 consecutive streams share one line per word); no-op on the host
+    WMX_HD void prefetch(int w, int n) const
+    {
+#if defined(__CUDA_ARCH__)
+        for (int k = 0; k < n; ++k) asm volatile("prefetch.global.L1 [%0];" ::"l"(p + (size_t)(w + k) * stride));
+#else
+        (void)w;
+        (void)n;
+#endif
+    }
 };
 
 }  // namespace wmx

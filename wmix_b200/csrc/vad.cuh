@@ -335,7 +335,13 @@ WMX_HD int gmm(const SoaWords& st, const int16_t* feat, int16_t total_power, con
 
         int32_t frame_counter = st.get(W_FRAMES);
         int16_t maxspe = 12800;
+        st.prefetch(W_AGE, 8);
+        st.prefetch(W_LOW, 8);
         for (int ch = 0; ch < 6; ++ch) {
+            if (ch < 5) {                                   // the next band's minimum lists arrive while this band is worked on
+                st.prefetch(W_AGE + (ch + 1) * 8, 8);
+                st.prefetch(W_LOW + (ch + 1) * 8, 8);
+            }
             int16_t fmin = find_minimum(st, feat[ch], ch, frame_counter);
             int32_t wnm = st.get(W_NMEAN + ch), wsm = st.get(W_SMEAN + ch);
             int32_t wns = st.get(W_NSTD + ch), wss = st.get(W_SSTD + ch);
@@ -458,6 +464,8 @@ WMX_HD int process_packet(const SoaWords& st, int16_t* x, const Params& P)
 {
     int16_t feat[6];
     int16_t power;
+    st.prefetch(W_NMEAN, 24);                               // the GMM is read right after the filterbank
+    st.prefetch(W_UPPER, 8);
     if (FS16) {
         int16_t nb[LEN8];
         int32_t s0 = st.get(W_DS), s1 = st.get(W_DS + 1);
