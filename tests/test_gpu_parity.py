@@ -972,4 +972,32 @@ def test_errors_are_loud():
     d = torch.zeros((4, 160), dtype=torch.int16, device=DEV)
     with pytest.raises(wmix_b200.WmixError):
         eng.tick_device(d, d, stages=AGC)
+    lib = wmix_b200.lib()
+    st = torch.cuda.current_stream().cuda_stream
+    # entry points that need state the engine was not created with refuse, they do not fall back
+    assert lib.wmixb_ns2_device(eng.h, d.data_ptr(), d.data_ptr(), d.data_ptr(), d.data_ptr(), st) != 0      # no ns_high_band
+    assert lib.wmixb_vad32_device(eng.h, d.data_ptr(), None, st) != 0                                         # no WMIXB_VAD
+    assert lib.wmixb_vad20_device(eng.h, d.data_ptr(), None, st) != 0
+    assert lib.wmixb_aec_device(eng.h, d.data_ptr(), d.data_ptr(), d.data_ptr(), 160, 0, st) != 0             # no WMIXB_AEC
+    rec = C.c_void_p()
+    assert lib.wmixb_record_create(eng.h, 400, C.byref(rec)) == 0
+    wide = torch.zeros((4, 320), dtype=torch.int16, device=DEV)
+    assert lib.wmixb_record_tick_device(rec, wide.data_ptr(), wide.data_ptr(), wide.data_ptr(), None, None, NS | AEC, st) != 0   # AEC not configured
+    assert lib.wmixb_record_tick_device(rec, wide.data_ptr(), wide.data_ptr(), wide.data_ptr(), None, None, NS, st) == 0
+    assert lib.wmixb_record_tick_device(rec, None, wide.data_ptr(), wide.data_ptr(), None, None, NS, st) != 0
+    lib.wmixb_record_destroy(rec)
     eng.close()
+    e8 = wmix_b200.Engine(4, 8000, stages=VAD)
+    d8 = torch.zeros((4, 320), dtype=torch.int16, device=DEV)
+    assert lib.wmixb_vad32_device(e8.h, d8.data_ptr(), None, st) != 0                                          # 32 kHz packets ride a 16 kHz engine
+    e8.close()
+    # resample-on-mix plan: empty producer list is a no-op that still advances the head; bad rings are refused
+    plan = C.c_void_p()
+    assert lib.wmixb_mixplan_create(2, 8000, 640, 16000, 0, C.byref(plan)) == 0
+    n = lib.wmixb_mixplan_out_samples(plan)
+    ring = torch.zeros((n + 8,), dtype=torch.int16, device=DEV)
+    pos = C.c_uint32(0)
+    assert lib.wmixb_mix_load_plan_device(plan, ring.data_ptr(), n + 8, 3, None, 0, None, C.byref(pos), st) == 0 and pos.value == (3 + n) % (n + 8)
+    assert lib.wmixb_mix_load_plan_device(plan, ring.data_ptr(), n + 8, n + 8, None, 0, None, None, st) != 0   # head outside the ring
+    assert lib.wmixb_mix_load_plan_device(plan, ring.data_ptr(), n + 8, 0, None, 2, None, None, st) != 0        # producers without samples
+    lib.wmixb_mixplan_destroy(plan)
