@@ -134,6 +134,9 @@ int wmixb_record_far_slot(const wmixb_record* r);   /* slot the NEXT get would r
 int wmixb_record_tick_device(wmixb_record* r, const int16_t* d_play, const int16_t* d_mic, int16_t* d_out, uint8_t* d_vad,
                              int16_t* d_far_used, int stages, void* stream);
 
+/* same with host buffers (pinned for overlap): H2D of play + mic, the tick, D2H of the result and the flags, then waits */
+int wmixb_record_tick_host(wmixb_record* r, const int16_t* h_play, const int16_t* h_mic, int16_t* h_out, uint8_t* h_vad, int stages);
+
 /* Persistent offline mode: every stream runs n_frames consecutive frames inside one launch per
  * stage.  d_in / d_out: int16 [n_streams][n_frames][frame].  d_vad (nullable): [n_streams][n_frames]. */
 int wmixb_offline_device(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int n_frames,

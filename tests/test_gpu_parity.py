@@ -800,6 +800,17 @@ def test_record_tick_at_wmix_cadence(freq, stages):
         got[t], got_far[t] = d_out.cpu().numpy(), d_far.cpu().numpy()
     lib.wmixb_record_destroy(rec)
     eng.close()
+    # the host-buffer form gives the same ticks
+    eng2 = wmix_b200.Engine(S, freq, stages=stages, aec_far_depth=64)
+    rec2 = C.c_void_p()
+    assert lib.wmixb_record_create(eng2.h, delay_ms, C.byref(rec2)) == 0
+    h_out, h_vad = np.empty((S, pkg), np.int16), np.empty(S, np.uint8)
+    for t in range(20):
+        assert lib.wmixb_record_tick_host(rec2, np.ascontiguousarray(play[:, t]).ctypes.data, np.ascontiguousarray(mic[:, t]).ctypes.data,
+                                          h_out.ctypes.data, h_vad.ctypes.data, stages) == 0
+        assert np.array_equal(h_out, got[t]), t
+    lib.wmixb_record_destroy(rec2)
+    eng2.close()
     want, want_far = np.empty_like(got), np.empty_like(got)
     fifo = (C.c_uint8 * (16 + 64 * 1280))()
     for s in range(S):

@@ -46,6 +46,7 @@ def lib():
         "wmixb_record_destroy": (None, [vp]),
         "wmixb_record_far_slot": (i, [vp]),
         "wmixb_record_tick_device": (i, [vp, vp, vp, vp, vp, vp, i, vp]),
+        "wmixb_record_tick_host": (i, [vp, vp, vp, vp, vp, i]),
         "wmixb_ns2_device": (i, [vp, vp, vp, vp, vp, vp]),
         "wmixb_ns2_host": (i, [vp, vp, vp, vp, vp]),
         "wmixb_vad32_device": (i, [vp, vp, vp, vp]),

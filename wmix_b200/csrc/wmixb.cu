@@ -911,6 +911,7 @@ struct wmixb_record {
     wmixb_engine* e = nullptr;
     int pkg = 0, n_pkg = 0, count = 0, delay_pkgs = 0;
     int16_t* fifo = nullptr;                // [n_pkg][n_streams][pkg]: slot-major, so a slot is a ready [n_streams][pkg] far-end batch
+    int16_t* stage = nullptr;               // play + mic staging of wmixb_record_tick_host
 };
 
 extern "C" int wmixb_record_create(wmixb_engine* e, int aec_interval_ms, wmixb_record** out)
@@ -942,6 +943,7 @@ extern "C" void wmixb_record_destroy(wmixb_record* r)
     if (!r) return;
     cudaSetDevice(r->e->cfg.device);
     cudaFree(r->fifo);
+    cudaFree(r->stage);
     delete r;
 }
 
@@ -984,6 +986,24 @@ extern "C" int wmixb_record_tick_device(wmixb_record* r, const int16_t* d_play, 
     }
     if (cur != d_out) CK(cudaMemcpyAsync(d_out, cur, slot_bytes, cudaMemcpyDeviceToDevice, st));
     if (stages & WMIXB_VAD) return wmixb_vad20_device(e, d_out, d_vad, st);     // vad_init(.., WMIX_INTERVAL_MS = 20, ..)
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_record_tick_host(wmixb_record* r, const int16_t* h_play, const int16_t* h_mic, int16_t* h_out, uint8_t* h_vad, int stages)
+{
+    if (!r || !h_play || !h_mic || !h_out) return WMIXB_EINVAL;
+    wmixb_engine* e = r->e;
+    CK(cudaSetDevice(e->cfg.device));
+    const size_t elems = (size_t)e->cfg.n_streams * r->pkg, bytes = elems * sizeof(int16_t);
+    if (!r->stage) CK(cudaMalloc(&r->stage, 2 * bytes));
+    int16_t *d_play = r->stage, *d_mic = r->stage + elems;
+    CK(cudaMemcpyAsync(d_play, h_play, bytes, cudaMemcpyHostToDevice, e->stream));
+    CK(cudaMemcpyAsync(d_mic, h_mic, bytes, cudaMemcpyHostToDevice, e->stream));
+    const int rc = wmixb_record_tick_device(r, d_play, d_mic, d_mic, h_vad ? e->d_vad : nullptr, nullptr, stages, e->stream);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h_out, d_mic, bytes, cudaMemcpyDeviceToHost, e->stream));
+    if (h_vad) CK(cudaMemcpyAsync(h_vad, e->d_vad, (size_t)e->cfg.n_streams, cudaMemcpyDeviceToHost, e->stream));
+    CK(cudaStreamSynchronize(e->stream));
     return WMIXB_OK;
 }
 
