@@ -9,14 +9,17 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
-int PCM2G711a(char *InAudioData, char *OutAudioData, int DataLen, int reserve);
-int PCM2G711u(char *InAudioData, char *OutAudioData, int DataLen, int reserve);
-int G711a2PCM(char *InAudioData, char *OutAudioData, int DataLen, int reserve);
-int G711u2PCM(char *InAudioData, char *OutAudioData, int DataLen, int reserve);
-int g711a_decode(short amp[], const unsigned char g711a_data[], int g711a_bytes);
-int g711u_decode(short amp[], const unsigned char g711u_data[], int g711u_bytes);
-int g711a_encode(unsigned char g711_data[], const short amp[], int len);
-int g711u_encode(unsigned char g711_data[], const short amp[], int len);
+/* encoders: pcm_bytes of int16 PCM in -> pcm_bytes / 2 codes out; the return value is the number of codes */
+int PCM2G711a(char *pcm, char *codes, int pcm_bytes, int reserve);
+int PCM2G711u(char *pcm, char *codes, int pcm_bytes, int reserve);
+/* decoders: n_codes codes in -> n_codes int16 samples out; the return value is the number of BYTES written */
+int G711a2PCM(char *codes, char *pcm, int n_codes, int reserve);
+int G711u2PCM(char *codes, char *pcm, int n_codes, int reserve);
+/* the array forms underneath them (same units: samples in, samples / bytes out as above) */
+int g711a_encode(unsigned char codes[], const short pcm[], int n_samples);
+int g711u_encode(unsigned char codes[], const short pcm[], int n_samples);
+int g711a_decode(short pcm[], const unsigned char codes[], int n_codes);
+int g711u_decode(short pcm[], const unsigned char codes[], int n_codes);
 #ifdef __cplusplus
 }
 #endif
