@@ -299,6 +299,19 @@ def test_ns_vs_checkers(freq):
             print("  -> bit-exact")
 
 
+def test_config2_long_run_ns_then_vad():
+    """BASELINE config 2 in shape (NS then VAD, 16 kHz) over 30 s of audio: 3000 ticks pass the start-up model (50), the gain
+    map (200) and five threshold re-learns (every 500 frames) and let the VAD's 100-frame minimum tracker turn over many
+    times.  Offline mode (60 frames per launch) so the run stays short; 16 of the streams are checked against the oracle."""
+    T, S, K = 3000, 40, 60
+    x = make_frames(S, 16000, 0, T, seed=71)
+    got, flags = run_gpu(x, 16000, NS | VAD, offline=K)
+    want = run_checker(oracle(), "orc_", x[:, :16], 16000, NS | VAD)
+    info = _ns_compare(got[:, :16], want, "config 2 long run")
+    assert info["mismatching"] == 0 or info["max_abs"] <= NS_MAX_ABS
+    assert flags.any() and not flags.all()                      # both decisions occur
+
+
 def test_full_chain_16k_and_vad_flags():
     x = make_frames(66, 16000, 0, 560, seed=51)
     got, vad = run_gpu(x, 16000, NS | AGC | VAD)
