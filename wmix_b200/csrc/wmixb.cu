@@ -102,7 +102,7 @@ ns_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Tables
         const int16_t* pi = in + (size_t)s * n_frames * G::kBlock;
         int16_t* po = out + (size_t)s * n_frames * G::kBlock;
         for (int f = 0; f < n_frames; ++f) {
-            if (align) __syncthreads();
+            if (align && (it % align) == 0) __syncthreads();
             if (!live) continue;
             if (f == n_frames - 1 && W.lane_id == 0 && s + total_warps < n_streams) {
                 // pull the next stream's record and first frame towards L2 while this one computes
@@ -517,7 +517,7 @@ static int upload_ns_tables(wmixb_engine* e)
     CK(cudaMemcpy(e->ns_tables, &T, sizeof T, cudaMemcpyHostToDevice));
     // register budget variant: 2 / 3 / 4 CTAs of 8 warps per SM (128 / 80 / 64 registers per lane)
     if (const char* v = getenv("WMIXB_NS_CFG")) { const int o = atoi(v); if (o >= 0 && o < (int)(sizeof kNsCfgs / sizeof kNsCfgs[0])) e->ns_cfg = o; }
-    if (const char* v = getenv("WMIXB_NS_ALIGN")) e->ns_align = atoi(v) != 0;
+    if (const char* v = getenv("WMIXB_NS_ALIGN")) { const int a = atoi(v); if (a >= 0 && a <= 64) e->ns_align = a; }   // 0 = never, k = every k-th stream
     const void* fn = ns_fn<ANA>(e->ns_cfg);
     const int warps = kNsCfgs[e->ns_cfg].warps;
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns_smem_bytes<ANA>(warps)));
