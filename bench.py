@@ -33,8 +33,8 @@ CONF_SIZE = 16
 NS_BYTES_PER_STREAM_TICK = 14.4e3      # NS state R+W + PCM in/out
 CHAIN_BYTES_PER_STREAM_TICK = 16.0e3   # NS + VAD + AGC + mix
 # dram__bytes_read.sum + dram__bytes_write.sum of one ns_kernel<256> launch per stream, from the `ncu --set full`
-# capture summarised in profiles/r1_f_summary.md (894.0 MB + 650.2 MB at 100 000 streams)
-NS_DRAM_TRAFFIC_PER_STREAM_NCU = (893.972480e6 + 650.158592e6) / 100_000
+# capture summarised in profiles/r1_g_summary.md (891.3 MB + 642.5 MB at 100 000 streams)
+NS_DRAM_TRAFFIC_PER_STREAM_NCU = (891.332864e6 + 642.490368e6) / 100_000
 
 
 def peaks():
@@ -280,7 +280,7 @@ def run_ours(args):
             "realtime_headroom": 10.0 / ms_step,
             "kernel_ms": {"ns_kernel": ns_ms, "post_kernel(agc+vad)": post_ms, "bus_sum_kernel": mix_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": S * NS_DRAM_TRAFFIC_PER_STREAM_NCU, "traffic_source": "ncu --set full, profiles/r1_f_summary.md",
+                         "traffic": S * NS_DRAM_TRAFFIC_PER_STREAM_NCU, "traffic_source": "ncu --set full, profiles/r1_g_summary.md",
                          "kernel": "ns_kernel<256>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": S * NS_BYTES_PER_STREAM_TICK,
                          "whole_tick_frac": S * CHAIN_BYTES_PER_STREAM_TICK / (ms_step * 1e-3) / 1e9 / peak},
