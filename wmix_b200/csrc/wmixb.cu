@@ -1035,6 +1035,16 @@ static int tick_host_impl(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, 
     if (n < 8192 && !pipelined) chunks = 1;
     if (pipelined && chunks < 3) chunks = 3;
     int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;     // whole post_kernel CTAs, line-aligned SoA rows
+    // (blocking call only: measured 1.40 against 1.44 ms; with pipelined ticks the unequal chunks unbalance the three
+    // streams, 1.08 against 1.06 ms)
+    if (!pipelined && chunks > 1 && (stages == 0 ? e->cfg.stages : stages) & WMIXB_NS) {
+        // the NS kernel is a persistent grid of ns_grid x warps warps, one stream each per round: a chunk that is a whole
+        // number of rounds wastes no tail (33 408 streams = 11.3 rounds ran as 12; 35 456 = 11.98 rounds does not)
+        const long long lanes = (long long)e->ns_grid * kNsCfgs[e->ns_cfg].warps;
+        const long long rounds = ((n + chunks - 1) / chunks + lanes - 1) / lanes;
+        const long long cand = rounds * lanes / 128 * 128;
+        if (cand >= 128 && cand * (chunks - 1) < n && cand * chunks >= n) per = (int)cand;
+    }
     const bool multi = chunks > 1;
     if (multi && !e->pipe[0]) {
         for (int k = 0; k < 3; ++k) {
