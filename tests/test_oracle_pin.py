@@ -425,6 +425,67 @@ def test_golden_streams():
 
 
 # ---------------------------------------------------------------- AEC
+def test_golden_handle_quirks_mix_resample_and_play_fifo():
+    """Committed fixtures made from the unmodified reference (tests/golden/make_golden.py) for the paths added after the first
+    capture: 32 kHz handles, stereo NS, the resampling branches of the real wmix_load_data, playPkgBuff_get.  Needs no
+    reference at run time."""
+    L = oracle()
+    g = json.load(open(os.path.join(GOLDEN, "hashes.json")))
+    for key, spec in g["handles"].items():
+        T, seed = spec["n_ticks"], spec["seed"]
+        if key.startswith("ns_stereo"):
+            freq = spec["freq"]
+            n = freq // 100
+            xf = _streams(freq, 4, T, seed)
+            outs = []
+            for a, b in spec["pairs"]:
+                h = C.c_void_p(L.orc_ns_init(2, freq))
+                st = np.empty((T, 2 * n), np.int16)
+                st[:, 0::2], st[:, 1::2] = xf[:, a], xf[:, b]
+                out = np.zeros_like(st)
+                for t in range(T):
+                    L.orc_ns_process(h, P(st[t].copy()), P(out[t]), n)
+                L.orc_ns_release(h)
+                outs.append(out.reshape(-1))
+            y = np.stack(outs)
+        else:
+            S, stage = spec["n_streams"], spec["stage"]
+            xs = _streams(16000, 2 * S, 2 * T, seed)
+            kw = dict(ns=stage in ("ns", "chain"), agc=stage in ("agc", "chain"), vad=stage in ("vad", "chain"))
+            outs = []
+            for s_ in range(S):
+                c = RefChain(L, 32000, prefix="orc_", **kw)
+                outs.append(c.run(np.ascontiguousarray(xs[:, s_, :]).reshape(-1)))
+                c.close()
+            y = np.stack(outs)
+        assert fnv1a64(y.tobytes()) == spec["hash"], key
+        assert y[:, -8:].tolist() == spec["tail"], key
+    # resample-on-mix
+    m = g["mix_resample"]
+    L.orc_mix_resample.restype = C.c_uint32
+    L.orc_mix_resample.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint8,
+                                   C.c_uint16, C.c_uint8, C.POINTER(C.c_uint32)]
+    rng = np.random.default_rng(m["seed"])
+    n = m["ring_samples"]
+    for cs in m["cases"]:
+        ring = rng.integers(-32768, 32768, n).astype(np.int16)
+        src = rng.integers(-32768, 32768, cs["frames"] * cs["chn"] + 2).astype(np.int16)
+        assert fnv1a64(ring.tobytes()) == cs["ring_in"] and fnv1a64(src.tobytes()) == cs["src_in"]
+        wr = C.c_uint32(0)
+        pos = L.orc_mix_resample(P(ring), n, cs["head"], P(src), cs["frames"] * cs["chn"] * 2, cs["freq"], cs["chn"], m["mix_freq"],
+                                 cs["rdce"], C.byref(wr))
+        assert fnv1a64(ring.tobytes()) == cs["ring_out"] and pos == cs["new_head"] and wr.value == cs["written"], cs
+    # play FIFO: which add does playPkgBuff_get(AEC_INTERVALMS) return after each add
+    f = g["play_fifo"]
+    fifo = (C.c_uint8 * (16 + 64 * 1280))()
+    L.orc_play_fifo_init(fifo, f["n_pkg"], 8)
+    for t, want in enumerate(f["got_tag"]):
+        L.orc_play_fifo_add(fifo, P(np.full(8, (t % 250) + 1, np.uint8)))
+        b = np.zeros(8, np.uint8)
+        L.orc_play_fifo_get(fifo, P(b), f["delay_pkgs"])
+        assert int(b[0]) == want, t
+
+
 @need_ref
 def test_aec_tables_vs_reference_symbols():
     """The oracle builds the AEC tables from formulas (+ eight one-ulp corrections of rdft_w); the reference
