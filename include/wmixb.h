@@ -206,6 +206,27 @@ int wmixb_mixplan_tables(const wmixb_mixplan* m, int32_t* h_map, uint16_t* h_ram
 int wmixb_mix_load_plan_device(const wmixb_mixplan* m, int16_t* d_ring, uint32_t ring_len, uint32_t pos, const int16_t* d_src,
                                int n_src, const uint8_t* d_rdce, uint32_t* new_pos, void* stream);
 
+/* wmix_load_data itself (R:src/wmix.h:40-49, R:src/wmix.c:1639-1956) for the daemon's HOST ring, mono 16-bit bus: the
+ * same arguments, with the WMix_Struct fields the reference reads — run, start / end, head, tick, reduceMode — and the
+ * two build constants WMIX_FREQ and VIEW_PLAY_CORRECT passed as a view.  Bookkeeping as in the reference (a producer
+ * without a head, or whose tick fell behind, restarts play_correct bytes ahead of the play pointer; its samples are
+ * divided by reduce_mode unless its own `reduce` equals it; *tick advances by the bytes written; 8- and 32-bit sources
+ * write nothing); the adds run on the GPU (same-format or the resampling branches), one round trip per call.  Returns
+ * the new head; on a CUDA failure the ring is untouched and the old head comes back (wmixb_last_error()). */
+typedef struct wmixb_mix_view {
+    uint8_t* ring_start;      /* wmix->start.U8                                     */
+    uint32_t ring_bytes;      /* wmix->end.U8 - wmix->start.U8 (WMIX_BUFF_SIZE)      */
+    uint32_t head_off;        /* wmix->head.U8 - wmix->start.U8: the play pointer    */
+    uint32_t tick;            /* wmix->tick                                         */
+    uint32_t play_correct;    /* VIEW_PLAY_CORRECT (bytes)                           */
+    uint16_t mix_freq;        /* WMIX_FREQ                                          */
+    uint8_t reduce_mode;      /* wmix->reduceMode                                   */
+    uint8_t run;              /* wmix->run                                          */
+    int device;               /* CUDA device ordinal                                */
+} wmixb_mix_view;
+uint8_t* wmixb_load_data_host(const wmixb_mix_view* w, const uint8_t* src, uint32_t src_bytes, uint16_t freq, uint8_t channels,
+                              uint8_t sample, uint8_t* head, uint8_t reduce, uint32_t* tick);
+
 /* state snapshot / restore of one stream (checkpointing; byte layout is engine-internal) */
 size_t wmixb_stream_state_bytes(const wmixb_engine* e);
 int wmixb_get_stream_state(wmixb_engine* e, int stream_index, void* h_buf);

@@ -47,6 +47,15 @@ void orc_bus_nminus1(int16_t *out, const int32_t *bus, const int16_t *own, int f
 uint32_t orc_mix_resample(int16_t *ring, uint32_t ring_len, uint32_t pos, const int16_t *src, uint32_t src_bytes,
                           uint16_t freq, uint8_t channels, uint16_t mix_freq, uint8_t rdce, uint32_t *written);
 
+/* the whole wmix_load_data (R:src/wmix.c:1639-1956) over a view of the WMix_Struct fields it reads; offsets in bytes */
+typedef struct {
+    uint32_t ring_bytes, head_off, tick, play_correct;
+    uint16_t mix_freq;
+    uint8_t reduce_mode, run;
+} orc_mix_view;
+int32_t orc_wmix_load_data(const orc_mix_view *w, uint8_t *ring, const uint8_t *src, uint32_t src_bytes, uint16_t freq,
+                           uint8_t channels, uint8_t sample, int32_t head_off, uint8_t reduce, uint32_t *tick);
+
 /* play-package FIFO feeding the AEC its far end (R:src/wmix.c:482-526), whole-package delays */
 #define ORC_FIFO_MAX_PKG 64
 #define ORC_FIFO_MAX_BYTES 1280

@@ -282,3 +282,39 @@ void orc_play_fifo_get(const orc_play_fifo *f, uint8_t *out, int delay_pkgs)
 {
     memcpy(out, f->buf[orc_play_fifo_slot(f->count, f->n_pkg, delay_pkgs)], (size_t)f->pkg_bytes);
 }
+
+/* ---- the whole of wmix_load_data for a mono 16-bit bus (R:src/wmix.c:1639-1956): bookkeeping around the adds ----
+ * The six WMix_Struct fields it reads are passed as a view (byte OFFSETS into the ring instead of pointers; head_off /
+ * the return value < 0 stand for a NULL head).  Order of business, as in the reference:
+ *   (1) nothing happens without a running mixer, a source or at least one byte (:1664);
+ *   (2) a producer with no head yet, or whose tick fell behind the play pointer's, restarts play_correct bytes ahead of
+ *       the play pointer (:1667-1674) — and is put at the ring START, not wrapped, if that lands on or past the end;
+ *   (3) its samples are divided by reduceMode unless its own `reduce` equals reduceMode (:1676-1677);
+ *   (4) same format: plain adds; 16-bit mono / stereo of another rate: the drop / ramp branches; anything else: no adds;
+ *   (5) the producer's tick advances by the bytes written (:1942-1953; the "fell behind" branch there cannot fire when
+ *       the view is a snapshot, since step (2) just made *tick >= view.tick). */
+int32_t orc_wmix_load_data(const orc_mix_view *w, uint8_t *ring, const uint8_t *src, uint32_t src_bytes, uint16_t freq,
+                           uint8_t channels, uint8_t sample, int32_t head_off, uint8_t reduce, uint32_t *tick)
+{
+    uint32_t written = 0, pos;
+    uint8_t d;
+    if (!w || !w->run || !src || src_bytes < 1)
+        return head_off;
+    if (head_off < 0 || *tick < w->tick) {
+        head_off = (int32_t)(w->head_off + w->play_correct);
+        *tick = w->tick + w->play_correct;
+        if ((uint32_t)head_off >= w->ring_bytes)
+            head_off = 0;
+    }
+    d = (reduce == w->reduce_mode) ? 1 : w->reduce_mode;
+    pos = (uint32_t)head_off / 2;
+    if (freq == w->mix_freq && channels == 1 && sample == 16) {
+        pos = orc_mix_same_format((int16_t *)ring, w->ring_bytes / 2, pos, (const int16_t *)src, src_bytes / 2, d);
+        written = src_bytes / 2;
+    } else if (sample == 16 && (channels == 1 || channels == 2)) {
+        pos = orc_mix_resample((int16_t *)ring, w->ring_bytes / 2, pos, (const int16_t *)src, src_bytes, freq, channels,
+                               w->mix_freq, d, &written);
+    }
+    *tick += written * 2;
+    return (int32_t)(pos * 2);
+}

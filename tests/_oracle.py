@@ -151,3 +151,17 @@ def aec_run_pairs(L, prefix, far, near, freq, interval_ms=10, delay_ms=0):
             out[t, s], _ = h.process2(far[t, s], near[t, s], d)
         h.close()
     return out
+
+
+class MixView(C.Structure):
+    """orc_mix_view (oracle/oracle.h)"""
+    _fields_ = [("ring_bytes", C.c_uint32), ("head_off", C.c_uint32), ("tick", C.c_uint32), ("play_correct", C.c_uint32),
+                ("mix_freq", C.c_uint16), ("reduce_mode", C.c_uint8), ("run", C.c_uint8)]
+
+
+def load_data_cases():
+    """(freq, channels, sample, frames, reduce) producers' calls used by the wmix_load_data tests: same format, both resampling
+    directions, mono / stereo, the empty 8-bit case"""
+    return [(16000, 1, 16, 320, 0), (8000, 1, 16, 160, 3), (44100, 2, 16, 441, 0), (16000, 2, 16, 200, 3), (16000, 1, 8, 100, 0),
+            (32000, 1, 16, 640, 1), (11025, 2, 16, 221, 0), (16000, 1, 16, 97, 3)]
+

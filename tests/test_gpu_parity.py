@@ -211,6 +211,43 @@ def test_mix_load_resample_vs_oracle():
     assert lib.wmixb_mixplan_create(2, 8000, 322, 16000, 0, C.byref(plan)) != 0
 
 
+def test_wmix_load_data_host_dropin():
+    """wmixb_load_data_host — wmix_load_data itself on a host ring (R:src/wmix.c:1639-1956) — against the oracle (pinned
+    to the real function in tests/test_oracle_pin.py): a producer's calls chained through the returned head and tick, same
+    format and both resampling directions, restarts, wrap-around, the empty 8-bit case"""
+    from tests._oracle import MixView as OrcView
+    from tests._oracle import load_data_cases
+    from wmix_b200._lib import MixView
+
+    lib, L = wmix_b200.lib(), oracle()
+    L.orc_wmix_load_data.restype = C.c_int32
+    L.orc_wmix_load_data.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint8, C.c_uint8, C.c_int32, C.c_uint8,
+                                     C.POINTER(C.c_uint32)]
+    rng = np.random.default_rng(19)
+    ring_bytes, correct, mix_freq = 32000, 6400, 16000
+    n = ring_bytes // 2
+    for play_head, play_tick, reduce_mode in ((1000, 0, 1), (ring_bytes - 200, 5000, 3), (ring_bytes - correct, 777, 16)):
+        ring_a = rng.integers(-32768, 32768, n).astype(np.int16)
+        ring_b = ring_a.copy()
+        va = MixView(ring_a.ctypes.data, ring_bytes, play_head, play_tick, correct, mix_freq, reduce_mode, 1, 0)
+        vb = OrcView(ring_bytes, play_head, play_tick, correct, mix_freq, reduce_mode, 1)
+        head_a, tick_a = None, C.c_uint32(0)
+        head_b, tick_b = -1, C.c_uint32(0)
+        for k, (freq, chn, sample, frames, reduce) in enumerate(load_data_cases() * 2):
+            nbytes = frames * chn * (sample // 8)
+            src = rng.integers(-32768, 32768, nbytes // 2 + 4).astype(np.int16)
+            if k == 5:
+                tick_a.value = tick_b.value = max(0, play_tick - 1)
+            head_a = lib.wmixb_load_data_host(C.byref(va), src.ctypes.data, nbytes, freq, chn, sample, head_a, reduce, C.byref(tick_a))
+            head_b = L.orc_wmix_load_data(C.byref(vb), P(ring_b), P(src), nbytes, freq, chn, sample, head_b, reduce, C.byref(tick_b))
+            off_a = (head_a - ring_a.ctypes.data) if head_a else -1
+            assert off_a == head_b and tick_a.value == tick_b.value, (play_head, k, off_a, head_b, tick_a.value, tick_b.value, lib.wmixb_last_error())
+            assert np.array_equal(ring_a, ring_b), (play_head, k)
+        va.run = 0
+        assert lib.wmixb_load_data_host(C.byref(va), src.ctypes.data, 64, mix_freq, 1, 16, ring_a.ctypes.data + 40, 0, C.byref(tick_a)) == ring_a.ctypes.data + 40
+        assert np.array_equal(ring_a, ring_b)
+
+
 @pytest.mark.parametrize("sizes", [[1, 2, 3, 58], [1024] * 3, [16] * 40, [5000]])
 def test_conference_bus(sizes):
     rng = np.random.default_rng(3)

@@ -182,6 +182,49 @@ def test_play_fifo_vs_reference():
         R.playPkgBuff_add(P(zero))
 
 
+@need_ref
+def test_wmix_load_data_bookkeeping_vs_reference():
+    """the whole wmix_load_data (R:src/wmix.c:1639-1956): head restart for a new / late producer (also past the ring end),
+    background-reduce choice, tick arithmetic, the empty 8-bit case — oracle against the real function, a producer's calls
+    chained through the returned head and tick"""
+    from tests._oracle import MixView, load_data_cases
+
+    R, L = ref(), oracle()
+    rng = np.random.default_rng(17)
+    ring_bytes, correct, mix_freq = R.oracle_ref_wmix_buff_size(), R.oracle_ref_wmix_play_correct(), R.oracle_ref_wmix_freq()
+    n = ring_bytes // 2
+
+    class WPoint(C.Union):
+        _fields_ = [("U8", C.c_void_p)]
+
+    R.wmix_load_data.restype = WPoint
+    R.wmix_load_data.argtypes = [C.c_void_p, WPoint, C.c_uint32, C.c_uint16, C.c_uint8, C.c_uint8, WPoint, C.c_uint8, C.POINTER(C.c_uint32)]
+    L.orc_wmix_load_data.restype = C.c_int32
+    L.orc_wmix_load_data.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint8, C.c_uint8, C.c_int32, C.c_uint8,
+                                     C.POINTER(C.c_uint32)]
+    wm = (C.c_uint8 * R.oracle_ref_sizeof_wmix())()
+    for play_head, play_tick, reduce_mode in ((1000, 0, 1), (ring_bytes - 200, 5000, 3), (ring_bytes - correct, 777, 16)):
+        ring_a = rng.integers(-32768, 32768, n).astype(np.int16)
+        ring_b = ring_a.copy()
+        R.oracle_ref_wmix_seat(wm, P(ring_a), ring_bytes, reduce_mode, play_head, play_tick)
+        view = MixView(ring_bytes, play_head, play_tick, correct, mix_freq, reduce_mode, 1)
+        head_a, tick_a = WPoint(None), C.c_uint32(0)
+        head_b, tick_b = -1, C.c_uint32(0)
+        for k, (freq, chn, sample, frames, reduce) in enumerate(load_data_cases() * 2):
+            nbytes = frames * chn * (sample // 8)
+            src = rng.integers(-32768, 32768, nbytes // 2 + 4).astype(np.int16)
+            if k == 5:                                   # the producer fell behind the play pointer: restart
+                tick_a.value = tick_b.value = max(0, play_tick - 1)
+            head_a = R.wmix_load_data(wm, WPoint(src.ctypes.data), nbytes, freq, chn, sample, head_a, reduce, C.byref(tick_a))
+            head_b = L.orc_wmix_load_data(C.byref(view), P(ring_b), P(src), nbytes, freq, chn, sample, head_b, reduce, C.byref(tick_b))
+            off_a = (head_a.U8 - ring_a.ctypes.data) if head_a.U8 else -1
+            assert off_a == head_b and tick_a.value == tick_b.value, (play_head, k, off_a, head_b, tick_a.value, tick_b.value)
+            assert np.array_equal(ring_a, ring_b), (play_head, k)
+        # a stopped mixer or an empty source changes nothing
+        view.run = 0
+        assert L.orc_wmix_load_data(C.byref(view), P(ring_b), P(src), 64, mix_freq, 1, 16, 40, 0, C.byref(tick_b)) == 40
+
+
 # ---------------------------------------------------------------- SPL primitives (reference unit-test KATs)
 def test_spl_kats():
     L = oracle()

@@ -17,6 +17,13 @@ class Config(C.Structure):
                 ("ns_high_band", C.c_int), ("reserved", C.c_int * 7)]
 
 
+class MixView(C.Structure):
+    """wmixb_mix_view (include/wmixb.h)"""
+    _fields_ = [("ring_start", C.c_void_p), ("ring_bytes", C.c_uint32), ("head_off", C.c_uint32), ("tick", C.c_uint32),
+                ("play_correct", C.c_uint32), ("mix_freq", C.c_uint16), ("reduce_mode", C.c_uint8), ("run", C.c_uint8),
+                ("device", C.c_int)]
+
+
 _lib = None
 
 
@@ -100,6 +107,7 @@ def lib():
         "wmixb_mixplan_out_samples": (u32, [vp]),
         "wmixb_mixplan_tables": (i, [vp, vp, vp]),
         "wmixb_mix_load_plan_device": (i, [vp, vp, u32, u32, vp, i, vp, C.POINTER(u32), vp]),
+        "wmixb_load_data_host": (vp, [vp, vp, u32, C.c_uint16, C.c_uint8, C.c_uint8, vp, C.c_uint8, C.POINTER(u32)]),
         # include/wmix_zoom.h
         "wmix_len_of_out": (u32, [C.c_uint8, C.c_uint16, u32, C.c_uint8, C.c_uint16]),
         "wmix_len_of_in": (u32, [C.c_uint8, C.c_uint16, C.c_uint8, C.c_uint16, u32]),

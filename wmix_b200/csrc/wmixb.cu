@@ -13,6 +13,9 @@
 #include <string.h>
 
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <tuple>
 #include <vector>
 
 #include "../../include/wmix_rtp.h"
@@ -1567,6 +1570,68 @@ extern "C" int wmixb_mix_load_plan_device(const wmixb_mixplan* m, int16_t* d_rin
     }
     if (new_pos) *new_pos = (uint32_t)(((uint64_t)pos + m->out_samples) % ring_len);
     return WMIXB_OK;
+}
+
+// ---- wmix_load_data itself, on the daemon's HOST ring (R:src/wmix.h:40-49, R:src/wmix.c:1639-1956) ----
+// The bookkeeping (head restart, background-reduce choice, tick) is the reference's, on the host; the adds run on the
+// GPU: the span of the ring the call touches goes up, the same kernels as wmixb_mix_load*_device add into it, and it
+// comes back.  A drop-in for the daemon's call sites, priced like the handle API: one round trip per call.
+extern "C" uint8_t* wmixb_load_data_host(const wmixb_mix_view* w, const uint8_t* src, uint32_t src_bytes, uint16_t freq,
+                                         uint8_t channels, uint8_t sample, uint8_t* head, uint8_t reduce, uint32_t* tick)
+{
+    if (!w || !w->run || !src || src_bytes < 1 || !tick || !w->ring_start || w->ring_bytes < 2) return head;   // R:src/wmix.c:1664
+    const uint32_t ring_len = w->ring_bytes / 2;
+    if (!head || *tick < w->tick) {                                                                          // :1667-1674
+        head = w->ring_start + w->head_off + w->play_correct;
+        *tick = w->tick + w->play_correct;
+        if (head >= w->ring_start + w->ring_bytes) head = w->ring_start;
+    }
+    const int rdce = (reduce == w->reduce_mode) ? 1 : (w->reduce_mode ? w->reduce_mode : 1);                 // :1676-1677
+    const uint32_t pos = (uint32_t)(head - w->ring_start) / 2;
+    const bool same = freq == w->mix_freq && channels == 1 && sample == 16;
+    if (!same && !(sample == 16 && (channels == 1 || channels == 2))) return head;                           // the empty 8 / 32-bit cases
+    struct Slot { wmixb_mixplan* plan = nullptr; };
+    static std::mutex mu;
+    static std::map<std::tuple<int, int, uint32_t, int>, Slot> plans;
+    static int16_t *d_span = nullptr, *d_src = nullptr;
+    static size_t span_cap = 0, src_cap = 0;
+    std::lock_guard<std::mutex> lock(mu);
+    uint32_t n_out = src_bytes / 2;
+    wmixb_mixplan* plan = nullptr;
+    if (!same) {
+        Slot& sl = plans[std::make_tuple((int)channels, (int)freq, src_bytes, (int)w->mix_freq)];
+        if (!sl.plan && wmixb_mixplan_create(channels, freq, src_bytes, w->mix_freq, w->device, &sl.plan) != WMIXB_OK) return head;
+        plan = sl.plan;
+        n_out = wmixb_mixplan_out_samples(plan);
+    }
+    if (n_out == 0) return head;
+    if (n_out > ring_len) { snprintf(g_err, sizeof g_err, "load_data: the chunk (%u samples) is longer than the ring", n_out); return head; }
+    if (cudaSetDevice(w->device) != cudaSuccess) return head;
+    const size_t src_elems = src_bytes / 2 + 2;
+    if (span_cap < n_out) { cudaFree(d_span); d_span = nullptr; span_cap = 0; if (cudaMalloc(&d_span, (size_t)n_out * 2) != cudaSuccess) return head; span_cap = n_out; }
+    if (src_cap < src_elems) { cudaFree(d_src); d_src = nullptr; src_cap = 0; if (cudaMalloc(&d_src, src_elems * 2) != cudaSuccess) return head; src_cap = src_elems; }
+    // the touched span [pos, pos + n_out) of the ring, unwrapped, becomes a private device ring of exactly n_out samples
+    int16_t* ring16 = reinterpret_cast<int16_t*>(w->ring_start);
+    const uint32_t first = n_out < ring_len - pos ? n_out : ring_len - pos;
+    bool ok = cudaMemcpy(d_span, ring16 + pos, (size_t)first * 2, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok && first < n_out) ok = cudaMemcpy(d_span + first, ring16, (size_t)(n_out - first) * 2, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok) ok = cudaMemcpy(d_src, src, src_bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    if (ok) {
+        if (same) ok = wmixb_mix_load_device(d_span, n_out, 0, d_src, n_out, rdce, nullptr, nullptr) == WMIXB_OK;
+        else {
+            uint8_t* d_rd = nullptr;
+            const uint8_t rd8 = (uint8_t)rdce;
+            ok = cudaMalloc(&d_rd, 16) == cudaSuccess && cudaMemcpy(d_rd, &rd8, 1, cudaMemcpyHostToDevice) == cudaSuccess &&
+                 wmixb_mix_load_plan_device(plan, d_span, n_out, 0, d_src, 1, d_rd, nullptr, nullptr) == WMIXB_OK &&
+                 cudaDeviceSynchronize() == cudaSuccess;
+            cudaFree(d_rd);
+        }
+    }
+    if (ok) ok = cudaMemcpy(ring16 + pos, d_span, (size_t)first * 2, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (ok && first < n_out) ok = cudaMemcpy(ring16, d_span + first, (size_t)(n_out - first) * 2, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (!ok) { snprintf(g_err, sizeof g_err, "load_data: CUDA call failed: %s", cudaGetErrorString(cudaGetLastError())); return head; }
+    *tick += n_out * 2;                                                                                      // :1942-1953
+    return w->ring_start + (size_t)((pos + n_out) % ring_len) * 2;
 }
 
 // ---- state snapshot ----
