@@ -425,6 +425,7 @@ __global__ void mix_load_kernel(int16_t* ring, uint32_t ring_len, uint32_t pos, 
 // ------------------------------------------------------------------------------------------
 // engine
 // ------------------------------------------------------------------------------------------
+constexpr int kPipe = 8;   // CUDA streams of the host-buffer chunk pipeline
 struct wmixb_engine {
     wmixb_config cfg;
     int frame = 0, ana = 0, sm_count = 0;
@@ -447,11 +448,11 @@ struct wmixb_engine {
     int32_t* conf_of = nullptr;             // [n_streams]
     int n_conf = 0, max_conf = 0;
     cudaStream_t stream = nullptr;
-    cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};   // chunk pipeline of the host-buffer tick
-    cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};
+    cudaStream_t pipe[kPipe] = {};                        // chunk pipeline of the host-buffer tick
+    cudaEvent_t pipe_ev[kPipe] = {};
     // pipelined submission (wmixb_tick_host_submit / _wait): two ticks in flight, d_out double-buffered
     int16_t* d_out2 = nullptr;
-    cudaEvent_t tail_ev[3] = {nullptr, nullptr, nullptr}, done_ev[2] = {nullptr, nullptr};
+    cudaEvent_t tail_ev[kPipe] = {}, done_ev[2] = {nullptr, nullptr};
     unsigned long long submitted = 0, waited = 0;
     int32_t* d_bus = nullptr;               // staging of the conference bus for the host-buffer tick
     size_t d_bus_bytes = 0;
@@ -584,11 +585,11 @@ extern "C" void wmixb_destroy(wmixb_engine* e)
     cudaFree(e->agc_words); cudaFree(e->vad_words); cudaFree(e->agc_table);
     cudaFree(e->agc_init); cudaFree(e->vad_init);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_out2); cudaFree(e->d_vad); cudaFree(e->d_pkt20);
-    for (int k = 0; k < 3; ++k) if (e->tail_ev[k]) cudaEventDestroy(e->tail_ev[k]);
+    for (int k = 0; k < kPipe; ++k) if (e->tail_ev[k]) cudaEventDestroy(e->tail_ev[k]);
     for (int k = 0; k < 2; ++k) if (e->done_ev[k]) cudaEventDestroy(e->done_ev[k]);
     cudaFree(e->conf_start); cudaFree(e->conf_of);
     cudaFree(e->aec_rec); cudaFree(e->aec_tables); cudaFree(e->aec_result); cudaFree(e->aec_stage);
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < kPipe; ++k) {
         if (e->pipe[k]) cudaStreamDestroy(e->pipe[k]);
         if (e->pipe_ev[k]) cudaEventDestroy(e->pipe_ev[k]);
     }
@@ -1030,10 +1031,10 @@ static int tick_host_impl(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, 
     if (h_bus && e->n_conf < 1) { snprintf(g_err, sizeof g_err, "tick_host_bus: call wmixb_set_conferences first"); return WMIXB_EINVAL; }
     CK(cudaSetDevice(e->cfg.device));
     const int n = e->cfg.n_streams;
-    // blocking call: 4 chunks measured best (1.54 ms per 100 k-stream tick against 1.60 / 1.58 / 1.53 / 1.67 for 3 / 5 / 6 / 8);
-    // pipelined ticks: one chunk per pipeline stream (1.12 ms against 1.47 / 1.31 / 1.45 for 4 / 6 / 9 — a fourth chunk doubles
-    // the work queued on one of the three streams)
-    int chunks = pipelined ? 3 : 4;
+    // One chunk per pipeline stream (a stream that gets two chunks serialises them and unbalances the pipeline).  Measured per
+    // 100 k-stream tick, chunks = streams: blocking call 1.50 / 1.39 / 1.35 / 1.32 / 1.27 ms for 3 / 4 / 5 / 6 / 8; pipelined
+    // ticks 1.07 / 0.96 / 0.96 / 0.97 / 0.99 ms.  WMIXB_HOST_CHUNKS / WMIXB_HOST_LANES override (experiments).
+    int chunks = pipelined ? 4 : 8;
     if (const char* v = getenv("WMIXB_HOST_CHUNKS")) { const int c = atoi(v); if (c >= 1 && c <= 64) chunks = c; }
     if (n < 8192 && !pipelined) chunks = 1;
     if (pipelined && chunks < 3) chunks = 3;
@@ -1049,8 +1050,10 @@ static int tick_host_impl(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, 
         if (cand >= 128 && cand * (chunks - 1) < n && cand * chunks >= n) per = (int)cand;
     }
     const bool multi = chunks > 1;
+    int lanes_used = chunks < kPipe ? chunks : kPipe;            // pipeline streams this tick deals its chunks to
+    if (const char* v = getenv("WMIXB_HOST_LANES")) { const int l = atoi(v); if (l >= 1 && l <= kPipe) lanes_used = l; }
     if (multi && !e->pipe[0]) {
-        for (int k = 0; k < 3; ++k) {
+        for (int k = 0; k < kPipe; ++k) {
             CK(cudaStreamCreateWithFlags(&e->pipe[k], cudaStreamNonBlocking));
             CK(cudaEventCreateWithFlags(&e->pipe_ev[k], cudaEventDisableTiming));
         }
@@ -1059,15 +1062,15 @@ static int tick_host_impl(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, 
     int used = 0;
     for (int first = 0, c = 0; first < n; first += per, ++c) {
         const int cnt = n - first < per ? n - first : per;
-        cudaStream_t st = multi ? e->pipe[c % 3] : e->stream;
+        cudaStream_t st = multi ? e->pipe[c % lanes_used] : e->stream;
         const size_t off = (size_t)first * e->frame, bytes = (size_t)cnt * e->frame * sizeof(int16_t);
         CK(cudaMemcpyAsync(e->d_in + off, h_in + off, bytes, cudaMemcpyHostToDevice, st));
         const int rc = run_stages(e, e->d_in + off, d_out + off, e->d_vad + first, 1, stages, st, nullptr, 0, first, cnt);
         if (rc) return rc;
-        if (multi && h_bus) CK(cudaEventRecord(e->pipe_ev[c % 3], st));   // last record per stream covers its chunks
+        if (multi && h_bus) CK(cudaEventRecord(e->pipe_ev[c % lanes_used], st));   // last record per stream covers its chunks
         CK(cudaMemcpyAsync(h_out + off, d_out + off, bytes, cudaMemcpyDeviceToHost, st));
         if (h_vad) CK(cudaMemcpyAsync(h_vad + first, e->d_vad + first, (size_t)cnt, cudaMemcpyDeviceToHost, st));
-        used = c + 1 < 3 ? c + 1 : 3;
+        used = c + 1 < lanes_used ? c + 1 : lanes_used;
     }
     if (h_bus) {
         if (multi)
@@ -1113,7 +1116,7 @@ extern "C" int wmixb_tick_host_submit(wmixb_engine* e, const int16_t* h_in, int1
     CK(cudaSetDevice(e->cfg.device));
     if (!e->d_out2) {
         CK(cudaMalloc(&e->d_out2, (size_t)e->cfg.n_streams * e->frame * sizeof(int16_t)));
-        for (int k = 0; k < 3; ++k) CK(cudaEventCreateWithFlags(&e->tail_ev[k], cudaEventDisableTiming));
+        for (int k = 0; k < kPipe; ++k) CK(cudaEventCreateWithFlags(&e->tail_ev[k], cudaEventDisableTiming));
         for (int k = 0; k < 2; ++k) CK(cudaEventCreateWithFlags(&e->done_ev[k], cudaEventDisableTiming));
     }
     const int rc = tick_host_impl(e, h_in, h_out, h_vad, h_bus, stages, true, (int)(e->submitted & 1));
