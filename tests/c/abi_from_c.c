@@ -1,0 +1,20 @@
+#include "webrtc.h"
+#include "g711codec.h"
+#include "wmix_zoom.h"
+#include "wmix_rtp.h"
+#include "wmixb.h"
+#include <stdio.h>
+int main(void)
+{
+    wmixb_config cfg = { .n_streams = 4, .freq = 16000, .stages = WMIXB_NS | WMIXB_AGC | WMIXB_VAD, .ns_policy = 2, .agc_gain_db = 5, .vad_mode = 3 };
+    wmixb_engine *e = 0;
+    int rc = wmixb_create(&cfg, &e);
+    printf("wmixb_create without a GPU -> %d (%s)\n", rc, wmixb_last_error());
+    void *h = ns_init(1, 16000, 0);
+    printf("ns_init without a GPU -> %p\n", h);
+    wmixb_mix_view v = {0};
+    uint32_t tick = 0;
+    printf("load_data on a stopped mixer -> %p\n", (void *)wmixb_load_data_host(&v, (const uint8_t *)"ab", 2, 16000, 1, 16, 0, 0, &tick));
+    printf("len_of_out %u\n", wmix_len_of_out(1, 8000, 320, 1, 16000));
+    return rc == WMIXB_ENODEV && !h ? 0 : 1;
+}

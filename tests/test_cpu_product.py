@@ -34,6 +34,29 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert not missing, missing
 
 
+def test_headers_are_plain_c_and_link(tmp_path):
+    """a C99 program (-pedantic) that includes every header under include/, links libwmix_b200.so and calls through the
+    C-ABI: the boundary wmix's own C sources would use (tests/c/abi_from_c.c).  Without a GPU it must see WMIXB_ENODEV / NULL."""
+    import subprocess
+
+    import __graft_entry__ as g
+
+    g.build()
+    exe = str(tmp_path / "abi_from_c")
+    libdir = os.path.join(ROOT, "wmix_b200")
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "tests", "c", "abi_from_c.c"), "-L", libdir, "-lwmix_b200", "-Wl,-rpath," + libdir, "-o", exe],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    import torch
+
+    run = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert "wmixb_create" in run.stdout                 # with a GPU the program reports success codes instead
+    else:
+        assert run.returncode == 0, run.stdout + run.stderr
+
+
 def test_no_gpu_means_loud_failure():
     import torch
 
