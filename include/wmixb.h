@@ -68,6 +68,9 @@ int wmixb_tick_host(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_
  * h_bus int32 [n_conf][frame] = what every producer adding its 10 ms into the mix ring through
  * wmix_load_data yields while no partial sum clips (R:src/wmix.c:1678-1702). */
 int wmixb_tick_host_bus(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int32_t* h_bus, int stages);
+/* Output selection: in the host-buffer ticks h_out, h_vad and h_bus are each nullable — a NULL output is computed on the
+ * device but not copied back (a mixer that only needs the conference bus and the speech flags moves 4 MB instead of
+ * 36 MB device -> host per 100 000-stream tick).  At least one of them must be given. */
 
 /* Pipelined form of the two calls above for a host that feeds ticks back to back (a media server's steady state):
  * _submit queues the tick's H2D copies, kernels, bus sum and D2H copies and returns; _wait returns when the OLDEST
@@ -168,6 +171,15 @@ int wmixb_bus_nminus1_device(wmixb_engine* e, const int32_t* d_bus, const int16_
 typedef struct wmixb_peer_bus wmixb_peer_bus;
 #define WMIXB_PEER_HANDLE_BYTES 80
 int wmixb_peer_bus_create(wmixb_engine* e, int rank, int world, wmixb_peer_bus** out);
+/* same with explicit options (NULL = defaults); tile / reduce_scatter must be identical on ALL ranks */
+typedef struct wmixb_peer_opts {
+    int tile;              /* 0 = automatic; 16, or the frame length (one tile per bus row)                          */
+    int reduce_scatter;    /* -1 = automatic; 0 / 1 = all-to-all / reduce-scatter + all-gather (row tiles only)       */
+    int timeout_ms;        /* 0 = 2000: how long a rank waits for a peer before it raises its error flag             */
+    int ranks_per_device;  /* 0 = 2: ranks whose peer kernels may be resident on this GPU at once (sizes the grid)    */
+    int reserved[4];
+} wmixb_peer_opts;
+int wmixb_peer_bus_create_ex(wmixb_engine* e, int rank, int world, const wmixb_peer_opts* opts, wmixb_peer_bus** out);
 void wmixb_peer_bus_destroy(wmixb_peer_bus* pb);
 int wmixb_peer_bus_handle(const wmixb_peer_bus* pb, void* handle_out);
 int wmixb_peer_bus_connect(wmixb_peer_bus* pb, const void* handles);
@@ -231,6 +243,26 @@ uint8_t* wmixb_load_data_host(const wmixb_mix_view* w, const uint8_t* src, uint3
 size_t wmixb_stream_state_bytes(const wmixb_engine* e);
 int wmixb_get_stream_state(wmixb_engine* e, int stream_index, void* h_buf);
 int wmixb_set_stream_state(wmixb_engine* e, int stream_index, const void* h_buf);
+
+/* Pinned host buffers for the host-buffer ticks, placed on the NUMA node of `device` (the calling thread is moved onto
+ * that node's CPUs while the pages are allocated and first touched).  flags: WMIXB_HOST_WRITE_COMBINED for buffers the
+ * host only writes (tick inputs).  NULL on failure (wmixb_last_error()). */
+enum { WMIXB_HOST_WRITE_COMBINED = 1 };
+void* wmixb_host_alloc(size_t bytes, int device, int flags);
+void wmixb_host_free(void* p);
+/* What the copy engines alone sustain for one tick's traffic: h2d_bytes up and d2h_bytes down as bare cudaMemcpyAsync
+ * calls on two streams, `reps` times back to back.  The ceiling a host-buffer tick can be compared with. */
+int wmixb_host_copy_ceiling(int device, const void* h_src, void* h_dst, size_t h2d_bytes, size_t d2h_bytes, int reps,
+                            double* ms_per_rep);
+
+/* device used by the drop-in entry points that have no device argument (include/webrtc.h handles, g711codec.h,
+ * wmix_pcm_zoom, wmix_load_data); default 0 */
+int wmixb_set_default_device(int device);
+int wmixb_default_device(void);
+
+/* experiment / test knobs; none changes results.  keys: "ns_cfg", "ns_align", "post_occ", "aec_pf", "aec_grid",
+ * "host_chunks", "host_lanes" */
+int wmixb_set_tuning(wmixb_engine* e, const char* key, int value);
 
 /* bookkeeping */
 int wmixb_sync(wmixb_engine* e);

@@ -1,5 +1,6 @@
 #include "webrtc.h"
 #include "g711codec.h"
+#include "wmix.h"
 #include "wmix_zoom.h"
 #include "wmix_rtp.h"
 #include "wmixb.h"
@@ -15,6 +16,17 @@ int main(void)
     wmixb_mix_view v = {0};
     uint32_t tick = 0;
     printf("load_data on a stopped mixer -> %p\n", (void *)wmixb_load_data_host(&v, (const uint8_t *)"ab", 2, 16000, 1, 16, 0, 0, &tick));
+    {
+        /* the mix entry point under the reference's own prototype, on a daemon-shaped struct */
+        int16_t ring[64] = {0}, pcm[8] = {1, 2, 3, 4, 5, 6, 7, 8};
+        WMix_Struct wm = {0};
+        WMix_Point src, head, ret;
+        wm.start.S16 = ring; wm.end.S16 = ring + 64; wm.head.S16 = ring; wm.run = false; wm.reduceMode = 1;
+        src.S16 = pcm; head.S16 = ring + 4;
+        ret = wmix_load_data(&wm, src, sizeof pcm, 8000, 1, 16, head, 1, &tick);
+        printf("wmix_load_data on a stopped mixer -> head %s\n", ret.U8 == head.U8 ? "unchanged" : "moved");
+        if (ret.U8 != head.U8) return 2;
+    }
     printf("len_of_out %u\n", wmix_len_of_out(1, 8000, 320, 1, 16000));
     return rc == WMIXB_ENODEV && !h ? 0 : 1;
 }

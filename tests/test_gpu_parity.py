@@ -248,6 +248,81 @@ def test_wmix_load_data_host_dropin():
         assert np.array_equal(ring_a, ring_b)
 
 
+def test_wmix_load_data_under_the_reference_prototype():
+    """wmix_load_data(WMix_Struct*, WMix_Point, ...) exported by the library (include/wmix.h) against the compiled reference's
+    own function, both driven through the SAME daemon-shaped struct (seated by the reference); falls back to the oracle when
+    oracle/_ref is absent.  Odd source lengths included: the reference consumes ceil(n / 2) samples."""
+    from tests._oracle import MixView as OrcView
+    from tests._oracle import load_data_cases, ref
+
+    lib, L, R = wmix_b200.lib(), oracle(), ref()
+
+    class WPoint(C.Union):
+        _fields_ = [("U8", C.c_void_p)]
+
+    lib.wmix_load_data.restype = WPoint
+    lib.wmix_load_data.argtypes = [C.c_void_p, WPoint, C.c_uint32, C.c_uint16, C.c_uint8, C.c_uint8, WPoint, C.c_uint8, C.POINTER(C.c_uint32)]
+    lib.wmix_load_data_config.argtypes = [C.c_uint16, C.c_uint32]
+    L.orc_wmix_load_data.restype = C.c_int32
+    L.orc_wmix_load_data.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint16, C.c_uint8, C.c_uint8, C.c_int32, C.c_uint8,
+                                     C.POINTER(C.c_uint32)]
+    if R is not None:
+        R.wmix_load_data.restype = WPoint
+        R.wmix_load_data.argtypes = lib.wmix_load_data.argtypes
+        R.oracle_ref_sizeof_wmix.restype = C.c_size_t
+        ring_bytes, correct, mix_freq = R.oracle_ref_wmix_buff_size(), R.oracle_ref_wmix_play_correct(), R.oracle_ref_wmix_freq()
+        wm_size = R.oracle_ref_sizeof_wmix()
+    else:
+        ring_bytes, correct, mix_freq, wm_size = 32000, 6400, 16000, 4096
+    lib.wmix_load_data_config(mix_freq, correct)
+    rng = np.random.default_rng(23)
+    n = ring_bytes // 2
+    try:
+        for play_head, play_tick, reduce_mode in ((1000, 0, 1), (ring_bytes - 200, 5000, 3), (ring_bytes - correct, 777, 16)):
+            ring_a = rng.integers(-32768, 32768, n).astype(np.int16)
+            ring_b = ring_a.copy()
+            wm_a = (C.c_uint8 * wm_size)()
+            wm_b = (C.c_uint8 * wm_size)()
+            if R is not None:
+                R.oracle_ref_wmix_seat(wm_a, P(ring_a), ring_bytes, reduce_mode, play_head, play_tick)
+                R.oracle_ref_wmix_seat(wm_b, P(ring_b), ring_bytes, reduce_mode, play_head, play_tick)
+            else:
+                from wmix_b200._lib import WMixStructPrefix
+
+                for wm, ring in ((wm_a, ring_a), (wm_b, ring_b)):
+                    st = WMixStructPrefix.from_buffer(wm)
+                    st.start = st.buff = ring.ctypes.data
+                    st.end = ring.ctypes.data + ring_bytes
+                    st.head = st.tail = ring.ctypes.data + play_head
+                    st.run, st.tick, st.reduceMode = 1, play_tick, reduce_mode
+            vb = OrcView(ring_bytes, play_head, play_tick, correct, mix_freq, reduce_mode, 1)
+            head_a, tick_a = WPoint(None), C.c_uint32(0)
+            head_b, tick_b = (WPoint(None) if R is not None else -1), C.c_uint32(0)
+            cases = load_data_cases() * 2 + [(mix_freq, 1, 16, 100, 0)]
+            for k, (freq, chn, sample, frames, reduce) in enumerate(cases):
+                nbytes = frames * chn * (sample // 8)
+                if k == len(cases) - 1:
+                    nbytes = 199                                  # odd length, same format: 100 samples, the last one half present
+                src = np.zeros(nbytes // 2 + 4, np.int16)
+                src[:(nbytes + 1) // 2] = rng.integers(-32768, 32768, (nbytes + 1) // 2)
+                if nbytes & 1:
+                    src[nbytes // 2] &= 0x00FF                    # the byte past the source is zero in both arms
+                if k == 5:
+                    tick_a.value = tick_b.value = max(0, play_tick - 1)
+                head_a = lib.wmix_load_data(wm_a, WPoint(src.ctypes.data), nbytes, freq, chn, sample, head_a, reduce, C.byref(tick_a))
+                off_a = (head_a.U8 - ring_a.ctypes.data) if head_a.U8 else -1
+                if R is not None:
+                    head_b = R.wmix_load_data(wm_b, WPoint(src.ctypes.data), nbytes, freq, chn, sample, head_b, reduce, C.byref(tick_b))
+                    off_b = (head_b.U8 - ring_b.ctypes.data) if head_b.U8 else -1
+                else:
+                    head_b = L.orc_wmix_load_data(C.byref(vb), P(ring_b), P(src), nbytes, freq, chn, sample, head_b, reduce, C.byref(tick_b))
+                    off_b = head_b
+                assert off_a == off_b and tick_a.value == tick_b.value, (play_head, k, off_a, off_b, tick_a.value, tick_b.value, lib.wmixb_last_error())
+                assert np.array_equal(ring_a, ring_b), (play_head, k)
+    finally:
+        lib.wmix_load_data_config(8000, 3200)
+
+
 @pytest.mark.parametrize("sizes", [[1, 2, 3, 58], [1024] * 3, [16] * 40, [5000]])
 def test_conference_bus(sizes):
     rng = np.random.default_rng(3)

@@ -44,9 +44,11 @@ def test_peer_bus_world1_matches_oracle(law, freq, sizes):
     conf.close()
 
 
-def _run_local_ranks(devices, law, sizes, T=5):
+def _run_local_ranks(devices, law, sizes, opts=None, T=5):
     """several ranks inside this process (wmixb_peer_bus_connect_local), one stream per rank"""
     world = len(devices)
+    opts = dict(opts or {})
+    opts.setdefault("ranks_per_device", max(devices.count(d) for d in set(devices)))
     plan = ConferencePlan(sizes, world, "striped")
     frame = 80
     legs = _legs(law, T, plan.total, frame, 11)
@@ -54,7 +56,7 @@ def _run_local_ranks(devices, law, sizes, T=5):
     for r, dev in enumerate(devices):
         b = CudaBackend(plan.local_count(r), 8000, dev)
         b.set_conferences(plan.local_conf_start(r))
-        b.peer_create(r, world)
+        b.peer_create(r, world, opts)
         backs.append(b)
     for b in backs:
         b.peer_connect_local(backs)
@@ -90,38 +92,32 @@ def test_peer_bus_two_ranks_on_one_device():
     _run_local_ranks([0, 0, 0], 1, [33] * 10)
 
 
-@pytest.mark.parametrize("env", [{"WMIXB_PEER_TILE": "row"}, {"WMIXB_PEER_TILE": "row", "WMIXB_PEER_RS": "1"}])
-def test_peer_bus_exchange_variants_on_one_device(env, monkeypatch):
+@pytest.mark.parametrize("opts", [{"tile": "row"}, {"tile": "row", "reduce_scatter": 1}])
+def test_peer_bus_exchange_variants_on_one_device(opts):
     """the shapes the fused kernel takes for MANY conferences — one tile per bus row, and the reduce-scatter / all-gather
-    exchange it uses from 4 ranks up — forced here on 2, 3 and 4 ranks sharing cuda:0 (the library reads the knobs when
-    the peer bus is created; normally they follow from n_conf and world alone)"""
-    for k, v in env.items():
-        monkeypatch.setenv(k, v)
-    _run_local_ranks([0, 0], 0, [40, 7, 64, 1, 9, 200])
-    _run_local_ranks([0, 0, 0], 1, [33] * 10)
-    _run_local_ranks([0, 0, 0, 0], -1, [5, 0, 17, 3, 1, 1, 2])
+    exchange it uses from 4 ranks up — forced here on 2, 3 and 4 ranks sharing cuda:0 (wmixb_peer_opts at
+    creation; normally they follow from n_conf and world alone)"""
+    _run_local_ranks([0, 0], 0, [40, 7, 64, 1, 9, 200], opts)
+    _run_local_ranks([0, 0, 0], 1, [33] * 10, dict(opts, ranks_per_device=3))
+    _run_local_ranks([0, 0, 0, 0], -1, [5, 0, 17, 3, 1, 1, 2], dict(opts, ranks_per_device=4))
 
 
 def test_peer_bus_missing_peer_times_out_instead_of_hanging():
-    os.environ["WMIXB_PEER_TIMEOUT_MS"] = "30"
-    try:
-        plan = ConferencePlan([8, 8], 2, "striped")
-        backs = []
-        for r in range(2):
-            b = CudaBackend(plan.local_count(r), 8000, 0)
-            b.set_conferences(plan.local_conf_start(r))
-            b.peer_create(r, 2)
-            backs.append(b)
-        for b in backs:
-            b.peer_connect_local(backs)
-        d_in = torch.zeros((plan.local_count(0), 80), dtype=torch.uint8, device="cuda:0")
-        d_out = torch.empty_like(d_in)
-        backs[0].peer_tick(0, d_in, d_out, None, None)  # rank 1 never ticks
-        assert backs[0].peer_status() == 2               # gave up waiting for rank 1
-        for b in backs:
-            b.close()
-    finally:
-        del os.environ["WMIXB_PEER_TIMEOUT_MS"]
+    plan = ConferencePlan([8, 8], 2, "striped")
+    backs = []
+    for r in range(2):
+        b = CudaBackend(plan.local_count(r), 8000, 0)
+        b.set_conferences(plan.local_conf_start(r))
+        b.peer_create(r, 2, {"timeout_ms": 30})
+        backs.append(b)
+    for b in backs:
+        b.peer_connect_local(backs)
+    d_in = torch.zeros((plan.local_count(0), 80), dtype=torch.uint8, device="cuda:0")
+    d_out = torch.empty_like(d_in)
+    backs[0].peer_tick(0, d_in, d_out, None, None)  # rank 1 never ticks
+    assert backs[0].peer_status() == 2               # gave up waiting for rank 1
+    for b in backs:
+        b.close()
 
 
 needs2 = pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs (gpurun --gpus 2)")
@@ -141,8 +137,7 @@ def _free_port():
     return p
 
 
-def _nccl_worker(rank, world, port, sizes, law, q, env=None):
-    os.environ.update(env or {})
+def _nccl_worker(rank, world, port, sizes, law, q, opts=None):
     sys.path.insert(0, ROOT)
     import torch
     import torch.distributed as dist
@@ -161,7 +156,7 @@ def _nccl_worker(rank, world, port, sizes, law, q, env=None):
         dev = "cuda:%d" % rank
         results = {}
         for mode in ("peer", "nccl"):
-            conf = ShardedConference(plan, rank, law=law, freq=8000, mode=mode, device=rank)
+            conf = ShardedConference(plan, rank, law=law, freq=8000, mode=mode, device=rank, peer_opts=opts)
             d_bus = torch.empty((plan.n_conf, frame), dtype=torch.int32, device=dev)
             outs = []
             for t in range(T):
@@ -183,16 +178,16 @@ def _nccl_worker(rank, world, port, sizes, law, q, env=None):
 
 
 @needs2
-@pytest.mark.parametrize("law,sizes,env", [(0, [1024] * 8, None), (1, [16] * 512, None), (-1, [1, 2, 3, 58, 7, 0, 5], None),
-                                           (1, [16] * 512, {"WMIXB_PEER_RS": "1"}),
-                                           (0, [3, 40, 1, 0, 9], {"WMIXB_PEER_TILE": "row", "WMIXB_PEER_RS": "1"})])
-def test_two_processes_peer_and_nccl_modes_agree_with_oracle(law, sizes, env):
+@pytest.mark.parametrize("law,sizes,opts", [(0, [1024] * 8, None), (1, [16] * 512, None), (-1, [1, 2, 3, 58, 7, 0, 5], None),
+                                            (1, [16] * 512, {"reduce_scatter": 1}),
+                                            (0, [3, 40, 1, 0, 9], {"tile": "row", "reduce_scatter": 1})])
+def test_two_processes_peer_and_nccl_modes_agree_with_oracle(law, sizes, opts):
     import torch.multiprocessing as mp
 
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, sizes, law, q, env)) for r in range(2)]
+    procs = [ctx.Process(target=_nccl_worker, args=(r, 2, port, sizes, law, q, opts)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=300) for _ in procs]

@@ -11,6 +11,8 @@ import numpy as np
 import pytest
 
 from tests._oracle import P, RefChain, fnv1a64, oracle, ref
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 from wmix_b200.synth import make_frames
 
 GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
@@ -223,6 +225,40 @@ def test_wmix_load_data_bookkeeping_vs_reference():
         # a stopped mixer or an empty source changes nothing
         view.run = 0
         assert L.orc_wmix_load_data(C.byref(view), P(ring_b), P(src), 64, mix_freq, 1, 16, 40, 0, C.byref(tick_b)) == 40
+
+
+@need_ref
+def test_wmix_struct_prefix_of_include_wmix_h_matches_the_reference_layout(tmp_path):
+    """include/wmix.h restates the leading fields of WMix_Struct (R:src/wmixConf.h:176-207) so that wmix_load_data can be
+    exported under the reference's own prototype: every field the function reads must sit at the offset the compiled
+    reference puts it.  The reference seats a struct with distinctive values; they are read back at OUR offsets."""
+    import subprocess
+
+    so = str(tmp_path / "libwmix_layout.so")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-shared", "-fPIC", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "wmix_layout.c"), "-o", so])
+    H = C.CDLL(so)
+    for f in ("start", "end", "head", "run", "tick", "reduce"):
+        getattr(H, "wmixh_off_" + f).restype = C.c_size_t
+    H.wmixh_sizeof.restype = C.c_size_t
+    R = ref()
+    R.oracle_ref_sizeof_wmix.restype = C.c_size_t
+    assert H.wmixh_sizeof() <= R.oracle_ref_sizeof_wmix()
+    wm = (C.c_uint8 * R.oracle_ref_sizeof_wmix())()
+    ring = np.zeros(4000, np.int16)
+    R.oracle_ref_wmix_seat(wm, P(ring), 8000, 13, 2468, 0x01020304)
+    raw = bytes(wm)
+
+    def u64(off):
+        return int.from_bytes(raw[off:off + 8], "little")
+
+    base = ring.ctypes.data
+    assert u64(H.wmixh_off_start()) == base
+    assert u64(H.wmixh_off_end()) == base + 8000
+    assert u64(H.wmixh_off_head()) == base + 2468
+    assert raw[H.wmixh_off_run()] == 1
+    assert int.from_bytes(raw[H.wmixh_off_tick():H.wmixh_off_tick() + 4], "little") == 0x01020304
+    assert raw[H.wmixh_off_reduce()] == 13
 
 
 # ---------------------------------------------------------------- SPL primitives (reference unit-test KATs)

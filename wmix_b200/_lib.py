@@ -24,6 +24,22 @@ class MixView(C.Structure):
                 ("device", C.c_int)]
 
 
+class WMixStructPrefix(C.Structure):
+    """leading fields of the daemon's WMix_Struct as include/wmix.h restates them (R:src/wmixConf.h:176-207)"""
+    _fields_ = [("objAo", C.c_void_p), ("objAi", C.c_void_p), ("buff", C.c_void_p), ("start", C.c_void_p), ("end", C.c_void_p),
+                ("head", C.c_void_p), ("tail", C.c_void_p), ("run", C.c_bool), ("loopWord", C.c_uint8),
+                ("loopWordRecord", C.c_uint8), ("loopWordFifo", C.c_uint8), ("loopWordRtp", C.c_uint8), ("tick", C.c_uint32),
+                ("thread_sys", C.c_uint32), ("thread_record", C.c_uint32), ("thread_play", C.c_uint32), ("playRun", C.c_bool),
+                ("recordRun", C.c_bool), ("shmemRun", C.c_int), ("msg_key", C.c_int), ("msg_fd", C.c_int),
+                ("reduceMode", C.c_uint8)]
+
+
+class PeerOpts(C.Structure):
+    """wmixb_peer_opts (include/wmixb.h)"""
+    _fields_ = [("tile", C.c_int), ("reduce_scatter", C.c_int), ("timeout_ms", C.c_int), ("ranks_per_device", C.c_int),
+                ("reserved", C.c_int * 4)]
+
+
 _lib = None
 
 
@@ -67,6 +83,7 @@ def lib():
         "wmixb_bus_sum_device": (i, [vp, vp, vp, vp]),
         "wmixb_bus_nminus1_device": (i, [vp, vp, vp, vp, vp]),
         "wmixb_peer_bus_create": (i, [vp, i, i, C.POINTER(vp)]),
+        "wmixb_peer_bus_create_ex": (i, [vp, i, i, C.POINTER(PeerOpts), C.POINTER(vp)]),
         "wmixb_peer_bus_destroy": (None, [vp]),
         "wmixb_peer_bus_handle": (i, [vp, vp]),
         "wmixb_peer_bus_connect": (i, [vp, vp]),
@@ -82,6 +99,12 @@ def lib():
         "wmixb_get_stream_state": (i, [vp, i, vp]),
         "wmixb_set_stream_state": (i, [vp, i, vp]),
         "wmixb_sync": (i, [vp]),
+        "wmixb_set_tuning": (i, [vp, C.c_char_p, i]),
+        "wmixb_set_default_device": (i, [i]),
+        "wmixb_default_device": (i, []),
+        "wmixb_host_alloc": (vp, [sz, i, i]),
+        "wmixb_host_free": (None, [vp]),
+        "wmixb_host_copy_ceiling": (i, [i, vp, vp, sz, sz, i, C.POINTER(C.c_double)]),
         "wmixb_last_error": (C.c_char_p, []),
         "wmixb_kernel_launches": (C.c_longlong, []),
         "wmixb_state_bytes_per_stream": (sz, [vp]),

@@ -20,7 +20,7 @@ import ctypes as C
 
 import numpy as np
 
-from ._lib import WmixError, check, lib
+from ._lib import PeerOpts, WmixError, check, lib
 
 PEER_HANDLE_BYTES = 80
 
@@ -107,9 +107,13 @@ class CudaBackend:
             self.eng.g711_nminus1(law, d_bus, d_in, d_out, stream)
 
     # fused peer path
-    def peer_create(self, rank, world):
+    def peer_create(self, rank, world, opts=None):
+        """opts: dict of wmixb_peer_opts fields (tile, reduce_scatter, timeout_ms, ranks_per_device); the same on all ranks"""
         h = C.c_void_p()
-        check(self.L.wmixb_peer_bus_create(self.eng.h, rank, world, C.byref(h)), "wmixb_peer_bus_create")
+        o = PeerOpts(tile=0, reduce_scatter=-1, timeout_ms=0, ranks_per_device=0)
+        for k, v in (opts or {}).items():
+            setattr(o, k, self.eng.frame if (k == "tile" and v == "row") else int(v))
+        check(self.L.wmixb_peer_bus_create_ex(self.eng.h, rank, world, C.byref(o), C.byref(h)), "wmixb_peer_bus_create_ex")
         self.pb = h
         blob = (C.c_ubyte * PEER_HANDLE_BYTES)()
         check(self.L.wmixb_peer_bus_handle(self.pb, blob), "wmixb_peer_bus_handle")
@@ -148,7 +152,8 @@ class ShardedConference:
     tick(d_in, d_out, d_bus): d_in / d_out are this rank's [n_local, frame] legs (uint8 codes or int16),
     d_bus int32 [n_conf, frame] receives the full bus (scratch for the nccl / local modes)."""
 
-    def __init__(self, plan, rank, law=0, freq=8000, mode="peer", device=None, group=None, backend=None, dist=None):
+    def __init__(self, plan, rank, law=0, freq=8000, mode="peer", device=None, group=None, backend=None, dist=None,
+                 peer_opts=None):
         if mode not in ("peer", "nccl", "local"):
             raise ValueError("mode must be 'peer', 'nccl' or 'local'")
         if mode == "local" and plan.spans_ranks():
@@ -166,7 +171,7 @@ class ShardedConference:
         self.backend = backend if backend is not None else CudaBackend(self.n_local, freq, rank if device is None else device)
         self.backend.set_conferences(plan.local_conf_start(rank))
         if mode == "peer":
-            mine = self.backend.peer_create(rank, self.world)
+            mine = self.backend.peer_create(rank, self.world, peer_opts) if peer_opts else self.backend.peer_create(rank, self.world)
             if self.world > 1:
                 blobs = [None] * self.world
                 self.dist.all_gather_object(blobs, mine, group=group)

@@ -6,7 +6,9 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <list>
 #include <map>
+#include <memory>
 #include <mutex>
 #include <tuple>
 #include <vector>
@@ -16,6 +18,7 @@
 #include "../../include/wmix_zoom.h"
 #include "../../include/wmixb.h"
 #include "host_tables.h"
+#include "scratch.h"
 
 namespace {
 
@@ -41,6 +44,7 @@ Handle* make(int stage, int chn, int freq, int gain, bool* debug, const char* wh
     c.agc_gain_db = gain; // compressionGaindB, R:src/webrtc.c:707
     c.vad_mode = 3;       // VAD_AGGRESSIVE, R:src/webrtc.c:16
     c.ns_high_band = ns_high_band ? 1 : 0;
+    c.device = wmixb_default_device();
     wmixb_engine* e = nullptr;
     if (wmixb_create(&c, &e) != WMIXB_OK) {
         if (dbg(debug)) printf("%s failed !! (%s)\r\n", who, wmixb_last_error());
@@ -320,18 +324,18 @@ void aec_release(void* fp) { drop(fp, "aec_release"); }
 static int g711_host(int law, bool encode, const void* in, void* out, int n)
 {
     if (n <= 0) return 0;
-    void *din = nullptr, *dout = nullptr;
+    // grow-only staging and a private stream per calling thread: no cudaMalloc / cudaFree / device-wide sync per call
+    wmx::host::Scratch* sc = wmx::host::scratch(wmixb_default_device());
+    if (!sc) return -1;
     const size_t in_b = encode ? (size_t)n * 2 : (size_t)n, out_b = encode ? (size_t)n : (size_t)n * 2;
-    int rc = -1;
-    if (cudaMalloc(&din, in_b) == cudaSuccess && cudaMalloc(&dout, out_b) == cudaSuccess &&
-        cudaMemcpy(din, in, in_b, cudaMemcpyHostToDevice) == cudaSuccess) {
-        const int r = encode ? wmixb_g711_encode_device(law, (const int16_t*)din, (uint8_t*)dout, (size_t)n, nullptr)
-                             : wmixb_g711_decode_device(law, (const uint8_t*)din, (int16_t*)dout, (size_t)n, nullptr);
-        if (r == WMIXB_OK && cudaMemcpy(out, dout, out_b, cudaMemcpyDeviceToHost) == cudaSuccess) rc = 0;
-    }
-    cudaFree(din);
-    cudaFree(dout);
-    return rc;
+    void *din = sc->need(0, in_b), *dout = sc->need(1, out_b);
+    if (!din || !dout) return -1;
+    if (cudaMemcpyAsync(din, in, in_b, cudaMemcpyHostToDevice, sc->st) != cudaSuccess) return -1;
+    const int r = encode ? wmixb_g711_encode_device(law, (const int16_t*)din, (uint8_t*)dout, (size_t)n, sc->st)
+                         : wmixb_g711_decode_device(law, (const uint8_t*)din, (int16_t*)dout, (size_t)n, sc->st);
+    if (r != WMIXB_OK) return -1;
+    if (cudaMemcpyAsync(out, dout, out_b, cudaMemcpyDeviceToHost, sc->st) != cudaSuccess) return -1;
+    return cudaStreamSynchronize(sc->st) == cudaSuccess ? 0 : -1;
 }
 
 int g711a_encode(unsigned char g711_data[], const short amp[], int len) { return g711_host(0, true, amp, g711_data, len) == 0 ? len : -1; }
@@ -359,8 +363,10 @@ uint32_t wmix_len_of_in(uint8_t inChn, uint16_t inFreq, uint8_t outChn, uint16_t
     return wmx::host::zoom_len_of_in(inChn, inFreq, outChn, outFreq, outLen);
 }
 
-// One plan (gather table) per (formats, length) is kept for the life of the process, like the reference's callers
-// reuse one buffer size per task; the samples make an H2D -> kernel -> D2H round trip.
+// Plans (gather tables) are cached per (formats, length) in a small LRU — the reference's callers reuse one buffer size
+// per task, but a short last read or a variable decode length must not grow the cache for the life of the daemon.  The
+// lock covers the cache lookup only; the samples make their H2D -> kernel -> D2H round trip on the calling thread's own
+// staging and stream (scratch.h), so concurrent task threads do not serialise on each other.
 uint32_t wmix_pcm_zoom(uint8_t inChn, uint16_t inFreq, uint8_t* in, uint32_t inLen, uint8_t outChn, uint16_t outFreq,
                        uint8_t* out)
 {
@@ -368,27 +374,40 @@ uint32_t wmix_pcm_zoom(uint8_t inChn, uint16_t inFreq, uint8_t* in, uint32_t inL
         memcpy(out, in, inLen);
         return inLen;
     }
-    struct Slot { wmixb_zoom* z = nullptr; int16_t *d_in = nullptr, *d_out = nullptr; };
+    typedef std::tuple<int, int, uint32_t, int, int, int> Key;
+    struct Plan {
+        wmixb_zoom* z = nullptr;
+        ~Plan() { if (z) wmixb_zoom_destroy(z); }
+    };
+    constexpr size_t kMaxPlans = 32;
     static std::mutex mu;
-    static std::map<std::tuple<int, int, uint32_t, int, int>, Slot> plans;
-    std::lock_guard<std::mutex> lock(mu);
-    Slot& sl = plans[std::make_tuple((int)inChn, (int)inFreq, inLen, (int)outChn, (int)outFreq)];
-    if (!sl.z) {
-        if (wmixb_zoom_create(inChn, inFreq, inLen, outChn, outFreq, 0, &sl.z) != WMIXB_OK) return 0;
-        const uint32_t ob = wmixb_zoom_out_bytes(sl.z);
-        if (cudaMalloc(&sl.d_in, (size_t)inLen + 2) != cudaSuccess || cudaMalloc(&sl.d_out, ob ? ob : 2) != cudaSuccess) {
-            cudaFree(sl.d_in);
-            wmixb_zoom_destroy(sl.z);
-            sl = Slot();
-            return 0;
-        }
-        cudaMemset(sl.d_in, 0, (size_t)inLen + 2);
+    static std::list<std::pair<Key, std::shared_ptr<Plan>>> lru;      // most recently used first
+    const int device = wmixb_default_device();
+    const Key key = std::make_tuple((int)inChn, (int)inFreq, inLen, (int)outChn, (int)outFreq, device);
+    std::shared_ptr<Plan> plan;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        for (auto it = lru.begin(); it != lru.end(); ++it)
+            if (it->first == key) { plan = it->second; lru.splice(lru.begin(), lru, it); break; }
     }
-    const uint32_t ob = wmixb_zoom_out_bytes(sl.z);
+    if (!plan) {
+        plan = std::make_shared<Plan>();
+        if (wmixb_zoom_create(inChn, inFreq, inLen, outChn, outFreq, device, &plan->z) != WMIXB_OK) return 0;
+        std::lock_guard<std::mutex> lock(mu);
+        lru.emplace_front(key, plan);
+        while (lru.size() > kMaxPlans) lru.pop_back();               // a plan still in use elsewhere lives until that call returns
+    }
+    const uint32_t ob = wmixb_zoom_out_bytes(plan->z);
     if (ob == 0) return 0;
-    if (cudaMemcpy(sl.d_in, in, inLen, cudaMemcpyHostToDevice) != cudaSuccess) return 0;
-    if (wmixb_zoom_device(sl.z, sl.d_in, sl.d_out, 1, nullptr) != WMIXB_OK) return 0;
-    if (cudaMemcpy(out, sl.d_out, ob, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    wmx::host::Scratch* sc = wmx::host::scratch(device);
+    if (!sc) return 0;
+    void *d_in = sc->need(0, (size_t)inLen + 2), *d_out = sc->need(1, ob);
+    if (!d_in || !d_out) return 0;
+    if (cudaMemsetAsync((char*)d_in + (inLen & ~1u), 0, 2 + (inLen & 1u), sc->st) != cudaSuccess) return 0;   // the walk may look one sample past
+    if (cudaMemcpyAsync(d_in, in, inLen, cudaMemcpyHostToDevice, sc->st) != cudaSuccess) return 0;
+    if (wmixb_zoom_device(plan->z, (const int16_t*)d_in, (int16_t*)d_out, 1, sc->st) != WMIXB_OK) return 0;
+    if (cudaMemcpyAsync(out, d_out, ob, cudaMemcpyDeviceToHost, sc->st) != cudaSuccess) return 0;
+    if (cudaStreamSynchronize(sc->st) != cudaSuccess) return 0;
     return ob;
 }
 

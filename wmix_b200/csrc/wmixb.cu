@@ -12,12 +12,16 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <sched.h>
+#include <unistd.h>
+
 #include <atomic>
 #include <map>
 #include <mutex>
 #include <tuple>
 #include <vector>
 
+#include "../../include/wmix.h"
 #include "../../include/wmix_rtp.h"
 #include "../../include/wmix_zoom.h"
 #include "../../include/wmixb.h"
@@ -27,6 +31,7 @@
 #include "host_tables.h"
 #include "ns.cuh"
 #include "peer_bus.cuh"
+#include "scratch.h"
 #include "vad.cuh"
 
 using namespace wmx;
@@ -36,6 +41,7 @@ using namespace wmx;
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_default_device{0};   // device of the drop-in handle / codec / zoom entry points
 
 static int fail_cuda(cudaError_t e, const char* what, int line)
 {
@@ -460,11 +466,12 @@ struct wmixb_engine {
     int ns_cfg = 2;                         // index into kNsCfgs: 2 CTAs of 10 warps at 96 registers per lane (measured best)
     int ns_align = 1;                       // CTA barrier at the top of every frame (instruction-cache sharing)
     int post_occ = 3;                       // same for post_kernel (3 CTAs of 128 threads, 168 registers per thread: measured best)
+    int host_chunks_sync = 8, host_chunks_pipe = 4, host_lanes = 0;   // chunk pipeline of the host-buffer tick (wmixb_set_tuning)
     float* aec_rec = nullptr;               // [n_streams][aec_rec_floats]
     void* aec_tables = nullptr;
     int* aec_result = nullptr;              // [2] flags OR, flagged count
     int16_t* aec_stage = nullptr;           // far / near / out staging of the host-buffer entry point
-    int aec_depth = 0, aec_grid = 0, aec_pf = 2;
+    int aec_depth = 0, aec_grid = 0, aec_grid_max = 0, aec_pf = 2;
     size_t aec_rec_floats = 0;
 };
 
@@ -503,6 +510,21 @@ static int launch_ns(wmixb_engine* e, int grid, cudaStream_t st, const int16_t* 
     return WMIXB_OK;
 }
 
+// launch shape of the NS kernel for e->ns_cfg: opt into its dynamic shared memory, size the persistent grid
+template <int ANA>
+static int ns_configure(wmixb_engine* e)
+{
+    const void* fn = ns_fn<ANA>(e->ns_cfg);
+    const int warps = kNsCfgs[e->ns_cfg].warps;
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns_smem_bytes<ANA>(warps)));
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, ns_smem_bytes<ANA>(warps)));
+    if (per_sm < 1) per_sm = 1;
+    e->ns_grid = e->sm_count * per_sm;
+    return WMIXB_OK;
+}
+
 template <int ANA>
 static int upload_ns_tables(wmixb_engine* e)
 {
@@ -519,18 +541,7 @@ static int upload_ns_tables(wmixb_engine* e)
     }
     CK(cudaMalloc(&e->ns_tables, sizeof T));
     CK(cudaMemcpy(e->ns_tables, &T, sizeof T, cudaMemcpyHostToDevice));
-    // register budget variant: 2 / 3 / 4 CTAs of 8 warps per SM (128 / 80 / 64 registers per lane)
-    if (const char* v = getenv("WMIXB_NS_CFG")) { const int o = atoi(v); if (o >= 0 && o < (int)(sizeof kNsCfgs / sizeof kNsCfgs[0])) e->ns_cfg = o; }
-    if (const char* v = getenv("WMIXB_NS_ALIGN")) { const int a = atoi(v); if (a >= 0 && a <= 64) e->ns_align = a; }   // 0 = never, k = every k-th stream
-    const void* fn = ns_fn<ANA>(e->ns_cfg);
-    const int warps = kNsCfgs[e->ns_cfg].warps;
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns_smem_bytes<ANA>(warps)));
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, ns_smem_bytes<ANA>(warps)));
-    if (per_sm < 1) per_sm = 1;
-    e->ns_grid = e->sm_count * per_sm;
-    return WMIXB_OK;
+    return ns_configure<ANA>(e);
 }
 
 static int upload_agc_table(wmixb_engine* e, int gain_db)
@@ -645,8 +656,7 @@ static int create_impl(const wmixb_config* cfg, wmixb_engine* e)
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aec_kernel, kAecWarps * 32, kAecSmemBytes));
         if (per_sm < 1) per_sm = 1;
         e->aec_grid = e->sm_count * per_sm;
-        if (const char* v = getenv("WMIXB_AEC_PF")) e->aec_pf = atoi(v);
-        if (const char* v = getenv("WMIXB_AEC_GRID")) { const int g = atoi(v); if (g > 0 && g < e->aec_grid) e->aec_grid = g; }
+        e->aec_grid_max = e->aec_grid;
     }
     if (cfg->stages & WMIXB_AGC) {
         int32_t init[agc::N_WORDS];
@@ -670,7 +680,6 @@ static int create_impl(const wmixb_config* cfg, wmixb_engine* e)
         host::vad_thresholds(cfg->vad_mode, 20, th);
         e->vp20 = vad::Params{th[0], th[1], th[2], th[3]};
     }
-    if (const char* v = getenv("WMIXB_POST_OCC")) { const int o = atoi(v); if (o >= 2 && o <= 5) e->post_occ = o; }
     CK(cudaMalloc(&e->d_in, n * e->frame * sizeof(int16_t)));
     CK(cudaMalloc(&e->d_out, n * e->frame * sizeof(int16_t)));
     CK(cudaMalloc(&e->d_vad, n));
@@ -1027,15 +1036,14 @@ extern "C" int wmixb_offline_device(wmixb_engine* e, const int16_t* d_in, int16_
 static int tick_host_impl(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int32_t* h_bus, int stages,
                           bool pipelined = false, int slot = 0)
 {
-    if (!e || !h_in || !h_out) return WMIXB_EINVAL;
+    if (!e || !h_in || (!h_out && !h_bus && !h_vad)) return WMIXB_EINVAL;
     if (h_bus && e->n_conf < 1) { snprintf(g_err, sizeof g_err, "tick_host_bus: call wmixb_set_conferences first"); return WMIXB_EINVAL; }
     CK(cudaSetDevice(e->cfg.device));
     const int n = e->cfg.n_streams;
     // One chunk per pipeline stream (a stream that gets two chunks serialises them and unbalances the pipeline).  Measured per
     // 100 k-stream tick, chunks = streams: blocking call 1.50 / 1.39 / 1.35 / 1.32 / 1.27 ms for 3 / 4 / 5 / 6 / 8; pipelined
-    // ticks 1.07 / 0.96 / 0.96 / 0.97 / 0.99 ms.  WMIXB_HOST_CHUNKS / WMIXB_HOST_LANES override (experiments).
-    int chunks = pipelined ? 4 : 8;
-    if (const char* v = getenv("WMIXB_HOST_CHUNKS")) { const int c = atoi(v); if (c >= 1 && c <= 64) chunks = c; }
+    // ticks 1.07 / 0.96 / 0.96 / 0.97 / 0.99 ms.  wmixb_set_tuning("host_chunks" / "host_lanes") overrides (experiments).
+    int chunks = pipelined ? e->host_chunks_pipe : e->host_chunks_sync;
     if (n < 8192 && !pipelined) chunks = 1;
     if (pipelined && chunks < 3) chunks = 3;
     int per = ((n + chunks - 1) / chunks + 127) / 128 * 128;     // whole post_kernel CTAs, line-aligned SoA rows
@@ -1051,7 +1059,7 @@ static int tick_host_impl(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, 
     }
     const bool multi = chunks > 1;
     int lanes_used = chunks < kPipe ? chunks : kPipe;            // pipeline streams this tick deals its chunks to
-    if (const char* v = getenv("WMIXB_HOST_LANES")) { const int l = atoi(v); if (l >= 1 && l <= kPipe) lanes_used = l; }
+    if (e->host_lanes >= 1 && e->host_lanes < lanes_used) lanes_used = e->host_lanes;
     if (multi && !e->pipe[0]) {
         for (int k = 0; k < kPipe; ++k) {
             CK(cudaStreamCreateWithFlags(&e->pipe[k], cudaStreamNonBlocking));
@@ -1068,7 +1076,7 @@ static int tick_host_impl(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, 
         const int rc = run_stages(e, e->d_in + off, d_out + off, e->d_vad + first, 1, stages, st, nullptr, 0, first, cnt);
         if (rc) return rc;
         if (multi && h_bus) CK(cudaEventRecord(e->pipe_ev[c % lanes_used], st));   // last record per stream covers its chunks
-        CK(cudaMemcpyAsync(h_out + off, d_out + off, bytes, cudaMemcpyDeviceToHost, st));
+        if (h_out) CK(cudaMemcpyAsync(h_out + off, d_out + off, bytes, cudaMemcpyDeviceToHost, st));
         if (h_vad) CK(cudaMemcpyAsync(h_vad + first, e->d_vad + first, (size_t)cnt, cudaMemcpyDeviceToHost, st));
         used = c + 1 < lanes_used ? c + 1 : lanes_used;
     }
@@ -1121,6 +1129,12 @@ extern "C" int wmixb_tick_host_submit(wmixb_engine* e, const int16_t* h_in, int1
     }
     const int rc = tick_host_impl(e, h_in, h_out, h_vad, h_bus, stages, true, (int)(e->submitted & 1));
     if (rc == WMIXB_OK) e->submitted++;
+    else {
+        // part of the tick may be queued with no completion event recorded: drain it before the caller frees its buffers
+        for (int k = 0; k < kPipe; ++k) if (e->pipe[k]) cudaStreamSynchronize(e->pipe[k]);
+        cudaStreamSynchronize(e->stream);
+        (void)cudaGetLastError();
+    }
     return rc;
 }
 
@@ -1254,6 +1268,17 @@ static void peer_set_ring(wmixb_peer_bus* pb, int r, void* base)
 
 extern "C" int wmixb_peer_bus_create(wmixb_engine* e, int rank, int world, wmixb_peer_bus** out)
 {
+    return wmixb_peer_bus_create_ex(e, rank, world, nullptr, out);
+}
+
+extern "C" int wmixb_peer_bus_create_ex(wmixb_engine* e, int rank, int world, const wmixb_peer_opts* opts, wmixb_peer_bus** out)
+{
+    wmixb_peer_opts o;
+    memset(&o, 0, sizeof o);
+    o.reduce_scatter = -1;
+    if (opts) o = *opts;
+    if (o.tile != 0 && o.tile != 16 && !(e && o.tile == e->frame)) { snprintf(g_err, sizeof g_err, "peer_bus: tile must be 0, 16 or the frame length"); return WMIXB_EINVAL; }
+    if (o.ranks_per_device < 0 || o.ranks_per_device > 8 || o.timeout_ms < 0) return WMIXB_EINVAL;
     if (!e || !out || world < 1 || world > peer::kMaxWorld || rank < 0 || rank >= world) return WMIXB_EINVAL;
     *out = nullptr;
     if (e->n_conf < 1) { snprintf(g_err, sizeof g_err, "peer_bus: call wmixb_set_conferences first"); return WMIXB_EINVAL; }
@@ -1267,9 +1292,9 @@ extern "C" int wmixb_peer_bus_create(wmixb_engine* e, int rank, int world, wmixb
     pb->rflag_bytes = ((size_t)2 * e->n_conf * sizeof(uint32_t) + 15) / 16 * 16;
     // tile = 16 samples or the whole bus row (the same on every rank: a function of n_conf only, peer::tile_for)
     pb->tile = peer::tile_for(e->n_conf, e->frame);
-    if (const char* v = getenv("WMIXB_PEER_TILE")) { const int t = strcmp(v, "row") == 0 ? e->frame : atoi(v); if (t == 16 || t == e->frame) pb->tile = t; }   // experiments / tests: set on ALL ranks
+    if (o.tile) pb->tile = o.tile;                                                       // experiments / tests: the same on ALL ranks
     pb->rs = peer::reduce_scatter_for(e->n_conf, e->frame, world) && pb->tile == e->frame;
-    if (const char* v = getenv("WMIXB_PEER_RS")) pb->rs = atoi(v) != 0 && pb->tile == e->frame;                                 // experiments: set on ALL ranks
+    if (o.reduce_scatter >= 0) pb->rs = o.reduce_scatter != 0 && pb->tile == e->frame;    // experiments: the same on ALL ranks
     // member slices per tile: a quarter of the largest local conference, power of two, 2..32 (1.. for row tiles),
     // as many as fit one CTA
     int slices = pb->tile == peer::kTile ? 2 : 1;
@@ -1285,7 +1310,7 @@ extern "C" int wmixb_peer_bus_create(wmixb_engine* e, int rank, int world, wmixb
     }
     const int groups = pb->threads / (slices * pb->tile);
     pb->smem = (size_t)groups * (slices + 1) * pb->tile * sizeof(int32_t);
-    if (const char* v = getenv("WMIXB_PEER_TIMEOUT_MS")) { const long ms = atol(v); if (ms > 0) pb->timeout_ns = (unsigned long long)ms * 1000000ull; }
+    if (o.timeout_ms > 0) pb->timeout_ns = (unsigned long long)o.timeout_ms * 1000000ull;
     const size_t mailbox_bytes = pb->slot_bytes + pb->flag_bytes + pb->result_bytes + pb->rflag_bytes;
     cudaError_t ce = cudaMalloc(&pb->mailbox, mailbox_bytes);
     if (ce == cudaSuccess) ce = cudaMemset(pb->mailbox, 0, mailbox_bytes);
@@ -1300,9 +1325,18 @@ extern "C" int wmixb_peer_bus_create(wmixb_engine* e, int rank, int world, wmixb
         else ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, peer::peer_bus_kernel<0, 160>, pb->threads, pb->smem);
     }
     if (ce != cudaSuccess) { cudaFree(pb->mailbox); cudaFree(pb->d_error); delete pb; return fail_cuda(ce, "peer_bus_create", __LINE__); }
-    // every CTA must be resident (phase 2 waits on other ranks): never more than one wave
-    // (half of it, so that a second rank living on the same device — tests — still fits beside this one)
-    const int cap = e->sm_count * (per_sm < 2 ? 1 : per_sm / 2);
+    // every CTA must be resident (phase 2 waits on other ranks): never more than one wave, shared between the ranks whose
+    // peer kernels may run on this GPU at the same time (opts->ranks_per_device; default 2, so that a second rank living
+    // on the same device — the one-process tests — still fits beside this one).  If the share is less than one CTA per
+    // SM the guarantee cannot be given: refuse instead of risking a spin until the timeout.
+    const int share = o.ranks_per_device > 0 ? o.ranks_per_device : 2;
+    if (per_sm < 1 || e->sm_count * per_sm / share < 1) {
+        cudaFree(pb->mailbox); cudaFree(pb->d_error); delete pb;
+        snprintf(g_err, sizeof g_err, "peer_bus: %d ranks per device cannot all be resident (%d CTAs per SM)", share, per_sm);
+        return WMIXB_EINVAL;
+    }
+    int cap = e->sm_count * per_sm / share;
+    if (cap < 1) cap = 1;
     const int n_steps = (e->n_conf * (e->frame / pb->tile) + groups - 1) / groups;
     pb->grid = n_steps < cap ? n_steps : cap;
     peer_set_ring(pb, rank, pb->mailbox);
@@ -1392,6 +1426,7 @@ extern "C" int wmixb_peer_bus_tick_device(wmixb_peer_bus* pb, int law, const voi
     wmixb_engine* e = pb->e;
     if (e->n_conf != pb->n_conf) { snprintf(g_err, sizeof g_err, "peer_bus: the conference table changed after create"); return WMIXB_EINVAL; }
     CK(cudaSetDevice(e->cfg.device));
+    const uint32_t seq_before = pb->seq;
     if (++pb->seq == 0) pb->seq = 2;     // 0 is the "never written" flag value; keep the parity sequence alternating
     cudaStream_t st = (cudaStream_t)stream;
 #define WMX_PEER(LAW, TILE) peer::peer_bus_kernel<LAW, TILE><<<pb->grid, pb->threads, pb->smem, st>>>(pb->ring, pb->rank, pb->world, pb->seq, d_in, d_out, d_bus, e->conf_start, pb->n_conf, e->frame, pb->slices, pb->timeout_ns, pb->d_error)
@@ -1404,7 +1439,12 @@ extern "C" int wmixb_peer_bus_tick_device(wmixb_peer_bus* pb, int law, const voi
 #undef WMX_PEER_RS
 #undef WMX_PEER_T
 #undef WMX_PEER
-    CK_LAUNCH();
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    const cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+        pb->seq = seq_before;            // nothing ran: this rank's tick parity must stay in step with its peers
+        return fail_cuda(le, "peer_bus kernel launch", __LINE__);
+    }
     return WMIXB_OK;
 }
 
@@ -1593,48 +1633,79 @@ extern "C" uint8_t* wmixb_load_data_host(const wmixb_mix_view* w, const uint8_t*
     const uint32_t pos = (uint32_t)(head - w->ring_start) / 2;
     const bool same = freq == w->mix_freq && channels == 1 && sample == 16;
     if (!same && !(sample == 16 && (channels == 1 || channels == 2))) return head;                           // the empty 8 / 32-bit cases
-    struct Slot { wmixb_mixplan* plan = nullptr; };
+    // plans are immutable once built and keyed by device; the lock covers the lookup only, the round trip runs on the calling
+    // thread's own staging and stream (scratch.h)
     static std::mutex mu;
-    static std::map<std::tuple<int, int, uint32_t, int>, Slot> plans;
-    static int16_t *d_span = nullptr, *d_src = nullptr;
-    static size_t span_cap = 0, src_cap = 0;
-    std::lock_guard<std::mutex> lock(mu);
-    uint32_t n_out = src_bytes / 2;
+    static std::map<std::tuple<int, int, uint32_t, int, int>, wmixb_mixplan*> plans;
+    // The reference's loop `for (count = 0; count < srcU8Len; count += 2)` (R:src/wmix.c:1681) consumes ceil(n / 2) samples
+    // of an odd-length source, reading one byte past it; here the last, half-present sample is completed with a zero byte.
+    uint32_t n_out = (src_bytes + 1) / 2;
     wmixb_mixplan* plan = nullptr;
     if (!same) {
-        Slot& sl = plans[std::make_tuple((int)channels, (int)freq, src_bytes, (int)w->mix_freq)];
-        if (!sl.plan && wmixb_mixplan_create(channels, freq, src_bytes, w->mix_freq, w->device, &sl.plan) != WMIXB_OK) return head;
-        plan = sl.plan;
+        std::lock_guard<std::mutex> lock(mu);
+        wmixb_mixplan*& slot = plans[std::make_tuple((int)channels, (int)freq, src_bytes, (int)w->mix_freq, w->device)];
+        if (!slot && wmixb_mixplan_create(channels, freq, src_bytes, w->mix_freq, w->device, &slot) != WMIXB_OK) { slot = nullptr; return head; }
+        plan = slot;
         n_out = wmixb_mixplan_out_samples(plan);
     }
     if (n_out == 0) return head;
     if (n_out > ring_len) { snprintf(g_err, sizeof g_err, "load_data: the chunk (%u samples) is longer than the ring", n_out); return head; }
-    if (cudaSetDevice(w->device) != cudaSuccess) return head;
-    const size_t src_elems = src_bytes / 2 + 2;
-    if (span_cap < n_out) { cudaFree(d_span); d_span = nullptr; span_cap = 0; if (cudaMalloc(&d_span, (size_t)n_out * 2) != cudaSuccess) return head; span_cap = n_out; }
-    if (src_cap < src_elems) { cudaFree(d_src); d_src = nullptr; src_cap = 0; if (cudaMalloc(&d_src, src_elems * 2) != cudaSuccess) return head; src_cap = src_elems; }
+    host::Scratch* sc = host::scratch(w->device);
+    if (!sc) return head;
+    const size_t src_elems = (src_bytes + 1) / 2 + 2;
+    int16_t* d_span = (int16_t*)sc->need(0, (size_t)n_out * 2);
+    int16_t* d_src = (int16_t*)sc->need(1, src_elems * 2);
+    uint8_t* d_rd = (uint8_t*)sc->need(2, 16);
+    if (!d_span || !d_src || !d_rd) return head;
+    cudaStream_t st = sc->st;
     // the touched span [pos, pos + n_out) of the ring, unwrapped, becomes a private device ring of exactly n_out samples
     int16_t* ring16 = reinterpret_cast<int16_t*>(w->ring_start);
     const uint32_t first = n_out < ring_len - pos ? n_out : ring_len - pos;
-    bool ok = cudaMemcpy(d_span, ring16 + pos, (size_t)first * 2, cudaMemcpyHostToDevice) == cudaSuccess;
-    if (ok && first < n_out) ok = cudaMemcpy(d_span + first, ring16, (size_t)(n_out - first) * 2, cudaMemcpyHostToDevice) == cudaSuccess;
-    if (ok) ok = cudaMemcpy(d_src, src, src_bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    bool ok = cudaMemcpyAsync(d_span, ring16 + pos, (size_t)first * 2, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (ok && first < n_out) ok = cudaMemcpyAsync(d_span + first, ring16, (size_t)(n_out - first) * 2, cudaMemcpyHostToDevice, st) == cudaSuccess;
+    if (ok && (src_bytes & 1)) ok = cudaMemsetAsync(d_src + src_bytes / 2, 0, 2, st) == cudaSuccess;
+    if (ok) ok = cudaMemcpyAsync(d_src, src, src_bytes, cudaMemcpyHostToDevice, st) == cudaSuccess;
     if (ok) {
-        if (same) ok = wmixb_mix_load_device(d_span, n_out, 0, d_src, n_out, rdce, nullptr, nullptr) == WMIXB_OK;
+        if (same) ok = wmixb_mix_load_device(d_span, n_out, 0, d_src, n_out, rdce, nullptr, st) == WMIXB_OK;
         else {
-            uint8_t* d_rd = nullptr;
             const uint8_t rd8 = (uint8_t)rdce;
-            ok = cudaMalloc(&d_rd, 16) == cudaSuccess && cudaMemcpy(d_rd, &rd8, 1, cudaMemcpyHostToDevice) == cudaSuccess &&
-                 wmixb_mix_load_plan_device(plan, d_span, n_out, 0, d_src, 1, d_rd, nullptr, nullptr) == WMIXB_OK &&
-                 cudaDeviceSynchronize() == cudaSuccess;
-            cudaFree(d_rd);
+            ok = cudaMemcpyAsync(d_rd, &rd8, 1, cudaMemcpyHostToDevice, st) == cudaSuccess &&
+                 wmixb_mix_load_plan_device(plan, d_span, n_out, 0, d_src, 1, d_rd, nullptr, st) == WMIXB_OK;
         }
     }
-    if (ok) ok = cudaMemcpy(ring16 + pos, d_span, (size_t)first * 2, cudaMemcpyDeviceToHost) == cudaSuccess;
-    if (ok && first < n_out) ok = cudaMemcpy(ring16, d_span + first, (size_t)(n_out - first) * 2, cudaMemcpyDeviceToHost) == cudaSuccess;
+    if (ok) ok = cudaMemcpyAsync(ring16 + pos, d_span, (size_t)first * 2, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (ok && first < n_out) ok = cudaMemcpyAsync(ring16, d_span + first, (size_t)(n_out - first) * 2, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+    if (ok) ok = cudaStreamSynchronize(st) == cudaSuccess;
     if (!ok) { snprintf(g_err, sizeof g_err, "load_data: CUDA call failed: %s", cudaGetErrorString(cudaGetLastError())); return head; }
     *tick += n_out * 2;                                                                                      // :1942-1953
     return w->ring_start + (size_t)((pos + n_out) % ring_len) * 2;
+}
+
+// wmix_load_data under the reference's own prototype (include/wmix.h): the view is read off the daemon's struct
+static std::atomic<uint32_t> g_mix_freq{8000}, g_play_correct{3200};   // R:platform/alsa/plat.h:17-21
+extern "C" void wmix_load_data_config(uint16_t mix_freq, uint32_t play_correct_bytes)
+{
+    g_mix_freq.store(mix_freq);
+    g_play_correct.store(play_correct_bytes);
+}
+extern "C" WMix_Point wmix_load_data(WMix_Struct* wmix, WMix_Point src, uint32_t srcU8Len, uint16_t freq, uint8_t channels,
+                                     uint8_t sample, WMix_Point head, uint8_t reduce, uint32_t* tick)
+{
+    if (!wmix) return head;                                                                                  // R:src/wmix.c:1664
+    wmixb_mix_view v;
+    memset(&v, 0, sizeof v);
+    v.ring_start = wmix->start.U8;
+    v.ring_bytes = (uint32_t)(wmix->end.U8 - wmix->start.U8);
+    v.head_off = (uint32_t)(wmix->head.U8 - wmix->start.U8);
+    v.tick = wmix->tick;
+    v.play_correct = g_play_correct.load();
+    v.mix_freq = (uint16_t)g_mix_freq.load();
+    v.reduce_mode = wmix->reduceMode;
+    v.run = wmix->run ? 1 : 0;
+    v.device = g_default_device.load();
+    WMix_Point out;
+    out.U8 = wmixb_load_data_host(&v, src.U8, srcU8Len, freq, channels, sample, head.U8, reduce, tick);
+    return out;
 }
 
 // ---- state snapshot ----
@@ -1898,6 +1969,144 @@ extern "C" int wmixb_selftest_fdiv(unsigned long long n, unsigned seed, float a_
 }
 
 // ---- bookkeeping ----
+// ---- experiment / test knobs (none of them changes results) ----
+extern "C" int wmixb_set_tuning(wmixb_engine* e, const char* key, int value)
+{
+    if (!e || !key) return WMIXB_EINVAL;
+    CK(cudaSetDevice(e->cfg.device));
+    if (!strcmp(key, "ns_cfg")) {
+        if (value < 0 || value >= (int)(sizeof kNsCfgs / sizeof kNsCfgs[0]) || !e->ns_rec) return WMIXB_EINVAL;
+        e->ns_cfg = value;
+        return e->ana == 256 ? ns_configure<256>(e) : ns_configure<128>(e);
+    }
+    if (!strcmp(key, "ns_align")) { if (value < 0 || value > 64) return WMIXB_EINVAL; e->ns_align = value; return WMIXB_OK; }
+    if (!strcmp(key, "post_occ")) { if (value < 2 || value > 5) return WMIXB_EINVAL; e->post_occ = value; return WMIXB_OK; }
+    if (!strcmp(key, "aec_pf")) { e->aec_pf = value; return WMIXB_OK; }
+    if (!strcmp(key, "aec_grid")) { if (value < 1 || value > e->aec_grid_max) return WMIXB_EINVAL; e->aec_grid = value; return WMIXB_OK; }
+    if (!strcmp(key, "host_chunks")) { if (value < 1 || value > 64) return WMIXB_EINVAL; e->host_chunks_sync = e->host_chunks_pipe = value; return WMIXB_OK; }
+    if (!strcmp(key, "host_lanes")) { if (value < 0 || value > kPipe) return WMIXB_EINVAL; e->host_lanes = value; return WMIXB_OK; }
+    snprintf(g_err, sizeof g_err, "set_tuning: unknown key '%s'", key);
+    return WMIXB_EINVAL;
+}
+
+extern "C" int wmixb_set_default_device(int device)
+{
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) { (void)cudaGetLastError(); return WMIXB_EINVAL; }
+    g_default_device.store(device);
+    return WMIXB_OK;
+}
+extern "C" int wmixb_default_device(void) { return g_default_device.load(); }
+
+// ---- pinned host buffers placed for a device ----
+// Pinned pages are allocated by the calling thread inside cudaHostAlloc, so the NUMA node they land on is the one the
+// thread runs on at that moment: the thread is moved onto the CPUs of the device's node (sysfs: the PCI function's
+// numa_node and that node's cpulist) for the duration of the allocation and the first touch, then put back.
+static bool numa_cpus_of_device(int device, cpu_set_t* set)
+{
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) { (void)cudaGetLastError(); return false; }
+    for (char* c = bus; *c; ++c) if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    int node = -1;
+    const int got = fscanf(f, "%d", &node);
+    fclose(f);
+    if (got != 1 || node < 0) return false;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return false;
+    char list[4096] = "";
+    const bool have = fgets(list, sizeof list, f) != nullptr;
+    fclose(f);
+    if (!have) return false;
+    CPU_ZERO(set);
+    int n = 0;
+    for (char* p = list; *p && *p != '\n';) {
+        char* end;
+        long a = strtol(p, &end, 10), b = a;
+        if (end == p) break;
+        if (*end == '-') { p = end + 1; b = strtol(p, &end, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; ++c) { CPU_SET((int)c, set); ++n; }
+        p = *end == ',' ? end + 1 : end;
+    }
+    return n > 0;
+}
+
+extern "C" void* wmixb_host_alloc(size_t bytes, int device, int flags)
+{
+    if (bytes == 0 || cudaSetDevice(device) != cudaSuccess) { (void)cudaGetLastError(); return nullptr; }
+    cpu_set_t old_set, node_set;
+    const bool have_old = sched_getaffinity(0, sizeof old_set, &old_set) == 0;
+    bool moved = false;
+    if (have_old && numa_cpus_of_device(device, &node_set)) {
+        cpu_set_t both;
+        CPU_AND(&both, &node_set, &old_set);                       // never leave the cpuset the process was given
+        if (CPU_COUNT(&both) > 0) moved = sched_setaffinity(0, sizeof both, &both) == 0;
+    }
+    void* p = nullptr;
+    unsigned f = cudaHostAllocPortable;
+    if (flags & WMIXB_HOST_WRITE_COMBINED) f |= cudaHostAllocWriteCombined;
+    const cudaError_t ce = cudaHostAlloc(&p, bytes, f);
+    if (ce == cudaSuccess && !(flags & WMIXB_HOST_WRITE_COMBINED)) memset(p, 0, bytes);   // first touch on the node
+    if (moved) sched_setaffinity(0, sizeof old_set, &old_set);
+    if (ce != cudaSuccess) { fail_cuda(ce, "cudaHostAlloc", __LINE__); return nullptr; }
+    return p;
+}
+
+extern "C" void wmixb_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+// What the copy engines alone sustain for one tick's traffic: h2d_bytes host -> device and d2h_bytes device -> host as
+// bare cudaMemcpyAsync calls on two streams (full duplex), `reps` times back to back; *ms_per_rep = wall time per rep.
+// The ceiling the host-buffer tick is measured against (no kernels, no library logic).
+extern "C" int wmixb_host_copy_ceiling(int device, const void* h_src, void* h_dst, size_t h2d_bytes, size_t d2h_bytes, int reps,
+                                       double* ms_per_rep)
+{
+    if (!ms_per_rep || reps < 1 || (h2d_bytes && !h_src) || (d2h_bytes && !h_dst)) return WMIXB_EINVAL;
+    CK(cudaSetDevice(device));
+    void *d_a = nullptr, *d_b = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    cudaError_t ce = cudaSuccess;
+    float ms = 0.f;
+#define WMX_TRY(x) do { if (ce == cudaSuccess) ce = (x); } while (0)
+    WMX_TRY(cudaMalloc(&d_a, h2d_bytes ? h2d_bytes : 16));
+    WMX_TRY(cudaMalloc(&d_b, d2h_bytes ? d2h_bytes : 16));
+    WMX_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    WMX_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    WMX_TRY(cudaEventCreate(&e0));
+    WMX_TRY(cudaEventCreate(&e1));
+    WMX_TRY(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+    for (int pass = 0; pass < 2 && ce == cudaSuccess; ++pass) {       // pass 0 warms the mappings up
+        WMX_TRY(cudaEventRecord(e0, s_in));
+        WMX_TRY(cudaStreamWaitEvent(s_out, e0, 0));
+        for (int r = 0; r < (pass ? reps : 2) && ce == cudaSuccess; ++r) {
+            if (h2d_bytes) WMX_TRY(cudaMemcpyAsync(d_a, h_src, h2d_bytes, cudaMemcpyHostToDevice, s_in));
+            if (d2h_bytes) WMX_TRY(cudaMemcpyAsync(h_dst, d_b, d2h_bytes, cudaMemcpyDeviceToHost, s_out));
+        }
+        WMX_TRY(cudaEventRecord(e2, s_out));
+        WMX_TRY(cudaStreamWaitEvent(s_in, e2, 0));
+        WMX_TRY(cudaEventRecord(e1, s_in));
+        WMX_TRY(cudaEventSynchronize(e1));
+    }
+    WMX_TRY(cudaEventElapsedTime(&ms, e0, e1));
+#undef WMX_TRY
+    cudaFree(d_a); cudaFree(d_b);
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_out) cudaStreamDestroy(s_out);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (e2) cudaEventDestroy(e2);
+    if (ce != cudaSuccess) return fail_cuda(ce, "host_copy_ceiling", __LINE__);
+    *ms_per_rep = (double)ms / reps;
+    return WMIXB_OK;
+}
+
 extern "C" int wmixb_sync(wmixb_engine* e)
 {
     if (!e) return WMIXB_EINVAL;

@@ -128,6 +128,10 @@ class Engine:
     def sync(self):
         check(self.L.wmixb_sync(self.h), "wmixb_sync")
 
+    def set_tuning(self, key, value):
+        """experiment / test knobs of include/wmixb.h (none changes results)"""
+        check(self.L.wmixb_set_tuning(self.h, key.encode(), int(value)), "wmixb_set_tuning(%s)" % key)
+
     def state_bytes_per_stream(self):
         return self.L.wmixb_state_bytes_per_stream(self.h)
 
@@ -154,6 +158,40 @@ def mix_load(d_ring, ring_len, pos, d_src, n, rdce, stream=None):
     check(lib().wmixb_mix_load_device(_ptr(d_ring), ring_len, pos, _ptr(d_src), n, rdce, C.byref(new_pos),
                                       _stream_ptr(stream)), "wmixb_mix_load_device")
     return new_pos.value
+
+
+class HostBuffer:
+    """Pinned host memory from wmixb_host_alloc (NUMA-local to `device`), viewed as a numpy array."""
+
+    def __init__(self, shape, dtype, device=0, write_combined=False):
+        self.L = lib()
+        self.shape, self.dtype = tuple(shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = self.L.wmixb_host_alloc(self.nbytes, device, 1 if write_combined else 0)
+        if not self.ptr:
+            raise RuntimeError("wmixb_host_alloc(%d bytes) failed: %s" % (self.nbytes, self.L.wmixb_last_error().decode()))
+        buf = (C.c_ubyte * self.nbytes).from_address(self.ptr)
+        self.array = np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.L.wmixb_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def host_copy_ceiling(device, h_src, h_dst, h2d_bytes, d2h_bytes, reps=20):
+    """ms per repetition of bare cudaMemcpyAsync traffic (wmixb_host_copy_ceiling)"""
+    ms = C.c_double(0.0)
+    check(lib().wmixb_host_copy_ceiling(device, _ptr(h_src), _ptr(h_dst), h2d_bytes, d2h_bytes, reps, C.byref(ms)),
+          "wmixb_host_copy_ceiling")
+    return ms.value
 
 
 def kernel_launches():
