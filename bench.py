@@ -10,8 +10,21 @@ B200 HBM roofline the dominant kernel (ns_kernel) reaches.
 
 A "step" is one 10 ms tick over every stream of the job: ns_kernel, post_kernel (AGC+VAD) and
 bus_sum_kernel.  Workload: BASELINE config 3, 100 000 streams per GPU (weak scaling: every rank
-owns its own 100 000 streams and its own conferences; the path has no cross-stream exchange, so
-there is no collective).  value = streams_total * 10 ms / ms_per_step.
+owns its own 100 000 streams and its own conferences; that path has no cross-stream exchange).
+value = streams_total * 10 ms / ms_per_step.
+
+Both arms age every handle by the same PRIME = 600 untimed ticks before the W warm-up ticks and the K
+timed ones ("timed after 600 warm-up"), whatever --warmup says: WebRtcNs is
+1.5-2x slower per frame inside its 50-frame start-up model and switches its gain map on at frame 200, so a
+run timed on fresh handles measures a different regime on both sides.
+
+Keyed sub-measurements in the same JSON line (none of them changes `value`):
+  conf5     (N > 1)  BASELINE config 5, the one collective of the path: the conference bus striped over all
+                     ranks — fused peer-memory kernel vs bus_sum -> NCCL all-reduce -> nminus1, with an in-run
+                     check of the exchanged bus against a torch int32 sum of all ranks' legs (parity_ok);
+  config4   (N = 1)  BASELINE config 4: NS -> AEC on 16 384 near/far pairs at 8 kHz;
+  full_load          >= 1 000 000 resident streams per GPU through one tick, so that `value` is backed by a
+                     run at that stream count and not only by extrapolation from 100 000.
 """
 import argparse
 import ctypes as C
@@ -30,11 +43,16 @@ sys.path.insert(0, ROOT)
 FREQ = 16000
 FRAME = 160
 CONF_SIZE = 16
+PRIME = 600                            # untimed ticks on every handle of BOTH arms before warm-up (config 3)
+METRIC = "real-time 16 kHz streams per GPU, NS+VAD+AGC+mix, 10 ms tick; % HBM roofline"   # BASELINE.json, both arms
+UNIT = "real-time 16 kHz streams (10 ms tick), whole job"                                  # both arms
 NS_BYTES_PER_STREAM_TICK = 14.4e3      # NS state R+W + PCM in/out
 CHAIN_BYTES_PER_STREAM_TICK = 16.0e3   # NS + VAD + AGC + mix
-# dram__bytes_read.sum + dram__bytes_write.sum of one ns_kernel<256> launch per stream, from the `ncu --set full`
-# capture summarised in profiles/r1_g_summary.md (891.3 MB + 642.5 MB at 100 000 streams)
+AEC_BYTES_PER_STREAM_TICK = 29.0e3     # AEC at 8 kHz
+# dram__bytes_read.sum + dram__bytes_write.sum of one NS launch per stream: a CONSTANT taken from the latest
+# `ncu --set full` capture (it cannot be measured inside an unprofiled run); see NS_TRAFFIC_SOURCE
 NS_DRAM_TRAFFIC_PER_STREAM_NCU = (891.332864e6 + 642.490368e6) / 100_000
+NS_TRAFFIC_SOURCE = "constant from ncu --set full capture r1_g (profiles/r1_g_summary.md), not measured in this run"
 
 
 def peaks():
@@ -99,7 +117,7 @@ def make_pool(n_streams, n_ring, seed):
     return np.ascontiguousarray(np.tile(x, (1, reps, 1))[:, :n_streams])
 
 
-def cpu_leg(n_streams, n_ticks, kind_pref="reference", prime=250):
+def cpu_leg(n_streams, n_ticks, kind_pref="reference", prime=PRIME):
     """The reference C chain on the host cores (bounded sample), timed after `prime` untimed ticks on the same handles —
     the regime the GPU arm is timed in (past the suppressor's start-up model and gain-map switch).  Returns dict for
     cpu_baseline."""
@@ -118,10 +136,15 @@ def cpu_leg(n_streams, n_ticks, kind_pref="reference", prime=250):
     if sec <= 0:
         raise RuntimeError("orc_bench_chain failed: %r" % sec)
     ms_per_tick = sec * 1e3 / n_ticks
-    return {"value": n_streams * 10.0 / ms_per_tick, "unit": "real-time 16 kHz streams (10 ms tick)", "cores": cores,
+    return {"value": n_streams * 10.0 / ms_per_tick, "unit": UNIT, "cores": cores,
             "kind": kind, "sample": "%d streams x %d ticks (after %d untimed ticks on the same handles), NS->AGC->VAD->bus, -O2 build, one pthread per core"
                       % (n_streams, n_ticks, prime),
             "ms_per_tick": ms_per_tick, "us_per_stream_tick_per_core": sec * 1e6 * cores / (n_streams * n_ticks)}
+
+
+def workload_text(streams_per_gpu):
+    return ("BASELINE config 3: NS->AGC(5 dB)->VAD(mode 3)->int32 conference bus, 16 kHz mono, %d streams per GPU in conferences "
+            "of %d; every handle aged %d untimed ticks before warm-up" % (streams_per_gpu, CONF_SIZE, PRIME))
 
 
 def run_reference(args):
@@ -130,27 +153,193 @@ def run_reference(args):
         return
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     n_streams = CONF_SIZE * cores * max(1, 2048 // (CONF_SIZE * cores))
-    # one "step" = one tick over the bounded sample; warm-up ticks run first and are not timed
+    # one "step" = one tick over the bounded sample; PRIME + W untimed ticks run first on the same handles
     steps = min(args.steps, 200)
-    cold = cpu_leg(n_streams, max(3, min(steps, 40)), prime=0)              # fresh handles: the start-up regime, for the record
-    leg = cpu_leg(n_streams, steps, prime=min(max(args.warmup, 3), 300))    # W warm-up ticks on the same handles, then K timed
-    line = {"impl": "reference", "metric": "real-time 16 kHz streams per host, NS+VAD+AGC+mix, 10 ms tick",
-            "value": leg["value"], "unit": leg["unit"], "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+    warm = min(max(args.warmup, 0), 300)
+    leg = cpu_leg(n_streams, steps, prime=PRIME + warm)
+    line = {"impl": "reference", "metric": METRIC,
+            "value": leg["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": leg["ms_per_tick"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32+i16 (reference C: float NS with double libm, integer AGC/VAD/mix)", "data": "synthetic",
-            "config": {"workload": "BASELINE config 3 chain on a bounded sample: %s" % leg["sample"],
-                       "note": "CPU arm: the unmodified reference (oracle/_ref) when it was built, else the C port"},
+            "dtype": "f32+i16 (float NS with double transcendentals, integer AGC/VAD/mix)", "data": "synthetic",
+            "config": {"workload": workload_text(args.streams),
+                       "sample": "CPU arm runs a bounded sample of that workload: %s" % leg["sample"],
+                       "note": "the unmodified reference (oracle/_ref) when it was built, else the C port; value = streams this "
+                               "host sustains in real time"},
             "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
-            "e2e": {"value": leg["value"], "unit": leg["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0, "cold_start_value": cold["value"]}
+            "e2e": {"value": leg["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
     print(json.dumps(line))
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# sub-measurements
+# ---------------------------------------------------------------------------------------------------------------
+def conf5_leg(torch, dist, world, rank, local, dev, conf_size, steps=200, warmup=30, per_gpu=8192, law=0):
+    """BASELINE config 5 on all ranks: `per_gpu` A-law legs per GPU at 8 kHz, conferences of `conf_size` striped over the
+    ranks so that every bus row crosses NVLink.  Returns {peer_us, nccl_us, bus_bytes, parity_ok, ...} (rank-max times)."""
+    from wmix_b200.conference import ConferencePlan, ShardedConference
+    from wmix_b200.engine import g711_decode, g711_encode
+
+    frame = 80
+    total = per_gpu * world
+    n_conf = max(1, total // conf_size)
+    per_conf_local = total // n_conf // world
+    plan = ConferencePlan([total // n_conf] * n_conf, world, "striped")
+    n_local = plan.local_count(rank)
+    g = torch.Generator(device="cpu").manual_seed(991 + rank)
+    R = 4
+    pool = torch.randint(0, 256, (R, n_local, frame), generator=g, dtype=torch.uint8).to(dev)
+    st = torch.cuda.current_stream()
+    res, outs, buses = {}, {}, {}
+    for mode in ("peer", "nccl"):
+        conf = ShardedConference(plan, rank, law=law, freq=8000, mode=mode, device=local)
+        d_out = torch.empty_like(pool[0])
+        d_bus = torch.empty((plan.n_conf, frame), dtype=torch.int32, device=dev)
+        for t in range(warmup):
+            conf.tick(pool[t % R], d_out, d_bus)
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for t in range(steps):
+            conf.tick(pool[t % R], d_out, d_bus)
+        e1.record(st)
+        dist.barrier()
+        torch.cuda.synchronize()
+        res[mode] = e0.elapsed_time(e1) / steps * 1e3
+        # one more tick on a known input for the parity check
+        conf.tick(pool[0], d_out, d_bus)
+        torch.cuda.synchronize()
+        outs[mode], buses[mode] = d_out.clone(), d_bus.clone()
+        healthy = conf.status() == 0
+        dist.barrier()
+        conf.close()
+        res[mode + "_ok"] = healthy
+    # in-run parity: the exchanged bus against an int32 sum, computed here with torch, of the decoded legs of ALL ranks
+    pcm = torch.empty((n_local, frame), dtype=torch.int16, device=dev)
+    g711_decode(law, pool[0], pcm, n_local * frame, st)
+    torch.cuda.synchronize()
+    gathered = [torch.empty_like(pcm) for _ in range(world)]
+    dist.all_gather(gathered, pcm)
+    # striped plan with equal sizes: rank r hosts per_conf_local members of every conference, conference-major
+    want_bus = torch.zeros((n_conf, frame), dtype=torch.int32, device=dev)
+    for r in range(world):
+        want_bus += gathered[r].view(n_conf, per_conf_local, frame).to(torch.int32).sum(dim=1)
+    own = pcm.view(n_conf, per_conf_local, frame).to(torch.int32)
+    want_pcm = (want_bus[:, None, :] - own).clamp_(-32768, 32767).to(torch.int16).reshape(n_local, frame).contiguous()
+    want_codes = torch.empty((n_local, frame), dtype=torch.uint8, device=dev)
+    g711_encode(law, want_pcm, want_codes, n_local * frame, st)
+    torch.cuda.synchronize()
+    ok = bool(torch.equal(buses["peer"], want_bus)) and bool(torch.equal(buses["nccl"], want_bus)) \
+        and bool(torch.equal(outs["peer"], want_codes)) and bool(torch.equal(outs["nccl"], want_codes)) \
+        and res["peer_ok"] and res["nccl_ok"]
+    stats = torch.tensor([res["peer"], res["nccl"], 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+    dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    peer_us, nccl_us, bad = [float(v) for v in stats.cpu()]
+    return {"participants": total, "conferences": n_conf, "conference_size": total // n_conf, "law": "A-law" if law == 0 else "mu-law",
+            "peer_us": peer_us, "nccl_us": nccl_us, "fused_le_nccl": peer_us <= nccl_us,
+            "bus_bytes": n_conf * frame * 4, "nvlink_bytes_per_rank_per_tick": n_conf * frame * 4 * (world - 1),
+            "parity_ok": bad == 0.0, "steps": steps,
+            "participants_realtime_per_10ms_tick": {"peer": total * 10.0 / (peer_us * 1e-3), "nccl": total * 10.0 / (nccl_us * 1e-3)},
+            "paths": {"peer": "wmixb_peer_bus_tick_device: one fused kernel per rank, partial rows stored into every peer's mailbox over NVLink",
+                      "nccl": "wmixb_g711_bus_sum_device -> all_reduce(int32, SUM) -> wmixb_g711_nminus1_device"}}
+
+
+def config4_leg(torch, dev, local, peak, steps=60, warmup=420, streams=16384):
+    """BASELINE config 4: NS -> AEC on near/far pairs at 8 kHz, timed past the AEC's start-up phase."""
+    import wmix_b200
+    from wmix_b200 import AEC, NS
+    from wmix_b200.synth import make_aec_pairs
+
+    L = 80
+    base = 256
+    T = warmup + steps
+    far, near = make_aec_pairs(base, 8000, 0, T, seed=41)
+    reps = (streams + base - 1) // base
+    eng = wmix_b200.Engine(streams, 8000, stages=AEC | NS, device=local)
+    d_far = torch.empty((streams, L), dtype=torch.int16, device=dev)
+    d_near = torch.empty((streams, L), dtype=torch.int16, device=dev)
+    d_out = torch.empty((streams, L), dtype=torch.int16, device=dev)
+    far_d, near_d = torch.from_numpy(far).to(dev), torch.from_numpy(near).to(dev)
+    st = torch.cuda.current_stream()
+
+    def load(t):
+        d_far.copy_(far_d[t].repeat(reps, 1)[:streams])
+        d_near.copy_(near_d[t].repeat(reps, 1)[:streams])
+
+    for t in range(warmup):
+        load(t)
+        eng.tick_chain_device(d_far, d_near, d_out, None, NS | AEC, 0, st)
+    torch.cuda.synchronize()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    for k in range(steps):
+        load(warmup + k)
+        ev[k][0].record(st)
+        eng.tick_device(d_near, d_out, None, NS, st)
+        ev[k][1].record(st)
+        eng.aec_device(d_far, d_out, d_out, L, 0, st)
+        ev[k][2].record(st)
+    torch.cuda.synchronize()
+    ns_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / steps
+    aec_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / steps
+    flags = eng.aec_status()
+    eng.close()
+    ach = streams * AEC_BYTES_PER_STREAM_TICK / (aec_ms * 1e-3) / 1e9
+    return {"workload": "BASELINE config 4: NS -> AEC (PBFDAF NLMS), 8 kHz mono near/far pairs, %d streams, timed after %d ticks" % (streams, warmup),
+            "ms_per_tick": ns_ms + aec_ms, "kernel_ms": {"ns_kernel<128>": ns_ms, "aec_kernel": aec_ms},
+            "realtime_streams": streams * 10.0 / (ns_ms + aec_ms), "steps": steps,
+            "roofline": {"bound": "hbm", "kernel": "aec_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "algorithmic_bytes_per_launch": streams * AEC_BYTES_PER_STREAM_TICK},
+            "aec_status": {"flags": flags[0], "flagged_streams": flags[1]}}
+
+
+def full_load_leg(torch, dev, local, streams, steps=10):
+    """`streams` resident streams on this GPU through the whole tick (NS, AGC+VAD, bus), aged PRIME ticks: is one tick
+    inside the 10 ms budget at that stream count?"""
+    import wmix_b200
+
+    NS, AGC, VAD = wmix_b200.NS, wmix_b200.AGC, wmix_b200.VAD
+    eng = wmix_b200.Engine(streams, FREQ, device=local)
+    eng.set_conferences(np.arange(0, streams + 1, CONF_SIZE, dtype=np.int32))
+    R = 2
+    base = make_pool(2048, R, seed=300)
+    reps = (streams + 2047) // 2048
+    d_pool = torch.from_numpy(base).to(dev).repeat(1, reps, 1)[:, :streams].contiguous()
+    d_pcm = torch.empty((streams, FRAME), dtype=torch.int16, device=dev)
+    d_vad = torch.zeros((streams,), dtype=torch.uint8, device=dev)
+    d_bus = torch.empty((streams // CONF_SIZE, FRAME), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream()
+
+    def step(t):
+        eng.tick_device(d_pool[t % R], d_pcm, None, NS, st)
+        eng.tick_device(d_pcm, d_pcm, d_vad, AGC | VAD, st)
+        eng.bus_sum(d_pcm, d_bus, st)
+
+    for t in range(PRIME):
+        step(t)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(st)
+    for t in range(steps):
+        step(PRIME + t)
+    e1.record(st)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    state_gb = streams * eng.state_bytes_per_stream() / 1e9
+    eng.close()
+    del d_pool, d_pcm, d_vad, d_bus
+    torch.cuda.empty_cache()
+    return {"streams_resident": streams, "ms_per_tick": ms, "fits_10ms_tick": ms <= 10.0, "state_gb": state_gb, "steps": steps,
+            "note": "measured at this stream count on this GPU (not extrapolated); PCM resident in HBM"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
 
     import wmix_b200
+    from wmix_b200.engine import HostBuffer, host_copy_ceiling
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -164,9 +353,10 @@ def run_ours(args):
     eng = wmix_b200.Engine(S, FREQ, device=local)
     eng.set_conferences(np.arange(0, S + 1, CONF_SIZE, dtype=np.int32))
     R = args.ring
-    pool = make_pool(S, R, seed=100 + rank)
-    h_pool = torch.from_numpy(pool).pin_memory()
-    d_pool = h_pool.to(dev)
+    # tick inputs live in pinned host memory placed for this GPU (wmixb_host_alloc), the device copy is made from it
+    h_pool = HostBuffer((R, S, FRAME), np.int16, device=local)
+    h_pool.array[...] = make_pool(S, R, seed=100 + rank)
+    d_pool = torch.from_numpy(h_pool.array).to(dev)
     d_pcm = torch.empty((S, FRAME), dtype=torch.int16, device=dev)
     d_vad = torch.zeros((S,), dtype=torch.uint8, device=dev)
     d_bus = torch.empty((n_conf, FRAME), dtype=torch.int32, device=dev)
@@ -192,8 +382,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for t in range(args.warmup):
+    for t in range(PRIME):               # ageing, the same for every --warmup
         step(t)
+    for t in range(args.warmup):
+        step(PRIME + t)
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -205,7 +397,7 @@ def run_ours(args):
     t_end = torch.cuda.Event(enable_timing=True)
     t_begin.record(stream)
     for k in range(args.steps):
-        step(args.warmup + k, evs[k])
+        step(PRIME + args.warmup + k, evs[k])
     t_end.record(stream)
     barrier()
     launches = wmix_b200.kernel_launches() - launches0
@@ -214,99 +406,150 @@ def run_ours(args):
     ns_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / args.steps
     post_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / args.steps
     mix_ms = sum(e[2].elapsed_time(e[3]) for e in evs) / args.steps
+    t_next = PRIME + args.warmup + args.steps
 
     # ---- end to end through the host-buffer C-ABI: pinned H2D of the tick, kernels, D2H of PCM + flags + bus
-    h_out = torch.empty((S, FRAME), dtype=torch.int16).pin_memory()
-    h_vad = torch.empty((S,), dtype=torch.uint8).pin_memory()
-    h_bus = torch.empty((n_conf, FRAME), dtype=torch.int32).pin_memory()
+    h_out = [HostBuffer((S, FRAME), np.int16, device=local) for _ in range(2)]
+    h_vad = [HostBuffer((S,), np.uint8, device=local) for _ in range(2)]
+    h_bus = [HostBuffer((n_conf, FRAME), np.int32, device=local) for _ in range(2)]
     e2e_steps = max(10, min(args.steps, 100))
 
-    def e2e_step(t):
+    def e2e_sync_step(t):
         # one C-ABI call: chunk-pipelined H2D, NS, AGC+VAD, bus, D2H of PCM + flags + bus; returns when the host has them
-        eng.tick_host_bus(h_pool[t % R].numpy(), h_out.numpy(), h_vad.numpy(), h_bus.numpy())
+        eng.tick_host_bus(h_pool.array[t % R], h_out[0].array, h_vad[0].array, h_bus[0].array)
 
     for t in range(3):
-        e2e_step(t)
+        e2e_sync_step(t_next + t)
     barrier()
     t0 = time.perf_counter()
     for t in range(e2e_steps):
-        e2e_step(args.warmup + args.steps + t)
+        e2e_sync_step(t_next + 3 + t)
     barrier()
     e2e_sync_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    t_next += 3 + e2e_steps
 
     # the same call in its pipelined form (wmixb_tick_host_submit / _wait): ticks are fed back to back, two in flight, so
     # tick t+1's H2D overlaps tick t's last kernels and D2H.  Every step's copies are inside the timed region; the step's
-    # result is on the host (and read) when its wait returns.
-    h_out2 = [h_out, torch.empty_like(h_out).pin_memory()]
-    h_vad2 = [h_vad, torch.empty_like(h_vad).pin_memory()]
-    h_bus2 = [h_bus, torch.empty_like(h_bus).pin_memory()]
+    # result is on the host (and read) when its wait returns.  with_pcm = False: output selection, only the conference bus
+    # and the speech flags come back (the tick's mix result) — the processed PCM stays on the device.
     sink = 0
 
-    def e2e_pipelined(first, count):
+    def e2e_pipelined(first, count, with_pcm=True):
         nonlocal sink
         for k in range(count):
             t = first + k
-            eng.tick_host_submit(h_pool[t % R].numpy(), h_out2[k & 1].numpy(), h_vad2[k & 1].numpy(), h_bus2[k & 1].numpy())
+            eng.tick_host_submit(h_pool.array[t % R], h_out[k & 1].array if with_pcm else None, h_vad[k & 1].array, h_bus[k & 1].array)
             if k >= 1:
                 eng.tick_host_wait()
-                sink += int(h_bus2[(k - 1) & 1][0, 0]) + int(h_vad2[(k - 1) & 1][0])
+                sink += int(h_bus[(k - 1) & 1].array[0, 0]) + int(h_vad[(k - 1) & 1].array[0])
         eng.tick_host_wait()
-        sink += int(h_bus2[(count - 1) & 1][0, 0])
+        sink += int(h_bus[(count - 1) & 1].array[0, 0])
 
-    e2e_pipelined(args.warmup + args.steps + e2e_steps, 4)
+    e2e = {}
+    for name, with_pcm in (("full", True), ("bus_only", False)):
+        e2e_pipelined(t_next, 4, with_pcm)
+        barrier()
+        t0 = time.perf_counter()
+        e2e_pipelined(t_next + 4, e2e_steps, with_pcm)
+        barrier()
+        e2e[name] = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        t_next += 4 + e2e_steps
+    h2d_bytes = S * FRAME * 2
+    d2h_full = S * FRAME * 2 + S + n_conf * FRAME * 4
+    d2h_bus_only = S + n_conf * FRAME * 4
+    # what the copy engines alone sustain for the same bytes, all ranks at once (no kernels): the ceiling of the host path
     barrier()
-    t0 = time.perf_counter()
-    e2e_pipelined(args.warmup + args.steps + e2e_steps + 4, e2e_steps)
+    h_sink = HostBuffer((d2h_full,), np.uint8, device=local)
+    ceil_full = host_copy_ceiling(local, h_pool.array[0], h_sink.array, h2d_bytes, d2h_full, 20)
     barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    ceil_bus = host_copy_ceiling(local, h_pool.array[0], h_sink.array, h2d_bytes, d2h_bus_only, 20)
+    barrier()
 
     ms_step = ms_total / args.steps
-    stats = torch.tensor([ms_step, e2e_ms, ns_ms, post_ms, mix_ms, e2e_sync_ms], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_step, e2e["full"], ns_ms, post_ms, mix_ms, e2e_sync_ms, e2e["bus_only"], ceil_full, ceil_bus],
+                         dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    ms_step, e2e_ms, ns_ms, post_ms, mix_ms, e2e_sync_ms = [float(v) for v in stats.cpu()]
+    ms_step, e2e_ms, ns_ms, post_ms, mix_ms, e2e_sync_ms, e2e_bus_ms, ceil_full, ceil_bus = [float(v) for v in stats.cpu()]
+    state_mb = S * eng.state_bytes_per_stream() / 1e6
+    eng.close()
+    del d_pool, d_pcm
+
+    conf5 = None
+    if world > 1:
+        conf5 = {"c1024": conf5_leg(torch, dist, world, rank, local, dev, 1024),
+                 "c16": conf5_leg(torch, dist, world, rank, local, dev, 16)}
+    full_load = None
+    if not args.no_full_load:
+        try:
+            full_load = full_load_leg(torch, dev, local, args.full_load_streams)
+            if world > 1:
+                fl = torch.tensor([full_load["ms_per_tick"]], dtype=torch.float64, device=dev)
+                dist.all_reduce(fl, op=dist.ReduceOp.MAX)
+                full_load["ms_per_tick"] = float(fl.item())
+                full_load["fits_10ms_tick"] = full_load["ms_per_tick"] <= 10.0
+                full_load["streams_resident_whole_job"] = args.full_load_streams * world
+        except Exception as ex:  # pragma: no cover
+            full_load = {"failed": str(ex)}
     if rank == 0:
         peak, peak_src = peaks()
         total_streams = S * world
         achieved = S * NS_BYTES_PER_STREAM_TICK / (ns_ms * 1e-3) / 1e9
         line = {
-            "metric": "real-time 16 kHz streams per GPU, NS+VAD+AGC+mix, 10 ms tick; % HBM roofline",
-            "value": total_streams * 10.0 / ms_step, "unit": "real-time 16 kHz streams (10 ms tick), whole job",
+            "metric": METRIC,
+            "value": total_streams * 10.0 / ms_step, "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32+i16 (float NS with double transcendentals, integer AGC/VAD/mix)", "data": "synthetic",
-            "config": {"workload": "BASELINE config 3: NS->AGC(5 dB)->VAD(mode 3)->int32 conference bus, 16 kHz mono, "
-                                   "%d streams per GPU in conferences of %d" % (S, CONF_SIZE),
-                       "streams_per_gpu": S, "tick_ms": 10, "parallelism": "streams sharded, no collective",
+            "config": {"workload": workload_text(S),
+                       "streams_per_gpu": S, "tick_ms": 10, "prime_ticks": PRIME,
+                       "parallelism": "streams sharded over the ranks, no collective on this path; the conference-bus exchange "
+                                      "(config 5) is measured in `conf5` when n_gpus > 1",
                        "l2_policy": "per-tick working set (state %.0f MB + PCM) exceeds the 126 MB L2; inputs rotate over %d ticks"
-                                    % (S * eng.state_bytes_per_stream() / 1e6, R)},
+                                    % (state_mb, R)},
             "realtime_headroom": 10.0 / ms_step,
             "kernel_ms": {"ns_kernel": ns_ms, "post_kernel(agc+vad)": post_ms, "bus_sum_kernel": mix_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": S * NS_DRAM_TRAFFIC_PER_STREAM_NCU, "traffic_source": "ncu --set full, profiles/r1_g_summary.md",
+                         "traffic": S * NS_DRAM_TRAFFIC_PER_STREAM_NCU, "traffic_source": NS_TRAFFIC_SOURCE,
                          "kernel": "ns_kernel<256>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": S * NS_BYTES_PER_STREAM_TICK,
                          "whole_tick_frac": S * CHAIN_BYTES_PER_STREAM_TICK / (ms_step * 1e-3) / 1e9 / peak},
-            "e2e": {"value": total_streams * 10.0 / e2e_ms, "unit": "real-time 16 kHz streams (10 ms tick), whole job",
-                    "ms_per_step": e2e_ms, "h2d_bytes_per_step": S * FRAME * 2,
-                    "d2h_bytes_per_step": S * FRAME * 2 + S + n_conf * FRAME * 4, "steps": e2e_steps,
+            "e2e": {"value": total_streams * 10.0 / e2e_ms, "unit": UNIT,
+                    "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_full, "steps": e2e_steps,
                     "path": "wmixb_tick_host_submit / _wait, ticks fed back to back (two in flight): pinned host PCM in -> NS -> "
-                            "AGC+VAD -> bus -> host PCM + VAD flags + bus, chunk-pipelined over 3 CUDA streams",
+                            "AGC+VAD -> bus -> host PCM + VAD flags + bus, one chunk per CUDA stream (4); host buffers from "
+                            "wmixb_host_alloc (pinned, placed on the GPU's NUMA node)",
+                    "copy_ceiling_ms_per_step": ceil_full,
+                    "frac_of_copy_ceiling": ceil_full / e2e_ms,
+                    "copy_ceiling_note": "bare cudaMemcpyAsync of the same bytes up and down on two streams, all ranks at once, no kernels",
+                    "bus_only": {"value": total_streams * 10.0 / e2e_bus_ms, "ms_per_step": e2e_bus_ms, "d2h_bytes_per_step": d2h_bus_only,
+                                 "copy_ceiling_ms_per_step": ceil_bus, "frac_of_copy_ceiling": ceil_bus / e2e_bus_ms,
+                                 "path": "same call with h_out = NULL (output selection): only the conference bus and the VAD flags "
+                                         "return to the host"},
                     "sync_call_ms_per_step": e2e_sync_ms,
                     "sync_call_value": total_streams * 10.0 / e2e_sync_ms,
                     "sync_call_path": "wmixb_tick_host_bus: one blocking call per tick (pipeline drains at every tick boundary)"},
             "gpu_launches": int(launches), "clocks": clocks,
         }
+        if conf5 is not None:
+            line["conf5"] = conf5
+        if full_load is not None:
+            line["full_load"] = full_load
+        if world == 1 and not args.no_config4:
+            try:
+                line["config4"] = config4_leg(torch, dev, local, peak)
+            except Exception as ex:  # pragma: no cover
+                line["config4"] = {"failed": str(ex)}
         if not args.no_cpu_baseline and world == 1:
             try:
-                leg = cpu_leg(2048, 40)
+                leg = cpu_leg(2048, 40, prime=PRIME + min(max(args.warmup, 0), 300))
                 line["cpu_baseline"] = {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")}
                 line["cpu_baseline"]["us_per_stream_tick_per_core"] = leg["us_per_stream_tick_per_core"]
             except Exception as ex:  # pragma: no cover
                 line["cpu_baseline"] = {"value": None, "unit": "", "cores": 0, "kind": "port", "sample": "failed: %s" % ex}
         print(json.dumps(line))
-    eng.close()
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -314,11 +557,14 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=300)
-    ap.add_argument("--warmup", type=int, default=250)
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--streams", type=int, default=100_000, help="streams per GPU")
     ap.add_argument("--ring", type=int, default=8, help="distinct input ticks kept resident")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true")
+    ap.add_argument("--no-full-load", action="store_true")
+    ap.add_argument("--full-load-streams", type=int, default=1_000_000)
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
