@@ -26,6 +26,10 @@ def emu():
         L.emu_ns_create.restype = C.c_void_p
         L.emu_int_create.restype = C.c_void_p
         L.emu_ns_record.restype = C.POINTER(C.c_float)
+        L.emu_nscta_create.restype = C.c_void_p
+        L.emu_nscta_record.restype = C.POINTER(C.c_float)
+        L.emu_nscta_hist.restype = C.POINTER(C.c_uint16)
+        L.emu_ns_hist.restype = C.POINTER(C.c_uint16)
         L.emu_mix_step.restype = C.c_int16
         L.emu_div_by_counter_mismatches.restype = C.c_long
         _emu = L

@@ -16,6 +16,7 @@
 #include "../../wmix_b200/csrc/g711_mix.cuh"
 #include "../../wmix_b200/csrc/host_tables.h"
 #include "../../wmix_b200/csrc/ns.cuh"
+#include "../../wmix_b200/csrc/ns_cta.cuh"
 #include "../../wmix_b200/csrc/vad.cuh"
 
 using namespace wmx;
@@ -40,6 +41,53 @@ struct EmuNs {
     ns::Tables<128> t128;
     ns::Warp<256> w256;
     ns::Warp<128> w128;
+};
+
+// ---- CTA-cooperative NS (ns_cta.cuh): W worker warps + one reducer warp, the segments called in barrier order ----
+template <int ANA>
+struct EmuNsCtaT {
+    typedef ns::Geo<ANA> G;
+    int W;
+    std::vector<float> rec, tiles;
+    std::vector<uint16_t> hist;
+    std::vector<uint16_t*> hptr;
+    std::vector<ns::WWarp<ANA>> ww;
+    ns::RWarp rw;
+    ns::Tables<ANA> T;
+    explicit EmuNsCtaT(int w) : W(w), rec((size_t)w * G::kRecFloats, 0.f), tiles((size_t)8 * G::kShFloats, 0.f), hist((size_t)w * 3 * ns::kHistBins, 0),
+                                hptr(8, nullptr), ww(w)
+    {
+        fill_tables(T, 2);
+        memset(&rw, 0, sizeof rw);
+        for (int j = 0; j < w; ++j) {
+            for (int l = 0; l < 32; ++l) ns::init_record_values<ANA>(rec.data() + (size_t)j * G::kRecFloats, l, 32);
+            hptr[j] = hist.data() + (size_t)j * 3 * ns::kHistBins;
+        }
+    }
+    // in / out: [W][kBlock]; live[j] = 0 leaves worker j idle this frame (a CTA at the ragged end of the stream range)
+    void frame(const int16_t* in, int16_t* out, const uint8_t* live)
+    {
+        bool act[8] = {};
+        for (int j = 0; j < W; ++j) {
+            float* sh = tiles.data() + (size_t)j * G::kShFloats;
+            if (live && !live[j]) { sh[G::kShScal + ns::C_ACTIVE] = 0.f; continue; }
+            act[j] = ns::w_seg1<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, in + (size_t)j * G::kBlock, out + (size_t)j * G::kBlock, sh, T);
+        }
+        ns::r_seg1<ANA>(rw, tiles.data(), G::kShFloats, W, T);
+        for (int j = 0; j < W; ++j)
+            if (act[j]) ns::w_seg2<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, tiles.data() + (size_t)j * G::kShFloats, T);
+        ns::r_seg2<ANA>(rw, tiles.data(), G::kShFloats, hptr.data(), T);
+        for (int j = 0; j < W; ++j)
+            if (act[j]) ns::w_seg3<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, hptr[j], tiles.data() + (size_t)j * G::kShFloats, T);
+        ns::r_seg3<ANA>(rw, tiles.data(), G::kShFloats, T);
+        for (int j = 0; j < W; ++j)
+            if (act[j]) ns::w_seg4<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, out + (size_t)j * G::kBlock, tiles.data() + (size_t)j * G::kShFloats, T);
+    }
+};
+struct EmuNsCta {
+    int ana;
+    EmuNsCtaT<256>* e256 = nullptr;
+    EmuNsCtaT<128>* e128 = nullptr;
 };
 
 extern "C" {
@@ -183,6 +231,40 @@ void emu_g711_dec(const uint8_t* codes, int n, int16_t* a, int16_t* u)
     for (int i = 0; i < n; ++i) { a[i] = alaw2linear(codes[i]); u[i] = ulaw2linear(codes[i]); }
 }
 int16_t emu_mix_step(int16_t bus, int16_t src, int rdce) { return mix_step(bus, src, rdce); }
+void* emu_nscta_create(int freq, int workers)
+{
+    if (workers < 1 || workers > 8) return nullptr;
+    EmuNsCta* e = new EmuNsCta();
+    e->ana = freq == 8000 ? 128 : 256;
+    if (e->ana == 256) e->e256 = new EmuNsCtaT<256>(workers);
+    else e->e128 = new EmuNsCtaT<128>(workers);
+    return e;
+}
+void emu_nscta_frame(void* h, const int16_t* in, int16_t* out, const uint8_t* live)
+{
+    EmuNsCta* e = (EmuNsCta*)h;
+    if (e->e256) e->e256->frame(in, out, live);
+    else e->e128->frame(in, out, live);
+}
+const float* emu_nscta_record(void* h, int j)
+{
+    EmuNsCta* e = (EmuNsCta*)h;
+    return e->e256 ? e->e256->rec.data() + (size_t)j * ns::Geo<256>::kRecFloats : e->e128->rec.data() + (size_t)j * ns::Geo<128>::kRecFloats;
+}
+const uint16_t* emu_nscta_hist(void* h, int j)
+{
+    EmuNsCta* e = (EmuNsCta*)h;
+    return (e->e256 ? e->e256->hist.data() : e->e128->hist.data()) + (size_t)j * 3 * ns::kHistBins;
+}
+void emu_nscta_destroy(void* h)
+{
+    EmuNsCta* e = (EmuNsCta*)h;
+    delete e->e256;
+    delete e->e128;
+    delete e;
+}
+int emu_ns_rec_floats(int freq) { return freq == 8000 ? ns::Geo<128>::kRecFloats : ns::Geo<256>::kRecFloats; }
+const uint16_t* emu_ns_hist(void* h) { return ((EmuNs*)h)->hist.data(); }
 int emu_agc_gain_table(int32_t* t, int comp, int target, int lim, int at) { return host::agc_gain_table(t, (int16_t)comp, (int16_t)target, lim, (int16_t)at); }
 int emu_agc_analog_target(int comp) { return host::agc_analog_target((int16_t)comp); }
 void emu_ns_window(int ana, int block, float* w) { host::ns_window(ana, block, w); }

@@ -30,6 +30,7 @@
 #include "g711_mix.cuh"
 #include "host_tables.h"
 #include "ns.cuh"
+#include "ns_cta.cuh"
 #include "peer_bus.cuh"
 #include "scratch.h"
 #include "vad.cuh"
@@ -119,6 +120,98 @@ ns_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Tables
                 l2_prefetch(in + (size_t)(s + total_warps) * n_frames * G::kBlock, G::kBlock * sizeof(int16_t));
             }
             ns::frame<ANA>(W, r, h, pi + (size_t)f * G::kBlock, po + (size_t)f * G::kBlock, tile, *T);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// NS kernel, CTA-cooperative form (ns_cta.cuh): W worker warps (one stream-frame each per round) + ONE reducer
+// warp that walks the in-order sums, the scalar model and the Nyquist bin of all W streams at once.  Persistent
+// grid; worker j of CTA b serves streams b*W + j + round * gridDim.x*W.  Hand-over through the worker tiles and six
+// named barriers per frame (ids 1..6; odd = workers arrive / reducer waits, even = reducer arrives / workers wait).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+
+template <int ANA>
+constexpr size_t ns_cta_smem_bytes(int workers)
+{
+    return (NsSmem<ANA>::kTableFloats + (size_t)workers * ns::Geo<ANA>::kShFloats) * sizeof(float) + 8 * sizeof(uint16_t*);
+}
+
+template <int ANA, int W, int MINB>
+__global__ void __launch_bounds__((W + 1) * 32, MINB)
+ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Tables<ANA>* __restrict__ tables,
+              const int16_t* in, int16_t* out, int n_streams, int n_frames)
+{
+    typedef ns::Geo<ANA> G;
+    static_assert(W >= 1 && W <= 8, "the reducer serves at most 8 workers (4 lanes each)");
+    constexpr int kThreads = (W + 1) * 32;
+    extern __shared__ __align__(16) float smem[];
+    ns::Tables<ANA>* T = reinterpret_cast<ns::Tables<ANA>*>(smem);
+    float* tiles = smem + NsSmem<ANA>::kTableFloats;
+    uint16_t** hptr = reinterpret_cast<uint16_t**>(tiles + (size_t)W * G::kShFloats);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
+        for (int i = threadIdx.x; i < (int)(sizeof(ns::Tables<ANA>) / 4); i += kThreads) dst[i] = src[i];
+        for (int i = threadIdx.x; i < W * G::kShFloats; i += kThreads) tiles[i] = 0.f;   // sum rows rely on +0.0f padding
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int total = gridDim.x * W;
+    const int first = blockIdx.x * W;
+    const int rounds = first < n_streams ? (n_streams - first + total - 1) / total : 0;
+    if (warp < W) {
+        float* tile = tiles + (size_t)warp * G::kShFloats;
+        ns::WWarp<ANA> Wk;
+        Wk.lane_id = lane;
+        for (int it = 0; it < rounds; ++it) {
+            const int s = first + warp + it * total;
+            const bool live = s < n_streams;
+            float* r = rec + (size_t)s * G::kRecFloats;
+            uint16_t* h = hist + (size_t)s * 3 * ns::kHistBins;
+            const int16_t* pi = in + (size_t)s * n_frames * G::kBlock;
+            int16_t* po = out + (size_t)s * n_frames * G::kBlock;
+            if (lane == 0) hptr[warp] = h;
+            for (int f = 0; f < n_frames; ++f) {
+                bool act = false;
+                if (live) {
+                    if (f == n_frames - 1 && lane == 0 && s + total < n_streams) {
+                        // pull the next stream's record and first frame towards L2 while this one computes
+                        l2_prefetch(rec + (size_t)(s + total) * G::kRecFloats, G::kRecFloats * sizeof(float));
+                        l2_prefetch(in + (size_t)(s + total) * n_frames * G::kBlock, G::kBlock * sizeof(int16_t));
+                    }
+                    act = ns::w_seg1<ANA>(Wk, r, pi + (size_t)f * G::kBlock, po + (size_t)f * G::kBlock, tile, *T);
+                } else if (lane == 0) {
+                    tile[G::kShScal + ns::C_ACTIVE] = 0.f;
+                }
+                named_bar_arrive(1, kThreads);
+                named_bar_sync(2, kThreads);
+                if (act) ns::w_seg2<ANA>(Wk, r, tile, *T);
+                named_bar_arrive(3, kThreads);
+                named_bar_sync(4, kThreads);
+                if (act) ns::w_seg3<ANA>(Wk, r, h, tile, *T);
+                named_bar_arrive(5, kThreads);
+                named_bar_sync(6, kThreads);
+                if (act) ns::w_seg4<ANA>(Wk, r, po + (size_t)f * G::kBlock, tile, *T);
+            }
+        }
+    } else {
+        ns::RWarp Rd;
+        Rd.lane_id = lane;
+        for (int it = 0; it < rounds; ++it) {
+            for (int f = 0; f < n_frames; ++f) {
+                named_bar_sync(1, kThreads);
+                ns::r_seg1<ANA>(Rd, tiles, G::kShFloats, W, *T);
+                named_bar_arrive(2, kThreads);
+                named_bar_sync(3, kThreads);
+                ns::r_seg2<ANA>(Rd, tiles, G::kShFloats, hptr, *T);
+                named_bar_arrive(4, kThreads);
+                named_bar_sync(5, kThreads);
+                ns::r_seg3<ANA>(Rd, tiles, G::kShFloats, *T);
+                named_bar_arrive(6, kThreads);
+            }
         }
     }
 }
@@ -463,7 +556,7 @@ struct wmixb_engine {
     int32_t* d_bus = nullptr;               // staging of the conference bus for the host-buffer tick
     size_t d_bus_bytes = 0;
     int ns_grid = 0;
-    int ns_cfg = 2;                         // index into kNsCfgs: 2 CTAs of 10 warps at 96 registers per lane (measured best)
+    int ns_cfg = 0;                         // index into kNsCfgs: 2 CTAs of 8 worker warps + 1 reducer warp
     int ns_align = 1;                       // CTA barrier at the top of every frame (instruction-cache sharing)
     int post_occ = 3;                       // same for post_kernel (3 CTAs of 128 threads, 168 registers per thread: measured best)
     int host_chunks_sync = 8, host_chunks_pipe = 4, host_lanes = 0;   // chunk pipeline of the host-buffer tick (wmixb_set_tuning)
@@ -477,25 +570,27 @@ struct wmixb_engine {
 
 static int ns_rec_floats(const wmixb_engine* e) { return e->ana == 256 ? ns::Geo<256>::kRecFloats : ns::Geo<128>::kRecFloats; }
 
-// compiled (warps per CTA, CTAs per SM) shapes of the NS kernel; WMIXB_NS_CFG=<index> picks one (default 0)
-struct NsCfg { int warps, minb; };
-static const NsCfg kNsCfgs[] = {{8, 2}, {8, 3}, {10, 2}, {6, 3}, {12, 1}, {4, 5}, {9, 2}, {4, 4}, {7, 4}, {6, 4}};
+// compiled shapes of the NS kernel; wmixb_set_tuning("ns_cfg", index) picks one (default 0).
+// cta = 1: ns_cta_kernel, `warps` WORKER warps + one reducer warp per CTA; cta = 0: ns_kernel (one self-contained warp per stream)
+struct NsCfg { int cta, warps, minb; };
+static const NsCfg kNsCfgs[] = {{1, 8, 2}, {1, 6, 3}, {1, 4, 4}, {1, 4, 5}, {1, 7, 2}, {1, 5, 3}, {0, 10, 2}, {0, 8, 2}};
 template <int ANA>
 static const void* ns_fn(int cfg)
 {
     switch (cfg) {
-    case 1: return (const void*)ns_kernel<ANA, 8, 3>;
-    case 2: return (const void*)ns_kernel<ANA, 10, 2>;
-    case 3: return (const void*)ns_kernel<ANA, 6, 3>;
-    case 4: return (const void*)ns_kernel<ANA, 12, 1>;
-    case 5: return (const void*)ns_kernel<ANA, 4, 5>;
-    case 6: return (const void*)ns_kernel<ANA, 9, 2>;
-    case 7: return (const void*)ns_kernel<ANA, 4, 4>;
-    case 8: return (const void*)ns_kernel<ANA, 7, 4>;
-    case 9: return (const void*)ns_kernel<ANA, 6, 4>;
-    default: return (const void*)ns_kernel<ANA, 8, 2>;
+    case 1: return (const void*)ns_cta_kernel<ANA, 6, 3>;
+    case 2: return (const void*)ns_cta_kernel<ANA, 4, 4>;
+    case 3: return (const void*)ns_cta_kernel<ANA, 4, 5>;
+    case 4: return (const void*)ns_cta_kernel<ANA, 7, 2>;
+    case 5: return (const void*)ns_cta_kernel<ANA, 5, 3>;
+    case 6: return (const void*)ns_kernel<ANA, 10, 2>;
+    case 7: return (const void*)ns_kernel<ANA, 8, 2>;
+    default: return (const void*)ns_cta_kernel<ANA, 8, 2>;
     }
 }
+static int ns_threads(int cfg) { return (kNsCfgs[cfg].warps + kNsCfgs[cfg].cta) * 32; }
+template <int ANA>
+static size_t ns_cfg_smem(int cfg) { return kNsCfgs[cfg].cta ? ns_cta_smem_bytes<ANA>(kNsCfgs[cfg].warps) : ns_smem_bytes<ANA>(kNsCfgs[cfg].warps); }
 
 template <int ANA>
 static int launch_ns(wmixb_engine* e, int grid, cudaStream_t st, const int16_t* in, int16_t* out, int first, int n, int n_frames)
@@ -504,9 +599,8 @@ static int launch_ns(wmixb_engine* e, int grid, cudaStream_t st, const int16_t* 
     uint16_t* hist = e->ns_hist + (size_t)first * 3 * ns::kHistBins;
     const ns::Tables<ANA>* T = (const ns::Tables<ANA>*)e->ns_tables;
     int align = e->ns_align;
-    void* args[] = {&rec, &hist, &T, &in, &out, &n, &n_frames, &align};
-    const int warps = kNsCfgs[e->ns_cfg].warps;
-    CK(cudaLaunchKernel(ns_fn<ANA>(e->ns_cfg), dim3(grid), dim3(warps * 32), args, ns_smem_bytes<ANA>(warps), st));
+    void* args[] = {&rec, &hist, &T, &in, &out, &n, &n_frames, &align};   // the CTA form takes the first seven
+    CK(cudaLaunchKernel(ns_fn<ANA>(e->ns_cfg), dim3(grid), dim3(ns_threads(e->ns_cfg)), args, ns_cfg_smem<ANA>(e->ns_cfg), st));
     return WMIXB_OK;
 }
 
@@ -515,11 +609,10 @@ template <int ANA>
 static int ns_configure(wmixb_engine* e)
 {
     const void* fn = ns_fn<ANA>(e->ns_cfg);
-    const int warps = kNsCfgs[e->ns_cfg].warps;
-    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns_smem_bytes<ANA>(warps)));
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ns_cfg_smem<ANA>(e->ns_cfg)));
     CK(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     int per_sm = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, warps * 32, ns_smem_bytes<ANA>(warps)));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, ns_threads(e->ns_cfg), ns_cfg_smem<ANA>(e->ns_cfg)));
     if (per_sm < 1) per_sm = 1;
     e->ns_grid = e->sm_count * per_sm;
     return WMIXB_OK;
