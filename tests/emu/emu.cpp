@@ -96,14 +96,15 @@ struct EmuNsCtaT {
                     ns::w_seg4<ANA>(ww[j], rec.data() + (size_t)s * G::kRecFloats, out + (size_t)s * G::kBlock, tile(j), syn_of(j, prev_parity), T);
                     prev_act[j] = false;
                 }
-            ns::r_seg2a<ANA>(rw, tiles.data(), CG::kTileFloats, hptr.data(), ones.data(), T);
-            // reducer segment 2b runs beside worker segment 3a: emulate the other order than the obvious one
-            ns::r_seg2b<ANA>(rw, tiles.data(), CG::kTileFloats, T);
+            for (int j = 0; j < W; ++j)
+                if (act[j]) ns::w_seg2b<ANA>(ww[j], hptr[j], tile(j), T);
+            // reducer segment 2 runs beside worker segment 3a: emulate the less obvious order
+            ns::r_seg2<ANA>(rw, tiles.data(), CG::kTileFloats, T);
             for (int j = 0; j < W; ++j)
                 if (act[j]) ns::w_seg3a<ANA>(ww[j], rec.data() + (size_t)(r * W + j) * G::kRecFloats, hptr[j], tile(j), T);
             for (int j = 0; j < W; ++j)
                 if (act[j]) ns::w_seg3b<ANA>(ww[j], rec.data() + (size_t)(r * W + j) * G::kRecFloats, tile(j), T);
-            ns::r_seg3<ANA>(rw, tiles.data(), CG::kTileFloats, ones.data(), T);
+            ns::r_seg3<ANA>(rw, tiles.data(), CG::kTileFloats, T);
             if (!defer) {
                 for (int j = 0; j < W; ++j)
                     if (act[j]) ns::w_seg4<ANA>(ww[j], rec.data() + (size_t)(r * W + j) * G::kRecFloats, out + (size_t)(r * W + j) * G::kBlock, tile(j), syn_of(j, parity), T);

@@ -23,6 +23,7 @@ from wmix_b200 import AEC, AGC, NS, VAD  # noqa: E402
 from wmix_b200.synth import make_aec_pairs, make_frames  # noqa: E402
 
 DEV = "cuda:0"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NS_MAX_ABS = 2
 NS_MIN_EQUAL = 0.999
 

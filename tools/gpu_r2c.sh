@@ -5,7 +5,7 @@ TAG="${1:-r2_c}"
 mkdir -p gpurun_out
 (time python -m pytest tests -m gpu -x -q) > gpurun_out/${TAG}_tests.txt 2>&1; tail -5 gpurun_out/${TAG}_tests.txt
 summ='import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print({k:d[k] for k in ("value","ms_per_step","kernel_ms")}, "frac=%.4f"%d["roofline"]["frac"], "e2e_ms=%.3f"%d["e2e"]["ms_per_step"])'
-for c in 0 4 2 1 5; do
+for c in 0 4 2 6; do
   echo "== ns_cfg $c"; python bench.py --no-cpu-baseline --no-config4 --no-full-load --steps 100 --warmup 10 --ns-cfg $c 2> gpurun_out/${TAG}_cfg$c.err | tee gpurun_out/${TAG}_cfg$c.json | python -c "$summ"
 done
 timeout 900 compute-sanitizer --tool racecheck --print-limit 20 python tools/sanitize_small.py > gpurun_out/${TAG}_racecheck.txt 2>&1; tail -4 gpurun_out/${TAG}_racecheck.txt

@@ -5,8 +5,7 @@
 // with one to four active lanes is done ONCE for all the streams of the CTA:
 //
 //   * the in-order float sums (129- and 256-term chains the reference accumulates serially: signal energy, sum of
-//     magnitudes, flatness numerator, pause average, the four spectral-difference sums, the two energies of the gain
-//     map) — in ns::frame four lanes of every warp walk them while 28 idle; here lane 4j+k of the reducer walks sum k
+//     magnitudes, flatness numerator, pause average, the two 256-term energies of the gain map) — in ns::frame four lanes of every warp walk them while 28 idle; here lane 4j+k of the reducer walks sum k
 //     of worker j, 32 chains per instruction;
 //   * the per-stream scalar model (start-up white/pink fit, flatness / difference features, histogram re-learning,
 //     the tanh indicators, prior update, gain-map factor): one lane per stream, eight streams per instruction;
@@ -15,23 +14,26 @@
 // ncu on ns::frame (profiles/r1_g): those three groups were 1 230 + ~380 of 4 587 warp instructions per stream-frame at
 // 1.7 - 5 active lanes.
 //
-// Worker and reducer hand over through the worker's shared tile and named barriers (bar.arrive / bar.sync).  The schedule
-// keeps the reducer's serial chains OFF the workers' critical path wherever the data flow allows it:
+// Worker and reducer hand over through the worker's shared tile and named barriers (bar.arrive / bar.sync).  The reducer's
+// serial chains run BESIDE worker segments that do not need their results yet:
 //     worker                                                     reducer
 //     seg1: load, window, forward FFT, real split, |X|, log,
 //           quantile trackers                         --1-->     seg1: Nyquist tracker, 4 sums, start-up model, flatness,
-//     seg2: noise blend, DD SNR, LRT average, exp(-LRT)                Nyquist SNR / LRT            (runs BESIDE seg2: the
-//           (needs nothing of reducer seg1 once the                    difference terms that need the two averages are
-//           start-up model is over)                   <--2--           formed by the reducer itself, from the staged rows)
-//     seg4 of the PREVIOUS stream (see below)         --3-->     seg2a: 4 sums, features, histograms, tanh x3, prior
-//                                                     <--4--
-//     seg3a: probability, noise update, Wiener gain,             seg2b: Nyquist probability + filter, input energy of the
-//            state arrays back                        <--8--            gain map                    (runs BESIDE seg3a)
+//     seg2: noise blend, DD SNR, LRT average, exp(-LRT)                Nyquist SNR / LRT / difference terms
+//           (needs nothing of reducer seg1 once the                    (runs BESIDE seg2)
+//           start-up model is over)                   <--2--
+//     seg4 of the PREVIOUS stream (see below)
+//     seg2b: difference terms, 4 sums, features,
+//            histograms, tanh x3, prior               --3-->     seg2: Nyquist probability + filter, input energy of the
+//     seg3a: probability, noise update, Wiener gain,                   gain map                    (runs BESIDE seg3a)
+//            state arrays back                        <--4--
 //     seg3b: inverse split, IFFT, scale, park         --5-->     seg3: output energy of the gain map, factor
 //     (next stream's seg1 ...)                                          (runs BESIDE the next stream's seg1)
 //     seg4: window, overlap-add, factor, saturate, emit — deferred until after barrier 2 of the NEXT stream, by which time
 //           the reducer has long finished seg3; only the very last frame of a launch waits for it (barrier 6).
-// The worker therefore waits for the reducer only at barrier 4 (and at barrier 2 during the 50 start-up frames).
+// The prior chain of seg2b (sums -> features -> tanh -> prior) stays in the worker although it is lane-sparse: everything
+// downstream waits for it, and a first version that handed it to the reducer spent longer in the hand-over than the ~550
+// instructions cost (profiles/r2_b, r2_c).
 // Other changes against ns::frame, all value-preserving: the last FFT pass leaves its results in registers and the
 // real split fetches the mirrored bin with warp shuffles (no exchange-tile round trip on either side of the split);
 // the filtered spectrum and the scaled IFFT output stay in registers; PCM moves as 32-bit pairs and the history /
@@ -896,192 +898,184 @@ WMX_HD void r_seg1(RWarpT& W, float* tiles, int tile_stride, int n_workers, cons
             bin_snr<ANA>(T, sv, G::kBody, frame_idx, use_pink != 0.f, sc[S_WHITE], pnum, pexp, R.mag, R.noise, nq[A_MAGN_PREV],
                          nq[A_NOISE_PREV], nq[A_SMOOTH], nq[A_LRT], R.prev, pn);
             if (frame_idx < kStartupShort) nq[A_PARAM_NOISE] = pn;
+            // ... and its spectral-difference terms (ns_core.c:617-622), into the rows the worker fills for the body bins once
+            // it has the two averages (rows 0-2 are free: the sums above are done)
+            const float am = sc[C_AVGMAGN], ap = sc[C_AVGPAUSE], pz = nq[A_PAUSE];
+            sv[0 * G::kSumStride + G::kBody] = (R.mag - am) * (pz - ap);
+            sv[1 * G::kSumStride + G::kBody] = (pz - ap) * (pz - ap);
+            sv[2 * G::kSumStride + G::kBody] = (R.mag - am) * (R.mag - am);
         }
     }
     WMX_CTA_PHASE_END
 }
 
-// segment 2a: sums (covariance, two variances, LRT sum), difference feature, histograms and threshold re-learning, indicator
-// functions, prior (ns_core.c:595-640, :689-738, :755-790, :293-520).  `ones` = a row of kSumStride 1.0f.
-template <int ANA, typename RWarpT>
-WMX_HD void r_seg2a(RWarpT& W, float* tiles, int tile_stride, uint16_t* const* hists, const float* ones, const Tables<ANA>& T)
+// segment 2b (after barrier 2: the reducer's averages and features are in the tile): spectral-difference terms of the body
+// bins, the four in-order sums of this phase (covariance, two variances, LRT sum) in lanes 0..3, difference feature,
+// histograms and threshold re-learning, indicator functions, prior (ns_core.c:595-640, :689-738, :755-790, :293-520).
+// This chain stays in the worker: everything downstream of it waits for the prior, so handing it to the reducer only adds
+// the hand-over to the critical path (measured: the wait was longer than these ~550 lane-sparse instructions).
+template <int ANA, typename WarpT>
+WMX_HD void w_seg2b(WarpT& W, uint16_t* hist, float* sh, const Tables<ANA>& T)
 {
     typedef Geo<ANA> G;
-    WMX_CTA_PHASE_BEGIN(RLane)
+    typedef WLane<ANA> L;
+    float* sv = sh + G::kShSum;
+    float* sc = sh + G::kShScal;
+    WMX_CTA_PHASE_BEGIN(L)
     {
-        const int j = lane >> 2, k = lane & 3;
-        float* sh = tiles + (size_t)j * tile_stride;
-        float* sv = sh + G::kShSum;
-        float* sc = sh + G::kShScal;
-        if (R.active) {
-            const float* mag = sv + 1 * G::kSumStride;                  // staged by segment 1 (|X| + 1 of every bin)
-            const float* pause = sv + 3 * G::kSumStride;                // staged when the frame was loaded
-            const float* lrt = sv + CtaGeo<ANA>::kLrtRow * G::kSumStride;
-            const float am = sc[C_AVGMAGN], ap = sc[C_AVGPAUSE];
-            const float* x = k == 1 ? pause : (k == 3 ? lrt : mag);
-            const float* y = k == 2 ? mag : (k == 3 ? ones : pause);
-            const float cx = k == 1 ? ap : (k == 3 ? 0.f : am);
-            const float cy = k == 2 ? am : (k == 3 ? 0.f : ap);
-            sc[C_SUM_B + k] = seq_sum_prod<G::kBody / 4, 1>(x, y, cx, cy);
+        const float am = sc[C_AVGMAGN], ap = sc[C_AVGPAUSE];
+#pragma unroll
+        for (int s = 0; s < G::kSlots; ++s) {
+            const int b = 32 * s + lane;
+            const float mag = R.mag[s], pause = R.st[A_PAUSE][s];
+            sv[0 * G::kSumStride + b] = (mag - am) * (pause - ap);
+            sv[1 * G::kSumStride + b] = (pause - ap) * (pause - ap);
+            sv[2 * G::kSumStride + b] = (mag - am) * (mag - am);
         }
     }
     WMX_CTA_PHASE_END
-    WMX_CTA_PHASE_BEGIN(RLane)
-    {
-        const int j = lane >> 2, k = lane & 3;
-        float* sh = tiles + (size_t)j * tile_stride;
-        float* sc = sh + G::kShScal;
-        if (R.active && k == 0) {
-            uint16_t* hist = hists[j];
-            const float nb = (float)G::kBins;
-            {
-                const float cov = sc[C_SUM_B + 0] / nb, vp = sc[C_SUM_B + 1] / nb, vm = sc[C_SUM_B + 2] / nb;
-                sc[S_FEAT6] = sc[S_FEAT6] + sc[C_SUM_A + 0];
-                float d = vm - (cov * cov) / (vp + 0.0001f);
-                d = (float)(d / (sc[S_FEAT5] + 0.0001f));
-                float f4 = sc[S_FEAT4];
-                f4 += 0.3f * (d - f4);
-                sc[S_FEAT4] = f4;
+    WMX_CTA_PHASE_BEGIN(L)
+    if (lane < 4) sc[C_SUM_B + lane] = seq_sum4<G::kSumStride / 4>(sv + (lane == 3 ? CtaGeo<ANA>::kLrtRow : lane) * G::kSumStride);
+    WMX_CTA_PHASE_END
+    WMX_CTA_PHASE_BEGIN(L)
+    if (lane == 0) {
+        const float nb = (float)G::kBins;
+        {
+            const float cov = sc[C_SUM_B + 0] / nb, vp = sc[C_SUM_B + 1] / nb, vm = sc[C_SUM_B + 2] / nb;
+            sc[S_FEAT6] = sc[S_FEAT6] + sc[C_SUM_A + 0];
+            float d = vm - (cov * cov) / (vp + 0.0001f);
+            d = (float)(d / (sc[S_FEAT5] + 0.0001f));
+            float f4 = sc[S_FEAT4];
+            f4 += 0.3f * (d - f4);
+            sc[S_FEAT4] = f4;
+        }
+        // histogram update / threshold re-learn (ns_core.c:755-790, :293-520); the LRT feature used here is still last
+        // frame's (featureData[3] is refreshed further down)
+        const int upd_mode = f2i(sc[S_UPD_MODE]);
+        sc[C_RELEARNED] = 0.f;
+        if (upd_mode >= 1) {
+            int countdown = f2i(sc[S_UPD_COUNTDOWN]) - 1;
+            if (countdown > 0) {
+                const float v3 = sc[S_FEAT3], v0 = sc[S_FEAT0], v4 = sc[S_FEAT4];
+                if (v3 < kHistBins * 0.1f && v3 >= 0.0) hist_inc(hist, 0 * kHistBins + (int)(v3 / 0.1f));
+                if (v0 < kHistBins * 0.05f && v0 >= 0.0) hist_inc(hist, 1 * kHistBins + (int)(v0 / 0.05f));
+                if (v4 < kHistBins * 0.1f && v4 >= 0.0) hist_inc(hist, 2 * kHistBins + (int)(v4 / 0.1f));
             }
-            // histogram update / threshold re-learn (ns_core.c:755-790, :293-520); the LRT feature used here is still last
-            // frame's (featureData[3] is refreshed further down)
-            const int upd_mode = f2i(sc[S_UPD_MODE]);
-            sc[C_RELEARNED] = 0.f;
-            if (upd_mode >= 1) {
-                int countdown = f2i(sc[S_UPD_COUNTDOWN]) - 1;
-                if (countdown > 0) {
-                    const float v3 = sc[S_FEAT3], v0 = sc[S_FEAT0], v4 = sc[S_FEAT4];
-                    if (v3 < kHistBins * 0.1f && v3 >= 0.0) hist_inc(hist, 0 * kHistBins + (int)(v3 / 0.1f));
-                    if (v0 < kHistBins * 0.05f && v0 >= 0.0) hist_inc(hist, 1 * kHistBins + (int)(v0 / 0.05f));
-                    if (v4 < kHistBins * 0.1f && v4 >= 0.0) hist_inc(hist, 2 * kHistBins + (int)(v4 / 0.1f));
+            if (countdown == 0) {
+                const int window = 500;
+                float avg = 0.f, avg_all = 0.f, avg_sq = 0.f;
+                int n = 0;
+                for (int i = 0; i < kHistBins; ++i) {
+                    const int h = hist[i];
+                    if (h == 0) continue;                      // adding 0.f never changes a float sum
+                    const float mid = ((float)i + 0.5f) * 0.1f;
+                    if (mid <= 1.f) { avg += h * mid; n += h; }
+                    avg_sq += h * mid * mid;
+                    avg_all += h * mid;
                 }
-                if (countdown == 0) {
-                    const int window = 500;
-                    float avg = 0.f, avg_all = 0.f, avg_sq = 0.f;
-                    int n = 0;
+                if (n > 0) avg = avg / ((float)n);
+                avg_all = avg_all / ((float)window);
+                avg_sq = avg_sq / ((float)window);
+                const float fluct = avg_sq - avg * avg_all;
+                float pm0;
+                if (fluct < 0.05f) pm0 = 1.f;
+                else {
+                    pm0 = 1.2f * avg;
+                    if (pm0 < 0.2f) pm0 = 0.2f;
+                    if (pm0 > 1.f) pm0 = 1.f;
+                }
+                sc[S_PM0] = pm0;
+                int use_flat = 1, use_diff = 1;
+                for (int which = 1; which <= 2; ++which) {
+                    const float bin = which == 1 ? 0.05f : 0.1f;
+                    const uint16_t* h = hist + which * kHistBins;
+                    int m1 = 0, m2 = 0, w1 = 0, w2 = 0;
+                    float p1 = 0.f, p2 = 0.f;
                     for (int i = 0; i < kHistBins; ++i) {
-                        const int h = hist[i];
-                        if (h == 0) continue;                      // adding 0.f never changes a float sum
-                        const float mid = ((float)i + 0.5f) * 0.1f;
-                        if (mid <= 1.f) { avg += h * mid; n += h; }
-                        avg_sq += h * mid * mid;
-                        avg_all += h * mid;
+                        const int v = h[i];
+                        const float mid = ((float)i + 0.5f) * bin;
+                        if (v > m1) { m2 = m1; w2 = w1; p2 = p1; m1 = v; w1 = v; p1 = mid; }
+                        else if (v > m2) { m2 = v; w2 = v; p2 = mid; }
                     }
-                    if (n > 0) avg = avg / ((float)n);
-                    avg_all = avg_all / ((float)window);
-                    avg_sq = avg_sq / ((float)window);
-                    const float fluct = avg_sq - avg * avg_all;
-                    float pm0;
-                    if (fluct < 0.05f) pm0 = 1.f;
-                    else {
-                        pm0 = 1.2f * avg;
-                        if (pm0 < 0.2f) pm0 = 0.2f;
-                        if (pm0 > 1.f) pm0 = 1.f;
-                    }
-                    sc[S_PM0] = pm0;
-                    int use_flat = 1, use_diff = 1;
-                    for (int which = 1; which <= 2; ++which) {
-                        const float bin = which == 1 ? 0.05f : 0.1f;
-                        const uint16_t* h = hist + which * kHistBins;
-                        int m1 = 0, m2 = 0, w1 = 0, w2 = 0;
-                        float p1 = 0.f, p2 = 0.f;
-                        for (int i = 0; i < kHistBins; ++i) {
-                            const int v = h[i];
-                            const float mid = ((float)i + 0.5f) * bin;
-                            if (v > m1) { m2 = m1; w2 = w1; p2 = p1; m1 = v; w1 = v; p1 = mid; }
-                            else if (v > m2) { m2 = v; w2 = v; p2 = mid; }
+                    if ((fabs(p2 - p1) < 2 * bin) && (w2 > 0.5f * w1)) { w1 += w2; p1 = 0.5f * (p1 + p2); }
+                    const int min_weight = (int)(0.3 * (window));
+                    if (which == 1) {
+                        if (w1 < min_weight || p1 < 0.6f) use_flat = 0;
+                        if (use_flat) {
+                            float pm1 = 0.9f * p1;
+                            if (pm1 < 0.1f) pm1 = 0.1f;
+                            if (pm1 > 0.95f) pm1 = 0.95f;
+                            sc[S_PM1] = pm1;
                         }
-                        if ((fabs(p2 - p1) < 2 * bin) && (w2 > 0.5f * w1)) { w1 += w2; p1 = 0.5f * (p1 + p2); }
-                        const int min_weight = (int)(0.3 * (window));
-                        if (which == 1) {
-                            if (w1 < min_weight || p1 < 0.6f) use_flat = 0;
-                            if (use_flat) {
-                                float pm1 = 0.9f * p1;
-                                if (pm1 < 0.1f) pm1 = 0.1f;
-                                if (pm1 > 0.95f) pm1 = 0.95f;
-                                sc[S_PM1] = pm1;
-                            }
-                        } else {
-                            float pm3 = 1.2f * p1;
-                            if (w1 < min_weight) use_diff = 0;
-                            if (pm3 < 0.16f) pm3 = 0.16f;
-                            if (pm3 > 1.f) pm3 = 1.f;
-                            sc[S_PM3] = pm3;
-                            if (fluct < 0.05f) use_diff = 0;
-                        }
-                    }
-                    const float fsum = (float)(1 + use_flat + use_diff);
-                    sc[S_PM4] = 1.f / fsum;
-                    sc[S_PM5] = ((float)use_flat) / fsum;
-                    sc[S_PM6] = ((float)use_diff) / fsum;
-                    sc[C_RELEARNED] = 1.f;                         // the worker clears the histograms in segment 3a
-                    countdown = window;
-                    if (upd_mode == 1) {
-                        sc[S_UPD_MODE] = i2f(0);
                     } else {
-                        float f6 = sc[S_FEAT6] / ((float)window);
-                        sc[S_FEAT5] = 0.5f * (f6 + sc[S_FEAT5]);
-                        sc[S_FEAT6] = 0.f;
+                        float pm3 = 1.2f * p1;
+                        if (w1 < min_weight) use_diff = 0;
+                        if (pm3 < 0.16f) pm3 = 0.16f;
+                        if (pm3 > 1.f) pm3 = 1.f;
+                        sc[S_PM3] = pm3;
+                        if (fluct < 0.05f) use_diff = 0;
                     }
                 }
-                sc[S_UPD_COUNTDOWN] = i2f(countdown);
+                const float fsum = (float)(1 + use_flat + use_diff);
+                sc[S_PM4] = 1.f / fsum;
+                sc[S_PM5] = ((float)use_flat) / fsum;
+                sc[S_PM6] = ((float)use_diff) / fsum;
+                sc[C_RELEARNED] = 1.f;                         // the whole warp clears the histograms in segment 3a
+                countdown = window;
+                if (upd_mode == 1) {
+                    sc[S_UPD_MODE] = i2f(0);
+                } else {
+                    float f6 = sc[S_FEAT6] / ((float)window);
+                    sc[S_FEAT5] = 0.5f * (f6 + sc[S_FEAT5]);
+                    sc[S_FEAT6] = 0.f;
+                }
             }
-            // arguments of the three indicator functions (ns_core.c:689-730)
-            {
-                const float thr0 = sc[S_PM0], thr1 = sc[S_PM1], thr2 = sc[S_PM3];
-                const int sgn = (int)(sc[S_PM2]);
-                float ksum = sc[C_SUM_B + 3];
-                ksum = (float)ksum / (G::kBins);
-                sc[S_FEAT3] = ksum;
-                float width = 4.f;
-                if (ksum < thr0) width = 2.f * 4.f;
-                sc[C_TANH + 0] = width * (ksum - thr0);
-                float x = sc[S_FEAT0];
-                width = 4.f;
-                if (sgn == 1 && (x > thr1)) width = 2.f * 4.f;
-                if (sgn == -1 && (x < thr1)) width = 2.f * 4.f;
-                sc[C_TANH + 1] = (float)sgn * width * (thr1 - x);
-                x = sc[S_FEAT4];
-                width = 4.f;
-                if (x < thr2) width = 2.f * 4.f;
-                sc[C_TANH + 2] = width * (x - thr2);
-            }
+            sc[S_UPD_COUNTDOWN] = i2f(countdown);
+        }
+        // arguments of the three indicator functions (ns_core.c:689-730)
+        {
+            const float thr0 = sc[S_PM0], thr1 = sc[S_PM1], thr2 = sc[S_PM3];
+            const int sgn = (int)(sc[S_PM2]);
+            float ksum = sc[C_SUM_B + 3];
+            ksum = (float)ksum / (G::kBins);
+            sc[S_FEAT3] = ksum;
+            float width = 4.f;
+            if (ksum < thr0) width = 2.f * 4.f;
+            sc[C_TANH + 0] = width * (ksum - thr0);
+            float x = sc[S_FEAT0];
+            width = 4.f;
+            if (sgn == 1 && (x > thr1)) width = 2.f * 4.f;
+            if (sgn == -1 && (x < thr1)) width = 2.f * 4.f;
+            sc[C_TANH + 1] = (float)sgn * width * (thr1 - x);
+            x = sc[S_FEAT4];
+            width = 4.f;
+            if (x < thr2) width = 2.f * 4.f;
+            sc[C_TANH + 2] = width * (x - thr2);
         }
     }
     WMX_CTA_PHASE_END
-    // the three indicator functions side by side in lanes k = 0..2 of every stream
-    WMX_CTA_PHASE_BEGIN(RLane)
-    {
-        const int j = lane >> 2, k = lane & 3;
-        float* sc = tiles + (size_t)j * tile_stride + G::kShScal;
-        if (R.active && k < 3) sc[C_TANH + k] = 0.5f * ((float)tanh((double)sc[C_TANH + k]) + 1.f);
-    }
+    // the three indicator functions side by side in lanes 0..2
+    WMX_CTA_PHASE_BEGIN(L)
+    if (lane < 3) sc[C_TANH + lane] = 0.5f * ((float)tanh((double)sc[C_TANH + lane]) + 1.f);
     WMX_CTA_PHASE_END
-    WMX_CTA_PHASE_BEGIN(RLane)
-    {
-        const int j = lane >> 2, k = lane & 3;
-        float* sc = tiles + (size_t)j * tile_stride + G::kShScal;
-        R.want_e = 0;
-        if (R.active && k == 0) {
-            // prior update (ns_core.c:731-738)
-            const float ind = sc[S_PM4] * sc[C_TANH + 0] + sc[S_PM5] * sc[C_TANH + 1] + sc[S_PM6] * sc[C_TANH + 2];
-            float pp = sc[S_PRIOR_PROB];
-            pp += 0.1f * (ind - pp);
-            if (pp > 1.f) pp = 1.f;
-            if (pp < 0.01f) pp = 0.01f;
-            sc[S_PRIOR_PROB] = pp;
-            R.pp = pp;
-            sc[C_GAIN_PRIOR] = fdiv(1.f - pp, pp + 0.0001f);
-        }
-        if (R.active) R.want_e = (T.gainmap == 1 && f2i(sc[S_FRAME_IDX]) > kStartupLong) ? 1 : 0;
+    WMX_CTA_PHASE_BEGIN(L)
+    if (lane == 0) {
+        // prior update (ns_core.c:731-738)
+        const float ind = sc[S_PM4] * sc[C_TANH + 0] + sc[S_PM5] * sc[C_TANH + 1] + sc[S_PM6] * sc[C_TANH + 2];
+        float pp = sc[S_PRIOR_PROB];
+        pp += 0.1f * (ind - pp);
+        if (pp > 1.f) pp = 1.f;
+        if (pp < 0.01f) pp = 0.01f;
+        sc[S_PRIOR_PROB] = pp;
+        sc[C_GAIN_PRIOR] = fdiv(1.f - pp, pp + 0.0001f);
     }
     WMX_CTA_PHASE_END
 }
 
-// segment 2b (beside the workers' segment 3a): the Nyquist bin's probability, noise update and gain; the gain map's input
+// segment 2 (beside the workers' segment 3a): the Nyquist bin's probability, noise update and gain; the gain map's input
 // energy, in sample order, in lane k = 1 (ns_core.c:741-747, :800-846, :985-1010, :951-960)
 template <int ANA, typename RWarpT>
-WMX_HD void r_seg2b(RWarpT& W, float* tiles, int tile_stride, const Tables<ANA>& T)
+WMX_HD void r_seg2(RWarpT& W, float* tiles, int tile_stride, const Tables<ANA>& T)
 {
     typedef Geo<ANA> G;
     WMX_CTA_PHASE_BEGIN(RLane)
@@ -1091,8 +1085,10 @@ WMX_HD void r_seg2b(RWarpT& W, float* tiles, int tile_stride, const Tables<ANA>&
         float* sv = sh + G::kShSum;
         float* sc = sh + G::kShScal;
         float* nq = sh + G::kShNyq;
+        R.want_e = R.active && T.gainmap == 1 && f2i(sc[S_FRAME_IDX]) > kStartupLong;
         if (R.active && k == 0) {
             const float gain_prior = sc[C_GAIN_PRIOR];
+            R.pp = sc[S_PRIOR_PROB];
             // the look-back neighbour (bin kBody-1) is re-derived from the LRT row the worker staged — the same arithmetic, so
             // the same value the worker computes
             const float p_prev = bin_prob<ANA>(T, sv[CtaGeo<ANA>::kLrtRow * G::kSumStride + G::kBody - 1], gain_prior);
@@ -1115,11 +1111,9 @@ WMX_HD void r_seg2b(RWarpT& W, float* tiles, int tile_stride, const Tables<ANA>&
 // (ns_core.c:1314-1342).  Reads only the parked signal and its own registers: the tile's scalar area already belongs to
 // the next stream.
 template <int ANA, typename RWarpT>
-WMX_HD void r_seg3(RWarpT& W, float* tiles, int tile_stride, const float* ones, const Tables<ANA>& T)
+WMX_HD void r_seg3(RWarpT& W, float* tiles, int tile_stride, const Tables<ANA>& T)
 {
     typedef Geo<ANA> G;
-    float e1_of_k1;
-    (void)e1_of_k1;
     WMX_CTA_SHFL(RLane, R.e1, R.e1, (lane & 3) == 0 ? lane + 1 : lane)      // lane k = 0 takes the input energy from lane k = 1
     WMX_CTA_PHASE_BEGIN(RLane)
     {
@@ -1147,7 +1141,6 @@ WMX_HD void r_seg3(RWarpT& W, float* tiles, int tile_stride, const float* ones, 
         }
     }
     WMX_CTA_PHASE_END
-    (void)ones;
 }
 
 }  // namespace ns

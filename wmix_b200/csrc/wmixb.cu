@@ -136,12 +136,11 @@ __device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm vola
 template <int ANA>
 constexpr size_t ns_cta_smem_bytes(int workers)
 {
-    return (NsSmem<ANA>::kTableFloats + (size_t)workers * ns::CtaGeo<ANA>::kTileFloats + ns::Geo<ANA>::kSumStride) * sizeof(float) +
-           8 * sizeof(uint16_t*);
+    return (NsSmem<ANA>::kTableFloats + (size_t)workers * ns::CtaGeo<ANA>::kTileFloats) * sizeof(float);
 }
 
 // barrier ids (see the schedule at the top of ns_cta.cuh)
-enum { NSB_W1 = 1, NSB_R1 = 2, NSB_W2 = 3, NSB_R2A = 4, NSB_W3 = 5, NSB_R3 = 6, NSB_R2B = 8 };
+enum { NSB_W1 = 1, NSB_R1 = 2, NSB_W2 = 3, NSB_R2 = 4, NSB_W3 = 5, NSB_R3 = 6 };
 
 template <int ANA, int W, int MINB>
 __global__ void __launch_bounds__((W + 1) * 32, MINB)
@@ -155,15 +154,12 @@ ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Ta
     extern __shared__ __align__(16) float smem[];
     ns::Tables<ANA>* T = reinterpret_cast<ns::Tables<ANA>*>(smem);
     float* tiles = smem + NsSmem<ANA>::kTableFloats;
-    float* ones = tiles + (size_t)W * CG::kTileFloats;
-    uint16_t** hptr = reinterpret_cast<uint16_t**>(ones + G::kSumStride);
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
         uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
         for (int i = threadIdx.x; i < (int)(sizeof(ns::Tables<ANA>) / 4); i += kThreads) dst[i] = src[i];
         float4* t4 = reinterpret_cast<float4*>(tiles);
         for (int i = threadIdx.x; i < W * CG::kTileFloats / 4; i += kThreads) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // sum rows rely on +0.0f padding
-        for (int i = threadIdx.x; i < G::kSumStride; i += kThreads) ones[i] = 1.f;
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -186,7 +182,6 @@ ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Ta
             uint16_t* h = hist + (size_t)s * 3 * ns::kHistBins;
             const int16_t* pi = in + (size_t)s * n_frames * G::kBlock;
             int16_t* po = out + (size_t)s * n_frames * G::kBlock;
-            if (lane == 0) hptr[warp] = h;
             for (int f = 0; f < n_frames; ++f, pi += G::kBlock, po += G::kBlock) {
                 bool act = false;
                 float* syn = tile + (parity ? CG::kSynB : G::kShSynth);
@@ -212,10 +207,10 @@ ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Ta
                                     tile + (parity ? G::kShSynth : CG::kSynB), *T);
                     pend = false;
                 }
+                if (act) ns::w_seg2b<ANA>(Wk, h, tile, *T);
                 named_bar_arrive(NSB_W2, kThreads);
-                named_bar_sync(NSB_R2A, kThreads);
-                if (act) ns::w_seg3a<ANA>(Wk, r, h, tile, *T);                  // beside the reducer's segment 2b
-                named_bar_sync(NSB_R2B, kThreads);
+                if (act) ns::w_seg3a<ANA>(Wk, r, h, tile, *T);                  // beside the reducer's segment 2
+                named_bar_sync(NSB_R2, kThreads);
                 if (act) ns::w_seg3b<ANA>(Wk, r, tile, *T);
                 named_bar_arrive(NSB_W3, kThreads);
                 if (defer) {
@@ -242,12 +237,10 @@ ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Ta
                 ns::r_seg1<ANA>(Rd, tiles, CG::kTileFloats, W, *T);
                 named_bar_arrive(NSB_R1, kThreads);
                 named_bar_sync(NSB_W2, kThreads);
-                ns::r_seg2a<ANA>(Rd, tiles, CG::kTileFloats, hptr, ones, *T);
-                named_bar_arrive(NSB_R2A, kThreads);
-                ns::r_seg2b<ANA>(Rd, tiles, CG::kTileFloats, *T);
-                named_bar_arrive(NSB_R2B, kThreads);
+                ns::r_seg2<ANA>(Rd, tiles, CG::kTileFloats, *T);
+                named_bar_arrive(NSB_R2, kThreads);
                 named_bar_sync(NSB_W3, kThreads);
-                ns::r_seg3<ANA>(Rd, tiles, CG::kTileFloats, ones, *T);
+                ns::r_seg3<ANA>(Rd, tiles, CG::kTileFloats, *T);
                 if (!defer) named_bar_arrive(NSB_R3, kThreads);
             }
         }
