@@ -43,82 +43,45 @@ struct EmuNs {
     ns::Warp<128> w128;
 };
 
-// ---- CTA-cooperative NS (ns_cta.cuh): W worker warps + one reducer warp, the segments called in an order the kernel's
-// barriers allow.  `rounds` stream sets share the W worker tiles one after another, like the rounds of the persistent
-// grid: the last segment of a stream is deferred until the NEXT stream of the same worker has run its first two ----
+// ---- CTA-cooperative NS (ns_cta.cuh): W worker warps + one reducer warp, the segments called in barrier order ----
 template <int ANA>
 struct EmuNsCtaT {
     typedef ns::Geo<ANA> G;
-    typedef ns::CtaGeo<ANA> CG;
-    int W, rounds;
-    unsigned long long frames_done = 0;
-    std::vector<float> rec, tiles, ones;
+    int W;
+    std::vector<float> rec, tiles;
     std::vector<uint16_t> hist;
     std::vector<uint16_t*> hptr;
     std::vector<ns::WWarp<ANA>> ww;
     ns::RWarp rw;
     ns::Tables<ANA> T;
-    EmuNsCtaT(int w, int r) : W(w), rounds(r), rec((size_t)w * r * G::kRecFloats, 0.f), tiles((size_t)8 * CG::kTileFloats, 0.f), ones(G::kSumStride, 1.f),
-                              hist((size_t)w * r * 3 * ns::kHistBins, 0), hptr(8, nullptr), ww(w)
+    explicit EmuNsCtaT(int w) : W(w), rec((size_t)w * G::kRecFloats, 0.f), tiles((size_t)8 * G::kShFloats, 0.f), hist((size_t)w * 3 * ns::kHistBins, 0),
+                                hptr(8, nullptr), ww(w)
     {
         fill_tables(T, 2);
         memset(&rw, 0, sizeof rw);
-        for (int s = 0; s < w * r; ++s)
-            for (int l = 0; l < 32; ++l) ns::init_record_values<ANA>(rec.data() + (size_t)s * G::kRecFloats, l, 32);
-    }
-    float* tile(int j) { return tiles.data() + (size_t)j * CG::kTileFloats; }
-    float* syn_of(int j, int parity) { return tile(j) + (parity ? CG::kSynB : G::kShSynth); }
-    // in / out: [rounds][W][kBlock]; live[r][j] = 0 leaves worker j idle in round r (the ragged end of the stream range);
-    // defer = 0 runs the last segment right away (what the kernel does when a stream has several frames per launch)
-    void frame(const int16_t* in, int16_t* out, const uint8_t* live, int defer)
-    {
-        bool act[8] = {}, prev_act[8] = {};
-        int prev_round = -1, prev_parity = 0;
-        for (int r = 0; r < rounds; ++r) {
-            const int parity = (int)(frames_done++ & 1);
-            for (int j = 0; j < W; ++j) {
-                const int s = r * W + j;
-                hptr[j] = hist.data() + (size_t)s * 3 * ns::kHistBins;
-                act[j] = false;
-                if (live && !live[s]) { tile(j)[G::kShScal + ns::C_ACTIVE] = 0.f; continue; }
-                act[j] = ns::w_seg1<ANA>(ww[j], rec.data() + (size_t)s * G::kRecFloats, in + (size_t)s * G::kBlock, out + (size_t)s * G::kBlock, tile(j),
-                                         syn_of(j, parity), T);
-            }
-            // steady-state frames run segment 2 beside the reducer's segment 1, start-up frames after it
-            for (int j = 0; j < W; ++j)
-                if (act[j] && ww[j].lane_regs[0].frame_idx >= ns::kStartupShort) ns::w_seg2<ANA>(ww[j], rec.data() + (size_t)(r * W + j) * G::kRecFloats, tile(j), T);
-            ns::r_seg1<ANA>(rw, tiles.data(), CG::kTileFloats, W, T);
-            for (int j = 0; j < W; ++j)
-                if (act[j] && ww[j].lane_regs[0].frame_idx < ns::kStartupShort) ns::w_seg2<ANA>(ww[j], rec.data() + (size_t)(r * W + j) * G::kRecFloats, tile(j), T);
-            for (int j = 0; j < W; ++j)
-                if (prev_act[j]) {
-                    const int s = prev_round * W + j;
-                    ns::w_seg4<ANA>(ww[j], rec.data() + (size_t)s * G::kRecFloats, out + (size_t)s * G::kBlock, tile(j), syn_of(j, prev_parity), T);
-                    prev_act[j] = false;
-                }
-            for (int j = 0; j < W; ++j)
-                if (act[j]) ns::w_seg2b<ANA>(ww[j], hptr[j], tile(j), T);
-            // reducer segment 2 runs beside worker segment 3a: emulate the less obvious order
-            ns::r_seg2<ANA>(rw, tiles.data(), CG::kTileFloats, T);
-            for (int j = 0; j < W; ++j)
-                if (act[j]) ns::w_seg3a<ANA>(ww[j], rec.data() + (size_t)(r * W + j) * G::kRecFloats, hptr[j], tile(j), T);
-            for (int j = 0; j < W; ++j)
-                if (act[j]) ns::w_seg3b<ANA>(ww[j], rec.data() + (size_t)(r * W + j) * G::kRecFloats, tile(j), T);
-            ns::r_seg3<ANA>(rw, tiles.data(), CG::kTileFloats, T);
-            if (!defer) {
-                for (int j = 0; j < W; ++j)
-                    if (act[j]) ns::w_seg4<ANA>(ww[j], rec.data() + (size_t)(r * W + j) * G::kRecFloats, out + (size_t)(r * W + j) * G::kBlock, tile(j), syn_of(j, parity), T);
-            } else {
-                for (int j = 0; j < W; ++j) prev_act[j] = act[j];
-                prev_round = r;
-                prev_parity = parity;
-            }
+        for (int j = 0; j < w; ++j) {
+            for (int l = 0; l < 32; ++l) ns::init_record_values<ANA>(rec.data() + (size_t)j * G::kRecFloats, l, 32);
+            hptr[j] = hist.data() + (size_t)j * 3 * ns::kHistBins;
         }
+    }
+    // in / out: [W][kBlock]; live[j] = 0 leaves worker j idle this frame (a CTA at the ragged end of the stream range)
+    void frame(const int16_t* in, int16_t* out, const uint8_t* live)
+    {
+        bool act[8] = {};
+        for (int j = 0; j < W; ++j) {
+            float* sh = tiles.data() + (size_t)j * G::kShFloats;
+            if (live && !live[j]) { sh[G::kShScal + ns::C_ACTIVE] = 0.f; continue; }
+            act[j] = ns::w_seg1<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, in + (size_t)j * G::kBlock, out + (size_t)j * G::kBlock, sh, T);
+        }
+        ns::r_seg1<ANA>(rw, tiles.data(), G::kShFloats, W, T);
         for (int j = 0; j < W; ++j)
-            if (prev_act[j]) {
-                const int s = prev_round * W + j;
-                ns::w_seg4<ANA>(ww[j], rec.data() + (size_t)s * G::kRecFloats, out + (size_t)s * G::kBlock, tile(j), syn_of(j, prev_parity), T);
-            }
+            if (act[j]) ns::w_seg2<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, tiles.data() + (size_t)j * G::kShFloats, T);
+        ns::r_seg2<ANA>(rw, tiles.data(), G::kShFloats, hptr.data(), T);
+        for (int j = 0; j < W; ++j)
+            if (act[j]) ns::w_seg3<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, hptr[j], tiles.data() + (size_t)j * G::kShFloats, T);
+        ns::r_seg3<ANA>(rw, tiles.data(), G::kShFloats, T);
+        for (int j = 0; j < W; ++j)
+            if (act[j]) ns::w_seg4<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, out + (size_t)j * G::kBlock, tiles.data() + (size_t)j * G::kShFloats, T);
     }
 };
 struct EmuNsCta {
@@ -268,20 +231,20 @@ void emu_g711_dec(const uint8_t* codes, int n, int16_t* a, int16_t* u)
     for (int i = 0; i < n; ++i) { a[i] = alaw2linear(codes[i]); u[i] = ulaw2linear(codes[i]); }
 }
 int16_t emu_mix_step(int16_t bus, int16_t src, int rdce) { return mix_step(bus, src, rdce); }
-void* emu_nscta_create(int freq, int workers, int rounds)
+void* emu_nscta_create(int freq, int workers)
 {
-    if (workers < 1 || workers > 8 || rounds < 1) return nullptr;
+    if (workers < 1 || workers > 8) return nullptr;
     EmuNsCta* e = new EmuNsCta();
     e->ana = freq == 8000 ? 128 : 256;
-    if (e->ana == 256) e->e256 = new EmuNsCtaT<256>(workers, rounds);
-    else e->e128 = new EmuNsCtaT<128>(workers, rounds);
+    if (e->ana == 256) e->e256 = new EmuNsCtaT<256>(workers);
+    else e->e128 = new EmuNsCtaT<128>(workers);
     return e;
 }
-void emu_nscta_frame(void* h, const int16_t* in, int16_t* out, const uint8_t* live, int defer)
+void emu_nscta_frame(void* h, const int16_t* in, int16_t* out, const uint8_t* live)
 {
     EmuNsCta* e = (EmuNsCta*)h;
-    if (e->e256) e->e256->frame(in, out, live, defer);
-    else e->e128->frame(in, out, live, defer);
+    if (e->e256) e->e256->frame(in, out, live);
+    else e->e128->frame(in, out, live);
 }
 const float* emu_nscta_record(void* h, int j)
 {

@@ -5,7 +5,8 @@
 // with one to four active lanes is done ONCE for all the streams of the CTA:
 //
 //   * the in-order float sums (129- and 256-term chains the reference accumulates serially: signal energy, sum of
-//     magnitudes, flatness numerator, pause average, the two 256-term energies of the gain map) — in ns::frame four lanes of every warp walk them while 28 idle; here lane 4j+k of the reducer walks sum k
+//     magnitudes, flatness numerator, pause average, the four spectral-difference sums, the two energies of the gain
+//     map) — in ns::frame four lanes of every warp walk them while 28 idle; here lane 4j+k of the reducer walks sum k
 //     of worker j, 32 chains per instruction;
 //   * the per-stream scalar model (start-up white/pink fit, flatness / difference features, histogram re-learning,
 //     the tanh indicators, prior update, gain-map factor): one lane per stream, eight streams per instruction;
@@ -14,26 +15,15 @@
 // ncu on ns::frame (profiles/r1_g): those three groups were 1 230 + ~380 of 4 587 warp instructions per stream-frame at
 // 1.7 - 5 active lanes.
 //
-// Worker and reducer hand over through the worker's shared tile and named barriers (bar.arrive / bar.sync).  The reducer's
-// serial chains run BESIDE worker segments that do not need their results yet:
-//     worker                                                     reducer
-//     seg1: load, window, forward FFT, real split, |X|, log,
-//           quantile trackers                         --1-->     seg1: Nyquist tracker, 4 sums, start-up model, flatness,
-//     seg2: noise blend, DD SNR, LRT average, exp(-LRT)                Nyquist SNR / LRT / difference terms
-//           (needs nothing of reducer seg1 once the                    (runs BESIDE seg2)
-//           start-up model is over)                   <--2--
-//     seg4 of the PREVIOUS stream (see below)
-//     seg2b: difference terms, 4 sums, features,
-//            histograms, tanh x3, prior               --3-->     seg2: Nyquist probability + filter, input energy of the
-//     seg3a: probability, noise update, Wiener gain,                   gain map                    (runs BESIDE seg3a)
-//            state arrays back                        <--4--
-//     seg3b: inverse split, IFFT, scale, park         --5-->     seg3: output energy of the gain map, factor
-//     (next stream's seg1 ...)                                          (runs BESIDE the next stream's seg1)
-//     seg4: window, overlap-add, factor, saturate, emit — deferred until after barrier 2 of the NEXT stream, by which time
-//           the reducer has long finished seg3; only the very last frame of a launch waits for it (barrier 6).
-// The prior chain of seg2b (sums -> features -> tanh -> prior) stays in the worker although it is lane-sparse: everything
-// downstream waits for it, and a first version that handed it to the reducer spent longer in the hand-over than the ~550
-// instructions cost (profiles/r2_b, r2_c).
+// Worker and reducer hand over through the worker's shared tile and named barriers (bar.arrive / bar.sync), three
+// round trips per frame:
+//     worker:  P0 load, window, forward FFT, real split, |X|, log, quantile trackers   --1-->  reducer: Nyquist tracker,
+//              4 sums, start-up model, flatness                                          <--2--
+//     worker:  noise blend, DD SNR, LRT average, difference terms                        --3-->  reducer: Nyquist SNR/LRT,
+//              4 sums, features, histograms, tanh x3, prior, Nyquist probability + filter <--4--
+//     worker:  probability, noise update, Wiener gain, inverse split, IFFT, scale        --5-->  reducer: two 256-term
+//              energies, gain-map factor                                                 <--6--
+//     worker:  window, overlap-add, saturate, emit
 // Other changes against ns::frame, all value-preserving: the last FFT pass leaves its results in registers and the
 // real split fetches the mirrored bin with warp shuffles (no exchange-tile round trip on either side of the split);
 // the filtered spectrum and the scaled IFFT output stay in registers; PCM moves as 32-bit pairs and the history /
@@ -52,32 +42,19 @@ enum CtaScal {
     C_ACTIVE = 32,     // 1.f: this worker holds a live, non-zero frame (the reducer has work for it)
     C_X0R, C_X0I,      // element 0 of the complex transform (DC and Nyquist before the real split)
     C_AVGMAGN, C_AVGPAUSE, C_PNUM, C_PEXP, C_USE_PINK,
-    C_GAIN_PRIOR, C_RELEARNED, C_NYQ_FRE,
-    C_SUM_A,           // +0..5: signal energy (/bins after reducer seg1), sum of magnitudes, flatness numerator, pause sum, 2 start-up sums
-    C_SUM_B = C_SUM_A + 6,   // +0..3: covariance, pause variance, magnitude variance, LRT sum
-    C_TANH = C_SUM_B + 4,    // +0..2: indicator arguments, then their values
-    C_COUNT_ = C_TANH + 3
+    C_GAIN_PRIOR, C_RELEARNED, C_NYQ_FRE, C_WANT_E, C_FACTOR,
+    C_COUNT_
 };
 static_assert(C_COUNT_ <= 64, "the scalar tile has 64 slots");
 
-// worker tile = Geo's tile + what the deferred last segment needs after the next stream has taken the tile over
-template <int ANA>
-struct CtaGeo {
-    typedef Geo<ANA> G;
-    static constexpr int kPark = G::kShFloats;            // [ANA] scaled IFFT output, natural sample order
-    static constexpr int kSynB = kPark + ANA;             // [kOverlap] second synthesis-tail buffer (odd frames)
-    static constexpr int kFac = kSynB + G::kOverlap;      // [4] gain-map factor of the parked frame
-    static constexpr int kTileFloats = kFac + 4;
-    static constexpr int kLrtRow = 4;                     // sum row the LRT values are staged in (free once start-up is over)
-};
 template <int ANA>
 struct WLane {
     static constexpr int NS = Geo<ANA>::kSlots;
     Cpx f[4];                      // transform data: element lane + 32 r (after a last pass) or the pass's operands
     Cpx m[4];                      // mirrored elements fetched by shuffle (real split)
     float st[kNumRegArrays][NS];   // state arrays, bin = 32*slot + lane
-    float mag[NS], noise[NS], prev[NS], prob[NS];   // prob: exp(-LRT) from seg2 until seg3a turns it into the probability
-    int flag, frame_idx;
+    float mag[NS], noise[NS], prev[NS], prob[NS];
+    int flag;
 };
 template <int ANA>
 struct WWarp {
@@ -90,8 +67,8 @@ struct WWarp {
 };
 // reducer lane state that lives across its three segments
 struct RLane {
-    float re, mag, noise, prev, pp, e1;
-    int frame_idx, active, want_e;
+    float re, mag, lm, noise, prev, prob127;
+    int frame_idx, active;
 };
 struct RWarp {
 #if defined(__CUDACC__)   // (not __CUDA_ARCH__: a non-template type must look the same in nvcc's host and device passes)
@@ -160,14 +137,12 @@ WMX_HD void bin_analyze(const Tables<ANA>& T, float* sv, int b, float re, float 
     noise_out = quant;
 }
 
-// start-up noise blend, decision-directed SNR, LRT average (ns_core.c:1109-1162, :566-589, :679-687); the LRT value is
-// staged in the sum row the reducer adds up.  The spectral-difference terms (ns_core.c:617-622) are NOT formed here: they
-// need the two averages of the reducer's first segment, and the reducer forms them itself from the magnitude and pause
-// rows (seq_sum_prod).  param_noise is written only during start-up.
+// start-up noise blend, decision-directed SNR, rows of the second group of sums, LRT average (ns_core.c:1109-1162, :566-589,
+// :617-622, :679-687).  param_noise is written only during start-up.
 template <int ANA>
 WMX_HD void bin_snr(const Tables<ANA>& T, float* sv, int b, int frame_idx, bool use_pink, float white, float pnum, float pexp,
-                    float mag, float& noise, float magn_prev, float noise_prev, float smooth, float& lrt, float& prev_out,
-                    float& param_noise)
+                    float avg_magn, float avg_pause, float mag, float& noise, float magn_prev, float noise_prev, float smooth,
+                    float pause, float& lrt, float& prev_out, float& param_noise)
 {
     typedef Geo<ANA> G;
     if (frame_idx < kStartupShort) {
@@ -189,23 +164,23 @@ WMX_HD void bin_snr(const Tables<ANA>& T, float* sv, int b, int frame_idx, bool 
     if (mag > noise) post = fdiv(mag, noise + 0.0001f) - 1.f;
     const float prior = 0.98f * prev + (1.f - 0.98f) * post;
     prev_out = prev;
+    sv[0 * G::kSumStride + b] = (mag - avg_magn) * (pause - avg_pause);
+    sv[1 * G::kSumStride + b] = (pause - avg_pause) * (pause - avg_pause);
+    sv[2 * G::kSumStride + b] = (mag - avg_magn) * (mag - avg_magn);
     const float a = 1.f + 2.f * prior;
     const float bb = fdiv(2.f * prior, a + 0.0001f);
     const float bessel = (post + 1.f) * bb;
     lrt += 0.5f * (bessel - log_f(a, T.dm) - lrt);
-    sv[CtaGeo<ANA>::kLrtRow * G::kSumStride + b] = lrt;
+    sv[3 * G::kSumStride + b] = lrt;
 }
 
-// speech probability of one bin (ns_core.c:741-747), and its second half for a caller that took exp(-lrt) ahead of time
-WMX_HD float prob_from_exp(float inv, float gain_prior)
-{
-    inv = (float)gain_prior * inv;
-    return fdiv(1.f, 1.f + inv);
-}
+// speech probability of one bin (ns_core.c:741-747)
 template <int ANA>
 WMX_HD float bin_prob(const Tables<ANA>& T, float lrt, float gain_prior)
 {
-    return prob_from_exp(exp_f(-lrt, T.dm), gain_prior);
+    float inv = exp_f(-lrt, T.dm);
+    inv = (float)gain_prior * inv;
+    return fdiv(1.f, 1.f + inv);
 }
 
 // noise update + Wiener gain of one bin (ns_core.c:800-846, :985-1010, :1276-1307); returns the gain
@@ -361,10 +336,9 @@ WMX_HD void cta_fetch_mirrors(WarpT& W)
 // ---------------------------------------------------------------------------------------------------------------
 
 // segment 1: load, window, forward transform, real split, magnitudes, trackers.  Returns false for a zero frame (the
-// worker has then already produced its output; the caller still walks the barriers).  `syn` = the synthesis-tail buffer
-// of this frame (Geo::kShSynth or CtaGeo::kSynB of the tile, alternating, see w_seg4).
+// worker has then already produced its output; the caller still walks the barriers).
 template <int ANA, typename WarpT>
-WMX_HD bool w_seg1(WarpT& W, float* rec, const int16_t* in, int16_t* out, float* sh, float* syn, const Tables<ANA>& T)
+WMX_HD bool w_seg1(WarpT& W, float* rec, const int16_t* in, int16_t* out, float* sh, const Tables<ANA>& T)
 {
     typedef Geo<ANA> G;
     typedef WLane<ANA> L;
@@ -372,6 +346,7 @@ WMX_HD bool w_seg1(WarpT& W, float* rec, const int16_t* in, int16_t* out, float*
     float* sv = sh + G::kShSum;
     float* sc = sh + G::kShScal;
     float* nq = sh + G::kShNyq;
+    float* syn = sh + G::kShSynth;
     float* sq = sh + G::kShSq;
     constexpr int HP = G::kOverlap / 2, BP = G::kBlock / 2;          // float2 / int16x2 pairs
     constexpr int NHP = (HP + 31) / 32, NBP = (BP + 31) / 32;
@@ -480,7 +455,6 @@ WMX_HD bool w_seg1(WarpT& W, float* rec, const int16_t* in, int16_t* out, float*
     WMX_CTA_PHASE_BEGIN(L)
     {
         const TrackerCtl c = tracker_ctl(sc);
-        R.frame_idx = c.frame_idx;
 #pragma unroll
         for (int s = 0; s < G::kSlots; ++s) {
             const int b = 32 * s + lane;
@@ -532,10 +506,7 @@ WMX_HD bool w_seg1(WarpT& W, float* rec, const int16_t* in, int16_t* out, float*
     return true;
 }
 
-// segment 2: start-up noise blend, decision-directed SNR, LRT average (per body bin); exp(-LRT) of the probability is taken
-// here, ahead of the prior it will be combined with.  Once the 50 start-up frames are over nothing in here depends on the
-// reducer's segment 1, so the kernel runs it BEFORE waiting for barrier 2 (the frame index rides in R.frame_idx because the
-// reducer is advancing the scalar line at that moment).
+// segment 2: start-up noise blend, decision-directed SNR, LRT average (per body bin)
 template <int ANA, typename WarpT>
 WMX_HD void w_seg2(WarpT& W, float* rec, float* sh, const Tables<ANA>& T)
 {
@@ -545,41 +516,43 @@ WMX_HD void w_seg2(WarpT& W, float* rec, float* sh, const Tables<ANA>& T)
     float* sc = sh + G::kShScal;
     WMX_CTA_PHASE_BEGIN(L)
     {
-        const int frame_idx = R.frame_idx;
-        const bool startup = frame_idx < kStartupShort;
-        // start-up only (then this segment runs after barrier 2): the reducer's white / pink fit
-        const float pnum = startup ? sc[C_PNUM] : 0.f, pexp = startup ? sc[C_PEXP] : 0.f;
-        const bool use_pink = startup && sc[C_USE_PINK] != 0.f;
-        const float white = startup ? sc[S_WHITE] : 0.f;
+        const int frame_idx = f2i(sc[S_FRAME_IDX]);
+        const float avg_magn = sc[C_AVGMAGN], avg_pause = sc[C_AVGPAUSE];
+        const float pnum = sc[C_PNUM], pexp = sc[C_PEXP];
+        const bool use_pink = sc[C_USE_PINK] != 0.f;
+        const float white = sc[S_WHITE];
 #pragma unroll
         for (int s = 0; s < G::kSlots; ++s) {
             const int b = 32 * s + lane;
             float pn = 0.f;
-            bin_snr<ANA>(T, sv, b, frame_idx, use_pink, white, pnum, pexp, R.mag[s], R.noise[s], R.st[A_MAGN_PREV][s], R.st[A_NOISE_PREV][s],
-                         R.st[A_SMOOTH][s], R.st[A_LRT][s], R.prev[s], pn);
-            if (startup) rec[G::kOffArrays + A_PARAM_NOISE * G::kBody + b] = pn;
-            R.prob[s] = exp_f(-R.st[A_LRT][s], T.dm);
+            bin_snr<ANA>(T, sv, b, frame_idx, use_pink, white, pnum, pexp, avg_magn, avg_pause, R.mag[s], R.noise[s], R.st[A_MAGN_PREV][s],
+                         R.st[A_NOISE_PREV][s], R.st[A_SMOOTH][s], R.st[A_PAUSE][s], R.st[A_LRT][s], R.prev[s], pn);
+            if (frame_idx < kStartupShort) rec[G::kOffArrays + A_PARAM_NOISE * G::kBody + b] = pn;
         }
     }
     WMX_CTA_PHASE_END
 }
 
-// segment 3a: probability, noise update, Wiener gain, filtered spectrum (kept in f[]), state arrays back
+// segment 3: probability, noise update, Wiener gain, state back, inverse split, inverse transform, scale.
+// Leaves the scaled time signal in f[] (element pair lane + 32 r -> samples 2c, 2c+1) and its squares in the sum rows.
 template <int ANA, typename WarpT>
-WMX_HD void w_seg3a(WarpT& W, float* rec, uint16_t* hist, float* sh, const Tables<ANA>& T)
+WMX_HD void w_seg3(WarpT& W, float* rec, uint16_t* hist, float* sh, const Tables<ANA>& T)
 {
     typedef Geo<ANA> G;
     typedef WLane<ANA> L;
+    constexpr int NR = G::kNc / 32;
     float* tb = sh + G::kShTime;
+    float* xb = sh + G::kShX;
     float* sv = sh + G::kShSum;
     float* sc = sh + G::kShScal;
+    float* nq = sh + G::kShNyq;
 
     WMX_CTA_PHASE_BEGIN(L)
     {
         const float gain_prior = sc[C_GAIN_PRIOR];
 #pragma unroll
         for (int s = 0; s < G::kSlots; ++s) {
-            const float p = prob_from_exp(R.prob[s], gain_prior);
+            const float p = bin_prob<ANA>(T, R.st[A_LRT][s], gain_prior);
             R.prob[s] = p;
             sv[0 * G::kSumStride + 32 * s + lane] = p;
         }
@@ -592,7 +565,7 @@ WMX_HD void w_seg3a(WarpT& W, float* rec, uint16_t* hist, float* sh, const Table
 
     WMX_CTA_PHASE_BEGIN(L)
     {
-        const int frame_idx = R.frame_idx;
+        const int frame_idx = f2i(sc[S_FRAME_IDX]);
         const bool startup = frame_idx < kStartupShort;
 #pragma unroll
         for (int s = 0; s < G::kSlots; ++s) {
@@ -619,30 +592,15 @@ WMX_HD void w_seg3a(WarpT& W, float* rec, uint16_t* hist, float* sh, const Table
 #pragma unroll
             for (int s = 0; s < G::kSlots; ++s) rec[G::kOffArrays + a * G::kBody + 32 * s + lane] = R.st[a][s];
         }
+        rec[G::kOffNyq + lane] = lane < 16 ? nq[lane] : 0.f;        // the reducer finished the Nyquist line before barrier 4
     }
     WMX_CTA_PHASE_END
-}
-
-// segment 3b (after the reducer finished the Nyquist bin): Nyquist and scalar lines back to the record, inverse real split,
-// inverse transform, scale by 2/N; the scaled signal is parked in the tile for the reducer's energy and for segment 4
-template <int ANA, typename WarpT>
-WMX_HD void w_seg3b(WarpT& W, float* rec, float* sh, const Tables<ANA>& T)
-{
-    typedef Geo<ANA> G;
-    typedef WLane<ANA> L;
-    constexpr int NR = G::kNc / 32;
-    float* xb = sh + G::kShX;
-    float* sc = sh + G::kShScal;
-    float* nq = sh + G::kShNyq;
-    float* park = sh + CtaGeo<ANA>::kPark;
 
     cta_fetch_mirrors<ANA>(W);
 
     // inverse real split (rdft isgn<0 head + rftbsub, fft4g.c:345-350, :1259-1283): every lane its elements lane + 32 r
     WMX_CTA_PHASE_BEGIN(L)
     {
-        rec[G::kOffNyq + lane] = lane < 16 ? nq[lane] : 0.f;
-        rec[G::kOffScal + lane] = sc[lane];                          // the scalar line is final since barrier 4
         const float nyq_fre = sc[C_NYQ_FRE];
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
@@ -686,47 +644,54 @@ WMX_HD void w_seg3b(WarpT& W, float* rec, float* sh, const Tables<ANA>& T)
     WMX_CTA_PHASE_END
     cta_passes<ANA>(W, sh, T.w, true);
 
-    // scale by 2/N (ns_core.c:941-943) and park: element pair c -> samples 2c, 2c+1
+    // scale by 2/N (ns_core.c:941-943); the squares are staged for the reducer's in-order output energy
     WMX_CTA_PHASE_BEGIN(L)
     {
-        F2* park2 = reinterpret_cast<F2*>(park);
+        const bool want_e = sc[C_WANT_E] != 0.f;
+        F2* sv2 = reinterpret_cast<F2*>(sv);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
-            F2 v;
-            v.x = R.f[r].r * (2.f / ANA);
-            v.y = R.f[r].i * (2.f / ANA);
-            park2[lane + 32 * r] = v;
+            const int c = lane + 32 * r;
+            const float a = R.f[r].r * (2.f / ANA), b = R.f[r].i * (2.f / ANA);
+            R.f[r].r = a;
+            R.f[r].i = b;
+            if (want_e) {
+                F2 e;
+                e.x = a * a;
+                e.y = b * b;
+                sv2[c] = e;
+            }
         }
     }
     WMX_CTA_PHASE_END
 }
 
-// segment 4: window, overlap-add with the gain-map factor, saturate, emit, synthesis tail back to the record
-// (ns_core.c:1344-1359).  `syn` = the synthesis-tail buffer segment 1 of THIS frame filled (the tile has two: the next
-// stream's segment 1 has usually run by now).
+// segment 4: window, overlap-add, gain-map factor, saturate, emit; scalar line back to the record
 template <int ANA, typename WarpT>
-WMX_HD void w_seg4(WarpT& W, float* rec, int16_t* out, float* sh, const float* syn, const Tables<ANA>& T)
+WMX_HD void w_seg4(WarpT& W, float* rec, int16_t* out, float* sh, const Tables<ANA>& T)
 {
     typedef Geo<ANA> G;
     typedef WLane<ANA> L;
     constexpr int NR = G::kNc / 32;
+    float* sv = sh + G::kShSum;
+    float* sc = sh + G::kShScal;
+    float* syn = sh + G::kShSynth;
     WMX_CTA_PHASE_BEGIN(L)
     {
-        const float factor = sh[CtaGeo<ANA>::kFac];
+        const float factor = sc[C_FACTOR];
         const F2* win2 = reinterpret_cast<const F2*>(T.window);
         const F2* syn2 = reinterpret_cast<const F2*>(syn);
-        const F2* park2 = reinterpret_cast<const F2*>(sh + CtaGeo<ANA>::kPark);
         S2* out2 = reinterpret_cast<S2*>(out);
         F2* rec2 = reinterpret_cast<F2*>(rec);
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
             const int c = lane + 32 * r;                               // samples 2c, 2c+1
-            const F2 w = win2[c], x = park2[c];
+            const F2 w = win2[c];
             F2 prev;
             prev.x = prev.y = 0.f;
             if (c < G::kOverlap / 2) prev = syn2[c];
-            const float v0 = prev.x + factor * (w.x * x.x);
-            const float v1 = prev.y + factor * (w.y * x.y);
+            const float v0 = prev.x + factor * (w.x * R.f[r].r);
+            const float v1 = prev.y + factor * (w.y * R.f[r].i);
             if (c < G::kBlock / 2) {
                 const float s0 = v0 > 32767 ? 32767 : (v0 < -32768 ? -32768 : v0);
                 const float s1 = v1 > 32767 ? 32767 : (v1 < -32768 ? -32768 : v1);
@@ -741,6 +706,13 @@ WMX_HD void w_seg4(WarpT& W, float* rec, int16_t* out, float* sh, const float* s
                 rec2[G::kOffSynth / 2 + c - G::kBlock / 2] = t;
             }
         }
+        rec[G::kOffScal + lane] = sc[lane];
+        // the energy staging ran over the zero padding of sum row 0 (and the rows behind it): restore what the sums rely on
+        if (sc[C_WANT_E] != 0.f) {
+#pragma unroll
+            for (int k = 0; k < G::kNumSums; ++k)
+                if (lane < G::kSumStride - G::kBins && k * G::kSumStride + G::kBins + lane < ANA) sv[k * G::kSumStride + G::kBins + lane] = 0.f;
+        }
     }
     WMX_CTA_PHASE_END
 }
@@ -749,35 +721,11 @@ WMX_HD void w_seg4(WarpT& W, float* rec, int16_t* out, float* sh, const float* s
 // reducer segments.  Lane 4j+k serves worker j (tile base + j * tile_stride): k = 0 is the stream's scalar /
 // Nyquist lane, k = 0..3 each walk one in-order sum.
 // ---------------------------------------------------------------------------------------------------------------
-
-// In-order sum of (x[i] - cx) * (y[i] - cy) over n = 4 * n4 + tail elements: the spectral-difference sums of
-// ns_core.c:617-622 with their terms formed on the fly from the staged magnitude and pause rows (same operations the
-// workers of ns::frame applied per bin, so the same values), and — with y = a row of ones, cx = cy = 0 — a plain sum
-// ((x - 0) * (1 - 0) == x exactly).  One add chain, operands fetched as 16-byte vectors a step ahead.
-template <int N4, int TAIL>
-WMX_HD float seq_sum_prod(const float* x, const float* y, float cx, float cy)
-{
-    const F4* px = reinterpret_cast<const F4*>(x);
-    const F4* py = reinterpret_cast<const F4*>(y);
-    float acc = 0.f;
-    F4 ax = px[0], ay = py[0];
-#pragma unroll 4
-    for (int g = 0; g < N4; ++g) {
-        F4 bx = ax, by = ay;
-        if (g + 1 < N4) { ax = px[g + 1]; ay = py[g + 1]; }
-        acc += (bx.x - cx) * (by.x - cy);
-        acc += (bx.y - cx) * (by.y - cy);
-        acc += (bx.z - cx) * (by.z - cy);
-        acc += (bx.w - cx) * (by.w - cy);
-    }
-#pragma unroll
-    for (int i = 0; i < TAIL; ++i) acc += (x[4 * N4 + i] - cx) * (y[4 * N4 + i] - cy);
-    return acc;
-}
+template <int ANA, int N4>
+WMX_HD float seq_sum_rows(const float* row) { return seq_sum4<N4>(row); }
 
 // segment 1: Nyquist tracker, sums (signal energy, sum of magnitudes, flatness numerator, pause average, start-up
-// regressors), counters, start-up model, flatness, then the Nyquist bin's SNR / LRT step
-// (ns_core.c:217-283, :1089-1162, :523-557, :566-589, :679-687)
+// regressors), counters, start-up model, flatness (ns_core.c:217-283, :1089-1162, :523-557)
 template <int ANA, typename RWarpT>
 WMX_HD void r_seg1(RWarpT& W, float* tiles, int tile_stride, int n_workers, const Tables<ANA>& T)
 {
@@ -799,7 +747,7 @@ WMX_HD void r_seg1(RWarpT& W, float* tiles, int tile_stride, int n_workers, cons
             tb[G::kBody] = re;
             bin_analyze<ANA>(T, sv, G::kBody, re, 0.f, c.startup, c.cf, c.rcf, c.cfm1, c.quant_from, nq[A_DENS0], nq[A_DENS1], nq[A_DENS2],
                              nq[A_LQ0], nq[A_LQ1], nq[A_LQ2], nq[A_QUANT], R.mag, R.noise);
-            // counters advance (ns_core.c:265-283); the workers took what they need of the old values before barrier 1
+            // counters advance (ns_core.c:265-283); the workers read the old values before barrier 1
             int cnt[3] = {c.counter[0], c.counter[1], c.counter[2]};
 #pragma unroll
             for (int t = 0; t < 3; ++t) {
@@ -821,9 +769,9 @@ WMX_HD void r_seg1(RWarpT& W, float* tiles, int tile_stride, int n_workers, cons
         float* sv = sh + G::kShSum;
         float* sc = sh + G::kShScal;
         if (R.active) {
-            sc[C_SUM_A + k] = seq_sum4<G::kSumStride / 4>(sv + k * G::kSumStride);
+            sc[C_COUNT_ + k] = seq_sum4<G::kSumStride / 4>(sv + k * G::kSumStride);
             const bool startup = f2i(sc[S_FRAME_IDX]) < kStartupShort;
-            if (startup && k < 2) sc[C_SUM_A + 4 + k] = seq_sum4<G::kSumStride / 4>(sv + (4 + k) * G::kSumStride);
+            if (startup && k < 2) sc[C_COUNT_ + 4 + k] = seq_sum4<G::kSumStride / 4>(sv + (4 + k) * G::kSumStride);
         }
     }
     WMX_CTA_PHASE_END
@@ -831,19 +779,17 @@ WMX_HD void r_seg1(RWarpT& W, float* tiles, int tile_stride, int n_workers, cons
     {
         const int j = lane >> 2, k = lane & 3;
         float* sh = tiles + (size_t)j * tile_stride;
-        float* sv = sh + G::kShSum;
         float* sc = sh + G::kShScal;
-        float* nq = sh + G::kShNyq;
         if (R.active && k == 0) {
             const int frame_idx = R.frame_idx;
             const float nb = (float)G::kBins;
-            const float sig_e = sc[C_SUM_A + 0] / nb;
-            const float sum_magn = sc[C_SUM_A + 1];
-            sc[C_SUM_A + 0] = sig_e;                                   // kept for the difference feature of segment 2
+            const float sig_e = sc[C_COUNT_ + 0] / nb;
+            const float sum_magn = sc[C_COUNT_ + 1];
+            sc[C_COUNT_ + 0] = sig_e;                                  // kept for the difference feature of segment 2
             float use_pink = 0.f, pnum = 0.f, pexp = 0.f;
             if (frame_idx < kStartupShort) {
                 const float s_li = T.sum_log_i, s_li2 = T.sum_log_i_sq;
-                const float s_lm = sc[C_SUM_A + 4], s_lilm = sc[C_SUM_A + 5];
+                const float s_lm = sc[C_COUNT_ + 4], s_lilm = sc[C_COUNT_ + 5];
                 float white = sc[S_WHITE], pink_num = sc[S_PINK_NUM], pink_exp = sc[S_PINK_EXP];
                 white += sum_magn / nb * T.overdrive;
                 float f1 = s_li2 * ((float)(G::kBins - 5));
@@ -882,8 +828,8 @@ WMX_HD void r_seg1(RWarpT& W, float* tiles, int tile_stride, int n_workers, cons
             // first entry
             {
                 float den = sum_magn;
-                den -= sv[1 * G::kSumStride + 0];
-                float num = sc[C_SUM_A + 2];
+                den -= (sh + G::kShSum)[1 * G::kSumStride + 0];
+                float num = sc[C_COUNT_ + 2];
                 den = den / G::kBins;
                 num = num / G::kBins;
                 const float v = exp_f(num, T.dm) / den;
@@ -891,191 +837,17 @@ WMX_HD void r_seg1(RWarpT& W, float* tiles, int tile_stride, int n_workers, cons
                 f0 += 0.3f * (v - f0);
                 sc[S_FEAT0] = f0;
             }
-            sc[C_AVGPAUSE] = sc[C_SUM_A + 3] / nb;
+            sc[C_AVGPAUSE] = sc[C_COUNT_ + 3] / nb;
             sc[C_AVGMAGN] = sum_magn / nb;
-            // the Nyquist bin's SNR / LRT step; its LRT value completes the row the workers are staging meanwhile
-            float pn = 0.f;
-            bin_snr<ANA>(T, sv, G::kBody, frame_idx, use_pink != 0.f, sc[S_WHITE], pnum, pexp, R.mag, R.noise, nq[A_MAGN_PREV],
-                         nq[A_NOISE_PREV], nq[A_SMOOTH], nq[A_LRT], R.prev, pn);
-            if (frame_idx < kStartupShort) nq[A_PARAM_NOISE] = pn;
-            // ... and its spectral-difference terms (ns_core.c:617-622), into the rows the worker fills for the body bins once
-            // it has the two averages (rows 0-2 are free: the sums above are done)
-            const float am = sc[C_AVGMAGN], ap = sc[C_AVGPAUSE], pz = nq[A_PAUSE];
-            sv[0 * G::kSumStride + G::kBody] = (R.mag - am) * (pz - ap);
-            sv[1 * G::kSumStride + G::kBody] = (pz - ap) * (pz - ap);
-            sv[2 * G::kSumStride + G::kBody] = (R.mag - am) * (R.mag - am);
         }
     }
     WMX_CTA_PHASE_END
 }
 
-// segment 2b (after barrier 2: the reducer's averages and features are in the tile): spectral-difference terms of the body
-// bins, the four in-order sums of this phase (covariance, two variances, LRT sum) in lanes 0..3, difference feature,
-// histograms and threshold re-learning, indicator functions, prior (ns_core.c:595-640, :689-738, :755-790, :293-520).
-// This chain stays in the worker: everything downstream of it waits for the prior, so handing it to the reducer only adds
-// the hand-over to the critical path (measured: the wait was longer than these ~550 lane-sparse instructions).
-template <int ANA, typename WarpT>
-WMX_HD void w_seg2b(WarpT& W, uint16_t* hist, float* sh, const Tables<ANA>& T)
-{
-    typedef Geo<ANA> G;
-    typedef WLane<ANA> L;
-    float* sv = sh + G::kShSum;
-    float* sc = sh + G::kShScal;
-    WMX_CTA_PHASE_BEGIN(L)
-    {
-        const float am = sc[C_AVGMAGN], ap = sc[C_AVGPAUSE];
-#pragma unroll
-        for (int s = 0; s < G::kSlots; ++s) {
-            const int b = 32 * s + lane;
-            const float mag = R.mag[s], pause = R.st[A_PAUSE][s];
-            sv[0 * G::kSumStride + b] = (mag - am) * (pause - ap);
-            sv[1 * G::kSumStride + b] = (pause - ap) * (pause - ap);
-            sv[2 * G::kSumStride + b] = (mag - am) * (mag - am);
-        }
-    }
-    WMX_CTA_PHASE_END
-    WMX_CTA_PHASE_BEGIN(L)
-    if (lane < 4) sc[C_SUM_B + lane] = seq_sum4<G::kSumStride / 4>(sv + (lane == 3 ? CtaGeo<ANA>::kLrtRow : lane) * G::kSumStride);
-    WMX_CTA_PHASE_END
-    WMX_CTA_PHASE_BEGIN(L)
-    if (lane == 0) {
-        const float nb = (float)G::kBins;
-        {
-            const float cov = sc[C_SUM_B + 0] / nb, vp = sc[C_SUM_B + 1] / nb, vm = sc[C_SUM_B + 2] / nb;
-            sc[S_FEAT6] = sc[S_FEAT6] + sc[C_SUM_A + 0];
-            float d = vm - (cov * cov) / (vp + 0.0001f);
-            d = (float)(d / (sc[S_FEAT5] + 0.0001f));
-            float f4 = sc[S_FEAT4];
-            f4 += 0.3f * (d - f4);
-            sc[S_FEAT4] = f4;
-        }
-        // histogram update / threshold re-learn (ns_core.c:755-790, :293-520); the LRT feature used here is still last
-        // frame's (featureData[3] is refreshed further down)
-        const int upd_mode = f2i(sc[S_UPD_MODE]);
-        sc[C_RELEARNED] = 0.f;
-        if (upd_mode >= 1) {
-            int countdown = f2i(sc[S_UPD_COUNTDOWN]) - 1;
-            if (countdown > 0) {
-                const float v3 = sc[S_FEAT3], v0 = sc[S_FEAT0], v4 = sc[S_FEAT4];
-                if (v3 < kHistBins * 0.1f && v3 >= 0.0) hist_inc(hist, 0 * kHistBins + (int)(v3 / 0.1f));
-                if (v0 < kHistBins * 0.05f && v0 >= 0.0) hist_inc(hist, 1 * kHistBins + (int)(v0 / 0.05f));
-                if (v4 < kHistBins * 0.1f && v4 >= 0.0) hist_inc(hist, 2 * kHistBins + (int)(v4 / 0.1f));
-            }
-            if (countdown == 0) {
-                const int window = 500;
-                float avg = 0.f, avg_all = 0.f, avg_sq = 0.f;
-                int n = 0;
-                for (int i = 0; i < kHistBins; ++i) {
-                    const int h = hist[i];
-                    if (h == 0) continue;                      // adding 0.f never changes a float sum
-                    const float mid = ((float)i + 0.5f) * 0.1f;
-                    if (mid <= 1.f) { avg += h * mid; n += h; }
-                    avg_sq += h * mid * mid;
-                    avg_all += h * mid;
-                }
-                if (n > 0) avg = avg / ((float)n);
-                avg_all = avg_all / ((float)window);
-                avg_sq = avg_sq / ((float)window);
-                const float fluct = avg_sq - avg * avg_all;
-                float pm0;
-                if (fluct < 0.05f) pm0 = 1.f;
-                else {
-                    pm0 = 1.2f * avg;
-                    if (pm0 < 0.2f) pm0 = 0.2f;
-                    if (pm0 > 1.f) pm0 = 1.f;
-                }
-                sc[S_PM0] = pm0;
-                int use_flat = 1, use_diff = 1;
-                for (int which = 1; which <= 2; ++which) {
-                    const float bin = which == 1 ? 0.05f : 0.1f;
-                    const uint16_t* h = hist + which * kHistBins;
-                    int m1 = 0, m2 = 0, w1 = 0, w2 = 0;
-                    float p1 = 0.f, p2 = 0.f;
-                    for (int i = 0; i < kHistBins; ++i) {
-                        const int v = h[i];
-                        const float mid = ((float)i + 0.5f) * bin;
-                        if (v > m1) { m2 = m1; w2 = w1; p2 = p1; m1 = v; w1 = v; p1 = mid; }
-                        else if (v > m2) { m2 = v; w2 = v; p2 = mid; }
-                    }
-                    if ((fabs(p2 - p1) < 2 * bin) && (w2 > 0.5f * w1)) { w1 += w2; p1 = 0.5f * (p1 + p2); }
-                    const int min_weight = (int)(0.3 * (window));
-                    if (which == 1) {
-                        if (w1 < min_weight || p1 < 0.6f) use_flat = 0;
-                        if (use_flat) {
-                            float pm1 = 0.9f * p1;
-                            if (pm1 < 0.1f) pm1 = 0.1f;
-                            if (pm1 > 0.95f) pm1 = 0.95f;
-                            sc[S_PM1] = pm1;
-                        }
-                    } else {
-                        float pm3 = 1.2f * p1;
-                        if (w1 < min_weight) use_diff = 0;
-                        if (pm3 < 0.16f) pm3 = 0.16f;
-                        if (pm3 > 1.f) pm3 = 1.f;
-                        sc[S_PM3] = pm3;
-                        if (fluct < 0.05f) use_diff = 0;
-                    }
-                }
-                const float fsum = (float)(1 + use_flat + use_diff);
-                sc[S_PM4] = 1.f / fsum;
-                sc[S_PM5] = ((float)use_flat) / fsum;
-                sc[S_PM6] = ((float)use_diff) / fsum;
-                sc[C_RELEARNED] = 1.f;                         // the whole warp clears the histograms in segment 3a
-                countdown = window;
-                if (upd_mode == 1) {
-                    sc[S_UPD_MODE] = i2f(0);
-                } else {
-                    float f6 = sc[S_FEAT6] / ((float)window);
-                    sc[S_FEAT5] = 0.5f * (f6 + sc[S_FEAT5]);
-                    sc[S_FEAT6] = 0.f;
-                }
-            }
-            sc[S_UPD_COUNTDOWN] = i2f(countdown);
-        }
-        // arguments of the three indicator functions (ns_core.c:689-730)
-        {
-            const float thr0 = sc[S_PM0], thr1 = sc[S_PM1], thr2 = sc[S_PM3];
-            const int sgn = (int)(sc[S_PM2]);
-            float ksum = sc[C_SUM_B + 3];
-            ksum = (float)ksum / (G::kBins);
-            sc[S_FEAT3] = ksum;
-            float width = 4.f;
-            if (ksum < thr0) width = 2.f * 4.f;
-            sc[C_TANH + 0] = width * (ksum - thr0);
-            float x = sc[S_FEAT0];
-            width = 4.f;
-            if (sgn == 1 && (x > thr1)) width = 2.f * 4.f;
-            if (sgn == -1 && (x < thr1)) width = 2.f * 4.f;
-            sc[C_TANH + 1] = (float)sgn * width * (thr1 - x);
-            x = sc[S_FEAT4];
-            width = 4.f;
-            if (x < thr2) width = 2.f * 4.f;
-            sc[C_TANH + 2] = width * (x - thr2);
-        }
-    }
-    WMX_CTA_PHASE_END
-    // the three indicator functions side by side in lanes 0..2
-    WMX_CTA_PHASE_BEGIN(L)
-    if (lane < 3) sc[C_TANH + lane] = 0.5f * ((float)tanh((double)sc[C_TANH + lane]) + 1.f);
-    WMX_CTA_PHASE_END
-    WMX_CTA_PHASE_BEGIN(L)
-    if (lane == 0) {
-        // prior update (ns_core.c:731-738)
-        const float ind = sc[S_PM4] * sc[C_TANH + 0] + sc[S_PM5] * sc[C_TANH + 1] + sc[S_PM6] * sc[C_TANH + 2];
-        float pp = sc[S_PRIOR_PROB];
-        pp += 0.1f * (ind - pp);
-        if (pp > 1.f) pp = 1.f;
-        if (pp < 0.01f) pp = 0.01f;
-        sc[S_PRIOR_PROB] = pp;
-        sc[C_GAIN_PRIOR] = fdiv(1.f - pp, pp + 0.0001f);
-    }
-    WMX_CTA_PHASE_END
-}
-
-// segment 2 (beside the workers' segment 3a): the Nyquist bin's probability, noise update and gain; the gain map's input
-// energy, in sample order, in lane k = 1 (ns_core.c:741-747, :800-846, :985-1010, :951-960)
+// segment 2: Nyquist SNR / LRT, sums (covariance, two variances, LRT sum), difference feature, histograms and threshold
+// re-learning, indicator functions, prior, Nyquist probability and filter (ns_core.c:566-846, :293-520, :985-1010)
 template <int ANA, typename RWarpT>
-WMX_HD void r_seg2(RWarpT& W, float* tiles, int tile_stride, const Tables<ANA>& T)
+WMX_HD void r_seg2(RWarpT& W, float* tiles, int tile_stride, uint16_t* const* hists, const Tables<ANA>& T)
 {
     typedef Geo<ANA> G;
     WMX_CTA_PHASE_BEGIN(RLane)
@@ -1085,13 +857,174 @@ WMX_HD void r_seg2(RWarpT& W, float* tiles, int tile_stride, const Tables<ANA>& 
         float* sv = sh + G::kShSum;
         float* sc = sh + G::kShScal;
         float* nq = sh + G::kShNyq;
-        R.want_e = R.active && T.gainmap == 1 && f2i(sc[S_FRAME_IDX]) > kStartupLong;
         if (R.active && k == 0) {
-            const float gain_prior = sc[C_GAIN_PRIOR];
-            R.pp = sc[S_PRIOR_PROB];
-            // the look-back neighbour (bin kBody-1) is re-derived from the LRT row the worker staged — the same arithmetic, so
-            // the same value the worker computes
-            const float p_prev = bin_prob<ANA>(T, sv[CtaGeo<ANA>::kLrtRow * G::kSumStride + G::kBody - 1], gain_prior);
+            float pn = 0.f;
+            bin_snr<ANA>(T, sv, G::kBody, R.frame_idx, sc[C_USE_PINK] != 0.f, sc[S_WHITE], sc[C_PNUM], sc[C_PEXP], sc[C_AVGMAGN], sc[C_AVGPAUSE],
+                         R.mag, R.noise, nq[A_MAGN_PREV], nq[A_NOISE_PREV], nq[A_SMOOTH], nq[A_PAUSE], nq[A_LRT], R.prev, pn);
+            if (R.frame_idx < kStartupShort) nq[A_PARAM_NOISE] = pn;
+        }
+    }
+    WMX_CTA_PHASE_END
+    WMX_CTA_PHASE_BEGIN(RLane)
+    {
+        const int j = lane >> 2, k = lane & 3;
+        float* sh = tiles + (size_t)j * tile_stride;
+        float* sv = sh + G::kShSum;
+        float* sc = sh + G::kShScal;
+        if (R.active) sc[C_COUNT_ + 8 + k] = seq_sum4<G::kSumStride / 4>(sv + k * G::kSumStride);
+    }
+    WMX_CTA_PHASE_END
+    WMX_CTA_PHASE_BEGIN(RLane)
+    {
+        const int j = lane >> 2, k = lane & 3;
+        float* sh = tiles + (size_t)j * tile_stride;
+        float* sc = sh + G::kShScal;
+        if (R.active && k == 0) {
+            uint16_t* hist = hists[j];
+            const float nb = (float)G::kBins;
+            {
+                const float cov = sc[C_COUNT_ + 8] / nb, vp = sc[C_COUNT_ + 9] / nb, vm = sc[C_COUNT_ + 10] / nb;
+                sc[S_FEAT6] = sc[S_FEAT6] + sc[C_COUNT_ + 0];
+                float d = vm - (cov * cov) / (vp + 0.0001f);
+                d = (float)(d / (sc[S_FEAT5] + 0.0001f));
+                float f4 = sc[S_FEAT4];
+                f4 += 0.3f * (d - f4);
+                sc[S_FEAT4] = f4;
+            }
+            // histogram update / threshold re-learn (ns_core.c:755-790, :293-520); the LRT feature used here is still last
+            // frame's (featureData[3] is refreshed further down)
+            const int upd_mode = f2i(sc[S_UPD_MODE]);
+            sc[C_RELEARNED] = 0.f;
+            if (upd_mode >= 1) {
+                int countdown = f2i(sc[S_UPD_COUNTDOWN]) - 1;
+                if (countdown > 0) {
+                    const float v3 = sc[S_FEAT3], v0 = sc[S_FEAT0], v4 = sc[S_FEAT4];
+                    if (v3 < kHistBins * 0.1f && v3 >= 0.0) hist_inc(hist, 0 * kHistBins + (int)(v3 / 0.1f));
+                    if (v0 < kHistBins * 0.05f && v0 >= 0.0) hist_inc(hist, 1 * kHistBins + (int)(v0 / 0.05f));
+                    if (v4 < kHistBins * 0.1f && v4 >= 0.0) hist_inc(hist, 2 * kHistBins + (int)(v4 / 0.1f));
+                }
+                if (countdown == 0) {
+                    const int window = 500;
+                    float avg = 0.f, avg_all = 0.f, avg_sq = 0.f;
+                    int n = 0;
+                    for (int i = 0; i < kHistBins; ++i) {
+                        const int h = hist[i];
+                        if (h == 0) continue;                      // adding 0.f never changes a float sum
+                        const float mid = ((float)i + 0.5f) * 0.1f;
+                        if (mid <= 1.f) { avg += h * mid; n += h; }
+                        avg_sq += h * mid * mid;
+                        avg_all += h * mid;
+                    }
+                    if (n > 0) avg = avg / ((float)n);
+                    avg_all = avg_all / ((float)window);
+                    avg_sq = avg_sq / ((float)window);
+                    const float fluct = avg_sq - avg * avg_all;
+                    float pm0;
+                    if (fluct < 0.05f) pm0 = 1.f;
+                    else {
+                        pm0 = 1.2f * avg;
+                        if (pm0 < 0.2f) pm0 = 0.2f;
+                        if (pm0 > 1.f) pm0 = 1.f;
+                    }
+                    sc[S_PM0] = pm0;
+                    int use_flat = 1, use_diff = 1;
+                    for (int which = 1; which <= 2; ++which) {
+                        const float bin = which == 1 ? 0.05f : 0.1f;
+                        const uint16_t* h = hist + which * kHistBins;
+                        int m1 = 0, m2 = 0, w1 = 0, w2 = 0;
+                        float p1 = 0.f, p2 = 0.f;
+                        for (int i = 0; i < kHistBins; ++i) {
+                            const int v = h[i];
+                            const float mid = ((float)i + 0.5f) * bin;
+                            if (v > m1) { m2 = m1; w2 = w1; p2 = p1; m1 = v; w1 = v; p1 = mid; }
+                            else if (v > m2) { m2 = v; w2 = v; p2 = mid; }
+                        }
+                        if ((fabs(p2 - p1) < 2 * bin) && (w2 > 0.5f * w1)) { w1 += w2; p1 = 0.5f * (p1 + p2); }
+                        const int min_weight = (int)(0.3 * (window));
+                        if (which == 1) {
+                            if (w1 < min_weight || p1 < 0.6f) use_flat = 0;
+                            if (use_flat) {
+                                float pm1 = 0.9f * p1;
+                                if (pm1 < 0.1f) pm1 = 0.1f;
+                                if (pm1 > 0.95f) pm1 = 0.95f;
+                                sc[S_PM1] = pm1;
+                            }
+                        } else {
+                            float pm3 = 1.2f * p1;
+                            if (w1 < min_weight) use_diff = 0;
+                            if (pm3 < 0.16f) pm3 = 0.16f;
+                            if (pm3 > 1.f) pm3 = 1.f;
+                            sc[S_PM3] = pm3;
+                            if (fluct < 0.05f) use_diff = 0;
+                        }
+                    }
+                    const float fsum = (float)(1 + use_flat + use_diff);
+                    sc[S_PM4] = 1.f / fsum;
+                    sc[S_PM5] = ((float)use_flat) / fsum;
+                    sc[S_PM6] = ((float)use_diff) / fsum;
+                    sc[C_RELEARNED] = 1.f;                         // the worker clears the histograms in segment 3
+                    countdown = window;
+                    if (upd_mode == 1) {
+                        sc[S_UPD_MODE] = i2f(0);
+                    } else {
+                        float f6 = sc[S_FEAT6] / ((float)window);
+                        sc[S_FEAT5] = 0.5f * (f6 + sc[S_FEAT5]);
+                        sc[S_FEAT6] = 0.f;
+                    }
+                }
+                sc[S_UPD_COUNTDOWN] = i2f(countdown);
+            }
+            // arguments of the three indicator functions (ns_core.c:689-730)
+            {
+                const float thr0 = sc[S_PM0], thr1 = sc[S_PM1], thr2 = sc[S_PM3];
+                const int sgn = (int)(sc[S_PM2]);
+                float ksum = sc[C_COUNT_ + 11];
+                ksum = (float)ksum / (G::kBins);
+                sc[S_FEAT3] = ksum;
+                float width = 4.f;
+                if (ksum < thr0) width = 2.f * 4.f;
+                sc[C_COUNT_ + 12] = width * (ksum - thr0);
+                float x = sc[S_FEAT0];
+                width = 4.f;
+                if (sgn == 1 && (x > thr1)) width = 2.f * 4.f;
+                if (sgn == -1 && (x < thr1)) width = 2.f * 4.f;
+                sc[C_COUNT_ + 13] = (float)sgn * width * (thr1 - x);
+                x = sc[S_FEAT4];
+                width = 4.f;
+                if (x < thr2) width = 2.f * 4.f;
+                sc[C_COUNT_ + 14] = width * (x - thr2);
+            }
+        }
+    }
+    WMX_CTA_PHASE_END
+    // the three indicator functions side by side in lanes k = 0..2 of every stream
+    WMX_CTA_PHASE_BEGIN(RLane)
+    {
+        const int j = lane >> 2, k = lane & 3;
+        float* sc = tiles + (size_t)j * tile_stride + G::kShScal;
+        if (R.active && k < 3) sc[C_COUNT_ + 12 + k] = 0.5f * ((float)tanh((double)sc[C_COUNT_ + 12 + k]) + 1.f);
+    }
+    WMX_CTA_PHASE_END
+    WMX_CTA_PHASE_BEGIN(RLane)
+    {
+        const int j = lane >> 2, k = lane & 3;
+        float* sh = tiles + (size_t)j * tile_stride;
+        float* sv = sh + G::kShSum;
+        float* sc = sh + G::kShScal;
+        float* nq = sh + G::kShNyq;
+        if (R.active && k == 0) {
+            // prior update (ns_core.c:731-738)
+            const float ind = sc[S_PM4] * sc[C_COUNT_ + 12] + sc[S_PM5] * sc[C_COUNT_ + 13] + sc[S_PM6] * sc[C_COUNT_ + 14];
+            float pp = sc[S_PRIOR_PROB];
+            pp += 0.1f * (ind - pp);
+            if (pp > 1.f) pp = 1.f;
+            if (pp < 0.01f) pp = 0.01f;
+            sc[S_PRIOR_PROB] = pp;
+            const float gain_prior = fdiv(1.f - pp, pp + 0.0001f);
+            sc[C_GAIN_PRIOR] = gain_prior;
+            // Nyquist bin: probability (its look-back neighbour, bin kBody-1, is re-derived here from the LRT row the worker
+            // staged — the same arithmetic, so the same value the worker will compute), noise update, gain, filtered value
+            const float p_prev = bin_prob<ANA>(T, sv[3 * G::kSumStride + G::kBody - 1], gain_prior);
             const float ps = bin_prob<ANA>(T, nq[A_LRT], gain_prior);
             float init_magn = nq[A_INIT_MAGN];
             const float h = bin_filter<ANA>(T, R.frame_idx, R.mag, ps, p_prev > 0.2f, nq[A_NOISE_PREV], nq[A_PAUSE], R.prev, init_magn,
@@ -1100,44 +1033,45 @@ WMX_HD void r_seg2(RWarpT& W, float* tiles, int tile_stride, const Tables<ANA>& 
             nq[A_SMOOTH] = h;
             nq[A_MAGN_PREV] = R.mag;
             sc[C_NYQ_FRE] = R.re * h;
+            sc[C_WANT_E] = (T.gainmap == 1 && R.frame_idx > kStartupLong) ? 1.f : 0.f;
+            sc[C_FACTOR] = 1.f;
         }
-        R.e1 = 0.f;
-        if (R.active && k == 1 && R.want_e) R.e1 = seq_sum4<ANA / 4>(sh + G::kShSq);
     }
     WMX_CTA_PHASE_END
 }
 
-// segment 3 (beside the next stream's segment 1): the gain map's output energy in sample order, then the factor
-// (ns_core.c:1314-1342).  Reads only the parked signal and its own registers: the tile's scalar area already belongs to
-// the next stream.
+// segment 3: the two energies of the gain map in sample order (lanes k = 0, 1), then the factor (ns_core.c:1314-1342)
 template <int ANA, typename RWarpT>
 WMX_HD void r_seg3(RWarpT& W, float* tiles, int tile_stride, const Tables<ANA>& T)
 {
     typedef Geo<ANA> G;
-    WMX_CTA_SHFL(RLane, R.e1, R.e1, (lane & 3) == 0 ? lane + 1 : lane)      // lane k = 0 takes the input energy from lane k = 1
     WMX_CTA_PHASE_BEGIN(RLane)
     {
         const int j = lane >> 2, k = lane & 3;
         float* sh = tiles + (size_t)j * tile_stride;
-        if (R.active && k == 0) {
-            float factor = 1.f;
-            if (R.want_e) {
-                const float* park = sh + CtaGeo<ANA>::kPark;
-                const float e2 = seq_sum_prod<ANA / 4, 0>(park, park, 0.f, 0.f);      // (x - 0) * (x - 0) == x * x
-                // (float)sqrt((double)x) == sqrtf(x): a double carries more than 2*24+2 bits, so rounding twice is innocuous
-                float gain = sqrtf(e2 / (R.e1 + 1.f));
-                float f1 = 1.f, f2 = 1.f;
-                if (gain > 0.5f) {
-                    f1 = 1.f + 1.3f * (gain - 0.5f);
-                    if (gain * f1 > 1.f) f1 = 1.f / gain;
-                }
-                if (gain < 0.5f) {
-                    if (gain <= T.floor_gain) gain = T.floor_gain;
-                    f2 = 1.f - 0.3f * (0.5f - gain);
-                }
-                factor = R.pp * f1 + (1.f - R.pp) * f2;
+        float* sc = sh + G::kShScal;
+        if (R.active && k < 2 && sc[C_WANT_E] != 0.f)
+            sc[C_COUNT_ + 16 + k] = seq_sum4<ANA / 4>(k == 0 ? sh + G::kShSq : sh + G::kShSum);
+    }
+    WMX_CTA_PHASE_END
+    WMX_CTA_PHASE_BEGIN(RLane)
+    {
+        const int j = lane >> 2, k = lane & 3;
+        float* sc = tiles + (size_t)j * tile_stride + G::kShScal;
+        if (R.active && k == 0 && sc[C_WANT_E] != 0.f) {
+            // (float)sqrt((double)x) == sqrtf(x): a double carries more than 2*24+2 bits, so rounding twice is innocuous
+            float gain = sqrtf(sc[C_COUNT_ + 17] / (sc[C_COUNT_ + 16] + 1.f));
+            float f1 = 1.f, f2 = 1.f;
+            if (gain > 0.5f) {
+                f1 = 1.f + 1.3f * (gain - 0.5f);
+                if (gain * f1 > 1.f) f1 = 1.f / gain;
             }
-            sh[CtaGeo<ANA>::kFac] = factor;
+            if (gain < 0.5f) {
+                if (gain <= T.floor_gain) gain = T.floor_gain;
+                f2 = 1.f - 0.3f * (0.5f - gain);
+            }
+            const float pp = sc[S_PRIOR_PROB];
+            sc[C_FACTOR] = pp * f1 + (1.f - pp) * f2;
         }
     }
     WMX_CTA_PHASE_END

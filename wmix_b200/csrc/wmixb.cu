@@ -136,11 +136,8 @@ __device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm vola
 template <int ANA>
 constexpr size_t ns_cta_smem_bytes(int workers)
 {
-    return (NsSmem<ANA>::kTableFloats + (size_t)workers * ns::CtaGeo<ANA>::kTileFloats) * sizeof(float);
+    return (NsSmem<ANA>::kTableFloats + (size_t)workers * ns::Geo<ANA>::kShFloats) * sizeof(float) + 8 * sizeof(uint16_t*);
 }
-
-// barrier ids (see the schedule at the top of ns_cta.cuh)
-enum { NSB_W1 = 1, NSB_R1 = 2, NSB_W2 = 3, NSB_R2 = 4, NSB_W3 = 5, NSB_R3 = 6 };
 
 template <int ANA, int W, int MINB>
 __global__ void __launch_bounds__((W + 1) * 32, MINB)
@@ -148,33 +145,28 @@ ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Ta
               const int16_t* in, int16_t* out, int n_streams, int n_frames)
 {
     typedef ns::Geo<ANA> G;
-    typedef ns::CtaGeo<ANA> CG;
     static_assert(W >= 1 && W <= 8, "the reducer serves at most 8 workers (4 lanes each)");
     constexpr int kThreads = (W + 1) * 32;
     extern __shared__ __align__(16) float smem[];
     ns::Tables<ANA>* T = reinterpret_cast<ns::Tables<ANA>*>(smem);
     float* tiles = smem + NsSmem<ANA>::kTableFloats;
+    uint16_t** hptr = reinterpret_cast<uint16_t**>(tiles + (size_t)W * G::kShFloats);
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
         uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
         for (int i = threadIdx.x; i < (int)(sizeof(ns::Tables<ANA>) / 4); i += kThreads) dst[i] = src[i];
         float4* t4 = reinterpret_cast<float4*>(tiles);
-        for (int i = threadIdx.x; i < W * CG::kTileFloats / 4; i += kThreads) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // sum rows rely on +0.0f padding
+        for (int i = threadIdx.x; i < W * G::kShFloats / 4; i += kThreads) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);   // sum rows rely on +0.0f padding
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int total = gridDim.x * W;
     const int first = blockIdx.x * W;
     const int rounds = first < n_streams ? (n_streams - first + total - 1) / total : 0;
-    // A stream with one frame per launch (ticks) finishes its last segment behind the NEXT stream's first two; with several
-    // frames per launch the next frame of the same stream needs this frame's synthesis tail, so nothing is deferred.
-    const bool defer = n_frames == 1;
     if (warp < W) {
-        float* tile = tiles + (size_t)warp * CG::kTileFloats;
+        float* tile = tiles + (size_t)warp * G::kShFloats;
         ns::WWarp<ANA> Wk;
         Wk.lane_id = lane;
-        bool pend = false;                 // a deferred segment 4 (of this worker's previous stream, s - total) is outstanding
-        int parity = 0;
         for (int it = 0; it < rounds; ++it) {
             const int s = first + warp + it * total;
             const bool live = s < n_streams;
@@ -182,69 +174,46 @@ ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Ta
             uint16_t* h = hist + (size_t)s * 3 * ns::kHistBins;
             const int16_t* pi = in + (size_t)s * n_frames * G::kBlock;
             int16_t* po = out + (size_t)s * n_frames * G::kBlock;
-            for (int f = 0; f < n_frames; ++f, pi += G::kBlock, po += G::kBlock) {
+            if (lane == 0) hptr[warp] = h;
+            for (int f = 0; f < n_frames; ++f) {
                 bool act = false;
-                float* syn = tile + (parity ? CG::kSynB : G::kShSynth);
                 if (live) {
                     if (f == n_frames - 1 && lane == 0 && s + total < n_streams) {
                         // pull the next stream's record and first frame towards L2 while this one computes
                         l2_prefetch(rec + (size_t)(s + total) * G::kRecFloats, G::kRecFloats * sizeof(float));
                         l2_prefetch(in + (size_t)(s + total) * n_frames * G::kBlock, G::kBlock * sizeof(int16_t));
                     }
-                    act = ns::w_seg1<ANA>(Wk, r, pi, po, tile, syn, *T);
+                    act = ns::w_seg1<ANA>(Wk, r, pi + (size_t)f * G::kBlock, po + (size_t)f * G::kBlock, tile, *T);
                 } else if (lane == 0) {
                     tile[G::kShScal + ns::C_ACTIVE] = 0.f;
                 }
-                named_bar_arrive(NSB_W1, kThreads);
-                // segment 2 runs beside the reducer's segment 1, except during the 50 start-up frames of a stream, when it needs the
-                // reducer's white / pink fit first
-                const bool startup = act && Wk.lane_regs.frame_idx < ns::kStartupShort;
-                if (startup) named_bar_sync(NSB_R1, kThreads);
+                named_bar_arrive(1, kThreads);
+                named_bar_sync(2, kThreads);
                 if (act) ns::w_seg2<ANA>(Wk, r, tile, *T);
-                if (!startup) named_bar_sync(NSB_R1, kThreads);
-                if (pend) {                                                      // only with defer: n_frames == 1
-                    ns::w_seg4<ANA>(Wk, rec + (size_t)(s - total) * G::kRecFloats, out + (size_t)(s - total) * G::kBlock, tile,
-                                    tile + (parity ? G::kShSynth : CG::kSynB), *T);
-                    pend = false;
-                }
-                if (act) ns::w_seg2b<ANA>(Wk, h, tile, *T);
-                named_bar_arrive(NSB_W2, kThreads);
-                if (act) ns::w_seg3a<ANA>(Wk, r, h, tile, *T);                  // beside the reducer's segment 2
-                named_bar_sync(NSB_R2, kThreads);
-                if (act) ns::w_seg3b<ANA>(Wk, r, tile, *T);
-                named_bar_arrive(NSB_W3, kThreads);
-                if (defer) {
-                    pend = act;
-                } else {
-                    named_bar_sync(NSB_R3, kThreads);
-                    if (act) ns::w_seg4<ANA>(Wk, r, po, tile, syn, *T);
-                }
-                parity ^= 1;
+                named_bar_arrive(3, kThreads);
+                named_bar_sync(4, kThreads);
+                if (act) ns::w_seg3<ANA>(Wk, r, h, tile, *T);
+                named_bar_arrive(5, kThreads);
+                named_bar_sync(6, kThreads);
+                if (act) ns::w_seg4<ANA>(Wk, r, po + (size_t)f * G::kBlock, tile, *T);
             }
-        }
-        if (defer && rounds > 0) {
-            named_bar_sync(NSB_R3, kThreads);
-            const int s_last = first + warp + (rounds - 1) * total;
-            if (pend) ns::w_seg4<ANA>(Wk, rec + (size_t)s_last * G::kRecFloats, out + (size_t)s_last * G::kBlock, tile,
-                                      tile + (parity ? G::kShSynth : CG::kSynB), *T);
         }
     } else {
         ns::RWarp Rd;
         Rd.lane_id = lane;
         for (int it = 0; it < rounds; ++it) {
             for (int f = 0; f < n_frames; ++f) {
-                named_bar_sync(NSB_W1, kThreads);
-                ns::r_seg1<ANA>(Rd, tiles, CG::kTileFloats, W, *T);
-                named_bar_arrive(NSB_R1, kThreads);
-                named_bar_sync(NSB_W2, kThreads);
-                ns::r_seg2<ANA>(Rd, tiles, CG::kTileFloats, *T);
-                named_bar_arrive(NSB_R2, kThreads);
-                named_bar_sync(NSB_W3, kThreads);
-                ns::r_seg3<ANA>(Rd, tiles, CG::kTileFloats, *T);
-                if (!defer) named_bar_arrive(NSB_R3, kThreads);
+                named_bar_sync(1, kThreads);
+                ns::r_seg1<ANA>(Rd, tiles, G::kShFloats, W, *T);
+                named_bar_arrive(2, kThreads);
+                named_bar_sync(3, kThreads);
+                ns::r_seg2<ANA>(Rd, tiles, G::kShFloats, hptr, *T);
+                named_bar_arrive(4, kThreads);
+                named_bar_sync(5, kThreads);
+                ns::r_seg3<ANA>(Rd, tiles, G::kShFloats, *T);
+                named_bar_arrive(6, kThreads);
             }
         }
-        if (defer && rounds > 0) named_bar_arrive(NSB_R3, kThreads);
     }
 }
 
