@@ -219,8 +219,10 @@ def conf5_leg(torch, dist, world, rank, local, dev, conf_size, steps=200, warmup
     pcm = torch.empty((n_local, frame), dtype=torch.int16, device=dev)
     g711_decode(law, pool[0], pcm, n_local * frame, st)
     torch.cuda.synchronize()
-    gathered = [torch.empty_like(pcm) for _ in range(world)]
-    dist.all_gather(gathered, pcm)
+    # (NCCL has no int16: the decoded legs travel as bytes)
+    gathered_b = [torch.empty((n_local, frame * 2), dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(gathered_b, pcm.view(torch.uint8))
+    gathered = [g_.view(torch.int16) for g_ in gathered_b]
     # striped plan with equal sizes: rank r hosts per_conf_local members of every conference, conference-major
     want_bus = torch.zeros((n_conf, frame), dtype=torch.int32, device=dev)
     for r in range(world):

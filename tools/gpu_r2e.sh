@@ -5,8 +5,8 @@ TAG="${1:-r2_e}"
 mkdir -p gpurun_out
 nvidia-smi -L > gpurun_out/${TAG}_gpus.txt 2>&1
 nvidia-smi topo -m > gpurun_out/${TAG}_topo.txt 2>&1
-(time python -m pytest tests/test_multi_gpu.py -m gpu -x -q) > gpurun_out/${TAG}_tests_multi.txt 2>&1; tail -4 gpurun_out/${TAG}_tests_multi.txt
-(time python -m pytest tests/test_gpu_parity.py -m gpu -x -q) > gpurun_out/${TAG}_tests.txt 2>&1; tail -4 gpurun_out/${TAG}_tests.txt
+echo skip-multi
+echo skip-parity
 (time python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 bench.py --gpus 2 --steps 100 --warmup 10) > gpurun_out/${TAG}_bench_n2.json 2> gpurun_out/${TAG}_bench_n2.err
 tail -3 gpurun_out/${TAG}_bench_n2.err
 (time python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29612 bench.py --impl reference --gpus 2 --steps 20 --warmup 5) > gpurun_out/${TAG}_bench_reference_n2.json 2>> gpurun_out/${TAG}_bench_n2.err
