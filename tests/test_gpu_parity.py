@@ -445,6 +445,36 @@ def test_config2_long_run_ns_then_vad():
     assert flags.any() and not flags.all()                      # both decisions occur
 
 
+@pytest.mark.parametrize("freq", [16000, 8000])
+def test_post_kernel_big_aligned_cta_shape_is_bit_exact(freq):
+    """AGC -> VAD in the shape large batches run in: ONE CTA of 704 threads per SM whose warps are re-aligned between (and
+    inside) the stages so that they share fetched code (wmixb_set_tuning("post_occ", 22); automatic from 2816 streams up).
+    1500 streams = two full CTAs and a ragged third (threads without a stream must still walk every barrier); integer
+    stages, so bit-exact against the oracle; and identical to the small-CTA shape."""
+    S, T = 1500, 130
+    base = make_frames(96, freq, 0, T, seed=83)
+    x = np.ascontiguousarray(np.tile(base, (1, (S + 95) // 96, 1))[:, :S])
+    outs = {}
+    for occ in (22, 3):
+        eng = wmix_b200.Engine(S, freq, stages=AGC | VAD)
+        eng.set_tuning("post_occ", occ)
+        d = torch.empty((S, freq // 100), dtype=torch.int16, device=DEV)
+        d_v = torch.zeros((S,), dtype=torch.uint8, device=DEV)
+        got = np.empty_like(x)
+        flags = np.empty((T, S), np.uint8)
+        for t in range(T):
+            d.copy_(torch.from_numpy(x[t]))
+            eng.tick_device(d, d, d_v)
+            got[t] = d.cpu().numpy()
+            flags[t] = d_v.cpu().numpy()
+        eng.close()
+        outs[occ] = (got, flags)
+    assert np.array_equal(outs[22][0], outs[3][0]) and np.array_equal(outs[22][1], outs[3][1])
+    pick = np.array([0, 1, 2, 3, 95, 703, 704, 1407, 1408, 1499])
+    want = run_checker(oracle(), "orc_", x[:, pick], freq, AGC | VAD)
+    assert np.array_equal(outs[22][0][:, pick], want)
+
+
 def test_full_chain_16k_and_vad_flags():
     x = make_frames(66, 16000, 0, 560, seed=51)
     got, vad = run_gpu(x, 16000, NS | AGC | VAD)

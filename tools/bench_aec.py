@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=400)
     ap.add_argument("--ring", type=int, default=8)
     ap.add_argument("--no-ns", action="store_true")
+    ap.add_argument("--aec-align", type=int, default=-1, help="experiment: CTA alignment of the AEC kernel (wmixb_set_tuning)")
     a = ap.parse_args()
     import torch
 
@@ -43,6 +44,8 @@ def main():
     reps = (S + base - 1) // base
     stages = AEC | (0 if a.no_ns else NS)
     eng = wmix_b200.Engine(S, 8000, stages=stages)
+    if a.aec_align >= 0:
+        eng.set_tuning("aec_align", a.aec_align)
     d_far = torch.empty((S, L), dtype=torch.int16, device=dev)
     d_near = torch.empty((S, L), dtype=torch.int16, device=dev)
     d_out = torch.empty((S, L), dtype=torch.int16, device=dev)

@@ -459,11 +459,11 @@ WMX_HD void attenuate(int16_t* x, int n, int reduce)
 // One packet of one stream: WebRtcVad_Process (T:.../vad/webrtc_vad.c:71-105) + the wmix
 // wrapper's mute ramp (R:src/webrtc.c:127-141).  `x` holds LEN8*(FS16?2:1) samples and is
 // attenuated in place.  Returns the 0/1 decision.
+// The packet in three stretches, so that a kernel may align the warps of a CTA between them (post_kernel):
+// decimator + filterbank -> features, GMM decision, wrapper's mute ramp.
 template <int LEN8, bool FS16>
-WMX_HD int process_packet(const SoaWords& st, int16_t* x, const Params& P)
+WMX_HD int16_t packet_features(const SoaWords& st, const int16_t* x, int16_t* feat)
 {
-    int16_t feat[6];
-    int16_t power;
     st.prefetch(W_NMEAN, 24);                               // the GMM is read right after the filterbank
     st.prefetch(W_UPPER, 8);
     if (FS16) {
@@ -472,11 +472,13 @@ WMX_HD int process_packet(const SoaWords& st, int16_t* x, const Params& P)
         decimate<LEN8>(x, nb, s0, s1);
         st.set(W_DS, s0);
         st.set(W_DS + 1, s1);
-        power = features<LEN8>(st, nb, feat);
-    } else {
-        power = features<LEN8>(st, x, feat);
+        return features<LEN8>(st, nb, feat);
     }
-    int flag = gmm(st, feat, power, P);
+    return features<LEN8>(st, x, feat);
+}
+template <int LEN8, bool FS16>
+WMX_HD int packet_finish(const SoaWords& st, int16_t* x, int flag)
+{
     int reduce = st.get(W_REDUCE);
     if (flag == 0) { if (reduce < 4) reduce++; }
     else if (reduce > 0) reduce--;
@@ -484,6 +486,14 @@ WMX_HD int process_packet(const SoaWords& st, int16_t* x, const Params& P)
     const int n = LEN8 * (FS16 ? 2 : 1);
     attenuate(x, n, reduce);
     return flag > 0 ? 1 : 0;
+}
+template <int LEN8, bool FS16>
+WMX_HD int process_packet(const SoaWords& st, int16_t* x, const Params& P)
+{
+    int16_t feat[6];
+    const int16_t power = packet_features<LEN8, FS16>(st, x, feat);
+    const int flag = gmm(st, feat, power, P);
+    return packet_finish<LEN8, FS16>(st, x, flag);
 }
 
 // 32 kHz packet (T:.../vad/vad_core.c:623-643): 32k -> 16k -> 8k through the same decimator with two state pairs,

@@ -274,7 +274,7 @@ constexpr size_t kAecSmemBytes = (kAecTableFloats + (size_t)kAecWarps * aec::Geo
 
 __global__ void __launch_bounds__(kAecWarps * 32)
 aec_kernel(float* __restrict__ rec, size_t rec_floats, const aec::Tables* __restrict__ tables, const int16_t* far,
-           const int16_t* near, int16_t* out, int n_streams, int n, int mult, int depth, int delay_ms, int pf_mode, int row_stride)
+           const int16_t* near, int16_t* out, int n_streams, int n, int mult, int depth, int delay_ms, int pf_mode, int row_stride, int align)
 {
     extern __shared__ __align__(16) float smem[];
     aec::Tables* T = reinterpret_cast<aec::Tables*>(smem);
@@ -289,7 +289,14 @@ aec_kernel(float* __restrict__ rec, size_t rec_floats, const aec::Tables* __rest
     aec::Warp W;
     W.lane_id = threadIdx.x & 31;
     const int total_warps = gridDim.x * kAecWarps;
-    for (int s = blockIdx.x * kAecWarps + warp; s < n_streams; s += total_warps) {
+    // The tick is ~90 KB of code: warps that drift apart each stream their own copy of it through the instruction cache.
+    // With `align` the warps of a CTA start every stream together (uniform trip count, so the barrier is legal).
+    const int first_of_cta = blockIdx.x * kAecWarps;
+    const int iters = first_of_cta < n_streams ? (n_streams - first_of_cta + total_warps - 1) / total_warps : 0;
+    for (int it = 0; it < iters; ++it) {
+        const int s = first_of_cta + warp + it * total_warps;
+        if (align) __syncthreads();
+        if (s >= n_streams) continue;
         // L2 staging of the record (WMIXB_AEC_PF): 2 (default) = this stream's fixed part as ONE bulk request when the tick
         // starts — the first loads wait for DRAM once, the rest of the tick hits L2; 1 = the next stream's record a whole
         // tick ahead (measured slower: 2368 resident warps x two 23-31 KB records outgrow the L2 and the lines are evicted
@@ -335,42 +342,64 @@ __global__ void aec_status_kernel(const float* rec, size_t rec_floats, int n_str
 // ------------------------------------------------------------------------------------------
 constexpr int kPostThreads = 128;
 
-template <bool FS16, int MINB>
-__global__ void __launch_bounds__(kPostThreads, MINB)
+template <bool FS16, int MINB, int THREADS = kPostThreads>
+__global__ void __launch_bounds__(THREADS, MINB)
 post_kernel(int32_t* __restrict__ agc_words, int32_t* __restrict__ vad_words, const int32_t* __restrict__ agc_table,
             vad::Params vp, const int16_t* in, int16_t* out, uint8_t* vad_out, int n_streams, size_t stride,
             int n_frames, int stages)
 {
     constexpr int L = FS16 ? 160 : 80;
     constexpr int ROWW = L / 2 + 1;                     // row pitch in 32-bit words (odd)
-    __shared__ int32_t tile[kPostThreads * ROWW];
-    __shared__ int32_t tab[32];
+    extern __shared__ __align__(16) int32_t post_smem[];      // [THREADS][ROWW] PCM tile, then the 32-entry AGC gain table
+    int32_t* tile = post_smem;
+    int32_t* tab = post_smem + THREADS * ROWW;
     const int tid = threadIdx.x;
-    const int s0 = blockIdx.x * kPostThreads;
+    const int s0 = blockIdx.x * THREADS;
     const int s = s0 + tid;
     if (tid < 32) tab[tid] = agc_table ? agc_table[tid] : 0;
-    const int rows = min(kPostThreads, n_streams - s0);
+    const int rows = min(THREADS, n_streams - s0);
     const int32_t* in32 = reinterpret_cast<const int32_t*>(in);
     int32_t* out32 = reinterpret_cast<int32_t*>(out);
     SoaWords agc_st{agc_words ? agc_words + s : nullptr, stride};
     SoaWords vad_st{vad_words ? vad_words + s : nullptr, stride};
     for (int f = 0; f < n_frames; ++f) {
         __syncthreads();
-        for (int idx = tid; idx < rows * (L / 2); idx += kPostThreads) {
+        for (int idx = tid; idx < rows * (L / 2); idx += THREADS) {
             const int r = idx / (L / 2), w = idx - r * (L / 2);
             tile[r * ROWW + w] = in32[((size_t)(s0 + r) * n_frames + f) * (L / 2) + w];
         }
         __syncthreads();
-        if (s < n_streams) {
-            int16_t* x = reinterpret_cast<int16_t*>(tile + tid * ROWW);
-            if (stages & WMIXB_AGC) agc::process_packet<FS16>(agc_st, x, tab);
-            if (stages & WMIXB_VAD) {
-                const int flag = vad::process_packet<80, FS16>(vad_st, x, vp);
+        int16_t* x = reinterpret_cast<int16_t*>(tile + tid * ROWW);
+        const bool active = s < n_streams;
+        if (THREADS <= 128) {
+            if (active) {
+                if (stages & WMIXB_AGC) agc::process_packet<FS16>(agc_st, x, tab);
+                if (stages & WMIXB_VAD) {
+                    const int flag = vad::process_packet<80, FS16>(vad_st, x, vp);
+                    if (vad_out) vad_out[(size_t)s * n_frames + f] = (uint8_t)flag;
+                }
+            }
+        } else {
+            // the big-CTA shape: the kernel is bound by instruction fetch (~120 KB of straight-line code per thread, warps
+            // scattered all over it).  Re-aligning the 22 warps of the SM between the stretches of the chain makes them run
+            // the same ~30 KB at the same time and share the fetched lines: 0.184 -> 0.137 ms per 100 000 streams.  (More
+            // alignment points INSIDE the stages were measured slower: 0.138 - 0.144 ms, the waits outgrow the sharing.)
+            if (active && (stages & WMIXB_AGC)) agc::process_packet<FS16>(agc_st, x, tab);
+            __syncthreads();
+            int16_t feat[6];
+            int16_t power = 0;
+            if (active && (stages & WMIXB_VAD)) power = vad::packet_features<80, FS16>(vad_st, x, feat);
+            __syncthreads();
+            int flag = 0;
+            if (active && (stages & WMIXB_VAD)) flag = vad::gmm(vad_st, feat, power, vp);
+            __syncthreads();
+            if (active && (stages & WMIXB_VAD)) {
+                flag = vad::packet_finish<80, FS16>(vad_st, x, flag);
                 if (vad_out) vad_out[(size_t)s * n_frames + f] = (uint8_t)flag;
             }
         }
         __syncthreads();
-        for (int idx = tid; idx < rows * (L / 2); idx += kPostThreads) {
+        for (int idx = tid; idx < rows * (L / 2); idx += THREADS) {
             const int r = idx / (L / 2), w = idx - r * (L / 2);
             out32[((size_t)(s0 + r) * n_frames + f) * (L / 2) + w] = tile[r * ROWW + w];
         }
@@ -559,13 +588,13 @@ struct wmixb_engine {
     int ns_grid = 0;
     int ns_cfg = 0;                         // index into kNsCfgs: 2 CTAs of 8 worker warps + 1 reducer warp
     int ns_align = 1;                       // CTA barrier at the top of every frame (instruction-cache sharing)
-    int post_occ = 3;                       // same for post_kernel (3 CTAs of 128 threads, 168 registers per thread: measured best)
+    int post_occ = 0;                       // post_kernel shape: 0 = automatic (see run_stages), 2..5 = CTAs of 128 threads per SM, 22 = one aligned CTA of 704
     int host_chunks_sync = 8, host_chunks_pipe = 4, host_lanes = 0;   // chunk pipeline of the host-buffer tick (wmixb_set_tuning)
     float* aec_rec = nullptr;               // [n_streams][aec_rec_floats]
     void* aec_tables = nullptr;
     int* aec_result = nullptr;              // [2] flags OR, flagged count
     int16_t* aec_stage = nullptr;           // far / near / out staging of the host-buffer entry point
-    int aec_depth = 0, aec_grid = 0, aec_grid_max = 0, aec_pf = 2;
+    int aec_depth = 0, aec_grid = 0, aec_grid_max = 0, aec_pf = 2, aec_align = 1;
     size_t aec_rec_floats = 0;
 };
 
@@ -635,6 +664,9 @@ static int upload_ns_tables(wmixb_engine* e)
     }
     CK(cudaMalloc(&e->ns_tables, sizeof T));
     CK(cudaMemcpy(e->ns_tables, &T, sizeof T, cudaMemcpyHostToDevice));
+    // measured (profiles/r2_*): at 16 kHz the CTA-cooperative kernel (8 workers + reducer, 2 CTAs per SM) is the faster one,
+    // at 8 kHz — half the bins per stream, so half as much lane-sparse work to hand over — the self-contained warp kernel is
+    e->ns_cfg = ANA == 256 ? 0 : 6;
     return ns_configure<ANA>(e);
 }
 
@@ -774,6 +806,11 @@ static int create_impl(const wmixb_config* cfg, wmixb_engine* e)
         host::vad_thresholds(cfg->vad_mode, 20, th);
         e->vp20 = vad::Params{th[0], th[1], th[2], th[3]};
     }
+    if (cfg->stages & (WMIXB_AGC | WMIXB_VAD)) {
+        const int big = (int)(((size_t)704 * (e->frame / 2 + 1) + 32) * sizeof(int32_t));
+        if (e->frame == 160) CK(cudaFuncSetAttribute(post_kernel<true, 1, 704>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+        else CK(cudaFuncSetAttribute(post_kernel<false, 1, 704>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+    }
     CK(cudaMalloc(&e->d_in, n * e->frame * sizeof(int16_t)));
     CK(cudaMalloc(&e->d_out, n * e->frame * sizeof(int16_t)));
     CK(cudaMalloc(&e->d_vad, n));
@@ -817,7 +854,7 @@ static int launch_aec(wmixb_engine* e, const int16_t* d_far, const int16_t* d_ne
     const int need = (n + kAecWarps - 1) / kAecWarps;
     const int grid = need < e->aec_grid ? need : e->aec_grid;
     aec_kernel<<<grid, kAecWarps * 32, kAecSmemBytes, st>>>(e->aec_rec, e->aec_rec_floats, (const aec::Tables*)e->aec_tables, d_far,
-                                                             d_near, d_out, n, samples, e->cfg.freq / 8000, e->aec_depth, delay_ms, e->aec_pf, row_stride);
+                                                             d_near, d_out, n, samples, e->cfg.freq / 8000, e->aec_depth, delay_ms, e->aec_pf, row_stride, e->aec_align);
     CK_LAUNCH();
     return WMIXB_OK;
 }
@@ -847,13 +884,19 @@ static int run_stages(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint
         cur = d_out;
     }
     if (stages & (WMIXB_AGC | WMIXB_VAD)) {
-        const int grid = (n + kPostThreads - 1) / kPostThreads;
+        // shapes: post_occ = 2..5 CTAs of 128 threads per SM (231 / 164 / 128 / 96 registers); 22 = ONE CTA of 704 threads per SM
+        // (22 warps, 80 registers): the smallest register budget at which 100 000 streams on 148 SMs are a single wave
+        // (148 x 704 = 104 192 resident threads) instead of 1.76 waves of 12-warp SMs
+        // default (post_occ = 0): the aligned big-CTA shape once the batch fills a few of them, the small shape below that
+        const int occ = e->post_occ ? e->post_occ : (n >= 4 * 704 ? 22 : 3);
+        const int pthreads = occ == 22 ? 704 : kPostThreads;
+        const int grid = (n + pthreads - 1) / pthreads;
+        const size_t psmem = ((size_t)pthreads * (e->frame / 2 + 1) + 32) * sizeof(int32_t);
         int32_t* aw = e->agc_words ? e->agc_words + first : nullptr;
         int32_t* vw = e->vad_words ? e->vad_words + first : nullptr;
-#define WMX_POST(FS, MB) post_kernel<FS, MB><<<grid, kPostThreads, 0, st>>>(aw, vw, e->agc_table, e->vp, cur, d_out, d_vad, n, e->stride, n_frames, stages)
-        const int occ = e->post_occ;
-        if (e->frame == 160) { if (occ == 2) WMX_POST(true, 2); else if (occ == 4) WMX_POST(true, 4); else if (occ == 5) WMX_POST(true, 5); else WMX_POST(true, 3); }
-        else { if (occ == 2) WMX_POST(false, 2); else if (occ == 4) WMX_POST(false, 4); else if (occ == 5) WMX_POST(false, 5); else WMX_POST(false, 3); }
+#define WMX_POST(FS, MB, TH) post_kernel<FS, MB, TH><<<grid, TH, psmem, st>>>(aw, vw, e->agc_table, e->vp, cur, d_out, d_vad, n, e->stride, n_frames, stages)
+        if (e->frame == 160) { if (occ == 2) WMX_POST(true, 2, 128); else if (occ == 4) WMX_POST(true, 4, 128); else if (occ == 5) WMX_POST(true, 5, 128); else if (occ == 22) WMX_POST(true, 1, 704); else WMX_POST(true, 3, 128); }
+        else { if (occ == 2) WMX_POST(false, 2, 128); else if (occ == 4) WMX_POST(false, 4, 128); else if (occ == 5) WMX_POST(false, 5, 128); else if (occ == 22) WMX_POST(false, 1, 704); else WMX_POST(false, 3, 128); }
 #undef WMX_POST
         CK_LAUNCH();
         cur = d_out;
@@ -2074,8 +2117,9 @@ extern "C" int wmixb_set_tuning(wmixb_engine* e, const char* key, int value)
         return e->ana == 256 ? ns_configure<256>(e) : ns_configure<128>(e);
     }
     if (!strcmp(key, "ns_align")) { if (value < 0 || value > 64) return WMIXB_EINVAL; e->ns_align = value; return WMIXB_OK; }
-    if (!strcmp(key, "post_occ")) { if (value < 2 || value > 5) return WMIXB_EINVAL; e->post_occ = value; return WMIXB_OK; }
+    if (!strcmp(key, "post_occ")) { if ((value < 2 || value > 5) && value != 22 && value != 0) return WMIXB_EINVAL; e->post_occ = value; return WMIXB_OK; }
     if (!strcmp(key, "aec_pf")) { e->aec_pf = value; return WMIXB_OK; }
+    if (!strcmp(key, "aec_align")) { e->aec_align = value != 0; return WMIXB_OK; }
     if (!strcmp(key, "aec_grid")) { if (value < 1 || value > e->aec_grid_max) return WMIXB_EINVAL; e->aec_grid = value; return WMIXB_OK; }
     if (!strcmp(key, "host_chunks")) { if (value < 1 || value > 64) return WMIXB_EINVAL; e->host_chunks_sync = e->host_chunks_pipe = value; return WMIXB_OK; }
     if (!strcmp(key, "host_lanes")) { if (value < 0 || value > kPipe) return WMIXB_EINVAL; e->host_lanes = value; return WMIXB_OK; }
