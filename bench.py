@@ -24,7 +24,8 @@ Keyed sub-measurements in the same JSON line (none of them changes `value`):
                      check of the exchanged bus against a torch int32 sum of all ranks' legs (parity_ok);
   config4   (N = 1)  BASELINE config 4: NS -> AEC on 16 384 near/far pairs at 8 kHz;
   full_load          >= 1 000 000 resident streams per GPU through one tick, so that `value` is backed by a
-                     run at that stream count and not only by extrapolation from 100 000.
+                     run at that stream count and not only by extrapolation from 100 000;
+  offline   (N = 1)  the persistent offline mode (K frames per stream per launch, NS state on chip) against K ticks.
 """
 import argparse
 import ctypes as C
@@ -335,6 +336,52 @@ def full_load_leg(torch, dev, local, streams, steps=10):
             "note": "measured at this stream count on this GPU (not extrapolated); PCM resident in HBM"}
 
 
+def offline_leg(torch, dev, local, streams=41440, K=60):
+    """Persistent offline mode against tick mode on the same frames: `streams` streams x K consecutive frames through
+    NS -> AGC -> VAD, (a) as K ticks (three launches each; every frame reads and writes its 14 KB record in HBM) and (b) as ONE
+    wmixb_offline_device call (the NS record of a stream is pulled into shared memory by one TMA bulk copy, all K frames run
+    against it, one bulk store writes it back).  Both after PRIME ticks of ageing; stream-frames per second, CUDA events."""
+    import wmix_b200
+
+    NS, AGC, VAD = wmix_b200.NS, wmix_b200.AGC, wmix_b200.VAD
+    base = make_pool(2048, K, seed=500)                                            # [K, 2048, L]
+    reps = (streams + 2047) // 2048
+    d_ticks = torch.from_numpy(base).to(dev).repeat(1, reps, 1)[:, :streams].contiguous()          # [K][S][L]
+    d_seq = d_ticks.permute(1, 0, 2).contiguous()                                                   # [S][K][L]
+    d_out = torch.empty((streams, FRAME), dtype=torch.int16, device=dev)
+    d_seq_out = torch.empty_like(d_seq)
+    d_vad = torch.zeros((streams,), dtype=torch.uint8, device=dev)
+    d_vad_seq = torch.zeros((streams, K), dtype=torch.uint8, device=dev)
+    st = torch.cuda.current_stream()
+    res = {}
+    for mode in ("ticks", "offline", "offline_unstaged"):
+        eng = wmix_b200.Engine(streams, FREQ, device=local)
+        if mode == "offline_unstaged":
+            eng.set_tuning("ns_offline_staged", 0)
+        for t in range(PRIME):
+            eng.tick_device(d_ticks[t % K], d_out, d_vad, NS | AGC | VAD, st)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps_t = 3
+        e0.record(st)
+        for _ in range(reps_t):
+            if mode == "ticks":
+                for f in range(K):
+                    eng.tick_device(d_ticks[f], d_out, d_vad, NS | AGC | VAD, st)
+            else:
+                eng.offline_device(d_seq, d_seq_out, K, d_vad_seq, NS | AGC | VAD, st)
+        e1.record(st)
+        torch.cuda.synchronize()
+        res[mode] = e0.elapsed_time(e1) / reps_t
+        eng.close()
+    frames = streams * K
+    return {"streams": streams, "frames_per_stream": K, "stages": "NS->AGC->VAD",
+            "ms": res, "stream_frames_per_s": {k: frames / (v * 1e-3) for k, v in res.items()},
+            "offline_vs_ticks": res["ticks"] / res["offline"], "staged_vs_unstaged": res["offline_unstaged"] / res["offline"],
+            "note": "offline = wmixb_offline_device, NS records staged in shared memory by TMA bulk copies for the whole run of frames; "
+                    "offline_unstaged = the same call with every frame going back to the record in HBM"}
+
+
 # ---------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -546,6 +593,11 @@ def run_ours(args):
                 line["config4"] = config4_leg(torch, dev, local, peak)
             except Exception as ex:  # pragma: no cover
                 line["config4"] = {"failed": str(ex)}
+        if world == 1 and not args.no_offline:
+            try:
+                line["offline"] = offline_leg(torch, dev, local)
+            except Exception as ex:  # pragma: no cover
+                line["offline"] = {"failed": str(ex)}
         if not args.no_cpu_baseline and world == 1:
             try:
                 leg = cpu_leg(2048, 40, prime=PRIME + min(max(args.warmup, 0), 300))
@@ -570,6 +622,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--no-full-load", action="store_true")
+    ap.add_argument("--no-offline", action="store_true")
     ap.add_argument("--full-load-streams", type=int, default=1_000_000)
     ap.add_argument("--ns-cfg", type=int, default=-1, help="experiment: NS kernel shape index (wmixb_set_tuning)")
     ap.add_argument("--post-occ", type=int, default=-1, help="experiment: AGC+VAD kernel shape (wmixb_set_tuning)")

@@ -629,11 +629,42 @@ def test_config1_wav_chain_through_the_batched_engine():
     assert np.array_equal(got[:, where, :], want)
 
 
-def test_offline_mode_equals_ticks():
-    x = make_frames(40, 16000, 0, 60, seed=61)
-    a, va = run_gpu(x, 16000, NS | AGC | VAD)
-    b, vb = run_gpu(x, 16000, NS | AGC | VAD, offline=20)
+@pytest.mark.parametrize("freq,S,staged", [(16000, 40, 1), (16000, 40, 0), (8000, 23, 1), (16000, 1000, 1)])
+def test_offline_mode_equals_ticks(freq, S, staged):
+    """Persistent offline mode (K frames per stream per launch; with `staged` the NS record lives in shared memory for the
+    whole run, pulled in and written back by TMA bulk copies) against the same frames as ticks: outputs, VAD flags and the
+    complete per-stream state afterwards, bit for bit.  1000 streams = several rounds of the persistent grid and a ragged
+    last CTA; the 8 kHz case has the smaller record."""
+    T, K = 60, 20
+    base = make_frames(min(S, 64), freq, 0, T, seed=61)
+    x = np.ascontiguousarray(np.tile(base, (1, (S + base.shape[1] - 1) // base.shape[1], 1))[:, :S])
+    L = freq // 100
+    eng_a = wmix_b200.Engine(S, freq)
+    eng_b = wmix_b200.Engine(S, freq)
+    eng_b.set_tuning("ns_offline_staged", staged)
+    d = torch.empty((S, L), dtype=torch.int16, device=DEV)
+    d_v = torch.zeros((S,), dtype=torch.uint8, device=DEV)
+    a = np.empty_like(x)
+    va = np.empty((T, S), np.uint8)
+    for t in range(T):
+        d.copy_(torch.from_numpy(x[t]))
+        eng_a.tick_device(d, d, d_v)
+        a[t] = d.cpu().numpy()
+        va[t] = d_v.cpu().numpy()
+    b = np.empty_like(x)
+    vb = np.empty((T, S), np.uint8)
+    for t0 in range(0, T, K):
+        blk = torch.from_numpy(np.ascontiguousarray(x[t0:t0 + K].transpose(1, 0, 2))).to(DEV)
+        d_out = torch.empty_like(blk)
+        d_vk = torch.zeros((S, K), dtype=torch.uint8, device=DEV)
+        eng_b.offline_device(blk, d_out, K, d_vk)
+        b[t0:t0 + K] = d_out.cpu().numpy().transpose(1, 0, 2)
+        vb[t0:t0 + K] = d_vk.cpu().numpy().T
     assert np.array_equal(a, b) and np.array_equal(va, vb)
+    for s_ in (0, 1, S // 2, S - 1):
+        assert np.array_equal(eng_a.get_state(s_), eng_b.get_state(s_)), "state of stream %d" % s_
+    eng_a.close()
+    eng_b.close()
 
 
 def test_snapshot_restore_and_reset():

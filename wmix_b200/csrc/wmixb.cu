@@ -133,13 +133,55 @@ ns_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Tables
 __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
-template <int ANA>
-constexpr size_t ns_cta_smem_bytes(int workers)
+// TMA bulk copies of a whole per-stream record (1-D cp.async.bulk, completion on an mbarrier / a bulk group)
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count)
 {
-    return (NsSmem<ANA>::kTableFloats + (size_t)workers * ns::Geo<ANA>::kShFloats) * sizeof(float) + 8 * sizeof(uint16_t*);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// every thread that wrote the buffer through the generic proxy runs this before the (one) thread that issues the bulk store
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* smem_src, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(smem_u32(smem_src)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// STAGED (the persistent offline mode): every worker also keeps its stream's whole record on chip
+template <int ANA>
+constexpr size_t ns_cta_smem_bytes(int workers, bool staged = false)
+{
+    return (NsSmem<ANA>::kTableFloats + (size_t)workers * ns::Geo<ANA>::kShFloats + (staged ? (size_t)workers * ns::Geo<ANA>::kRecFloats : 0)) * sizeof(float) +
+           8 * sizeof(uint16_t*) + (staged ? 8 * sizeof(uint64_t) : 0);
 }
 
-template <int ANA, int W, int MINB>
+// STAGED = persistent offline mode: a worker pulls its stream's whole record (8 KB at 16 kHz) into shared memory with ONE
+// TMA bulk copy, runs all n_frames frames of the stream against that copy — every state access of the segments becomes a
+// shared-memory access, the only DRAM traffic per frame is the PCM — and writes the record back with one bulk store.
+template <int ANA, int W, int MINB, bool STAGED = false>
 __global__ void __launch_bounds__((W + 1) * 32, MINB)
 ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Tables<ANA>* __restrict__ tables,
               const int16_t* in, int16_t* out, int n_streams, int n_frames)
@@ -150,7 +192,10 @@ ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Ta
     extern __shared__ __align__(16) float smem[];
     ns::Tables<ANA>* T = reinterpret_cast<ns::Tables<ANA>*>(smem);
     float* tiles = smem + NsSmem<ANA>::kTableFloats;
-    uint16_t** hptr = reinterpret_cast<uint16_t**>(tiles + (size_t)W * G::kShFloats);
+    float* recs = tiles + (size_t)W * G::kShFloats;                                   // [W][kRecFloats], STAGED only
+    uint16_t** hptr = reinterpret_cast<uint16_t**>(recs + (STAGED ? (size_t)W * G::kRecFloats : 0));
+    uint64_t* mbars = reinterpret_cast<uint64_t*>(hptr + 8);                         // [W], STAGED only
+    if (STAGED && threadIdx.x < W) mbar_init(&mbars[threadIdx.x], 1);
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
         uint32_t* dst = reinterpret_cast<uint32_t*>(smem);
@@ -167,14 +212,25 @@ ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Ta
         float* tile = tiles + (size_t)warp * G::kShFloats;
         ns::WWarp<ANA> Wk;
         Wk.lane_id = lane;
+        float* staged = recs + (size_t)warp * G::kRecFloats;
+        uint32_t stage_phase = 0;
         for (int it = 0; it < rounds; ++it) {
             const int s = first + warp + it * total;
             const bool live = s < n_streams;
-            float* r = rec + (size_t)s * G::kRecFloats;
+            float* r_global = rec + (size_t)s * G::kRecFloats;
+            float* r = STAGED ? staged : r_global;
             uint16_t* h = hist + (size_t)s * 3 * ns::kHistBins;
             const int16_t* pi = in + (size_t)s * n_frames * G::kBlock;
             int16_t* po = out + (size_t)s * n_frames * G::kBlock;
             if (lane == 0) hptr[warp] = h;
+            if (STAGED && live) {
+                if (lane == 0) {
+                    bulk_store_wait_read();                                   // the previous stream's write-back has left the buffer
+                    bulk_load(staged, r_global, G::kRecFloats * sizeof(float), &mbars[warp]);
+                }
+                mbar_wait(&mbars[warp], stage_phase);
+                stage_phase ^= 1;
+            }
             for (int f = 0; f < n_frames; ++f) {
                 bool act = false;
                 if (live) {
@@ -183,6 +239,7 @@ ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Ta
                         l2_prefetch(rec + (size_t)(s + total) * G::kRecFloats, G::kRecFloats * sizeof(float));
                         l2_prefetch(in + (size_t)(s + total) * n_frames * G::kBlock, G::kBlock * sizeof(int16_t));
                     }
+                    if (STAGED && lane == 0 && f + 1 < n_frames) l2_prefetch(pi + (size_t)(f + 1) * G::kBlock, G::kBlock * sizeof(int16_t));
                     act = ns::w_seg1<ANA>(Wk, r, pi + (size_t)f * G::kBlock, po + (size_t)f * G::kBlock, tile, *T);
                 } else if (lane == 0) {
                     tile[G::kShScal + ns::C_ACTIVE] = 0.f;
@@ -197,7 +254,13 @@ ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Ta
                 named_bar_sync(6, kThreads);
                 if (act) ns::w_seg4<ANA>(Wk, r, po + (size_t)f * G::kBlock, tile, *T);
             }
+            if (STAGED && live) {
+                fence_async_smem();
+                __syncwarp();
+                if (lane == 0) bulk_store(r_global, staged, G::kRecFloats * sizeof(float));
+            }
         }
+        if (STAGED && lane == 0) bulk_store_wait_all();
     } else {
         ns::RWarp Rd;
         Rd.lane_id = lane;
@@ -585,7 +648,8 @@ struct wmixb_engine {
     unsigned long long submitted = 0, waited = 0;
     int32_t* d_bus = nullptr;               // staging of the conference bus for the host-buffer tick
     size_t d_bus_bytes = 0;
-    int ns_grid = 0;
+    int ns_grid = 0, ns_staged_grid = 0;
+    int ns_offline_staged = 1;              // several frames per launch: records staged in shared memory (persistent offline mode)
     int ns_cfg = 0;                         // index into kNsCfgs: 2 CTAs of 8 worker warps + 1 reducer warp
     int ns_align = 1;                       // CTA barrier at the top of every frame (instruction-cache sharing)
     int post_occ = 0;                       // post_kernel shape: 0 = automatic (see run_stages), 2..5 = CTAs of 128 threads per SM, 22 = one aligned CTA of 704
@@ -602,6 +666,7 @@ static int ns_rec_floats(const wmixb_engine* e) { return e->ana == 256 ? ns::Geo
 
 // compiled shapes of the NS kernel; wmixb_set_tuning("ns_cfg", index) picks one (default 0).
 // cta = 1: ns_cta_kernel, `warps` WORKER warps + one reducer warp per CTA; cta = 0: ns_kernel (one self-contained warp per stream)
+constexpr int kNsStagedWorkers = 7;
 struct NsCfg { int cta, warps, minb; };
 static const NsCfg kNsCfgs[] = {{1, 8, 2}, {1, 6, 3}, {1, 4, 4}, {1, 4, 5}, {1, 7, 2}, {1, 5, 3}, {0, 10, 2}, {0, 8, 2}};
 template <int ANA>
@@ -630,6 +695,14 @@ static int launch_ns(wmixb_engine* e, int grid, cudaStream_t st, const int16_t* 
     const ns::Tables<ANA>* T = (const ns::Tables<ANA>*)e->ns_tables;
     int align = e->ns_align;
     void* args[] = {&rec, &hist, &T, &in, &out, &n, &n_frames, &align};   // the CTA form takes the first seven
+    if (n_frames > 1 && e->ns_offline_staged) {
+        // persistent offline mode: state on chip for the whole run of frames (7 workers + reducer, 2 CTAs per SM: 225 KB of smem)
+        const int need = (n + kNsStagedWorkers - 1) / kNsStagedWorkers;
+        const int g = need < e->ns_staged_grid ? need : e->ns_staged_grid;
+        CK(cudaLaunchKernel((const void*)ns_cta_kernel<ANA, kNsStagedWorkers, 2, true>, dim3(g), dim3((kNsStagedWorkers + 1) * 32), args,
+                            ns_cta_smem_bytes<ANA>(kNsStagedWorkers, true), st));
+        return WMIXB_OK;
+    }
     CK(cudaLaunchKernel(ns_fn<ANA>(e->ns_cfg), dim3(grid), dim3(ns_threads(e->ns_cfg)), args, ns_cfg_smem<ANA>(e->ns_cfg), st));
     return WMIXB_OK;
 }
@@ -645,6 +718,14 @@ static int ns_configure(wmixb_engine* e)
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, ns_threads(e->ns_cfg), ns_cfg_smem<ANA>(e->ns_cfg)));
     if (per_sm < 1) per_sm = 1;
     e->ns_grid = e->sm_count * per_sm;
+    // the staged (persistent offline) shape
+    const void* sfn = (const void*)ns_cta_kernel<ANA, kNsStagedWorkers, 2, true>;
+    const size_t ssm = ns_cta_smem_bytes<ANA>(kNsStagedWorkers, true);
+    CK(cudaFuncSetAttribute(sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ssm));
+    CK(cudaFuncSetAttribute(sfn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sfn, (kNsStagedWorkers + 1) * 32, ssm));
+    if (per_sm < 1) per_sm = 1;
+    e->ns_staged_grid = e->sm_count * per_sm;
     return WMIXB_OK;
 }
 
@@ -2116,6 +2197,7 @@ extern "C" int wmixb_set_tuning(wmixb_engine* e, const char* key, int value)
         e->ns_cfg = value;
         return e->ana == 256 ? ns_configure<256>(e) : ns_configure<128>(e);
     }
+    if (!strcmp(key, "ns_offline_staged")) { e->ns_offline_staged = value != 0; return WMIXB_OK; }
     if (!strcmp(key, "ns_align")) { if (value < 0 || value > 64) return WMIXB_EINVAL; e->ns_align = value; return WMIXB_OK; }
     if (!strcmp(key, "post_occ")) { if ((value < 2 || value > 5) && value != 22 && value != 0) return WMIXB_EINVAL; e->post_occ = value; return WMIXB_OK; }
     if (!strcmp(key, "aec_pf")) { e->aec_pf = value; return WMIXB_OK; }
