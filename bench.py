@@ -52,8 +52,8 @@ CHAIN_BYTES_PER_STREAM_TICK = 16.0e3   # NS + VAD + AGC + mix
 AEC_BYTES_PER_STREAM_TICK = 29.0e3     # AEC at 8 kHz
 # dram__bytes_read.sum + dram__bytes_write.sum of one NS launch per stream: a CONSTANT taken from the latest
 # `ncu --set full` capture (it cannot be measured inside an unprofiled run); see NS_TRAFFIC_SOURCE
-NS_DRAM_TRAFFIC_PER_STREAM_NCU = (891.332864e6 + 642.490368e6) / 100_000
-NS_TRAFFIC_SOURCE = "constant from ncu --set full capture r1_g (profiles/r1_g_summary.md), not measured in this run"
+NS_DRAM_TRAFFIC_PER_STREAM_NCU = (874.749184e6 + 643.318784e6) / 100_000
+NS_TRAFFIC_SOURCE = "constant from ncu --set full capture r2_k (profiles/r2_k_summary.md), not measured in this run"
 
 
 def peaks():
@@ -564,7 +564,7 @@ def run_ours(args):
             "kernel_ms": {"ns_kernel": ns_ms, "post_kernel(agc+vad)": post_ms, "bus_sum_kernel": mix_ms},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": S * NS_DRAM_TRAFFIC_PER_STREAM_NCU, "traffic_source": NS_TRAFFIC_SOURCE,
-                         "kernel": "ns_kernel<256>", "peak_source": peak_src,
+                         "kernel": "ns_cta_kernel<256, 8, 2>", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": S * NS_BYTES_PER_STREAM_TICK,
                          "whole_tick_frac": S * CHAIN_BYTES_PER_STREAM_TICK / (ms_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": total_streams * 10.0 / e2e_ms, "unit": UNIT,
