@@ -88,3 +88,13 @@ done
 
 g++ -shared -o "$OUT/libwmix_ref$SUFFIX.so" "${objs[@]}" "$OBJ"/r_*.o "$OBJ"/s_*.o -lpthread -lm
 echo "build_ref: wrote $OUT/libwmix_ref$SUFFIX.so ($OPT)"
+
+# The same library with the reference's own NS switch thrown (R:src/webrtc.c:511-523: `#define MAKE_WEBRTC_NSX`,
+# commented out as shipped): ns_init / ns_process then run the fixed-point WebRtcNsx_* core.  Only webrtc.c differs.
+"$CC" "${CFLAGS[@]}" "${INC[@]}" "${WM[@]}" -DMAKE_WEBRTC_NSX -c "$REF/src/webrtc.c" -o "$OBJ/x_webrtc_nsx.o"
+nsx_objs=()
+for o in "$OBJ"/r_*.o; do
+    [ "$o" = "$OBJ/r_webrtc.o" ] || nsx_objs+=("$o")
+done
+g++ -shared -o "$OUT/libwmix_ref_nsx$SUFFIX.so" "${objs[@]}" "${nsx_objs[@]}" "$OBJ/x_webrtc_nsx.o" "$OBJ"/s_*.o -lpthread -lm
+echo "build_ref: wrote $OUT/libwmix_ref_nsx$SUFFIX.so (MAKE_WEBRTC_NSX)"

@@ -170,6 +170,21 @@ void orc_ns_release(orc_ns *h);
 int orc_ns_block_index(const orc_ns *h);
 const float *orc_ns_prior_model(const orc_ns *h);
 
+/* ---- NS fixed-point core, "nsx" (T:webrtc/modules/audio_processing/ns/nsx_core.c, nsx_core_c.c; the handle layer
+ * of R:src/webrtc.c:563-660 built with MAKE_WEBRTC_NSX, R:src/webrtc.c:512) ---- */
+typedef struct orc_nsx_core orc_nsx_core;
+typedef struct {
+    orc_nsx_core *core;
+    int chn, freq, pkg;
+} orc_nsx;
+orc_nsx *orc_nsx_init(int chn, int freq);                       /* policy 2 = wmix's NS_AGGRESSIVE */
+orc_nsx *orc_nsx_init_policy(int chn, int freq, int policy);
+void orc_nsx_process(orc_nsx *h, const int16_t *in, int16_t *out, int frame_num);
+void orc_nsx_release(orc_nsx *h);
+int orc_nsx_block_index(const orc_nsx *h);
+int orc_nsx_state(const orc_nsx *h, int32_t *out, int cap);     /* canonical state dump, returns the word count */
+int orc_nsx_tables(int16_t *out, int cap);                      /* derived constant tables, returns the entry count */
+
 /* ---- AEC float core as wmix drives it (T:webrtc/modules/audio_processing/aec; R:src/webrtc.c:217-500) ---- */
 typedef struct orc_aec orc_aec;
 orc_aec *orc_aec_init(int chn, int freq, int interval_ms);

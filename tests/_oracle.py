@@ -62,6 +62,90 @@ def ref():
     return _ref
 
 
+_ref_nsx = None
+
+
+def ref_nsx():
+    """The reference with its own NS switch thrown (R:src/webrtc.c:512, MAKE_WEBRTC_NSX): ns_init / ns_process run the
+    fixed-point core.  None when oracle/_ref was not built."""
+    global _ref_nsx
+    if _ref_nsx is None:
+        so = os.path.join(ORACLE_DIR, "_ref", "libwmix_ref_nsx.so")
+        if not os.path.exists(so):
+            return None
+        L = C.CDLL(so)
+        for f in ("ns_init", "vad_init", "agc_init", "aec_init"):
+            getattr(L, f).restype = C.c_void_p
+        _ref_nsx = L
+    return _ref_nsx
+
+
+class NsxCore:
+    """WebRtcNsx_* of the compiled reference driven directly (any policy; one or two bands)."""
+
+    def __init__(self, L, freq, policy=2):
+        self.L = L
+        self.h = C.c_void_p()
+        assert L.WebRtcNsx_Create(C.byref(self.h)) == 0
+        assert L.WebRtcNsx_Init(self.h, freq) == 0
+        assert L.WebRtcNsx_set_policy(self.h, policy) == 0
+        self.n = 80 if freq == 8000 else 160
+
+    def frame(self, lo, hi=None):
+        lo = np.ascontiguousarray(lo, np.int16)
+        o = np.zeros(self.n, np.int16)
+        if hi is None:
+            self.L.WebRtcNsx_Process(self.h, (C.c_void_p * 1)(lo.ctypes.data), 1, (C.c_void_p * 1)(o.ctypes.data))
+            return o
+        hi = np.ascontiguousarray(hi, np.int16)
+        oh = np.zeros(self.n, np.int16)
+        self.L.WebRtcNsx_Process(self.h, (C.c_void_p * 2)(lo.ctypes.data, hi.ctypes.data), 2,
+                                 (C.c_void_p * 2)(o.ctypes.data, oh.ctypes.data))
+        return o, oh
+
+    def close(self):
+        self.L.WebRtcNsx_Free(self.h)
+
+
+def nsx_handle_run(L, prefix, chn, freq, pcm, policy=None):
+    """pcm int16 [T, n*chn] (interleaved) through ns_init / ns_process of a checker: the reference built with
+    MAKE_WEBRTC_NSX (prefix "") or the oracle (prefix "orc_nsx")."""
+    pcm = np.ascontiguousarray(pcm, np.int16)
+    T = pcm.shape[0]
+    n = freq // 100
+    out = np.zeros_like(pcm)
+    if prefix:
+        L.orc_nsx_init.restype = C.c_void_p
+        L.orc_nsx_init_policy.restype = C.c_void_p
+        h = C.c_void_p(L.orc_nsx_init(chn, freq) if policy is None else L.orc_nsx_init_policy(chn, freq, policy))
+        assert h
+        for t in range(T):
+            L.orc_nsx_process(h, P(pcm[t]), P(out[t]), n)
+        L.orc_nsx_release(h)
+    else:
+        h = C.c_void_p(L.ns_init(chn, freq, None))
+        assert h
+        for t in range(T):
+            L.ns_process(h, P(pcm[t]), P(out[t]), n)
+        L.ns_release(h)
+    return out
+
+
+def nsx_quiet_streams(freq, T=700, seed=5):
+    """near-silent / gapped / full-scale corner streams [T, 8, n]: amplitudes 1, 2, 3 reach the modulo-32 shift of
+    nsx_core.c:1140 / :1716 on x86, stream 6 saturates, all see 30 all-zero frames"""
+    rng = np.random.default_rng(seed)
+    n = freq // 100
+    q = np.zeros((T, 8, n), np.int16)
+    for s, amp in enumerate([1, 2, 3, 8, 40, 300, 32767, 5]):
+        q[:, s] = rng.integers(-amp, amp + 1, size=(T, n))
+    q[100:130] = 0
+    q[300:310, :, ::2] = 0
+    q[400:420, 6] = 32767
+    q[420:440, 6] = -32768
+    return q
+
+
 class RefChain:
     """NS -> AGC -> VAD through the reference's own handle API, one 10 ms frame at a time."""
 
