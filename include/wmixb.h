@@ -42,7 +42,9 @@ typedef struct wmixb_config {
     int aec_far_depth;  /* far-end history kept per stream, in 64-sample partitions; 0 = 32.  The
                            reference keeps 250 (T:.../aec/aec_core.c:37); the handle API uses 252.   */
     int ns_high_band;   /* 1: allocate the high-band history wmixb_ns2_* needs (wmix's stereo NS, see below)      */
-    int reserved[7];
+    int ns_core;        /* 0: WebRtcNs_* float core (what wmix ships); 1: WebRtcNsx_* fixed-point core — the reference's
+                           own switch, `#define MAKE_WEBRTC_NSX` (R:src/webrtc.c:511-523), as a run-time choice          */
+    int reserved[6];
 } wmixb_config;
 
 typedef struct wmixb_engine wmixb_engine;
@@ -260,7 +262,7 @@ int wmixb_host_copy_ceiling(int device, const void* h_src, void* h_dst, size_t h
 int wmixb_set_default_device(int device);
 int wmixb_default_device(void);
 
-/* experiment / test knobs; none changes results.  keys: "ns_cfg", "ns_align", "post_occ", "aec_pf", "aec_grid",
+/* experiment / test knobs; none changes results.  keys: "ns_cfg", "nsx_cfg", "ns_align", "post_occ", "aec_pf", "aec_grid",
  * "host_chunks", "host_lanes" */
 int wmixb_set_tuning(wmixb_engine* e, const char* key, int value);
 

@@ -17,6 +17,7 @@
 #include "../../wmix_b200/csrc/host_tables.h"
 #include "../../wmix_b200/csrc/ns.cuh"
 #include "../../wmix_b200/csrc/ns_cta.cuh"
+#include "../../wmix_b200/csrc/nsx.cuh"
 #include "../../wmix_b200/csrc/vad.cuh"
 
 using namespace wmx;
@@ -262,6 +263,95 @@ void emu_nscta_destroy(void* h)
     delete e->e256;
     delete e->e128;
     delete e;
+}
+// ---- fixed-point NS (nsx.cuh): one warp per stream, phases as lane loops, warp reductions as loops over the lanes ----
+struct EmuNsx {
+    int ana;
+    std::vector<uint32_t> rec, tile;
+    std::vector<int16_t> hist;
+    nsx::Tables T;
+    nsx::Warp<256> w256;
+    nsx::Warp<128> w128;
+};
+void* emu_nsx_create(int freq, int policy)
+{
+    EmuNsx* e = new EmuNsx();
+    int32_t thr = 0;
+    if (host::nsx_tables(freq, policy, &e->T, &thr) != 0) { delete e; return nullptr; }
+    e->ana = freq == 8000 ? 128 : 256;
+    e->hist.assign(3 * nsx::kHistBins, 0);
+    memset(&e->w256, 0, sizeof e->w256);
+    memset(&e->w128, 0, sizeof e->w128);
+    if (e->ana == 256) {
+        e->rec.assign(nsx::Geo<256>::kRecWords, 0u);
+        e->tile.assign(nsx::Geo<256>::kShWords, 0u);
+        nsx::init_record<256>(e->rec.data(), e->hist.data(), 0, 1, thr);
+    } else {
+        e->rec.assign(nsx::Geo<128>::kRecWords, 0u);
+        e->tile.assign(nsx::Geo<128>::kShWords, 0u);
+        nsx::init_record<128>(e->rec.data(), e->hist.data(), 0, 1, thr);
+    }
+    return e;
+}
+void emu_nsx_frame(void* h, const int16_t* in, int16_t* out)
+{
+    EmuNsx* e = (EmuNsx*)h;
+    if (e->ana == 256) nsx::frame<256>(e->w256, e->rec.data(), e->hist.data(), in, out, e->tile.data(), e->T);
+    else nsx::frame<128>(e->w128, e->rec.data(), e->hist.data(), in, out, e->tile.data(), e->T);
+}
+void emu_nsx_destroy(void* h) { delete (EmuNsx*)h; }
+const uint32_t* emu_nsx_record(void* h) { return ((EmuNsx*)h)->rec.data(); }
+const int16_t* emu_nsx_hist(void* h) { return ((EmuNsx*)h)->hist.data(); }
+int emu_nsx_rec_words(int freq) { return freq == 8000 ? nsx::Geo<128>::kRecWords : nsx::Geo<256>::kRecWords; }
+}   // extern "C"
+// the record in the canonical order of oracle/orc_nsx.c's orc_nsx_state (tests compare the two word for word)
+template <int ANA>
+static int nsx_canonical(const uint32_t* rec, int32_t* out)
+{
+    typedef nsx::Geo<ANA> G;
+    const int32_t* sc = (const int32_t*)(rec + G::kOffScal);
+    auto word = [&](int a, int bin) { return bin < G::kHalf ? rec[G::kOffArrays + a * G::kHalf + bin] : rec[G::kOffNyq + a]; };
+    int k = 0;
+    const int order[25] = {nsx::S_FRAME_IDX, nsx::S_MODEL_COUNT, nsx::S_COUNTER0, nsx::S_COUNTER1, nsx::S_COUNTER2, nsx::S_Q_NOISE, nsx::S_Q_NOISE_PREV,
+                           nsx::S_Q_MAGN_PREV, nsx::S_MIN_NORM, nsx::S_PRIOR, nsx::S_FEAT_LRT, nsx::S_THR_LRT, nsx::S_FEAT_FLAT, nsx::S_THR_FLAT,
+                           nsx::S_FEAT_DIFF, nsx::S_THR_DIFF, nsx::S_W_LRT, nsx::S_W_FLAT, nsx::S_W_DIFF, nsx::S_CUR_AVG_E, nsx::S_TIME_AVG_E,
+                           nsx::S_TIME_AVG_ACC, nsx::S_WHITE, nsx::S_PINK_NUM, nsx::S_PINK_EXP};
+    for (int i = 0; i < 25; ++i) out[k++] = sc[order[i]];
+    while (k < 40) out[k++] = 0;
+    for (int b = 0; b < G::kBins; ++b) out[k++] = (int32_t)(word(nsx::A_QF, b) >> 16);
+    for (int e = 0; e < 3; ++e)
+        for (int b = 0; b < G::kBins; ++b) out[k++] = lo16((int32_t)word(nsx::A_LQD0 + e, b));
+    for (int e = 0; e < 3; ++e)
+        for (int b = 0; b < G::kBins; ++b) out[k++] = hi16((int32_t)word(nsx::A_LQD0 + e, b));
+    for (int b = 0; b < G::kBins; ++b) out[k++] = lo16((int32_t)word(nsx::A_QF, b));
+    for (int b = 0; b < G::kBins; ++b) out[k++] = (int32_t)word(nsx::A_LRT, b);
+    for (int b = 0; b < G::kBins; ++b) out[k++] = (int32_t)word(nsx::A_PAUSE, b);
+    for (int b = 0; b < G::kBins; ++b) out[k++] = (int32_t)word(nsx::A_INIT, b);
+    for (int b = 0; b < G::kBins; ++b) out[k++] = (int32_t)word(nsx::A_NPREV, b);
+    for (int b = 0; b < G::kBins; ++b) out[k++] = (int32_t)(word(nsx::A_MPREV, b) & 0xFFFFu);
+    const int16_t* hist = (const int16_t*)(rec + G::kOffHist);
+    const int16_t* syn = (const int16_t*)(rec + G::kOffSyn);
+    for (int i = 0; i < G::kKeep; ++i) out[k++] = hist[i];
+    for (int i = 0; i < G::kKeep; ++i) out[k++] = syn[i];
+    return k;
+}
+extern "C" {
+int emu_nsx_canonical(int freq, const uint32_t* rec, int32_t* out) { return freq == 8000 ? nsx_canonical<128>(rec, out) : nsx_canonical<256>(rec, out); }
+// the parallel two-peak search against the reference's scan order: h int16 [1000] -> pos1, pos2, w1, w2
+void emu_nsx_two_peaks(const int16_t* h, int32_t* out4)
+{
+    static nsx::Warp<256> w;
+    std::vector<uint32_t> tile(nsx::Geo<256>::kShWords, 0u);
+    const nsx::Peaks pk = nsx::two_peaks<256>(w, h, tile.data());
+    out4[0] = (int32_t)pk.pos1; out4[1] = (int32_t)pk.pos2; out4[2] = pk.w1; out4[3] = pk.w2;
+}
+int emu_nsx_tables(int freq, int policy, void* out, int cap)
+{
+    nsx::Tables T;
+    int32_t thr = 0;
+    if (cap < (int)sizeof T || host::nsx_tables(freq, policy, &T, &thr) != 0) return -(int)sizeof T;
+    memcpy(out, &T, sizeof T);
+    return (int)sizeof T;
 }
 int emu_ns_rec_floats(int freq) { return freq == 8000 ? ns::Geo<128>::kRecFloats : ns::Geo<256>::kRecFloats; }
 const uint16_t* emu_ns_hist(void* h) { return ((EmuNs*)h)->hist.data(); }

@@ -1,0 +1,157 @@
+"""GPU parity of the fixed-point suppressor (ns_core = 1; nsx.cuh / nsx_kernel) through the C-ABI.  Integer work: the bar
+is BIT-EXACT, outputs and complete per-stream state, against oracle/orc_nsx.c, the compiled reference's WebRtcNsx_* when it
+travelled with the snapshot, and the committed fixtures of tests/golden/nsx.json (recorded from the unmodified reference)."""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+import wmix_b200  # noqa: E402
+from tests._oracle import NsxCore, P, fnv1a64, nsx_quiet_streams, oracle, ref  # noqa: E402
+from tests.test_nsx_oracle_pin import check, oracle_core_run  # noqa: E402
+from wmix_b200 import AGC, NS, VAD  # noqa: E402
+from wmix_b200.synth import make_frames  # noqa: E402
+
+DEV = "cuda:0"
+G = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "nsx.json")))
+
+
+def run_gpu_nsx(x, freq, policy=2, stages=NS, offline=0, tuning=None):
+    """x int16 [T, S, L] -> out [T, S, L] through a batched engine with the fixed-point core"""
+    T, S, L = x.shape
+    eng = wmix_b200.Engine(S, freq, stages=stages, ns_policy=policy, ns_core=1)
+    for k, v in (tuning or {}).items():
+        eng.set_tuning(k, v)
+    out = np.empty_like(x)
+    if offline:
+        assert T % offline == 0
+        for t0 in range(0, T, offline):
+            d_in = torch.from_numpy(np.ascontiguousarray(x[t0:t0 + offline].transpose(1, 0, 2))).to(DEV)
+            d_out = torch.empty_like(d_in)
+            eng.offline_device(d_in, d_out, offline)
+            out[t0:t0 + offline] = d_out.cpu().numpy().transpose(1, 0, 2)
+    else:
+        d = torch.empty((S, L), dtype=torch.int16, device=DEV)
+        for t in range(T):
+            d.copy_(torch.from_numpy(x[t]))
+            eng.tick_device(d, d)                                   # in place, like wmix
+            out[t] = d.cpu().numpy()
+    eng.close()
+    return out
+
+
+@pytest.mark.parametrize("freq", [16000, 8000])
+@pytest.mark.parametrize("policy", [2, 0, 1, 3])
+def test_nsx_golden_fixtures_through_the_gpu(freq, policy):
+    """the reference's own outputs (1100 ticks: start-up model, gain map from frame 200, two threshold re-learnings)"""
+    d = G["core"]["synth_%d_p%d" % (freq, policy)]
+    x = make_frames(d["n_streams"], freq, 0, d["n_ticks"], seed=d["seed"])
+    check(d, run_gpu_nsx(x, freq, policy))
+
+
+@pytest.mark.parametrize("freq", [16000, 8000])
+def test_nsx_vs_checkers_70_streams(freq):
+    """a ragged batch (70 streams: partial CTA, every cohort of the synthetic set) over 650 ticks"""
+    x = make_frames(70, freq, 0, 650, seed=41)
+    got = run_gpu_nsx(x, freq)
+    want = oracle_core_run(freq, x[:, :24])
+    assert np.array_equal(got[:, :24], want)
+    R = ref()
+    if R is not None:
+        for s in (0, 1, 2, 3, 17, 64, 65, 69):
+            c = NsxCore(R, freq, 2)
+            for t in range(650):
+                assert np.array_equal(c.frame(x[t, s]), got[t, s]), (s, t)
+            c.close()
+
+
+@pytest.mark.parametrize("freq", [16000, 8000])
+def test_nsx_quiet_gapped_saturated(freq):
+    """near-silent streams (the modulo-32 shifts of the x86 reference), 30 all-zero frames (the zero-input path), full scale"""
+    check(G["core"]["quiet_%d" % freq], run_gpu_nsx(nsx_quiet_streams(freq), freq))
+
+
+@pytest.mark.parametrize("freq", [16000, 8000])
+def test_nsx_state_word_for_word(freq):
+    """complete per-stream state after 40, 230 and 600 ticks against the oracle's canonical dump (the emulator's
+    record-to-canonical mapping is reused through wmixb_get_stream_state)"""
+    from tests._emu import emu
+    E = emu()
+    O = oracle()
+    O.orc_nsx_init_policy.restype = C.c_void_p
+    S, L = 40, freq // 100
+    x = make_frames(S, freq, 0, 600, seed=19)
+    eng = wmix_b200.Engine(S, freq, stages=NS, ns_core=1)
+    hs = [C.c_void_p(O.orc_nsx_init_policy(1, freq, 2)) for _ in range(S)]
+    d = torch.empty((S, L), dtype=torch.int16, device=DEV)
+    words = E.emu_nsx_rec_words(freq)
+    for t in range(600):
+        d.copy_(torch.from_numpy(x[t]))
+        eng.tick_device(d, d)
+        for s in range(S):
+            y = np.zeros(L, np.int16)
+            O.orc_nsx_process(hs[s], P(x[t, s].copy()), P(y), L)
+        if t + 1 in (40, 230, 600):
+            for s in range(S):
+                raw = eng.get_state(s)
+                rec = np.ascontiguousarray(raw[:words * 4]).view(np.uint32)
+                hist = np.ascontiguousarray(raw[words * 4:words * 4 + 6000]).view(np.int16)
+                a = np.zeros(4096, np.int32)
+                b = np.zeros(4096, np.int32)
+                n = O.orc_nsx_state(hs[s], P(a), 4096)
+                assert E.emu_nsx_canonical(freq, P(rec), P(b)) == n
+                assert np.array_equal(a[:n], b[:n]), (t, s, np.nonzero(a[:n] != b[:n])[0][:8])
+                assert 0 <= int(hist.sum()) <= 3 * 511                          # at most three increments per counted frame of a window
+    for h in hs:
+        O.orc_nsx_release(h)
+    eng.close()
+
+
+def test_nsx_offline_mode_and_every_launch_shape_agree():
+    """K frames per launch == K ticks; every compiled shape of the kernel (registers capped at 128 / 80 / 64, 4 / 8 / 16
+    warps per CTA) gives the same bits"""
+    x = make_frames(70, 16000, 0, 240, seed=57)
+    base = run_gpu_nsx(x, 16000)
+    assert np.array_equal(base, run_gpu_nsx(x, 16000, offline=60))
+    for cfg in range(1, 6):
+        assert np.array_equal(base, run_gpu_nsx(x, 16000, tuning={"nsx_cfg": cfg})), cfg
+    assert np.array_equal(base, run_gpu_nsx(x, 16000, tuning={"ns_align": 0}))
+
+
+def test_nsx_chain_with_agc_and_vad_and_config1_wav():
+    """NSX -> AGC -> VAD (the record chain with the switch thrown) against the oracle chain; config 1's wav through NSX"""
+    from tests._oracle import RefChain
+    O = oracle()
+    O.orc_nsx_init_policy.restype = C.c_void_p
+    x = make_frames(12, 16000, 0, 400, seed=61)
+    got = run_gpu_nsx(x, 16000, stages=NS | AGC | VAD)
+    nsx = oracle_core_run(16000, x)
+    for s in range(12):
+        c = RefChain(O, 16000, ns=False, prefix="orc_")
+        for t in range(400):
+            assert np.array_equal(c.frame(nsx[t, s]), got[t, s]), (s, t)
+        c.close()
+    wav = np.fromfile(os.path.join(os.path.dirname(__file__), "golden", "config1_in_20s.s16"), np.int16).reshape(-1, 1, 80)
+    check(G["config1_nsx"], run_gpu_nsx(wav, 8000).reshape(-1, 80))
+
+
+def test_nsx_full_size_replication_property():
+    """100 000 streams (BASELINE config 3's size): replicated inputs give replicated outputs equal to the small run"""
+    S, base, T = 100000, 50, 12
+    x = make_frames(base, 16000, 0, T, seed=67)
+    small = run_gpu_nsx(x, 16000)
+    eng = wmix_b200.Engine(S, 16000, stages=NS, ns_core=1)
+    d = torch.empty((S, 160), dtype=torch.int16, device=DEV)
+    for t in range(T):
+        d.copy_(torch.from_numpy(x[t]).to(DEV).repeat(S // base, 1))
+        eng.tick_device(d, d)
+        y = d.view(S // base, base, 160)
+        assert bool((y == y[0:1]).all())
+        assert np.array_equal(y[0].cpu().numpy(), small[t])
+    eng.close()

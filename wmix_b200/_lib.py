@@ -14,7 +14,7 @@ NS, AGC, VAD, AEC = 1, 2, 4, 8
 class Config(C.Structure):
     _fields_ = [("n_streams", C.c_int), ("freq", C.c_int), ("stages", C.c_int), ("ns_policy", C.c_int),
                 ("agc_gain_db", C.c_int), ("vad_mode", C.c_int), ("device", C.c_int), ("aec_far_depth", C.c_int),
-                ("ns_high_band", C.c_int), ("reserved", C.c_int * 7)]
+                ("ns_high_band", C.c_int), ("ns_core", C.c_int), ("reserved", C.c_int * 6)]
 
 
 class MixView(C.Structure):

@@ -5,6 +5,7 @@
 // emulation harness under tests/emu/ (CPU CI for the kernel logic; it is never part of the
 // shipped library, and libwmix_b200.so has no CPU execution path).
 #pragma once
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)

@@ -3,6 +3,7 @@
 // of an engine, are computed once on the CPU (with the same libm the reference uses, so the
 // floats agree bit for bit) and uploaded.  No per-sample work happens here.
 #include "host_tables.h"
+#include "nsx.cuh"
 
 #include <math.h>
 #include <stdio.h>
@@ -426,6 +427,92 @@ int play_fifo_slot(int count, int n_pkg, int delay_pkgs)
     if (k >= n_pkg) k -= n_pkg;
     else if (k < 0) k += n_pkg;
     return k;
+}
+
+
+// ---- NS, fixed-point core ---------------------------------------------------------------------
+// The reference ships these as literal tables (T:.../ns/nsx_core.c:28-300, nsx_core_c.c:17,
+// T:.../signal_processing/complex_fft_tables.h:17).  All but the 17-entry sigmoid have closed forms that reproduce the
+// literals exactly (tests pin every entry against hashes of the reference's sources): rounded logarithms and reciprocals,
+// a quarter-sine-edged window in Q14, the gain-map curves of the comments at nsx_core.c:125-169 evaluated on
+// gain = sqrt(energy ratio) and TRUNCATED to Q13, sums of log2(i) for the pink-noise fit, and a truncated Q15 sine.
+static int nearest_int(double x) { return (int)floor(x + 0.5); }
+
+int nsx_tables(int freq, int policy, nsx::Tables* T, int32_t* thr_lrt)
+{
+    if (policy < 0 || policy > 3) return -1;
+    if (freq != 8000 && freq != 16000 && freq != 32000) return -1;
+    memset(T, 0, sizeof *T);
+    const bool nb = freq == 8000;
+    const int ana = nb ? 128 : 256, ramp = nb ? 48 : 96, step = 1024 / ana;
+    const double pi = 3.14159265358979323846;
+    for (int m = 0; m < ana / 2; ++m) {
+        const int j = m * step;
+        const int16_t sn = (int16_t)(32767.0 * sin(2.0 * pi * j / 1024.0)), cs = (int16_t)(32767.0 * sin(2.0 * pi * (j + 256) / 1024.0));
+        T->twiddle[m] = ((uint32_t)(uint16_t)cs << 16) | (uint16_t)sn;
+    }
+    for (int i = 0; i < ana; ++i) {
+        const int k = i < ana - i ? i : ana - i;
+        T->window[i] = (int16_t)(k >= ramp ? 16384 : nearest_int(16384.0 * sin(pi * k / (2.0 * ramp))));
+    }
+    for (int i = 0; i < 256; ++i) T->log_frac[i] = (int16_t)nearest_int(256.0 * log2(1.0 + i / 256.0));
+    for (int i = 0; i < 201; ++i) {
+        const int v = nearest_int(32768.0 / (i + 1));
+        T->counter_div[i] = (int16_t)(v > 32767 ? 32767 : v);
+    }
+    for (int i = 1; i <= 128; ++i) T->log_index[i] = (int16_t)nearest_int(4096.0 * log2((double)i));
+    static const double floor_amp[4] = {0.5, 0.25, 0.125, 0.09};
+    for (int i = 0; i <= 256; ++i) {
+        const double g = sqrt(i / 256.0);
+        double f1 = 1.0, f2 = 1.0;
+        if (g > 0.5) {
+            f1 = 1.0 + 1.3 * (g - 0.5);
+            if (g * f1 > 1.0) f1 = 1.0 / g;
+        } else {
+            f2 = 1.0 - 0.3 * (0.5 - (g <= floor_amp[policy] ? floor_amp[policy] : g));
+        }
+        T->factor1[i] = (int16_t)(8192.0 * f1);
+        T->factor2[i] = (int16_t)(8192.0 * f2);   // policy 0 never reads it (gain_map = 0)
+    }
+    static const int16_t sigmoid[17] = {0, 2017, 3809, 5227, 6258, 6963, 7424, 7718, 7901, 8014, 8084, 8126, 8152, 8168, 8177, 8183, 8187};
+    memcpy(T->sigmoid, sigmoid, sizeof sigmoid);
+    for (int i = 0; i < 9; ++i) T->log_stage[i] = (int16_t)nearest_int(i * log(2.0) * 256.0);
+    // pink-noise fit over bins kStartBand .. 128, cut back to .. 64 for the narrow band (nsx_core.c:1364-1377)
+    auto sums = [](int from, int16_t* s5, int16_t* q2, int16_t* det) {
+        double s = 0.0, q = 0.0;
+        for (int j = from; j <= 128; ++j) {
+            const double l = log2((double)j);
+            s += l;
+            q += l * l;
+        }
+        *s5 = (int16_t)nearest_int(32.0 * s);
+        *q2 = (int16_t)nearest_int(4.0 * q);
+        *det = (int16_t)nearest_int((129 - from) * q - s * s);
+    };
+    int16_t s5, q2, det, s65, q65, d65;
+    sums(nsx::kStartBand, &s5, &q2, &det);
+    sums(65, &s65, &q65, &d65);
+    if (nb) {
+        int32_t t = det;
+        t += (s65 * s5) >> 9;
+        t -= (s65 * s65) >> 10;
+        t -= (int32_t)q2 << 4;
+        t -= ((65 - nsx::kStartBand) * q65) >> 2;
+        det = (int16_t)t;
+        s5 = (int16_t)(s5 - s65);
+        q2 = (int16_t)(q2 - q65);
+    }
+    T->fit_det = det;
+    T->fit_sum_log = s5;
+    T->fit_sum_sq = q2;
+    static const int over[4] = {256, 256, 282, 320}, bound[4] = {8192, 4096, 2048, 1475};   // nsx_core.c:786-814
+    T->overdrive = over[policy];
+    T->floor_gain = bound[policy];
+    T->gain_map = policy != 0;
+    T->lrt_max = nb ? 0x0040000 : 0x0080000;     // nsx_core.c:647-663
+    T->lrt_min = nb ? 52429 : 104858;
+    *thr_lrt = nb ? 131072 : 212644;
+    return 0;
 }
 
 }  // namespace host

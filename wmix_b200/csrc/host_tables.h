@@ -3,7 +3,13 @@
 #include <stdint.h>
 
 namespace wmx {
+namespace nsx {
+struct Tables;
+}
 namespace host {
+// fixed-point suppressor: every constant table of T:.../ns/nsx_core.c, nsx_core_c.c and the SPL twiddles, for one rate
+// (8000, or 16000 / 32000 which share the 256-point geometry) and policy 0..3; *thr_lrt = the initial LRT threshold
+int nsx_tables(int freq, int policy, nsx::Tables* T, int32_t* thr_lrt);
 void ns_window(int ana, int block, float* w);
 void fft_w_table(int nw, float* w);
 void fft_c_table(int nc, float* c);

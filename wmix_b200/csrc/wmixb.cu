@@ -31,6 +31,7 @@
 #include "host_tables.h"
 #include "ns.cuh"
 #include "ns_cta.cuh"
+#include "nsx.cuh"
 #include "peer_bus.cuh"
 #include "scratch.h"
 #include "vad.cuh"
@@ -278,6 +279,64 @@ ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Ta
             }
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// NSX kernel: the fixed-point suppressor (nsx.cuh), persistent grid, one self-contained warp per stream-frame.
+// All sums are warp reductions, so there is nothing to hand to a reducer warp: the CTA is just WARPS independent warps
+// sharing the constant tables; `align` starts the warps of a CTA together on every stream (instruction-cache sharing).
+// ------------------------------------------------------------------------------------------
+constexpr size_t kNsxTableWords = (sizeof(nsx::Tables) + 15) / 16 * 4;
+template <int ANA>
+constexpr size_t nsx_smem_bytes(int warps) { return (kNsxTableWords + (size_t)warps * ((nsx::Geo<ANA>::kShWords + 3) / 4 * 4)) * sizeof(uint32_t); }
+
+template <int ANA, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
+nsx_kernel(uint32_t* __restrict__ rec, int16_t* __restrict__ hist, const nsx::Tables* __restrict__ tables, const int16_t* in, int16_t* out,
+           int n_streams, int n_frames, int align)
+{
+    typedef nsx::Geo<ANA> G;
+    constexpr int kTile = (G::kShWords + 3) / 4 * 4;
+    extern __shared__ __align__(16) uint32_t smem_u[];
+    nsx::Tables* T = reinterpret_cast<nsx::Tables*>(smem_u);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        for (int i = threadIdx.x; i < (int)(sizeof(nsx::Tables) / 4); i += blockDim.x) smem_u[i] = src[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    uint32_t* tile = smem_u + kNsxTableWords + (size_t)warp * kTile;
+    nsx::Warp<ANA> W;
+    W.lane_id = threadIdx.x & 31;
+    const int total_warps = gridDim.x * WARPS;
+    const int iters = (n_streams - blockIdx.x * WARPS + total_warps - 1) / total_warps;   // of warp 0; >= every other warp's
+    for (int it = 0; it < iters; ++it) {
+        const int s = blockIdx.x * WARPS + warp + it * total_warps;
+        const bool live = s < n_streams;
+        uint32_t* r = rec + (size_t)s * G::kRecWords;
+        int16_t* h = hist + (size_t)s * 3 * nsx::kHistBins;
+        const int16_t* pi = in + (size_t)s * n_frames * G::kBlock;
+        int16_t* po = out + (size_t)s * n_frames * G::kBlock;
+        for (int f = 0; f < n_frames; ++f) {
+            if (align) __syncthreads();
+            if (!live) continue;
+            if (f == n_frames - 1 && W.lane_id == 0 && s + total_warps < n_streams) {
+                // pull the next stream's record and first frame towards L2 while this one computes
+                l2_prefetch(rec + (size_t)(s + total_warps) * G::kRecWords, G::kRecWords * sizeof(uint32_t));
+                l2_prefetch(in + (size_t)(s + total_warps) * n_frames * G::kBlock, G::kBlock * sizeof(int16_t));
+            }
+            nsx::frame<ANA>(W, r, h, pi + (size_t)f * G::kBlock, po + (size_t)f * G::kBlock, tile, *T);
+        }
+    }
+}
+
+template <int ANA>
+__global__ void nsx_init_kernel(uint32_t* rec, int16_t* hist, int first, int count, int32_t thr_lrt)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= count) return;
+    const int s = first + warp;
+    nsx::init_record<ANA>(rec + (size_t)s * nsx::Geo<ANA>::kRecWords, hist + (size_t)s * 3 * nsx::kHistBins, lane, 32, thr_lrt);
 }
 
 // wmix's stereo case (ns_init(2, ..)): the right channel rides through WebRtcNs as a "high band" (ns.cuh, frame<ANA, true>).
@@ -627,6 +686,10 @@ struct wmixb_engine {
     int16_t* ns_stage = nullptr;            // 4 x [n][frame] staging of wmixb_ns2_host
     uint16_t* ns_hist = nullptr;
     void* ns_tables = nullptr;
+    uint32_t* nsx_rec = nullptr;            // cfg.ns_core = 1: records of the fixed-point suppressor (nsx.cuh); ns_hist holds its histograms
+    void* nsx_tables = nullptr;
+    int32_t nsx_thr_lrt = 0;
+    int nsx_grid = 0, nsx_cfg = 0;
     int32_t* agc_words = nullptr;
     int32_t* vad_words = nullptr;
     int32_t* agc_table = nullptr;
@@ -662,6 +725,7 @@ struct wmixb_engine {
     size_t aec_rec_floats = 0;
 };
 
+static int nsx_rec_words(const wmixb_engine* e) { return e->ana == 256 ? nsx::Geo<256>::kRecWords : nsx::Geo<128>::kRecWords; }
 static int ns_rec_floats(const wmixb_engine* e) { return e->ana == 256 ? ns::Geo<256>::kRecFloats : ns::Geo<128>::kRecFloats; }
 
 // compiled shapes of the NS kernel; wmixb_set_tuning("ns_cfg", index) picks one (default 0).
@@ -751,6 +815,60 @@ static int upload_ns_tables(wmixb_engine* e)
     return ns_configure<ANA>(e);
 }
 
+// compiled shapes of the NSX kernel; wmixb_set_tuning("nsx_cfg", index) picks one
+struct NsxCfg { int warps, minb; };
+static const NsxCfg kNsxCfgs[] = {{8, 2}, {8, 3}, {8, 4}, {4, 6}, {16, 1}, {8, 1}};
+template <int ANA>
+static const void* nsx_fn(int cfg)
+{
+    switch (cfg) {
+    case 1: return (const void*)nsx_kernel<ANA, 8, 3>;
+    case 2: return (const void*)nsx_kernel<ANA, 8, 4>;
+    case 3: return (const void*)nsx_kernel<ANA, 4, 6>;
+    case 4: return (const void*)nsx_kernel<ANA, 16, 1>;
+    case 5: return (const void*)nsx_kernel<ANA, 8, 1>;
+    default: return (const void*)nsx_kernel<ANA, 8, 2>;
+    }
+}
+template <int ANA>
+static int nsx_configure(wmixb_engine* e)
+{
+    const void* fn = nsx_fn<ANA>(e->nsx_cfg);
+    const int threads = kNsxCfgs[e->nsx_cfg].warps * 32;
+    const size_t smem = nsx_smem_bytes<ANA>(kNsxCfgs[e->nsx_cfg].warps);
+    CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem));
+    if (per_sm < 1) per_sm = 1;
+    e->nsx_grid = e->sm_count * per_sm;
+    return WMIXB_OK;
+}
+template <int ANA>
+static int launch_nsx(wmixb_engine* e, cudaStream_t st, const int16_t* in, int16_t* out, int first, int n, int n_frames)
+{
+    uint32_t* rec = e->nsx_rec + (size_t)first * nsx::Geo<ANA>::kRecWords;
+    int16_t* hist = reinterpret_cast<int16_t*>(e->ns_hist) + (size_t)first * 3 * nsx::kHistBins;
+    const nsx::Tables* T = (const nsx::Tables*)e->nsx_tables;
+    int align = e->ns_align;
+    const int nw = kNsxCfgs[e->nsx_cfg].warps;
+    const int need = (n + nw - 1) / nw;
+    const int grid = need < e->nsx_grid ? need : e->nsx_grid;
+    void* args[] = {&rec, &hist, &T, &in, &out, &n, &n_frames, &align};
+    CK(cudaLaunchKernel(nsx_fn<ANA>(e->nsx_cfg), dim3(grid), dim3(nw * 32), args, nsx_smem_bytes<ANA>(nw), st));
+    return WMIXB_OK;
+}
+static int upload_nsx_tables(wmixb_engine* e)
+{
+    nsx::Tables T;
+    if (host::nsx_tables(e->cfg.freq, e->cfg.ns_policy, &T, &e->nsx_thr_lrt) != 0) {
+        snprintf(g_err, sizeof g_err, "ns_policy %d out of range 0..3", e->cfg.ns_policy);
+        return WMIXB_EINVAL;
+    }
+    CK(cudaMalloc(&e->nsx_tables, sizeof T));
+    CK(cudaMemcpy(e->nsx_tables, &T, sizeof T, cudaMemcpyHostToDevice));
+    return e->ana == 256 ? nsx_configure<256>(e) : nsx_configure<128>(e);
+}
+
 static int upload_agc_table(wmixb_engine* e, int gain_db)
 {
     int32_t tab[32];
@@ -778,6 +896,13 @@ extern "C" int wmixb_reset(wmixb_engine* e, int first, int count)
             CK(cudaMemsetAsync(e->ns_hb + (size_t)first * ov, 0, (size_t)count * ov * sizeof(float), e->stream));
         }
     }
+    if (e->nsx_rec) {
+        const int blocks = (count * 32 + 255) / 256;
+        int16_t* hist = reinterpret_cast<int16_t*>(e->ns_hist);
+        if (e->ana == 256) nsx_init_kernel<256><<<blocks, 256, 0, e->stream>>>(e->nsx_rec, hist, first, count, e->nsx_thr_lrt);
+        else nsx_init_kernel<128><<<blocks, 256, 0, e->stream>>>(e->nsx_rec, hist, first, count, e->nsx_thr_lrt);
+        CK_LAUNCH();
+    }
     if (e->aec_rec) {
         aec_init_kernel<<<(count * 32 + 255) / 256, 256, 0, e->stream>>>(e->aec_rec, e->aec_rec_floats, e->aec_depth, first, count);
         CK_LAUNCH();
@@ -799,7 +924,7 @@ extern "C" void wmixb_destroy(wmixb_engine* e)
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->ns_rec); cudaFree(e->ns_hist); cudaFree(e->ns_tables); cudaFree(e->ns_hb); cudaFree(e->ns_stage);
+    cudaFree(e->ns_rec); cudaFree(e->nsx_rec); cudaFree(e->nsx_tables); cudaFree(e->ns_hist); cudaFree(e->ns_tables); cudaFree(e->ns_hb); cudaFree(e->ns_stage);
     cudaFree(e->agc_words); cudaFree(e->vad_words); cudaFree(e->agc_table);
     cudaFree(e->agc_init); cudaFree(e->vad_init);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_out2); cudaFree(e->d_vad); cudaFree(e->d_pkt20);
@@ -832,7 +957,15 @@ static int create_impl(const wmixb_config* cfg, wmixb_engine* e)
     CK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
     const size_t n = (size_t)cfg->n_streams;
     e->stride = (n + 31) / 32 * 32;
-    if (cfg->stages & WMIXB_NS) {
+    if ((cfg->stages & WMIXB_NS) && cfg->ns_core == 1) {
+        // the fixed-point suppressor (R:src/webrtc.c:512, MAKE_WEBRTC_NSX)
+        if (cfg->ns_high_band) { snprintf(g_err, sizeof g_err, "ns_high_band is built for ns_core 0 (float) only"); return WMIXB_EINVAL; }
+        const size_t words = e->ana == 256 ? nsx::Geo<256>::kRecWords : nsx::Geo<128>::kRecWords;
+        CK(cudaMalloc(&e->nsx_rec, n * words * sizeof(uint32_t)));
+        CK(cudaMalloc(&e->ns_hist, n * 3 * nsx::kHistBins * sizeof(uint16_t)));
+        int rc = upload_nsx_tables(e);
+        if (rc) return rc;
+    } else if (cfg->stages & WMIXB_NS) {
         CK(cudaMalloc(&e->ns_rec, n * ns_rec_floats(e) * sizeof(float)));
         CK(cudaMalloc(&e->ns_hist, n * 3 * ns::kHistBins * sizeof(uint16_t)));
         int rc = e->ana == 256 ? upload_ns_tables<256>(e) : upload_ns_tables<128>(e);
@@ -908,6 +1041,7 @@ extern "C" int wmixb_create(const wmixb_config* cfg, wmixb_engine** out)
     // the batched engine covers the two rates BASELINE.json's configs use
     if (cfg->freq != 8000 && cfg->freq != 16000) { snprintf(g_err, sizeof g_err, "freq %d: batched engine supports 8000 and 16000", cfg->freq); return WMIXB_EINVAL; }
     if ((cfg->stages & ~(WMIXB_NS | WMIXB_AGC | WMIXB_VAD | WMIXB_AEC)) != 0) { snprintf(g_err, sizeof g_err, "unknown stage bits"); return WMIXB_EINVAL; }
+    if (cfg->ns_core != 0 && cfg->ns_core != 1) { snprintf(g_err, sizeof g_err, "ns_core %d: 0 = float core, 1 = fixed-point core", cfg->ns_core); return WMIXB_EINVAL; }
     wmixb_engine* e = new (std::nothrow) wmixb_engine();
     if (!e) return WMIXB_ENOMEM;
     e->cfg = *cfg;
@@ -949,7 +1083,12 @@ static int run_stages(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint
     if (stages & ~e->cfg.stages) { snprintf(g_err, sizeof g_err, "stage mask 0x%x not configured (engine has 0x%x)", stages, e->cfg.stages); return WMIXB_EINVAL; }
     if (n < 0) n = e->cfg.n_streams - first;
     const int16_t* cur = d_in;
-    if (stages & WMIXB_NS) {
+    if ((stages & WMIXB_NS) && e->nsx_rec) {
+        const int rc = e->ana == 256 ? launch_nsx<256>(e, st, cur, d_out, first, n, n_frames) : launch_nsx<128>(e, st, cur, d_out, first, n, n_frames);
+        if (rc) return rc;
+        CK_LAUNCH();
+        cur = d_out;
+    } else if (stages & WMIXB_NS) {
         const int nw = kNsCfgs[e->ns_cfg].warps;
         const int need = (n + nw - 1) / nw;
         const int grid = need < e->ns_grid ? need : e->ns_grid;
@@ -1932,6 +2071,7 @@ extern "C" size_t wmixb_stream_state_bytes(const wmixb_engine* e)
     if (!e) return 0;
     size_t b = 0;
     if (e->ns_rec) b += (size_t)ns_rec_floats(e) * 4 + 3 * ns::kHistBins * 2;
+    if (e->nsx_rec) b += (size_t)nsx_rec_words(e) * 4 + 3 * nsx::kHistBins * 2;
     if (e->ns_hb) b += (size_t)(e->ana - e->frame) * 4;
     if (e->agc_words) b += agc::N_WORDS * 4;
     if (e->vad_words) b += vad::N_WORDS * 4;
@@ -1961,6 +2101,10 @@ static int state_xfer(wmixb_engine* e, int s, void* buf, bool get)
         CK(xfer(e->ns_rec + (size_t)s * ns_rec_floats(e), (size_t)ns_rec_floats(e) * 4));
         CK(xfer(e->ns_hist + (size_t)s * 3 * ns::kHistBins, 3 * ns::kHistBins * 2));
         if (e->ns_hb) CK(xfer(e->ns_hb + (size_t)s * (e->ana - e->frame), (size_t)(e->ana - e->frame) * 4));
+    }
+    if (e->nsx_rec) {
+        CK(xfer(e->nsx_rec + (size_t)s * nsx_rec_words(e), (size_t)nsx_rec_words(e) * 4));
+        CK(xfer(e->ns_hist + (size_t)s * 3 * nsx::kHistBins, 3 * nsx::kHistBins * 2));
     }
     if (e->agc_words) CK(xfer2d(e->agc_words, agc::N_WORDS));
     if (e->vad_words) CK(xfer2d(e->vad_words, vad::N_WORDS));
@@ -2196,6 +2340,11 @@ extern "C" int wmixb_set_tuning(wmixb_engine* e, const char* key, int value)
         if (value < 0 || value >= (int)(sizeof kNsCfgs / sizeof kNsCfgs[0]) || !e->ns_rec) return WMIXB_EINVAL;
         e->ns_cfg = value;
         return e->ana == 256 ? ns_configure<256>(e) : ns_configure<128>(e);
+    }
+    if (!strcmp(key, "nsx_cfg")) {
+        if (value < 0 || value >= (int)(sizeof kNsxCfgs / sizeof kNsxCfgs[0]) || !e->nsx_rec) return WMIXB_EINVAL;
+        e->nsx_cfg = value;
+        return e->ana == 256 ? nsx_configure<256>(e) : nsx_configure<128>(e);
     }
     if (!strcmp(key, "ns_offline_staged")) { e->ns_offline_staged = value != 0; return WMIXB_OK; }
     if (!strcmp(key, "ns_align")) { if (value < 0 || value > 64) return WMIXB_EINVAL; e->ns_align = value; return WMIXB_OK; }

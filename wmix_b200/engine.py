@@ -29,10 +29,11 @@ class Engine:
     """N independent mono streams of wmix's record chain NS -> AGC -> VAD on one GPU."""
 
     def __init__(self, n_streams, freq=16000, stages=NS | AGC | VAD, ns_policy=2, agc_gain_db=5, vad_mode=3, device=0,
-                 aec_far_depth=0, ns_high_band=0):
+                 aec_far_depth=0, ns_high_band=0, ns_core=0):
         self.L = lib()
         cfg = Config(n_streams=n_streams, freq=freq, stages=stages, ns_policy=ns_policy, agc_gain_db=agc_gain_db,
-                     vad_mode=vad_mode, device=device, aec_far_depth=aec_far_depth, ns_high_band=ns_high_band)
+                     vad_mode=vad_mode, device=device, aec_far_depth=aec_far_depth, ns_high_band=ns_high_band,
+                     ns_core=ns_core)
         h = C.c_void_p()
         check(self.L.wmixb_create(C.byref(cfg), C.byref(h)), "wmixb_create")
         self.h, self.n, self.freq, self.frame, self.stages, self.device = h, n_streams, freq, freq // 100, stages, device
