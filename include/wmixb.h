@@ -261,6 +261,11 @@ int wmixb_host_copy_ceiling(int device, const void* h_src, void* h_dst, size_t h
  * wmix_pcm_zoom, wmix_load_data); default 0 */
 int wmixb_set_default_device(int device);
 int wmixb_default_device(void);
+/* suppressor behind the drop-in ns_init / ns_process: 0 = WebRtcNs_* float core (default, what wmix ships), 1 = WebRtcNsx_*
+ * fixed-point core.  The reference makes this choice at compile time (`#define MAKE_WEBRTC_NSX`, R:src/webrtc.c:511-523);
+ * building this library with -DMAKE_WEBRTC_NSX makes 1 the default.  Applies to handles created afterwards. */
+int wmixb_set_default_ns_core(int ns_core);
+int wmixb_default_ns_core(void);
 
 /* experiment / test knobs; none changes results.  keys: "ns_cfg", "nsx_cfg", "ns_align", "post_occ", "aec_pf", "aec_grid",
  * "host_chunks", "host_lanes" */

@@ -299,6 +299,18 @@ void emu_nsx_frame(void* h, const int16_t* in, int16_t* out)
     if (e->ana == 256) nsx::frame<256>(e->w256, e->rec.data(), e->hist.data(), in, out, e->tile.data(), e->T);
     else nsx::frame<128>(e->w128, e->rec.data(), e->hist.data(), in, out, e->tile.data(), e->T);
 }
+// two bands (wmix's stereo): hb = the second band's delay line, int16 [kKeep], owned by the caller
+void emu_nsx_frame_hb(void* h, const int16_t* in, int16_t* out, int16_t* hb, const int16_t* in_hb, int16_t* out_hb)
+{
+    EmuNsx* e = (EmuNsx*)h;
+    if (e->ana == 256) {
+        const int g = nsx::frame<256, true>(e->w256, e->rec.data(), e->hist.data(), in, out, e->tile.data(), e->T);
+        nsx::second_band<256>(e->w256, hb, in_hb, out_hb, g);
+    } else {
+        const int g = nsx::frame<128, true>(e->w128, e->rec.data(), e->hist.data(), in, out, e->tile.data(), e->T);
+        nsx::second_band<128>(e->w128, hb, in_hb, out_hb, g);
+    }
+}
 void emu_nsx_destroy(void* h) { delete (EmuNsx*)h; }
 const uint32_t* emu_nsx_record(void* h) { return ((EmuNsx*)h)->rec.data(); }
 const int16_t* emu_nsx_hist(void* h) { return ((EmuNsx*)h)->hist.data(); }

@@ -155,3 +155,48 @@ def test_nsx_full_size_replication_property():
         assert bool((y == y[0:1]).all())
         assert np.array_equal(y[0].cpu().numpy(), small[t])
     eng.close()
+
+
+@pytest.mark.parametrize("freq", [8000, 16000, 32000])
+@pytest.mark.parametrize("chn", [1, 2])
+def test_nsx_dropin_handles_with_the_switch_thrown(chn, freq):
+    """ns_init / ns_process after wmixb_set_default_ns_core(1) — the reference's `#define MAKE_WEBRTC_NSX` — against the
+    outputs of the reference built with that define (tests/golden/nsx.json), the oracle, and the reference itself when it
+    is here: mono and stereo (right channel as the second band), 8 / 16 / 32 kHz (320-sample packets)."""
+    from tests._oracle import nsx_handle_run, ref_nsx
+    lib = wmix_b200.lib()
+    d = G["handle"]["%d_%d" % (chn, freq)]
+    x = make_frames(chn, freq, 0, d["n_ticks"], seed=d["seed"])
+    pcm = np.ascontiguousarray(x.transpose(0, 2, 1).reshape(d["n_ticks"], -1))
+    assert lib.wmixb_set_default_ns_core(1) == 0 and lib.wmixb_default_ns_core() == 1
+    try:
+        got = nsx_handle_run(lib, "", chn, freq, pcm)
+    finally:
+        assert lib.wmixb_set_default_ns_core(0) == 0
+    check(d, got)
+    assert np.array_equal(got, nsx_handle_run(oracle(), "orc_nsx", chn, freq, pcm))
+    if ref_nsx() is not None:
+        assert np.array_equal(got, nsx_handle_run(ref_nsx(), "", chn, freq, pcm))
+    assert lib.wmixb_set_default_ns_core(2) != 0                      # only 0 and 1 exist
+
+
+@pytest.mark.parametrize("freq", [16000, 8000])
+def test_nsx_second_band_batched(freq):
+    """wmixb_ns2_device on an engine with ns_core = 1 and ns_high_band = 1 against the reference's two-band fixtures"""
+    d = G["core"]["stereo_%d" % freq]
+    lo = make_frames(4, freq, 0, 1100, seed=d["seed"])
+    hi = make_frames(4, freq, 0, 1100, seed=d["seed_hb"])
+    L = freq // 100
+    eng = wmix_b200.Engine(4, freq, stages=NS, ns_core=1, ns_high_band=1)
+    a = torch.empty((4, L), dtype=torch.int16, device=DEV)
+    b = torch.empty((4, L), dtype=torch.int16, device=DEV)
+    out_lo, out_hi = np.empty_like(lo), np.empty_like(hi)
+    st = torch.cuda.current_stream().cuda_stream
+    for t in range(1100):
+        a.copy_(torch.from_numpy(lo[t]))
+        b.copy_(torch.from_numpy(hi[t]))
+        assert eng.L.wmixb_ns2_device(eng.h, a.data_ptr(), b.data_ptr(), a.data_ptr(), b.data_ptr(), st) == 0     # in place
+        out_lo[t], out_hi[t] = a.cpu().numpy(), b.cpu().numpy()
+    eng.close()
+    check(d["lo"], out_lo)
+    check(d["hi"], out_hi)

@@ -126,3 +126,28 @@ def test_nsx_host_tables_match_the_reference_literals():
             m = np.arange(n_win // 2)
             want = ((sine[m * step + 256] & 0xFFFF) << 16) | (sine[m * step] & 0xFFFF)
             assert np.array_equal(tw[:n_win // 2].astype(np.int64), want)
+
+
+@pytest.mark.parametrize("freq", [16000, 8000])
+def test_nsx_kernel_body_second_band(freq):
+    """frame<ANA, true> + second_band (wmix's stereo: the right channel as WebRtcNsx's second band) against the oracle's
+    two-band handle, zero-input frames included"""
+    O, E = _libs()
+    n, keep = freq // 100, {16000: 96, 8000: 48}[freq]
+    lo = make_frames(3, freq, 0, 600, seed=5)
+    hi = make_frames(3, freq, 0, 600, seed=6)
+    lo[100:130] = 0
+    for s in range(3):
+        o = C.c_void_p(O.orc_nsx_init_policy(2, freq, 2))
+        e = C.c_void_p(E.emu_nsx_create(freq, 2))
+        hb = np.zeros(keep, np.int16)
+        for t in range(600):
+            x = np.stack([lo[t, s], hi[t, s]], axis=1).reshape(-1).copy()
+            y = np.zeros(2 * n, np.int16)
+            O.orc_nsx_process(o, P(x), P(y), n)
+            a = np.zeros(n, np.int16)
+            b = np.zeros(n, np.int16)
+            E.emu_nsx_frame_hb(e, P(lo[t, s].copy()), P(a), P(hb), P(hi[t, s].copy()), P(b))
+            assert np.array_equal(a, y[0::2]) and np.array_equal(b, y[1::2]), (freq, s, t)
+        O.orc_nsx_release(o)
+        E.emu_nsx_destroy(e)

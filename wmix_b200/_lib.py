@@ -102,6 +102,8 @@ def lib():
         "wmixb_set_tuning": (i, [vp, C.c_char_p, i]),
         "wmixb_set_default_device": (i, [i]),
         "wmixb_default_device": (i, []),
+        "wmixb_set_default_ns_core": (i, [i]),
+        "wmixb_default_ns_core": (i, []),
         "wmixb_host_alloc": (vp, [sz, i, i]),
         "wmixb_host_free": (None, [vp]),
         "wmixb_host_copy_ceiling": (i, [i, vp, vp, sz, sz, i, C.POINTER(C.c_double)]),

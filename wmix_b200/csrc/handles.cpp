@@ -44,6 +44,7 @@ Handle* make(int stage, int chn, int freq, int gain, bool* debug, const char* wh
     c.agc_gain_db = gain; // compressionGaindB, R:src/webrtc.c:707
     c.vad_mode = 3;       // VAD_AGGRESSIVE, R:src/webrtc.c:16
     c.ns_high_band = ns_high_band ? 1 : 0;
+    c.ns_core = (stage & WMIXB_NS) ? wmixb_default_ns_core() : 0;   // the reference's MAKE_WEBRTC_NSX switch, R:src/webrtc.c:511-523
     c.device = wmixb_default_device();
     wmixb_engine* e = nullptr;
     if (wmixb_create(&c, &e) != WMIXB_OK) {

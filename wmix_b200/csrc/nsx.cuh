@@ -132,6 +132,30 @@ WMX_HD int32_t c_re(uint32_t w) { return (int32_t)(int16_t)(w & 0xFFFFu); }
 WMX_HD int32_t c_im(uint32_t w) { return (int32_t)w >> 16; }
 WMX_HD uint32_t c_pack(int32_t re, int32_t im) { return ((uint32_t)im << 16) | ((uint32_t)re & 0xFFFFu); }
 
+// per-halfword signed max / min of three packed int16 pairs (one VIMNMX3.S16x2 on the device)
+WMX_HD uint32_t max3_s16x2(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __vimax3_s16x2(a, b, c);
+#else
+    int32_t r = c_re(a), i = c_im(a);
+    r = c_re(b) > r ? c_re(b) : r; r = c_re(c) > r ? c_re(c) : r;
+    i = c_im(b) > i ? c_im(b) : i; i = c_im(c) > i ? c_im(c) : i;
+    return c_pack(r, i);
+#endif
+}
+WMX_HD uint32_t min3_s16x2(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    return __vimin3_s16x2(a, b, c);
+#else
+    int32_t r = c_re(a), i = c_im(a);
+    r = c_re(b) < r ? c_re(b) : r; r = c_re(c) < r ? c_re(c) : r;
+    i = c_im(b) < i ? c_im(b) : i; i = c_im(c) < i ? c_im(c) : i;
+    return c_pack(r, i);
+#endif
+}
+
 // position of FFT point p in the exchange tile: the bits above the bank index are folded into the bank bits so that every
 // register-group layout (lanes spanning any five of p's bits) hits 32 different banks
 template <int ANA>
@@ -231,6 +255,26 @@ WMX_HD int32_t warp_min_s(Warp<ANA>& W)
 #endif
 }
 
+// histogram bin += 1 (counts stay below 512: no carry into the neighbouring half-word).  On the device a fire-and-forget
+// RED on the containing 32-bit word: nothing waits for the histogram line to arrive
+WMX_HD void hist_inc(int16_t* h, uint32_t idx)
+{
+#if defined(__CUDA_ARCH__)
+    atomicAdd(reinterpret_cast<unsigned int*>(h) + (idx >> 1), (idx & 1) ? 0x10000u : 1u);
+#else
+    h[idx]++;
+#endif
+}
+// pull the stream's record towards L1 ahead of the phases that walk it (one 128-byte line per lane and call)
+WMX_HD void l1_prefetch(const void* p)
+{
+#if defined(__CUDA_ARCH__)
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+
 // state word of bin slot k of array a
 template <int ANA>
 WMX_HD uint32_t* bin_word(uint32_t* rec, int a, int k, int lane)
@@ -264,22 +308,25 @@ WMX_HD int fft_run(Warp<ANA>& W, uint32_t* tile, const Tables& T)
         for (int s = g * RB; s < s_end; ++s) {
             int shift = 1, round2 = 16384;
             if (INV) {
-                // complex_fft.c:170-187: scale a pass down by one or two bits when the data is large
+                // complex_fft.c:170-187: scale a pass down by one or two bits when the data is large.  max|x| over all
+                // points from the per-halfword signed max and min of the packed pairs (|-32768| caps at 32767 there too)
                 WMX_NSX_PHASE_BEGIN
-                int32_t m = 0;
+                uint32_t mx = R.x[0], mn = R.x[0];
 #pragma unroll
-                for (int r = 0; r < NR; ++r) {
-                    const int32_t ar = iabs(c_re(R.x[r])), ai = iabs(c_im(R.x[r]));
-                    m = ar > m ? ar : m;
-                    m = ai > m ? ai : m;
+                for (int r = 1; r + 1 < NR; r += 2) {
+                    mx = max3_s16x2(mx, R.x[r], R.x[r + 1]);
+                    mn = min3_s16x2(mn, R.x[r], R.x[r + 1]);
                 }
-                R.a[0] = (uint32_t)m;
+                mx = max3_s16x2(mx, R.x[NR - 1], R.x[NR - 1]);
+                mn = min3_s16x2(mn, R.x[NR - 1], R.x[NR - 1]);
+                const int32_t hi = c_re(mx) > c_im(mx) ? c_re(mx) : c_im(mx), lo = c_re(mn) < c_im(mn) ? c_re(mn) : c_im(mn);
+                R.a[0] = (uint32_t)(hi > -lo ? hi : -lo);
                 WMX_NSX_PHASE_END
                 const uint32_t peak = umin(warp_max_u<0>(W), 32767u);
-                shift = 0;
-                round2 = 8192;
-                if (peak > 13573u) { ++shift; ++scale; round2 <<= 1; }
-                if (peak > 27146u) { ++shift; ++scale; round2 <<= 1; }
+                // as arithmetic on the two comparisons, not as branches: one copy of the pass for all three scalings
+                shift = (int)(peak > 13573u) + (int)(peak > 27146u);
+                round2 = 8192 << shift;
+                scale += shift;
             }
             WMX_NSX_PHASE_BEGIN
             const int ll = g == 0 ? rev_bits(lane, 5) : lane;   // the first layout is indexed by the bit-reversed lane
@@ -410,8 +457,10 @@ WMX_HD void synth_read_out_only(Warp<ANA>& W, uint32_t* rec, int16_t* out)
 // one frame of one stream.  rec: the stream's record; hist: int16 [3][1000] (LRT, flatness, difference);
 // in / out: kBlock samples, may alias; tile: Geo::kShWords words of shared memory owned by this warp.
 // ------------------------------------------------------------------------------------------
-template <int ANA>
-WMX_HD void frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, int16_t* out, uint32_t* tile, const Tables& T)
+// HB: also returns the time-domain gain (Q14) of wmix's second band for this frame (nsx_core.c:2054-2107), or -1 when the
+// frame was all zeros and the second band passes unscaled (:1577-1592); 0 otherwise.
+template <int ANA, bool HB = false>
+WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, int16_t* out, uint32_t* tile, const Tables& T)
 {
     typedef Geo<ANA> G;
     constexpr int K = G::kK, NR = G::kR, ST = G::kStages, HALF = G::kHalf;
@@ -422,6 +471,9 @@ WMX_HD void frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in,
 
     // ---- analysis buffer, window, peak (nsx_core.c:524-541, :1221-1227) ----
     WMX_NSX_PHASE_BEGIN
+    // the record (the start-up array only while it is in use) is wanted in L1 by the time the transform is done
+    for (int line = lane; line < (sc[S_FRAME_IDX] < kStartupShort ? G::kOffHist : (int)A_INIT * HALF) / 32; line += 32) l1_prefetch(rec + 32 * line);
+    if (lane < (G::kOffHist - G::kOffNyq) / 32) l1_prefetch(rec + G::kOffNyq + 32 * lane);
     int32_t peak = 0, smax = -1;
 #pragma unroll
     for (int r = 0; r < NR; ++r) {
@@ -463,7 +515,7 @@ WMX_HD void frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in,
     if (peak == 0) {
         // zero input: only the buffers move (nsx_core.c:1228-1232, :1574-1594)
         synth_read_out_only<ANA>(W, rec, out);
-        return;
+        return -1;
     }
 
     int frame_idx = sc[S_FRAME_IDX];
@@ -629,16 +681,13 @@ WMX_HD void frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in,
                 uint32_t* wp = bin_word<ANA>(rec, A_LQD0 + e, k, lane);
                 const uint32_t w = *wp;
                 int lq = lo16((int32_t)w), dn = hi16((int32_t)w);
-                int delta;
-                if (dn > 512) delta = (int16_t)(2621440 >> (14 - norm_w16(dn)));
-                else delta = frame_idx < kStartupLong ? 1024 : 5120;
-                int step = (int16_t)((delta * cdiv) >> 14);
+                // delta = FACTOR_Q16 >> (14 - NormW16(density)): for density > 512 that is 40 << 16 >> floor(log2(density))
+                const uint32_t delta = dn > 512 ? 2621440u >> (31 - clz32((uint32_t)dn)) : (frame_idx < kStartupLong ? 1024u : 5120u);
+                const uint32_t step = (delta * (uint32_t)cdiv) >> 14;   // positive, < 2^15: the reference's int16 casts and signed divisions are plain shifts
                 if (lmagn > lq) {
-                    step = (int16_t)(step + 2);
-                    lq = (int16_t)(lq + step / 4);
+                    lq = (int16_t)(lq + (int)((step + 2) >> 2));
                 } else {
-                    step = (int16_t)(step + 1);
-                    lq = (int16_t)(lq - (int16_t)((step / 2) * 3 / 2));
+                    lq = (int16_t)(lq - (int)((((step + 1) >> 1) * 3) >> 1));
                     if (lq < logval) lq = logval;
                 }
                 if (iabs(lmagn - lq) < 3) dn = (int16_t)((int16_t)mul_round(dn, cprod, 15) + (int16_t)mul_round(21845, cdiv, 15));
@@ -835,12 +884,12 @@ WMX_HD void frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in,
         WMX_NSX_PHASE_BEGIN
         if (lane == 0) {
             uint32_t idx = (uint32_t)feat_lrt;
-            if (idx < (uint32_t)kHistBins) h_lrt[idx]++;
+            if (idx < (uint32_t)kHistBins) hist_inc(h_lrt, idx);
             idx = (feat_flat * 5u) >> 8;
-            if (idx < (uint32_t)kHistBins) h_flat[idx]++;
+            if (idx < (uint32_t)kHistBins) hist_inc(h_flat, idx);
             idx = kHistBins;
             if (time_avg_e > 0) idx = ((feat_diff * 5u) >> ST) / time_avg_e;
-            if (idx < (uint32_t)kHistBins) h_diff[idx]++;
+            if (idx < (uint32_t)kHistBins) hist_inc(h_diff, idx);
         }
         WMX_NSX_PHASE_END
     } else {
@@ -1113,8 +1162,25 @@ WMX_HD void frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in,
         const int32_t re = (int16_t)((c_re(R.spec[k]) * (int32_t)(int16_t)filt) >> 14);
         const int32_t im = (int16_t)((c_im(R.spec[k]) * (int32_t)(int16_t)filt) >> 14);
         tbins[k < K ? 32 * k + lane : HALF] = c_pack(re, (int16_t)-im);
+        if (HB) {
+            // the second band's gain averages speech probability and filter over the upper quarter of the low band
+            const int bin = k < K ? 32 * k + lane : HALF;
+            if (k == 0) { R.a[0] = 0; R.a[1] = 0; }
+            if (bin >= HALF - (HALF >> 2) && bin < HALF) { R.a[0] += R.nonsp[k]; R.a[1] += filt; }
+        }
     }
     WMX_NSX_PHASE_END
+    int hb_gain = 0;
+    if (HB) {
+        const uint32_t sum_prob = warp_add<0>(W) & 0xFFFFu, sum_filter = warp_add<1>(W);
+        const int avg_prob = (int16_t)(4096 - (int)(sum_prob >> (ST - 7)));
+        const int avg_filter = (int16_t)(sum_filter >> (ST - 3));
+        const int gain_mod = avg_prob < 3607 ? avg_prob : 3607;
+        int g;
+        if (avg_prob < 2048) g = (int16_t)((gain_mod << 1) + (avg_filter >> 1));
+        else g = (int16_t)((int16_t)((3 * avg_filter) >> 2) + gain_mod);
+        hb_gain = g > 16384 ? 16384 : (g < (int16_t)T.floor_gain ? (int16_t)T.floor_gain : g);
+    }
 
     // ---- scalars of the model are final: store them (lane 0) ----
     WMX_NSX_PHASE_BEGIN
@@ -1202,6 +1268,36 @@ WMX_HD void frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in,
         const int i = lane + 32 * r;
         if (i < G::kBlock) out[i] = (int16_t)R.x[r];
         else syn16[i - G::kBlock] = (int16_t)R.x[r];
+    }
+    WMX_NSX_PHASE_END
+    return hb_gain;
+}
+
+// wmix's stereo case: the right channel rides along as a second band — delayed by the analysis overlap (dataBufHBFX,
+// nsx_core.c:2045-2053) and scaled by the frame's gain (:2111-2116); gain < 0 = unscaled (zero-input frame).
+// hb: int16 [kKeep] history of the band; in_hb / out_hb: kBlock samples, may alias.
+template <int ANA>
+WMX_HD void second_band(Warp<ANA>& W, int16_t* hb, const int16_t* in_hb, int16_t* out_hb, int gain)
+{
+    typedef Geo<ANA> G;
+    // the delay line holds the last kKeep samples: output sample i is hb[i] while i < kKeep, else in_hb[i - kKeep]
+    WMX_NSX_PHASE_BEGIN
+#pragma unroll
+    for (int r = 0; r < G::kR; ++r) {
+        const int i = lane + 32 * r;
+        int32_t v = 0;
+        if (i < G::kBlock) v = i < G::kKeep ? hb[i] : in_hb[i - G::kKeep];
+        else if (i < G::kBlock + G::kKeep) v = in_hb[i - G::kKeep];          // becomes the new history
+        R.x[r] = (uint32_t)v;
+    }
+    WMX_NSX_PHASE_END
+    WMX_NSX_PHASE_BEGIN
+#pragma unroll
+    for (int r = 0; r < G::kR; ++r) {
+        const int i = lane + 32 * r;
+        const int32_t v = (int32_t)R.x[r];
+        if (i < G::kBlock) out_hb[i] = gain < 0 ? (int16_t)v : (int16_t)((gain * v) >> 14);
+        else if (i < G::kBlock + G::kKeep) hb[i - G::kBlock] = (int16_t)v;
     }
     WMX_NSX_PHASE_END
 }

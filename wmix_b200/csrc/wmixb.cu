@@ -330,6 +330,33 @@ nsx_kernel(uint32_t* __restrict__ rec, int16_t* __restrict__ hist, const nsx::Ta
     }
 }
 
+// wmix's stereo case with the fixed-point core: the right channel as WebRtcNsx's second band (nsx.cuh, frame<ANA, true> +
+// second_band).  One frame per launch; the drop-in handle's path, kept apart so the mono kernel is untouched.
+template <int ANA>
+__global__ void __launch_bounds__(256, 2)
+nsx_hb_kernel(uint32_t* __restrict__ rec, int16_t* __restrict__ hist, int16_t* __restrict__ hb, const nsx::Tables* __restrict__ tables,
+              const int16_t* in, int16_t* out, const int16_t* in_hb, int16_t* out_hb, int n_streams)
+{
+    typedef nsx::Geo<ANA> G;
+    constexpr int kTile = (G::kShWords + 3) / 4 * 4;
+    extern __shared__ __align__(16) uint32_t smem_u[];
+    nsx::Tables* T = reinterpret_cast<nsx::Tables*>(smem_u);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(tables);
+        for (int i = threadIdx.x; i < (int)(sizeof(nsx::Tables) / 4); i += blockDim.x) smem_u[i] = src[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5;
+    uint32_t* tile = smem_u + kNsxTableWords + (size_t)warp * kTile;
+    nsx::Warp<ANA> W;
+    W.lane_id = threadIdx.x & 31;
+    for (int s = blockIdx.x * 8 + warp; s < n_streams; s += gridDim.x * 8) {
+        const int gain = nsx::frame<ANA, true>(W, rec + (size_t)s * G::kRecWords, hist + (size_t)s * 3 * nsx::kHistBins, in + (size_t)s * G::kBlock,
+                                               out + (size_t)s * G::kBlock, tile, *T);
+        nsx::second_band<ANA>(W, hb + (size_t)s * G::kKeep, in_hb + (size_t)s * G::kBlock, out_hb + (size_t)s * G::kBlock, gain);
+    }
+}
+
 template <int ANA>
 __global__ void nsx_init_kernel(uint32_t* rec, int16_t* hist, int first, int count, int32_t thr_lrt)
 {
@@ -688,6 +715,7 @@ struct wmixb_engine {
     void* ns_tables = nullptr;
     uint32_t* nsx_rec = nullptr;            // cfg.ns_core = 1: records of the fixed-point suppressor (nsx.cuh); ns_hist holds its histograms
     void* nsx_tables = nullptr;
+    int16_t* nsx_hb = nullptr;              // [n][kKeep] second-band history (cfg.ns_high_band with ns_core = 1)
     int32_t nsx_thr_lrt = 0;
     int nsx_grid = 0, nsx_cfg = 0;
     int32_t* agc_words = nullptr;
@@ -902,6 +930,7 @@ extern "C" int wmixb_reset(wmixb_engine* e, int first, int count)
         if (e->ana == 256) nsx_init_kernel<256><<<blocks, 256, 0, e->stream>>>(e->nsx_rec, hist, first, count, e->nsx_thr_lrt);
         else nsx_init_kernel<128><<<blocks, 256, 0, e->stream>>>(e->nsx_rec, hist, first, count, e->nsx_thr_lrt);
         CK_LAUNCH();
+        if (e->nsx_hb) CK(cudaMemsetAsync(e->nsx_hb + (size_t)first * (e->ana - e->frame), 0, (size_t)count * (e->ana - e->frame) * sizeof(int16_t), e->stream));
     }
     if (e->aec_rec) {
         aec_init_kernel<<<(count * 32 + 255) / 256, 256, 0, e->stream>>>(e->aec_rec, e->aec_rec_floats, e->aec_depth, first, count);
@@ -924,7 +953,7 @@ extern "C" void wmixb_destroy(wmixb_engine* e)
     if (!e) return;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    cudaFree(e->ns_rec); cudaFree(e->nsx_rec); cudaFree(e->nsx_tables); cudaFree(e->ns_hist); cudaFree(e->ns_tables); cudaFree(e->ns_hb); cudaFree(e->ns_stage);
+    cudaFree(e->ns_rec); cudaFree(e->nsx_rec); cudaFree(e->nsx_tables); cudaFree(e->nsx_hb); cudaFree(e->ns_hist); cudaFree(e->ns_tables); cudaFree(e->ns_hb); cudaFree(e->ns_stage);
     cudaFree(e->agc_words); cudaFree(e->vad_words); cudaFree(e->agc_table);
     cudaFree(e->agc_init); cudaFree(e->vad_init);
     cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_out2); cudaFree(e->d_vad); cudaFree(e->d_pkt20);
@@ -959,8 +988,12 @@ static int create_impl(const wmixb_config* cfg, wmixb_engine* e)
     e->stride = (n + 31) / 32 * 32;
     if ((cfg->stages & WMIXB_NS) && cfg->ns_core == 1) {
         // the fixed-point suppressor (R:src/webrtc.c:512, MAKE_WEBRTC_NSX)
-        if (cfg->ns_high_band) { snprintf(g_err, sizeof g_err, "ns_high_band is built for ns_core 0 (float) only"); return WMIXB_EINVAL; }
         const size_t words = e->ana == 256 ? nsx::Geo<256>::kRecWords : nsx::Geo<128>::kRecWords;
+        if (cfg->ns_high_band) {
+            CK(cudaMalloc(&e->nsx_hb, n * (size_t)(e->ana - e->frame) * sizeof(int16_t)));
+            if (e->ana == 256) CK(cudaFuncSetAttribute(nsx_hb_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsx_smem_bytes<256>(8)));
+            else CK(cudaFuncSetAttribute(nsx_hb_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)nsx_smem_bytes<128>(8)));
+        }
         CK(cudaMalloc(&e->nsx_rec, n * words * sizeof(uint32_t)));
         CK(cudaMalloc(&e->ns_hist, n * 3 * nsx::kHistBins * sizeof(uint16_t)));
         int rc = upload_nsx_tables(e);
@@ -1162,10 +1195,18 @@ extern "C" int wmixb_vad20_host(wmixb_engine* e, int16_t* h_pcm, uint8_t* h_vad)
 extern "C" int wmixb_ns2_device(wmixb_engine* e, const int16_t* d_in, const int16_t* d_in_hb, int16_t* d_out, int16_t* d_out_hb, void* stream)
 {
     if (!e || !d_in || !d_in_hb || !d_out || !d_out_hb) return WMIXB_EINVAL;
-    if (!e->ns_hb) { snprintf(g_err, sizeof g_err, "ns2: the engine was created without WMIXB_NS + ns_high_band"); return WMIXB_EINVAL; }
+    if (!e->ns_hb && !e->nsx_hb) { snprintf(g_err, sizeof g_err, "ns2: the engine was created without WMIXB_NS + ns_high_band"); return WMIXB_EINVAL; }
     CK(cudaSetDevice(e->cfg.device));
     const int n = e->cfg.n_streams;
     const int need = (n + 7) / 8, cap = e->sm_count * 2, grid = need < cap ? need : cap;
+    if (e->nsx_hb) {
+        int16_t* hist = reinterpret_cast<int16_t*>(e->ns_hist);
+        const nsx::Tables* T = (const nsx::Tables*)e->nsx_tables;
+        if (e->ana == 256) nsx_hb_kernel<256><<<grid, 256, nsx_smem_bytes<256>(8), (cudaStream_t)stream>>>(e->nsx_rec, hist, e->nsx_hb, T, d_in, d_out, d_in_hb, d_out_hb, n);
+        else nsx_hb_kernel<128><<<grid, 256, nsx_smem_bytes<128>(8), (cudaStream_t)stream>>>(e->nsx_rec, hist, e->nsx_hb, T, d_in, d_out, d_in_hb, d_out_hb, n);
+        CK_LAUNCH();
+        return WMIXB_OK;
+    }
     if (e->ana == 256)
         ns_hb_kernel<256><<<grid, 256, ns_hb_smem_bytes<256>(), (cudaStream_t)stream>>>(e->ns_rec, e->ns_hist, e->ns_hb, (const ns::Tables<256>*)e->ns_tables,
                                                                                       d_in, d_out, d_in_hb, d_out_hb, n);
@@ -2072,6 +2113,7 @@ extern "C" size_t wmixb_stream_state_bytes(const wmixb_engine* e)
     size_t b = 0;
     if (e->ns_rec) b += (size_t)ns_rec_floats(e) * 4 + 3 * ns::kHistBins * 2;
     if (e->nsx_rec) b += (size_t)nsx_rec_words(e) * 4 + 3 * nsx::kHistBins * 2;
+    if (e->nsx_hb) b += (size_t)(e->ana - e->frame) * 2;
     if (e->ns_hb) b += (size_t)(e->ana - e->frame) * 4;
     if (e->agc_words) b += agc::N_WORDS * 4;
     if (e->vad_words) b += vad::N_WORDS * 4;
@@ -2105,6 +2147,7 @@ static int state_xfer(wmixb_engine* e, int s, void* buf, bool get)
     if (e->nsx_rec) {
         CK(xfer(e->nsx_rec + (size_t)s * nsx_rec_words(e), (size_t)nsx_rec_words(e) * 4));
         CK(xfer(e->ns_hist + (size_t)s * 3 * nsx::kHistBins, 3 * nsx::kHistBins * 2));
+        if (e->nsx_hb) CK(xfer(e->nsx_hb + (size_t)s * (e->ana - e->frame), (size_t)(e->ana - e->frame) * 2));
     }
     if (e->agc_words) CK(xfer2d(e->agc_words, agc::N_WORDS));
     if (e->vad_words) CK(xfer2d(e->vad_words, vad::N_WORDS));
@@ -2366,6 +2409,21 @@ extern "C" int wmixb_set_default_device(int device)
     return WMIXB_OK;
 }
 extern "C" int wmixb_default_device(void) { return g_default_device.load(); }
+
+// The reference picks its suppressor at compile time (R:src/webrtc.c:511-523, `#define MAKE_WEBRTC_NSX`); the drop-in
+// ns_init picks it from this process-wide switch (a build with -DMAKE_WEBRTC_NSX starts with the fixed-point core).
+#ifdef MAKE_WEBRTC_NSX
+static std::atomic<int> g_default_ns_core{1};
+#else
+static std::atomic<int> g_default_ns_core{0};
+#endif
+extern "C" int wmixb_set_default_ns_core(int ns_core)
+{
+    if (ns_core != 0 && ns_core != 1) return WMIXB_EINVAL;
+    g_default_ns_core.store(ns_core);
+    return WMIXB_OK;
+}
+extern "C" int wmixb_default_ns_core(void) { return g_default_ns_core.load(); }
 
 // ---- pinned host buffers placed for a device ----
 // Pinned pages are allocated by the calling thread inside cudaHostAlloc, so the NUMA node they land on is the one the
