@@ -25,6 +25,7 @@ Keyed sub-measurements in the same JSON line (none of them changes `value`):
   config4   (N = 1)  BASELINE config 4: NS -> AEC on 16 384 near/far pairs at 8 kHz;
   full_load          >= 1 000 000 resident streams per GPU through one tick, so that `value` is backed by a
                      run at that stream count and not only by extrapolation from 100 000;
+  nsx       (N = 1)  the same tick with the reference's other suppressor, the fixed-point WebRtcNsx_* core (ns_core = 1);
   offline   (N = 1)  the persistent offline mode (K frames per stream per launch, NS state on chip) against K ticks.
 """
 import argparse
@@ -50,6 +51,7 @@ UNIT = "real-time 16 kHz streams (10 ms tick), whole job"                       
 NS_BYTES_PER_STREAM_TICK = 14.4e3      # NS state R+W + PCM in/out
 CHAIN_BYTES_PER_STREAM_TICK = 16.0e3   # NS + VAD + AGC + mix
 AEC_BYTES_PER_STREAM_TICK = 29.0e3     # AEC at 8 kHz
+NSX_BYTES_PER_STREAM_TICK = 9.93e3     # fixed-point NS: 4.64 KB of record read + 4.64 KB written + PCM in/out
 # dram__bytes_read.sum + dram__bytes_write.sum of one NS launch per stream: a CONSTANT taken from the latest
 # `ncu --set full` capture (it cannot be measured inside an unprofiled run); see NS_TRAFFIC_SOURCE
 NS_DRAM_TRAFFIC_PER_STREAM_NCU = (874.749184e6 + 643.318784e6) / 100_000
@@ -294,6 +296,56 @@ def config4_leg(torch, dev, local, peak, steps=60, warmup=420, streams=16384):
             "roofline": {"bound": "hbm", "kernel": "aec_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                          "algorithmic_bytes_per_launch": streams * AEC_BYTES_PER_STREAM_TICK},
             "aec_status": {"flags": flags[0], "flagged_streams": flags[1]}}
+
+
+def nsx_leg(torch, dev, local, peak, streams, steps=60):
+    """The same tick with the reference's OTHER suppressor, the fixed-point WebRtcNsx_* core (its `#define MAKE_WEBRTC_NSX`,
+    R:src/webrtc.c:511-523; wmixb_config.ns_core = 1): NSX -> AGC -> VAD -> bus, aged PRIME ticks, CUDA events per kernel."""
+    import wmix_b200
+
+    NS, AGC, VAD = wmix_b200.NS, wmix_b200.AGC, wmix_b200.VAD
+    eng = wmix_b200.Engine(streams, FREQ, device=local, ns_core=1)
+    eng.set_conferences(np.arange(0, streams + 1, CONF_SIZE, dtype=np.int32))
+    R = 8
+    base = make_pool(min(2048, streams), R, seed=700)
+    reps = (streams + base.shape[1] - 1) // base.shape[1]
+    d_pool = torch.from_numpy(base).to(dev).repeat(1, reps, 1)[:, :streams].contiguous()
+    d_pcm = torch.empty((streams, FRAME), dtype=torch.int16, device=dev)
+    d_vad = torch.zeros((streams,), dtype=torch.uint8, device=dev)
+    d_bus = torch.empty((streams // CONF_SIZE, FRAME), dtype=torch.int32, device=dev)
+    st = torch.cuda.current_stream()
+
+    def step(t, ev=None):
+        if ev:
+            ev[0].record(st)
+        eng.tick_device(d_pool[t % R], d_pcm, None, NS, st)
+        if ev:
+            ev[1].record(st)
+        eng.tick_device(d_pcm, d_pcm, d_vad, AGC | VAD, st)
+        eng.bus_sum(d_pcm, d_bus, st)
+        if ev:
+            ev[2].record(st)
+
+    for t in range(PRIME):
+        step(t)
+    torch.cuda.synchronize()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(steps)]
+    for k in range(steps):
+        step(PRIME + k, evs[k])
+    torch.cuda.synchronize()
+    nsx_ms = sum(e[0].elapsed_time(e[1]) for e in evs) / steps
+    rest_ms = sum(e[1].elapsed_time(e[2]) for e in evs) / steps
+    state = eng.state_bytes_per_stream()
+    eng.close()
+    ach = streams * NSX_BYTES_PER_STREAM_TICK / (nsx_ms * 1e-3) / 1e9
+    return {"workload": "config 3 with the fixed-point suppressor: NSX->AGC->VAD->bus, 16 kHz mono, %d streams, aged %d ticks" % (streams, PRIME),
+            "ms_per_tick": nsx_ms + rest_ms, "realtime_streams": streams * 10.0 / (nsx_ms + rest_ms), "steps": steps,
+            "kernel_ms": {"nsx_kernel<256, 32, 1>": nsx_ms, "post_kernel + bus_sum_kernel": rest_ms},
+            "state_bytes_per_stream": state,
+            "roofline": {"bound": "hbm", "kernel": "nsx_kernel<256, 32, 1>", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                         "algorithmic_bytes_per_launch": streams * NSX_BYTES_PER_STREAM_TICK,
+                         "note": "integer pipeline, bit-exact; bound by instruction issue (~5 500 warp instructions per stream-frame, "
+                                 "two 256-point complex 16-bit FFTs), not by HBM — profiles/r2_p_nsx_summary.md"}}
 
 
 def full_load_leg(torch, dev, local, streams, steps=10):
@@ -593,6 +645,11 @@ def run_ours(args):
                 line["config4"] = config4_leg(torch, dev, local, peak)
             except Exception as ex:  # pragma: no cover
                 line["config4"] = {"failed": str(ex)}
+        if world == 1 and not args.no_nsx:
+            try:
+                line["nsx"] = nsx_leg(torch, dev, local, peak, S)
+            except Exception as ex:  # pragma: no cover
+                line["nsx"] = {"failed": str(ex)}
         if world == 1 and not args.no_offline:
             try:
                 line["offline"] = offline_leg(torch, dev, local)
@@ -623,6 +680,7 @@ def main():
     ap.add_argument("--no-config4", action="store_true")
     ap.add_argument("--no-full-load", action="store_true")
     ap.add_argument("--no-offline", action="store_true")
+    ap.add_argument("--no-nsx", action="store_true")
     ap.add_argument("--full-load-streams", type=int, default=1_000_000)
     ap.add_argument("--ns-cfg", type=int, default=-1, help="experiment: NS kernel shape index (wmixb_set_tuning)")
     ap.add_argument("--post-occ", type=int, default=-1, help="experiment: AGC+VAD kernel shape (wmixb_set_tuning)")

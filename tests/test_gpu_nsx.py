@@ -119,9 +119,12 @@ def test_nsx_offline_mode_and_every_launch_shape_agree():
     x = make_frames(70, 16000, 0, 240, seed=57)
     base = run_gpu_nsx(x, 16000)
     assert np.array_equal(base, run_gpu_nsx(x, 16000, offline=60))
-    for cfg in range(1, 6):
+    for cfg in range(1, 10):
         assert np.array_equal(base, run_gpu_nsx(x, 16000, tuning={"nsx_cfg": cfg})), cfg
-    assert np.array_equal(base, run_gpu_nsx(x, 16000, tuning={"ns_align": 0}))
+    # alignment barriers inside the frame: none, all, some — with a ragged last CTA (70 streams) and all-zero streams in the
+    # batch (cohort 1 leaves the frame early and must still meet the others at every barrier)
+    for mask in (0, 255, 0b10101011, 2):
+        assert np.array_equal(base, run_gpu_nsx(x, 16000, tuning={"nsx_sync": mask, "nsx_cfg": 4})), mask
 
 
 def test_nsx_chain_with_agc_and_vad_and_config1_wav():

@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--prime", type=int, default=600)
     ap.add_argument("--cfgs", default="0,1,2,3,4,5")
-    ap.add_argument("--align", default="1,0")
+    ap.add_argument("--align", default="1,0", help="nsx_sync masks: bit 0 = frame start, bits 1..7 = points inside the frame")
     ap.add_argument("--float-core", action="store_true", help="also time the float core's kernel on the same input")
     a = ap.parse_args()
     import torch
@@ -48,7 +48,7 @@ def main():
         for cfg, al in variants:
             if core == 1:
                 eng.set_tuning("nsx_cfg", cfg)
-                eng.set_tuning("ns_align", al)
+                eng.set_tuning("nsx_sync", al)
             for t in range(10):
                 eng.tick_device(d_pool[t % R], d_out, None, wmix_b200.NS, st)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

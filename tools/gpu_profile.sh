@@ -21,11 +21,11 @@ for f in ("gpurun_out/${TAG}_bench_w5.json", "gpurun_out/${TAG}_bench.json", "gp
 PY
 # PRIME (600) + warm-up (10) ticks x 3 launches, plus a handful of init launches
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1840 -c 60 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 30 --warmup 10 --no-cpu-baseline --no-config4 --no-full-load --no-offline > /dev/null 2>&1
+    python bench.py --steps 30 --warmup 10 --no-cpu-baseline --no-config4 --no-full-load --no-offline --no-nsx > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:ns_cta_kernel -s 605 -c 1 -o gpurun_out/${TAG}_ns -f \
-    python bench.py --steps 20 --warmup 10 --no-cpu-baseline --no-config4 --no-full-load --no-offline > /dev/null 2>&1
+    python bench.py --steps 20 --warmup 10 --no-cpu-baseline --no-config4 --no-full-load --no-offline --no-nsx > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:post_kernel -s 605 -c 1 -o gpurun_out/${TAG}_post -f \
-    python bench.py --steps 20 --warmup 10 --no-cpu-baseline --no-config4 --no-full-load --no-offline > /dev/null 2>&1
+    python bench.py --steps 20 --warmup 10 --no-cpu-baseline --no-config4 --no-full-load --no-offline --no-nsx > /dev/null 2>&1
 ncu --set full --clock-control none --import-source on -k regex:aec_kernel -s 420 -c 1 -o gpurun_out/${TAG}_aec -f \
     python tools/bench_aec.py --steps 30 --warmup 400 --no-ns > /dev/null 2>&1
 # the staged (persistent offline) NS kernel: DRAM bytes per frame against the tick kernel

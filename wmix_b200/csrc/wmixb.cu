@@ -318,14 +318,19 @@ nsx_kernel(uint32_t* __restrict__ rec, int16_t* __restrict__ hist, const nsx::Ta
         const int16_t* pi = in + (size_t)s * n_frames * G::kBlock;
         int16_t* po = out + (size_t)s * n_frames * G::kBlock;
         for (int f = 0; f < n_frames; ++f) {
-            if (align) __syncthreads();
-            if (!live) continue;
+            // align: bit 0 = the warps of the CTA start every frame together, bits 1.. = nsx::kSyncPoints more meeting points
+            // inside the frame (nsx.cuh, WMX_NSX_SYNC); a warp without a stream walks the same number of barriers
+            if (align & 1) nsx::cta_sync();
+            if (!live) {
+                for (int i = nsx::popcount_mask(align >> 1); i > 0; --i) nsx::cta_sync();
+                continue;
+            }
             if (f == n_frames - 1 && W.lane_id == 0 && s + total_warps < n_streams) {
                 // pull the next stream's record and first frame towards L2 while this one computes
                 l2_prefetch(rec + (size_t)(s + total_warps) * G::kRecWords, G::kRecWords * sizeof(uint32_t));
                 l2_prefetch(in + (size_t)(s + total_warps) * n_frames * G::kBlock, G::kBlock * sizeof(int16_t));
             }
-            nsx::frame<ANA>(W, r, h, pi + (size_t)f * G::kBlock, po + (size_t)f * G::kBlock, tile, *T);
+            nsx::frame<ANA>(W, r, h, pi + (size_t)f * G::kBlock, po + (size_t)f * G::kBlock, tile, *T, align >> 1);
         }
     }
 }
@@ -718,6 +723,7 @@ struct wmixb_engine {
     int16_t* nsx_hb = nullptr;              // [n][kKeep] second-band history (cfg.ns_high_band with ns_core = 1)
     int32_t nsx_thr_lrt = 0;
     int nsx_grid = 0, nsx_cfg = 0;
+    int nsx_sync = 1;                       // nsx_kernel's `align` mask: bit 0 = frame start, bits 1..7 = the points inside the frame
     int32_t* agc_words = nullptr;
     int32_t* vad_words = nullptr;
     int32_t* agc_table = nullptr;
@@ -845,7 +851,7 @@ static int upload_ns_tables(wmixb_engine* e)
 
 // compiled shapes of the NSX kernel; wmixb_set_tuning("nsx_cfg", index) picks one
 struct NsxCfg { int warps, minb; };
-static const NsxCfg kNsxCfgs[] = {{8, 2}, {8, 3}, {8, 4}, {4, 6}, {16, 1}, {8, 1}};
+static const NsxCfg kNsxCfgs[] = {{8, 2}, {8, 3}, {8, 4}, {4, 6}, {16, 1}, {8, 1}, {24, 1}, {32, 1}, {16, 2}, {12, 2}};
 template <int ANA>
 static const void* nsx_fn(int cfg)
 {
@@ -855,6 +861,10 @@ static const void* nsx_fn(int cfg)
     case 3: return (const void*)nsx_kernel<ANA, 4, 6>;
     case 4: return (const void*)nsx_kernel<ANA, 16, 1>;
     case 5: return (const void*)nsx_kernel<ANA, 8, 1>;
+    case 6: return (const void*)nsx_kernel<ANA, 24, 1>;
+    case 7: return (const void*)nsx_kernel<ANA, 32, 1>;
+    case 8: return (const void*)nsx_kernel<ANA, 16, 2>;
+    case 9: return (const void*)nsx_kernel<ANA, 12, 2>;
     default: return (const void*)nsx_kernel<ANA, 8, 2>;
     }
 }
@@ -877,7 +887,7 @@ static int launch_nsx(wmixb_engine* e, cudaStream_t st, const int16_t* in, int16
     uint32_t* rec = e->nsx_rec + (size_t)first * nsx::Geo<ANA>::kRecWords;
     int16_t* hist = reinterpret_cast<int16_t*>(e->ns_hist) + (size_t)first * 3 * nsx::kHistBins;
     const nsx::Tables* T = (const nsx::Tables*)e->nsx_tables;
-    int align = e->ns_align;
+    int align = e->nsx_sync;
     const int nw = kNsxCfgs[e->nsx_cfg].warps;
     const int need = (n + nw - 1) / nw;
     const int grid = need < e->nsx_grid ? need : e->nsx_grid;
@@ -894,6 +904,10 @@ static int upload_nsx_tables(wmixb_engine* e)
     }
     CK(cudaMalloc(&e->nsx_tables, sizeof T));
     CK(cudaMemcpy(e->nsx_tables, &T, sizeof T, cudaMemcpyHostToDevice));
+    // measured (profiles/r2_p_nsx_sweep.jsonl): ONE CTA of 32 warps per SM (64 registers), its warps starting every frame
+    // together, is the fastest shape at both rates — 0.750 ms per 100 000-stream tick against 1.008 ms for 2 CTAs of 8 warps at
+    // 128 registers: the frame is ~90 KB of straight-line code and what the warps of an SM share of it decides the speed
+    e->nsx_cfg = 7;
     return e->ana == 256 ? nsx_configure<256>(e) : nsx_configure<128>(e);
 }
 
@@ -2389,6 +2403,7 @@ extern "C" int wmixb_set_tuning(wmixb_engine* e, const char* key, int value)
         e->nsx_cfg = value;
         return e->ana == 256 ? nsx_configure<256>(e) : nsx_configure<128>(e);
     }
+    if (!strcmp(key, "nsx_sync")) { if (value < 0 || value >= (2 << nsx::kSyncPoints)) return WMIXB_EINVAL; e->nsx_sync = value; return WMIXB_OK; }
     if (!strcmp(key, "ns_offline_staged")) { e->ns_offline_staged = value != 0; return WMIXB_OK; }
     if (!strcmp(key, "ns_align")) { if (value < 0 || value > 64) return WMIXB_EINVAL; e->ns_align = value; return WMIXB_OK; }
     if (!strcmp(key, "post_occ")) { if ((value < 2 || value > 5) && value != 22 && value != 0) return WMIXB_EINVAL; e->post_occ = value; return WMIXB_OK; }
