@@ -33,7 +33,10 @@ enum { WMIXB_NS = 1, WMIXB_AGC = 2, WMIXB_VAD = 4, WMIXB_AEC = 8 };
 
 typedef struct wmixb_config {
     int n_streams;      /* independent mono streams on this GPU                                  */
-    int freq;           /* 8000 or 16000 (10 ms tick = 80 / 160 samples per stream)              */
+    int freq;           /* 8000 or 16000 (10 ms tick = 80 / 160 samples per stream), or 32000: rows of 320 samples through
+                           the 16 kHz cores the way the reference's handles treat that rate (NS on the first 160 samples,
+                           the rest zero; AGC on two 5 ms packets; VAD on the 320-sample packet) — NS / AGC / VAD with
+                           wmixb_tick_device and wmixb_tick_host only                                                  */
     int stages;         /* OR of WMIXB_NS / WMIXB_AGC / WMIXB_VAD: state is allocated for these   */
     int ns_policy;      /* 0..3; wmix uses 2   (R:src/webrtc.c:532 NS_AGGRESSIVE)                */
     int agc_gain_db;    /* compressionGaindB = wmix's `value` (R:src/webrtc.c:707), e.g. 5        */

@@ -203,3 +203,60 @@ def test_nsx_second_band_batched(freq):
     eng.close()
     check(d["lo"], out_lo)
     check(d["hi"], out_hi)
+
+
+@pytest.mark.parametrize("ns_core", [0, 1])
+def test_32khz_batched_engine_like_the_reference_handles(ns_core):
+    """wmixb_create(freq = 32000): 320-sample rows through the 16 kHz cores exactly as ns_init / agc_init / vad_init(.., 32000, ..)
+    of the reference treat them — NS on the first 160 samples with zeros behind, AGC on two 5 ms packets, VAD on the
+    320-sample packet — for both suppressors, device and host ticks, stage by stage and chained, against the oracle's 32 kHz
+    handles (pinned to the reference's at that rate, tests/test_oracle_pin.py)."""
+    O = oracle()
+    O.orc_nsx_init.restype = C.c_void_p
+    S, T = 40, 230
+    x = make_frames(S, 16000, 0, 2 * T, seed=87)                         # [2T, S, 160] -> packets of 320
+    pk = np.ascontiguousarray(x.transpose(1, 0, 2)).reshape(S, T, 320)
+    for stages in (NS, AGC, VAD, NS | AGC | VAD):
+        eng = wmix_b200.Engine(S, 32000, stages=stages, ns_core=ns_core)
+        assert eng.L.wmixb_frame_len(eng.h) == 320
+        hs = []
+        for s in range(S):
+            ns = C.c_void_p((O.orc_nsx_init if ns_core else O.orc_ns_init)(1, 32000)) if stages & NS else None
+            agc = C.c_void_p(O.orc_agc_init(1, 32000, 10, 5)) if stages & AGC else None
+            vad = C.c_void_p(O.orc_vad_init(1, 32000, 10)) if stages & VAD else None
+            hs.append((ns, agc, vad))
+        d = torch.empty((S, 320), dtype=torch.int16, device=DEV)
+        d_v = torch.zeros((S,), dtype=torch.uint8, device=DEV)
+        h_out = np.empty((S, 320), np.int16)
+        for t in range(T):
+            want = pk[:, t].copy()
+            for s, (ns, agc, vad) in enumerate(hs):
+                f = want[s]
+                if ns:
+                    (O.orc_nsx_process if ns_core else O.orc_ns_process)(ns, P(f), P(f), 320)
+                if agc:
+                    assert O.orc_agc_process(agc, P(f), P(f), 320) == 0
+                if vad:
+                    O.orc_vad_process(vad, P(f), 320)
+            if t % 2 == 0:
+                d.copy_(torch.from_numpy(np.ascontiguousarray(pk[:, t])))
+                eng.tick_device(d, d, d_v)
+                got = d.cpu().numpy()
+            else:
+                eng.tick_host(np.ascontiguousarray(pk[:, t]), h_out)
+                got = h_out
+            assert np.array_equal(got, want), (stages, t, np.nonzero((got != want).any(axis=1))[0][:5])
+        for ns, agc, vad in hs:
+            if ns:
+                (O.orc_nsx_release if ns_core else O.orc_ns_release)(ns)
+            if agc:
+                O.orc_agc_release(agc)
+            if vad:
+                O.orc_vad_release(vad)
+        eng.close()
+    # what does not exist at this rate is refused, not approximated
+    eng = wmix_b200.Engine(4, 32000, stages=NS)
+    assert eng.L.wmixb_set_conferences(eng.h, np.array([0, 4], np.int32).ctypes.data, 1) != 0
+    eng.close()
+    with pytest.raises(wmix_b200.WmixError):
+        wmix_b200.Engine(4, 24000, stages=NS)

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--cfgs", default="0,1,2,3,4,5")
     ap.add_argument("--align", default="1,0", help="nsx_sync masks: bit 0 = frame start, bits 1..7 = points inside the frame")
     ap.add_argument("--float-core", action="store_true", help="also time the float core's kernel on the same input")
+    ap.add_argument("--float-cfgs", default="-1", help="ns_cfg shapes of the float core to time (-1 = the library's default)")
     a = ap.parse_args()
     import torch
 
@@ -44,11 +45,13 @@ def main():
         for t in range(a.prime):
             eng.tick_device(d_pool[t % R], d_out, None, wmix_b200.NS, st)
         torch.cuda.synchronize()
-        variants = [(int(c), int(al)) for c in a.cfgs.split(",") for al in a.align.split(",")] if core == 1 else [(-1, 1)]
+        variants = [(int(c), int(al)) for c in a.cfgs.split(",") for al in a.align.split(",")] if core == 1 else [(int(c), 1) for c in a.float_cfgs.split(",")]
         for cfg, al in variants:
             if core == 1:
                 eng.set_tuning("nsx_cfg", cfg)
                 eng.set_tuning("nsx_sync", al)
+            elif cfg >= 0:
+                eng.set_tuning("ns_cfg", cfg)
             for t in range(10):
                 eng.tick_device(d_pool[t % R], d_out, None, wmix_b200.NS, st)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -712,6 +712,8 @@ constexpr int kPipe = 8;   // CUDA streams of the host-buffer chunk pipeline
 struct wmixb_engine {
     wmixb_config cfg;
     int frame = 0, ana = 0, sm_count = 0;
+    int row = 0;                            // samples per stream and tick in the caller's buffers: frame, or 320 for a 32 kHz engine
+    int16_t* pack32 = nullptr;              // [n][160] staging of a 32 kHz engine's NS stage
     size_t stride = 0;                      // SoA row pitch (streams rounded up to 32)
     float* ns_rec = nullptr;
     float* ns_hb = nullptr;                 // [n][OVERLAP] high-band history (cfg.ns_high_band: wmix's stereo NS)
@@ -766,7 +768,7 @@ static int ns_rec_floats(const wmixb_engine* e) { return e->ana == 256 ? ns::Geo
 // cta = 1: ns_cta_kernel, `warps` WORKER warps + one reducer warp per CTA; cta = 0: ns_kernel (one self-contained warp per stream)
 constexpr int kNsStagedWorkers = 7;
 struct NsCfg { int cta, warps, minb; };
-static const NsCfg kNsCfgs[] = {{1, 8, 2}, {1, 6, 3}, {1, 4, 4}, {1, 4, 5}, {1, 7, 2}, {1, 5, 3}, {0, 10, 2}, {0, 8, 2}};
+static const NsCfg kNsCfgs[] = {{1, 8, 2}, {1, 6, 3}, {1, 4, 4}, {1, 4, 5}, {1, 7, 2}, {1, 5, 3}, {0, 10, 2}, {0, 8, 2}, {0, 20, 1}, {0, 24, 1}, {0, 16, 1}, {0, 28, 1}};
 template <int ANA>
 static const void* ns_fn(int cfg)
 {
@@ -778,6 +780,10 @@ static const void* ns_fn(int cfg)
     case 5: return (const void*)ns_cta_kernel<ANA, 5, 3>;
     case 6: return (const void*)ns_kernel<ANA, 10, 2>;
     case 7: return (const void*)ns_kernel<ANA, 8, 2>;
+    case 8: return (const void*)ns_kernel<ANA, 20, 1>;
+    case 9: return (const void*)ns_kernel<ANA, 24, 1>;
+    case 10: return (const void*)ns_kernel<ANA, 16, 1>;
+    case 11: return (const void*)ns_kernel<ANA, 28, 1>;
     default: return (const void*)ns_cta_kernel<ANA, 8, 2>;
     }
 }
@@ -970,7 +976,7 @@ extern "C" void wmixb_destroy(wmixb_engine* e)
     cudaFree(e->ns_rec); cudaFree(e->nsx_rec); cudaFree(e->nsx_tables); cudaFree(e->nsx_hb); cudaFree(e->ns_hist); cudaFree(e->ns_tables); cudaFree(e->ns_hb); cudaFree(e->ns_stage);
     cudaFree(e->agc_words); cudaFree(e->vad_words); cudaFree(e->agc_table);
     cudaFree(e->agc_init); cudaFree(e->vad_init);
-    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->d_out2); cudaFree(e->d_vad); cudaFree(e->d_pkt20);
+    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->pack32); cudaFree(e->d_out2); cudaFree(e->d_vad); cudaFree(e->d_pkt20);
     for (int k = 0; k < kPipe; ++k) if (e->tail_ev[k]) cudaEventDestroy(e->tail_ev[k]);
     for (int k = 0; k < 2; ++k) if (e->done_ev[k]) cudaEventDestroy(e->done_ev[k]);
     cudaFree(e->conf_start); cudaFree(e->conf_of);
@@ -1072,8 +1078,9 @@ static int create_impl(const wmixb_config* cfg, wmixb_engine* e)
         if (e->frame == 160) CK(cudaFuncSetAttribute(post_kernel<true, 1, 704>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         else CK(cudaFuncSetAttribute(post_kernel<false, 1, 704>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
     }
-    CK(cudaMalloc(&e->d_in, n * e->frame * sizeof(int16_t)));
-    CK(cudaMalloc(&e->d_out, n * e->frame * sizeof(int16_t)));
+    CK(cudaMalloc(&e->d_in, n * e->row * sizeof(int16_t)));
+    CK(cudaMalloc(&e->d_out, n * e->row * sizeof(int16_t)));
+    if (e->row != e->frame && (cfg->stages & WMIXB_NS)) CK(cudaMalloc(&e->pack32, n * e->frame * sizeof(int16_t)));
     CK(cudaMalloc(&e->d_vad, n));
     CK(cudaMalloc(&e->conf_of, n * sizeof(int32_t)));
     return wmixb_reset(e, 0, cfg->n_streams);
@@ -1086,14 +1093,18 @@ extern "C" int wmixb_create(const wmixb_config* cfg, wmixb_engine** out)
     if (cfg->n_streams < 1) { snprintf(g_err, sizeof g_err, "n_streams must be >= 1"); return WMIXB_EINVAL; }
     // the reference accepts freq <= 32000 && freq % 8000 == 0 (R:src/webrtc.c:43, :563, :711);
     // the batched engine covers the two rates BASELINE.json's configs use
-    if (cfg->freq != 8000 && cfg->freq != 16000) { snprintf(g_err, sizeof g_err, "freq %d: batched engine supports 8000 and 16000", cfg->freq); return WMIXB_EINVAL; }
+    // 32000 runs on the 16 kHz cores exactly as the reference's handles do at that rate (see run_stages_32k); 24000 passes the
+    // reference's rate test too but every WebRTC call then fails there, so it is refused here
+    if (cfg->freq != 8000 && cfg->freq != 16000 && cfg->freq != 32000) { snprintf(g_err, sizeof g_err, "freq %d: batched engine supports 8000, 16000 and 32000", cfg->freq); return WMIXB_EINVAL; }
+    if (cfg->freq == 32000 && ((cfg->stages & WMIXB_AEC) || cfg->ns_high_band)) { snprintf(g_err, sizeof g_err, "32 kHz engine: NS, AGC and VAD only (the reference's AEC stops at 16 kHz, R:src/webrtc.c:233)"); return WMIXB_EINVAL; }
     if ((cfg->stages & ~(WMIXB_NS | WMIXB_AGC | WMIXB_VAD | WMIXB_AEC)) != 0) { snprintf(g_err, sizeof g_err, "unknown stage bits"); return WMIXB_EINVAL; }
     if (cfg->ns_core != 0 && cfg->ns_core != 1) { snprintf(g_err, sizeof g_err, "ns_core %d: 0 = float core, 1 = fixed-point core", cfg->ns_core); return WMIXB_EINVAL; }
     wmixb_engine* e = new (std::nothrow) wmixb_engine();
     if (!e) return WMIXB_ENOMEM;
     e->cfg = *cfg;
-    e->frame = cfg->freq / 100;
-    e->ana = cfg->freq == 16000 ? 256 : 128;
+    e->row = cfg->freq / 100;
+    e->frame = cfg->freq == 32000 ? 160 : e->row;          // the cores' frame: a 32 kHz engine is the 16 kHz machinery on 320-sample rows
+    e->ana = cfg->freq == 8000 ? 128 : 256;
     const int rc = create_impl(cfg, e);
     if (rc != WMIXB_OK) { wmixb_destroy(e); return rc; }
     *out = e;
@@ -1124,9 +1135,50 @@ static int launch_aec(wmixb_engine* e, const int16_t* d_far, const int16_t* d_ne
 // Streams [first, first+n) of the engine; d_in / d_out / d_vad / d_far point at stream `first`.
 // `first` must be a multiple of 32 (SoA rows stay line-aligned).
 static int run_stages(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int n_frames, int stages,
-                      cudaStream_t st, const int16_t* d_far = nullptr, int delay_ms = 0, int first = 0, int n = -1)
+                      cudaStream_t st, const int16_t* d_far = nullptr, int delay_ms = 0, int first = 0, int n = -1);
+
+// One 10 ms tick of a 32 kHz engine: rows of 320 samples through the 16 kHz cores, the way the reference's own handles treat
+// that rate.  NS (R:src/webrtc.c:563-644): WebRtcNs(x) keeps its 160-sample block at every rate above 8 kHz and wmix hands it
+// channels, not bands, so the first 160 samples of the row are suppressed and the rest of the reference's calloc'ed output
+// stays zero.  AGC (R:src/webrtc.c:724-728, :786-818): 5 ms packets of 160 samples through the 16 kHz path — the row is two
+// consecutive frames.  VAD (R:src/webrtc.c:56-67; CalcVad32khz, T:.../vad/vad_core.c:623-643): one 320-sample packet,
+// decimated 32k -> 16k -> 8k.  Whole engine per call.
+static int run_stages_32k(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int stages, cudaStream_t st)
+{
+    const int n = e->cfg.n_streams;
+    const size_t row_b = (size_t)e->row * 2, core_b = (size_t)e->frame * 2;
+    const int16_t* cur = d_in;
+    if (stages & WMIXB_NS) {
+        CK(cudaMemcpy2DAsync(e->pack32, core_b, cur, row_b, core_b, (size_t)n, cudaMemcpyDeviceToDevice, st));
+        const int rc = run_stages(e, e->pack32, e->pack32, nullptr, 1, WMIXB_NS, st, nullptr, 0, 0, -2);
+        if (rc) return rc;
+        CK(cudaMemcpy2DAsync(d_out, row_b, e->pack32, core_b, core_b, (size_t)n, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemset2DAsync(d_out + e->frame, row_b, 0, row_b - core_b, (size_t)n, st));
+        cur = d_out;
+    }
+    if (stages & WMIXB_AGC) {
+        const int rc = run_stages(e, cur, d_out, nullptr, 2, WMIXB_AGC, st, nullptr, 0, 0, -2);   // [n][2][160]
+        if (rc) return rc;
+        cur = d_out;
+    }
+    if (cur == d_in && d_in != d_out) CK(cudaMemcpyAsync(d_out, d_in, (size_t)n * row_b, cudaMemcpyDeviceToDevice, st));
+    if (stages & WMIXB_VAD) {
+        vad_packet32_kernel<<<(n + 63) / 64, 64, 0, st>>>(e->vad_words, e->vp, d_out, d_vad, n, e->stride);
+        CK_LAUNCH();
+    }
+    return WMIXB_OK;
+}
+
+static int run_stages(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, uint8_t* d_vad, int n_frames, int stages,
+                      cudaStream_t st, const int16_t* d_far, int delay_ms, int first, int n)
 {
     if (stages == 0) stages = e->cfg.stages;
+    if (e->row != e->frame && n != -2) {
+        if (stages & ~e->cfg.stages) { snprintf(g_err, sizeof g_err, "stage mask 0x%x not configured (engine has 0x%x)", stages, e->cfg.stages); return WMIXB_EINVAL; }
+        if (n_frames != 1 || first != 0 || (n >= 0 && n != e->cfg.n_streams)) { snprintf(g_err, sizeof g_err, "32 kHz engine: one tick of the whole engine per call"); return WMIXB_EINVAL; }
+        return run_stages_32k(e, d_in, d_out, d_vad, stages, st);
+    }
+    if (n == -2) n = -1;                                     // a core stage of the 32 kHz path
     if (stages & ~e->cfg.stages) { snprintf(g_err, sizeof g_err, "stage mask 0x%x not configured (engine has 0x%x)", stages, e->cfg.stages); return WMIXB_EINVAL; }
     if (n < 0) n = e->cfg.n_streams - first;
     const int16_t* cur = d_in;
@@ -1343,6 +1395,7 @@ extern "C" int wmixb_record_create(wmixb_engine* e, int aec_interval_ms, wmixb_r
 {
     if (!e || !out) return WMIXB_EINVAL;
     *out = nullptr;
+    if (e->row != e->frame) { snprintf(g_err, sizeof g_err, "record: the daemon's record tick runs at 8 or 16 kHz (R:src/wmixConf.h WMIX_FREQ)"); return WMIXB_EINVAL; }
     const int interval = 20;                                         // WMIX_INTERVAL_MS, R:src/wmixConf.h:112
     if (aec_interval_ms < 0 || aec_interval_ms % interval != 0 || aec_interval_ms > 2000) {
         snprintf(g_err, sizeof g_err, "record: AEC_INTERVALMS %d must be a whole number of 20 ms packages (with a remainder the reference reads before its ring row)", aec_interval_ms);
@@ -1452,6 +1505,18 @@ static int tick_host_impl(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, 
     if (h_bus && e->n_conf < 1) { snprintf(g_err, sizeof g_err, "tick_host_bus: call wmixb_set_conferences first"); return WMIXB_EINVAL; }
     CK(cudaSetDevice(e->cfg.device));
     const int n = e->cfg.n_streams;
+    if (e->row != e->frame) {
+        // 32 kHz engine: one blocking round trip (the chunk pipeline and the conference bus are built for the 8 / 16 kHz rows)
+        if (h_bus || pipelined) { snprintf(g_err, sizeof g_err, "32 kHz engine: wmixb_tick_device / wmixb_tick_host only"); return WMIXB_EINVAL; }
+        const size_t bytes = (size_t)n * e->row * sizeof(int16_t);
+        CK(cudaMemcpyAsync(e->d_in, h_in, bytes, cudaMemcpyHostToDevice, e->stream));
+        const int rc = run_stages(e, e->d_in, e->d_out, e->d_vad, 1, stages, e->stream);
+        if (rc) return rc;
+        if (h_out) CK(cudaMemcpyAsync(h_out, e->d_out, bytes, cudaMemcpyDeviceToHost, e->stream));
+        if (h_vad) CK(cudaMemcpyAsync(h_vad, e->d_vad, (size_t)n, cudaMemcpyDeviceToHost, e->stream));
+        CK(cudaStreamSynchronize(e->stream));
+        return WMIXB_OK;
+    }
     // One chunk per pipeline stream (a stream that gets two chunks serialises them and unbalances the pipeline).  Measured per
     // 100 k-stream tick, chunks = streams: blocking call 1.50 / 1.39 / 1.35 / 1.32 / 1.27 ms for 3 / 4 / 5 / 6 / 8; pipelined
     // ticks 1.07 / 0.96 / 0.96 / 0.97 / 0.99 ms.  wmixb_set_tuning("host_chunks" / "host_lanes") overrides (experiments).
@@ -1532,6 +1597,7 @@ static int tick_host_impl(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, 
 extern "C" int wmixb_tick_host_submit(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int32_t* h_bus, int stages)
 {
     if (!e) return WMIXB_EINVAL;
+    if (e->row != e->frame) { snprintf(g_err, sizeof g_err, "32 kHz engine: wmixb_tick_device / wmixb_tick_host only"); return WMIXB_EINVAL; }
     if (e->submitted - e->waited >= 2) { snprintf(g_err, sizeof g_err, "tick_host_submit: two ticks already in flight — call wmixb_tick_host_wait"); return WMIXB_EINVAL; }
     CK(cudaSetDevice(e->cfg.device));
     if (!e->d_out2) {
@@ -1575,6 +1641,7 @@ extern "C" int wmixb_tick_host_bus(wmixb_engine* e, const int16_t* h_in, int16_t
 extern "C" int wmixb_set_conferences(wmixb_engine* e, const int32_t* h_conf_start, int n_conf)
 {
     if (!e || !h_conf_start || n_conf < 1) return WMIXB_EINVAL;
+    if (e->row != e->frame) { snprintf(g_err, sizeof g_err, "32 kHz engine: the conference bus is built for 8 / 16 kHz rows"); return WMIXB_EINVAL; }
     if (h_conf_start[0] != 0 || h_conf_start[n_conf] != e->cfg.n_streams) { snprintf(g_err, sizeof g_err, "conference ranges must cover [0, n_streams)"); return WMIXB_EINVAL; }
     std::vector<int32_t> of((size_t)e->cfg.n_streams);
     int biggest = 0;
@@ -2558,7 +2625,7 @@ extern "C" int wmixb_sync(wmixb_engine* e)
 }
 extern "C" const char* wmixb_last_error(void) { return g_err; }
 extern "C" long long wmixb_kernel_launches(void) { return g_launches.load(); }
-extern "C" int wmixb_frame_len(const wmixb_engine* e) { return e ? e->frame : 0; }
+extern "C" int wmixb_frame_len(const wmixb_engine* e) { return e ? e->row : 0; }
 extern "C" void wmixb_ns_window(int ana, int block, float* out) { host::ns_window(ana, block, out); }
 extern "C" int wmixb_agc_gain_table(int32_t table[32], int comp_db, int target_dbfs, int limiter, int analog_target)
 {
