@@ -114,17 +114,16 @@ def test_nsx_state_word_for_word(freq):
 
 
 def test_nsx_offline_mode_and_every_launch_shape_agree():
-    """K frames per launch == K ticks; every compiled shape of the kernel (registers capped at 128 / 80 / 64, 4 / 8 / 16
+    """K frames per launch == K ticks; every compiled shape of the kernel (registers capped at 128 / 80 / 64, 4 .. 32
     warps per CTA) gives the same bits"""
     x = make_frames(70, 16000, 0, 240, seed=57)
     base = run_gpu_nsx(x, 16000)
     assert np.array_equal(base, run_gpu_nsx(x, 16000, offline=60))
     for cfg in range(1, 10):
         assert np.array_equal(base, run_gpu_nsx(x, 16000, tuning={"nsx_cfg": cfg})), cfg
-    # alignment barriers inside the frame: none, all, some — with a ragged last CTA (70 streams) and all-zero streams in the
-    # batch (cohort 1 leaves the frame early and must still meet the others at every barrier)
-    for mask in (0, 255, 0b10101011, 2):
-        assert np.array_equal(base, run_gpu_nsx(x, 16000, tuning={"nsx_sync": mask, "nsx_cfg": 4})), mask
+    # with and without the frame-start barrier, ragged last CTA (70 streams), all-zero streams in the batch
+    for cfg in (4, 7):
+        assert np.array_equal(base, run_gpu_nsx(x, 16000, tuning={"nsx_sync": 0, "nsx_cfg": cfg})), cfg
 
 
 def test_nsx_chain_with_agc_and_vad_and_config1_wav():

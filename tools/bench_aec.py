@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--ring", type=int, default=8)
     ap.add_argument("--no-ns", action="store_true")
     ap.add_argument("--aec-align", type=int, default=-1, help="experiment: CTA alignment of the AEC kernel (wmixb_set_tuning)")
+    ap.add_argument("--aec-warps", type=int, default=-1, help="experiment: warps per CTA of the AEC kernel, 8 or 16 (wmixb_set_tuning)")
     a = ap.parse_args()
     import torch
 
@@ -46,6 +47,8 @@ def main():
     eng = wmix_b200.Engine(S, 8000, stages=stages)
     if a.aec_align >= 0:
         eng.set_tuning("aec_align", a.aec_align)
+    if a.aec_warps > 0:
+        eng.set_tuning("aec_warps", a.aec_warps)
     d_far = torch.empty((S, L), dtype=torch.int16, device=dev)
     d_near = torch.empty((S, L), dtype=torch.int16, device=dev)
     d_out = torch.empty((S, L), dtype=torch.int16, device=dev)

@@ -22,7 +22,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--prime", type=int, default=600)
     ap.add_argument("--cfgs", default="0,1,2,3,4,5")
-    ap.add_argument("--align", default="1,0", help="nsx_sync masks: bit 0 = frame start, bits 1..7 = points inside the frame")
+    ap.add_argument("--align", default="1,0", help="nsx_sync values: 1 = the warps of a CTA start every frame together, 0 = free running")
     ap.add_argument("--float-core", action="store_true", help="also time the float core's kernel on the same input")
     ap.add_argument("--float-cfgs", default="-1", help="ns_cfg shapes of the float core to time (-1 = the library's default)")
     a = ap.parse_args()

@@ -49,6 +49,42 @@ def main():
         torch.cuda.synchronize()
         eng.close()
         print("ns/agc/vad/bus %d Hz ok" % freq, flush=True)
+    # the fixed-point suppressor: mono ticks in the default shape and two others (all-zero stream 1 leaves the frame early),
+    # offline frames, the second band, a 32 kHz engine
+    if os.environ.get("SAN_ONLY", "") in ("", "nsx"):
+        for freq, S in ((16000, 83), (8000, 45)):
+            L = freq // 100
+            x = make_frames(S, freq, 0, ticks, seed=4)
+            for cfg, mask in ((7, 1), (0, 1), (4, 0)):
+                eng = wmix_b200.Engine(S, freq, stages=NS, ns_core=1)
+                eng.set_tuning("nsx_cfg", cfg)
+                eng.set_tuning("nsx_sync", mask)
+                d_in = torch.empty((S, L), dtype=torch.int16, device=dev)
+                for t in range(ticks):
+                    d_in.copy_(torch.from_numpy(x[t]))
+                    eng.tick_device(d_in, d_in, None, NS, st)
+                d_seq = torch.from_numpy(np.ascontiguousarray(x.transpose(1, 0, 2))).to(dev)
+                eng.offline_device(d_seq, torch.empty_like(d_seq), ticks, None, NS, st)
+                torch.cuda.synchronize()
+                eng.close()
+            eng = wmix_b200.Engine(S, freq, stages=NS, ns_core=1, ns_high_band=1)
+            a = torch.from_numpy(x[0]).to(dev)
+            b = torch.from_numpy(x[1]).to(dev)
+            for t in range(ticks):
+                assert eng.L.wmixb_ns2_device(eng.h, a.data_ptr(), b.data_ptr(), a.data_ptr(), b.data_ptr(), st.cuda_stream) == 0
+            torch.cuda.synchronize()
+            eng.close()
+            print("nsx %d Hz ok" % freq, flush=True)
+        eng = wmix_b200.Engine(21, 32000, ns_core=1)
+        d = torch.randint(-3000, 3000, (21, 320), dtype=torch.int16, device=dev)
+        d_v = torch.zeros((21,), dtype=torch.uint8, device=dev)
+        for t in range(ticks):
+            eng.tick_device(d, d, d_v, 0, st)
+        torch.cuda.synchronize()
+        eng.close()
+        print("nsx 32 kHz engine ok", flush=True)
+        if os.environ.get("SAN_ONLY", "") == "nsx":
+            return
     # AEC + NS chain at 8 kHz
     S, L = 37, 80
     far, near = make_aec_pairs(S, 8000, 0, ticks + 2, seed=9)

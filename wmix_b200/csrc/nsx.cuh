@@ -265,25 +265,6 @@ WMX_HD void hist_inc(int16_t* h, uint32_t idx)
     h[idx]++;
 #endif
 }
-// CTA-wide alignment points inside a frame (device only; `bar.sync 0` pairs up by barrier id, not by program counter, so a
-// warp that leaves the frame early — all-zero input — or has no stream walks the same NUMBER of barriers elsewhere).
-// Why: the frame is ~90 KB of straight-line code; warps that drift apart each stream their own copy of it through the
-// instruction cache.  sync_mask bit i enables point i; kSyncPoints of them exist.
-constexpr int kSyncPoints = 7;
-WMX_HD void cta_sync()
-{
-#if defined(__CUDA_ARCH__)
-    asm volatile("bar.sync 0;" ::: "memory");
-#endif
-}
-WMX_HD int popcount_mask(int m)
-{
-    int n = 0;
-    for (int i = 0; i < kSyncPoints; ++i) n += (m >> i) & 1;
-    return n;
-}
-#define WMX_NSX_SYNC(i) do { if (sync_mask & (1 << (i))) cta_sync(); } while (0)
-
 // pull the stream's record towards L1 ahead of the phases that walk it (one 128-byte line per lane and call)
 WMX_HD void l1_prefetch(const void* p)
 {
@@ -479,8 +460,7 @@ WMX_HD void synth_read_out_only(Warp<ANA>& W, uint32_t* rec, int16_t* out)
 // HB: also returns the time-domain gain (Q14) of wmix's second band for this frame (nsx_core.c:2054-2107), or -1 when the
 // frame was all zeros and the second band passes unscaled (:1577-1592); 0 otherwise.
 template <int ANA, bool HB = false>
-WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, int16_t* out, uint32_t* tile, const Tables& T,
-                 const int sync_mask = 0)
+WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, int16_t* out, uint32_t* tile, const Tables& T)
 {
     typedef Geo<ANA> G;
     constexpr int K = G::kK, NR = G::kR, ST = G::kStages, HALF = G::kHalf;
@@ -535,7 +515,6 @@ WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, 
     if (peak == 0) {
         // zero input: only the buffers move (nsx_core.c:1228-1232, :1574-1594)
         synth_read_out_only<ANA>(W, rec, out);
-        for (int i = popcount_mask(sync_mask); i > 0; --i) cta_sync();
         return -1;
     }
 
@@ -558,7 +537,6 @@ WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, 
     WMX_NSX_PHASE_END
     fft_run<ANA, false>(W, tile, T);
 
-    WMX_NSX_SYNC(0);
     // ---- magnitudes, their sums, the start-up model (nsx_core.c:1248-1418) ----
     WMX_NSX_PHASE_BEGIN
     uint32_t e_sum = 0, m_sum = 0;
@@ -675,7 +653,6 @@ WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, 
         }
     }
 
-    WMX_NSX_SYNC(1);
     // ---- quantile noise estimate (nsx_core.c:334-453) ----
     int q_noise = sc[S_Q_NOISE];
     {
@@ -814,7 +791,6 @@ WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, 
         }
     }
 
-    WMX_NSX_SYNC(2);
     // ---- step 1: posterior / prior SNR (nsx_core.c:1724-1785); spectral-difference sums (:1107-1137) ----
     const int q_magn_prev = sc[S_Q_MAGN_PREV], q_noise_prev = sc[S_Q_NOISE_PREV];
     WMX_NSX_PHASE_BEGIN
@@ -992,7 +968,6 @@ WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, 
         cur_avg_e = 0;
     }
 
-    WMX_NSX_SYNC(3);
     // ---- speech / noise probability (nsx_core_c.c:26-260) ----
     WMX_NSX_PHASE_BEGIN
     int32_t lrt_sum = 0;
@@ -1100,7 +1075,6 @@ WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, 
     }
     WMX_NSX_PHASE_END
 
-    WMX_NSX_SYNC(4);
     // ---- step 2: noise update (nsx_core.c:1840-1946).  The update weight of bin i starts from the one bin i-1 chose ----
     WMX_NSX_PHASE_BEGIN
     const int post_shifts = q_noise_prev - q_magn;
@@ -1219,7 +1193,6 @@ WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, 
     }
     WMX_NSX_PHASE_END
 
-    WMX_NSX_SYNC(5);
     // ---- inverse transform: bins above ANA/2 by conjugate symmetry (real_fft.c:75-103), input in bit-reversed order ----
     WMX_NSX_PHASE_BEGIN
     uint32_t t[NR];
@@ -1238,7 +1211,6 @@ WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, 
     WMX_NSX_PHASE_END
     const int scale_ifft = fft_run<ANA, true>(W, tile, T);
 
-    WMX_NSX_SYNC(6);
     // ---- denormalise (nsx_core.c:477-487), output energy and the gain map (:1462-1495) ----
     WMX_NSX_PHASE_BEGIN
     int32_t smax2 = -1;

@@ -318,19 +318,18 @@ nsx_kernel(uint32_t* __restrict__ rec, int16_t* __restrict__ hist, const nsx::Ta
         const int16_t* pi = in + (size_t)s * n_frames * G::kBlock;
         int16_t* po = out + (size_t)s * n_frames * G::kBlock;
         for (int f = 0; f < n_frames; ++f) {
-            // align: bit 0 = the warps of the CTA start every frame together, bits 1.. = nsx::kSyncPoints more meeting points
-            // inside the frame (nsx.cuh, WMX_NSX_SYNC); a warp without a stream walks the same number of barriers
-            if (align & 1) nsx::cta_sync();
-            if (!live) {
-                for (int i = nsx::popcount_mask(align >> 1); i > 0; --i) nsx::cta_sync();
-                continue;
-            }
+            // the warps of the CTA start every frame together: they then run the same ~90 KB of code at about the same time
+            // and share the fetched lines (uniform trip count, so the barrier is in uniform control flow).  Meeting points
+            // INSIDE the frame were measured too (profiles/r2_p_nsx_summary.md): they help small CTAs, cost the shipped
+            // 32-warp one, and need warps that leave the frame early to arrive at a different bar.sync — removed.
+            if (align) __syncthreads();
+            if (!live) continue;
             if (f == n_frames - 1 && W.lane_id == 0 && s + total_warps < n_streams) {
                 // pull the next stream's record and first frame towards L2 while this one computes
                 l2_prefetch(rec + (size_t)(s + total_warps) * G::kRecWords, G::kRecWords * sizeof(uint32_t));
                 l2_prefetch(in + (size_t)(s + total_warps) * n_frames * G::kBlock, G::kBlock * sizeof(int16_t));
             }
-            nsx::frame<ANA>(W, r, h, pi + (size_t)f * G::kBlock, po + (size_t)f * G::kBlock, tile, *T, align >> 1);
+            nsx::frame<ANA>(W, r, h, pi + (size_t)f * G::kBlock, po + (size_t)f * G::kBlock, tile, *T);
         }
     }
 }
@@ -422,11 +421,14 @@ __global__ void ns_init_kernel(float* rec, uint16_t* hist, int first, int count)
 // ------------------------------------------------------------------------------------------
 // AEC kernel: persistent grid, one warp per stream (aec.cuh)
 // ------------------------------------------------------------------------------------------
-constexpr int kAecWarps = 8;
+constexpr int kAecWarps = 8;   // grid sizing unit; the shipped shape is ONE 16-warp CTA per SM (aec_warps = 16: 0.424 ms per 16 384-stream
+                               // tick against 0.435 ms for two CTAs of 8, profiles/r2_s_aec_warps.txt); wmixb_set_tuning("aec_warps", 8) for the other
 constexpr size_t kAecTableFloats = (sizeof(aec::Tables) + 15) / 16 * 4;
-constexpr size_t kAecSmemBytes = (kAecTableFloats + (size_t)kAecWarps * aec::Geo::kShFloats) * sizeof(float);
+constexpr size_t aec_smem_bytes(int warps) { return (kAecTableFloats + (size_t)warps * aec::Geo::kShFloats) * sizeof(float); }
+constexpr size_t kAecSmemBytes = aec_smem_bytes(kAecWarps);
 
-__global__ void __launch_bounds__(kAecWarps * 32)
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 16 / WARPS)
 aec_kernel(float* __restrict__ rec, size_t rec_floats, const aec::Tables* __restrict__ tables, const int16_t* far,
            const int16_t* near, int16_t* out, int n_streams, int n, int mult, int depth, int delay_ms, int pf_mode, int row_stride, int align)
 {
@@ -442,10 +444,10 @@ aec_kernel(float* __restrict__ rec, size_t rec_floats, const aec::Tables* __rest
     float* tile = smem + kAecTableFloats + (size_t)warp * aec::Geo::kShFloats;
     aec::Warp W;
     W.lane_id = threadIdx.x & 31;
-    const int total_warps = gridDim.x * kAecWarps;
+    const int total_warps = gridDim.x * WARPS;
     // The tick is ~90 KB of code: warps that drift apart each stream their own copy of it through the instruction cache.
     // With `align` the warps of a CTA start every stream together (uniform trip count, so the barrier is legal).
-    const int first_of_cta = blockIdx.x * kAecWarps;
+    const int first_of_cta = blockIdx.x * WARPS;
     const int iters = first_of_cta < n_streams ? (n_streams - first_of_cta + total_warps - 1) / total_warps : 0;
     for (int it = 0; it < iters; ++it) {
         const int s = first_of_cta + warp + it * total_warps;
@@ -725,7 +727,7 @@ struct wmixb_engine {
     int16_t* nsx_hb = nullptr;              // [n][kKeep] second-band history (cfg.ns_high_band with ns_core = 1)
     int32_t nsx_thr_lrt = 0;
     int nsx_grid = 0, nsx_cfg = 0;
-    int nsx_sync = 1;                       // nsx_kernel's `align` mask: bit 0 = frame start, bits 1..7 = the points inside the frame
+    int nsx_sync = 1;                       // nsx_kernel: the warps of a CTA start every frame together
     int32_t* agc_words = nullptr;
     int32_t* vad_words = nullptr;
     int32_t* agc_table = nullptr;
@@ -757,7 +759,7 @@ struct wmixb_engine {
     void* aec_tables = nullptr;
     int* aec_result = nullptr;              // [2] flags OR, flagged count
     int16_t* aec_stage = nullptr;           // far / near / out staging of the host-buffer entry point
-    int aec_depth = 0, aec_grid = 0, aec_grid_max = 0, aec_pf = 2, aec_align = 1;
+    int aec_depth = 0, aec_grid = 0, aec_grid_max = 0, aec_pf = 2, aec_align = 1, aec_warps = 16;
     size_t aec_rec_floats = 0;
 };
 
@@ -1044,9 +1046,10 @@ static int create_impl(const wmixb_config* cfg, wmixb_engine* e)
         CK(ce1);
         CK(cudaMalloc(&e->aec_rec, n * e->aec_rec_floats * sizeof(float)));
         CK(cudaMalloc(&e->aec_result, 2 * sizeof(int)));
-        CK(cudaFuncSetAttribute(aec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAecSmemBytes));
+        CK(cudaFuncSetAttribute(aec_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aec_smem_bytes(8)));
+        CK(cudaFuncSetAttribute(aec_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)aec_smem_bytes(16)));
         int per_sm = 0;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aec_kernel, kAecWarps * 32, kAecSmemBytes));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aec_kernel<8>, kAecWarps * 32, kAecSmemBytes));
         if (per_sm < 1) per_sm = 1;
         e->aec_grid = e->sm_count * per_sm;
         e->aec_grid_max = e->aec_grid;
@@ -1124,9 +1127,12 @@ static int launch_aec(wmixb_engine* e, const int16_t* d_far, const int16_t* d_ne
 {
     if (row_stride == 0) row_stride = samples;
     const int n = e->cfg.n_streams;
-    const int need = (n + kAecWarps - 1) / kAecWarps;
+    const int aw = e->aec_warps;
+    const int need = (n + aw - 1) / aw;
     const int grid = need < e->aec_grid ? need : e->aec_grid;
-    aec_kernel<<<grid, kAecWarps * 32, kAecSmemBytes, st>>>(e->aec_rec, e->aec_rec_floats, (const aec::Tables*)e->aec_tables, d_far,
+    if (aw == 16) aec_kernel<16><<<(grid + 1) / 2, 512, aec_smem_bytes(16), st>>>(e->aec_rec, e->aec_rec_floats, (const aec::Tables*)e->aec_tables, d_far,
+                                                             d_near, d_out, n, samples, e->cfg.freq / 8000, e->aec_depth, delay_ms, e->aec_pf, row_stride, e->aec_align);
+    else aec_kernel<8><<<grid, 256, aec_smem_bytes(8), st>>>(e->aec_rec, e->aec_rec_floats, (const aec::Tables*)e->aec_tables, d_far,
                                                              d_near, d_out, n, samples, e->cfg.freq / 8000, e->aec_depth, delay_ms, e->aec_pf, row_stride, e->aec_align);
     CK_LAUNCH();
     return WMIXB_OK;
@@ -2470,11 +2476,12 @@ extern "C" int wmixb_set_tuning(wmixb_engine* e, const char* key, int value)
         e->nsx_cfg = value;
         return e->ana == 256 ? nsx_configure<256>(e) : nsx_configure<128>(e);
     }
-    if (!strcmp(key, "nsx_sync")) { if (value < 0 || value >= (2 << nsx::kSyncPoints)) return WMIXB_EINVAL; e->nsx_sync = value; return WMIXB_OK; }
+    if (!strcmp(key, "nsx_sync")) { e->nsx_sync = value != 0; return WMIXB_OK; }
     if (!strcmp(key, "ns_offline_staged")) { e->ns_offline_staged = value != 0; return WMIXB_OK; }
     if (!strcmp(key, "ns_align")) { if (value < 0 || value > 64) return WMIXB_EINVAL; e->ns_align = value; return WMIXB_OK; }
     if (!strcmp(key, "post_occ")) { if ((value < 2 || value > 5) && value != 22 && value != 0) return WMIXB_EINVAL; e->post_occ = value; return WMIXB_OK; }
     if (!strcmp(key, "aec_pf")) { e->aec_pf = value; return WMIXB_OK; }
+    if (!strcmp(key, "aec_warps")) { if (value != 8 && value != 16) return WMIXB_EINVAL; e->aec_warps = value; return WMIXB_OK; }
     if (!strcmp(key, "aec_align")) { e->aec_align = value != 0; return WMIXB_OK; }
     if (!strcmp(key, "aec_grid")) { if (value < 1 || value > e->aec_grid_max) return WMIXB_EINVAL; e->aec_grid = value; return WMIXB_OK; }
     if (!strcmp(key, "host_chunks")) { if (value < 1 || value > 64) return WMIXB_EINVAL; e->host_chunks_sync = e->host_chunks_pipe = value; return WMIXB_OK; }
