@@ -259,3 +259,43 @@ def test_32khz_batched_engine_like_the_reference_handles(ns_core):
     eng.close()
     with pytest.raises(wmix_b200.WmixError):
         wmix_b200.Engine(4, 24000, stages=NS)
+
+
+def test_nsx_in_the_record_tick_at_wmix_cadence():
+    """the daemon's 20 ms record tick (wmixb_record_*) with the switch thrown: NSX on two 10 ms packets -> AGC -> VAD on one
+    20 ms packet (the re-staged packet kernel), against the oracle's handles in wmix's own geometry"""
+    lib, O = wmix_b200.lib(), oracle()
+    O.orc_nsx_init.restype = C.c_void_p
+    freq, S, K = 16000, 70, 120
+    pkg = freq // 50
+    x = make_frames(S, freq, 0, 2 * K, seed=73)
+    mic = np.ascontiguousarray(x.transpose(1, 0, 2)).reshape(S, K, pkg)
+    play = np.zeros_like(mic)
+    stages = NS | AGC | VAD
+    eng = wmix_b200.Engine(S, freq, stages=stages, ns_core=1)
+    rec = C.c_void_p()
+    assert lib.wmixb_record_create(eng.h, 400, C.byref(rec)) == 0
+    d_play = torch.zeros((S, pkg), dtype=torch.int16, device=DEV)
+    d_mic, d_out = torch.empty_like(d_play), torch.empty_like(d_play)
+    d_vad = torch.zeros((S,), dtype=torch.uint8, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    got = np.empty((K, S, pkg), np.int16)
+    for t in range(K):
+        d_mic.copy_(torch.from_numpy(np.ascontiguousarray(mic[:, t])))
+        assert lib.wmixb_record_tick_device(rec, d_play.data_ptr(), d_mic.data_ptr(), d_out.data_ptr(), d_vad.data_ptr(), None, stages, st) == 0
+        got[t] = d_out.cpu().numpy()
+    lib.wmixb_record_destroy(rec)
+    eng.close()
+    for s in list(range(0, S, 3)):
+        ns = C.c_void_p(O.orc_nsx_init(1, freq))
+        agc = C.c_void_p(O.orc_agc_init(1, freq, 20, 5))
+        vad = C.c_void_p(O.orc_vad_init(1, freq, 20))
+        for t in range(K):
+            f = mic[s, t].copy()
+            O.orc_nsx_process(ns, P(f), P(f), pkg)
+            assert O.orc_agc_process(agc, P(f), P(f), pkg) == 0
+            O.orc_vad_process(vad, P(f), pkg)
+            assert np.array_equal(got[t, s], f), (s, t)
+        O.orc_nsx_release(ns)
+        O.orc_agc_release(agc)
+        O.orc_vad_release(vad)

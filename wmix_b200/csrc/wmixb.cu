@@ -565,36 +565,72 @@ post_kernel(int32_t* __restrict__ agc_words, int32_t* __restrict__ vad_words, co
 // VAD on 20 ms packets (what wmix itself asks for: vad_init(.., WMIX_INTERVAL_MS = 20, ..), R:src/wmix.c:703,
 // R:src/webrtc.c:56-65; the 20 ms threshold column of T:.../vad/vad_core.c:149-164).  One stream per thread,
 // the packet staged in local memory: a correctness path for the drop-in handle, not a throughput path.
+// VAD on whole packets that are not the tick's 10 ms frame: 20 ms packets (what wmix itself configures) and the 32 kHz
+// handle packets.  One stream per thread like post_kernel, and like there the packets of a CTA's 64 streams move between
+// global and shared memory as one coalesced block (row pitch odd in 32-bit words: conflict-free per-thread rows) — a thread
+// walking its own 640-byte row in global memory touches a different line than each of its 31 neighbours on every access,
+// and a per-thread local array is the same pattern behind the L1.
+constexpr int kPktThreads = 64;
+template <int L>
+constexpr size_t pkt_smem_bytes() { return (size_t)kPktThreads * (L / 2 + 1) * sizeof(int32_t); }
+
+template <int L>
+__device__ __forceinline__ int16_t* pkt_stage_in(int32_t* tile, const int16_t* pcm, int s0, int rows)
+{
+    constexpr int ROWW = L / 2 + 1;
+    const int32_t* in32 = reinterpret_cast<const int32_t*>(pcm);
+    for (int idx = threadIdx.x; idx < rows * (L / 2); idx += kPktThreads) {
+        const int r = idx / (L / 2), w = idx - r * (L / 2);
+        tile[r * ROWW + w] = in32[(size_t)(s0 + r) * (L / 2) + w];
+    }
+    __syncthreads();
+    return reinterpret_cast<int16_t*>(tile + threadIdx.x * ROWW);
+}
+template <int L>
+__device__ __forceinline__ void pkt_stage_out(const int32_t* tile, int16_t* pcm, int s0, int rows)
+{
+    constexpr int ROWW = L / 2 + 1;
+    int32_t* out32 = reinterpret_cast<int32_t*>(pcm);
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < rows * (L / 2); idx += kPktThreads) {
+        const int r = idx / (L / 2), w = idx - r * (L / 2);
+        out32[(size_t)(s0 + r) * (L / 2) + w] = tile[r * ROWW + w];
+    }
+}
+
 template <bool FS16>
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(kPktThreads)
 vad_packet20_kernel(int32_t* __restrict__ vad_words, vad::Params vp, int16_t* pcm, uint8_t* vad_out, int n_streams, size_t stride)
 {
     constexpr int L = FS16 ? 320 : 160;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_streams) return;
-    int16_t x[L];
-    int16_t* row = pcm + (size_t)s * L;
-    for (int i = 0; i < L; ++i) x[i] = row[i];
-    SoaWords st{vad_words + s, stride};
-    const int flag = vad::process_packet<160, FS16>(st, x, vp);
-    for (int i = 0; i < L; ++i) row[i] = x[i];
-    if (vad_out) vad_out[s] = (uint8_t)flag;
+    extern __shared__ __align__(16) int32_t pkt_smem[];
+    const int s0 = blockIdx.x * kPktThreads, s = s0 + threadIdx.x;
+    const int rows = min(kPktThreads, n_streams - s0);
+    int16_t* x = pkt_stage_in<L>(pkt_smem, pcm, s0, rows);
+    if (s < n_streams) {
+        SoaWords st{vad_words + s, stride};
+        const int flag = vad::process_packet<160, FS16>(st, x, vp);
+        if (vad_out) vad_out[s] = (uint8_t)flag;
+    }
+    pkt_stage_out<L>(pkt_smem, pcm, s0, rows);
 }
 
-// VAD on 32 kHz packets of 10 ms (CalcVad32khz, T:.../vad/vad_core.c:623-643): the handle API's 32 kHz case.
-__global__ void __launch_bounds__(64)
+// VAD on 32 kHz packets of 10 ms (CalcVad32khz, T:.../vad/vad_core.c:623-643): the handle API's 32 kHz case and the VAD
+// stage of a 32 kHz engine.
+__global__ void __launch_bounds__(kPktThreads)
 vad_packet32_kernel(int32_t* __restrict__ vad_words, vad::Params vp, int16_t* pcm, uint8_t* vad_out, int n_streams, size_t stride)
 {
     constexpr int L = 320;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= n_streams) return;
-    int16_t x[L];
-    int16_t* row = pcm + (size_t)s * L;
-    for (int i = 0; i < L; ++i) x[i] = row[i];
-    SoaWords st{vad_words + s, stride};
-    const int flag = vad::process_packet32<80>(st, x, vp);
-    for (int i = 0; i < L; ++i) row[i] = x[i];
-    if (vad_out) vad_out[s] = (uint8_t)flag;
+    extern __shared__ __align__(16) int32_t pkt_smem[];
+    const int s0 = blockIdx.x * kPktThreads, s = s0 + threadIdx.x;
+    const int rows = min(kPktThreads, n_streams - s0);
+    int16_t* x = pkt_stage_in<L>(pkt_smem, pcm, s0, rows);
+    if (s < n_streams) {
+        SoaWords st{vad_words + s, stride};
+        const int flag = vad::process_packet32<80>(st, x, vp);
+        if (vad_out) vad_out[s] = (uint8_t)flag;
+    }
+    pkt_stage_out<L>(pkt_smem, pcm, s0, rows);
 }
 
 __global__ void words_init_kernel(int32_t* words, const int32_t* init, int n_words, size_t stride, int first, int count)
@@ -1169,7 +1205,7 @@ static int run_stages_32k(wmixb_engine* e, const int16_t* d_in, int16_t* d_out, 
     }
     if (cur == d_in && d_in != d_out) CK(cudaMemcpyAsync(d_out, d_in, (size_t)n * row_b, cudaMemcpyDeviceToDevice, st));
     if (stages & WMIXB_VAD) {
-        vad_packet32_kernel<<<(n + 63) / 64, 64, 0, st>>>(e->vad_words, e->vp, d_out, d_vad, n, e->stride);
+        vad_packet32_kernel<<<(n + kPktThreads - 1) / kPktThreads, kPktThreads, pkt_smem_bytes<320>(), st>>>(e->vad_words, e->vp, d_out, d_vad, n, e->stride);
         CK_LAUNCH();
     }
     return WMIXB_OK;
@@ -1243,8 +1279,8 @@ extern "C" int wmixb_vad20_device(wmixb_engine* e, int16_t* d_pcm, uint8_t* d_va
     if (!e->vad_words) { snprintf(g_err, sizeof g_err, "vad20: the engine was created without WMIXB_VAD"); return WMIXB_EINVAL; }
     CK(cudaSetDevice(e->cfg.device));
     const int n = e->cfg.n_streams, grid = (n + 63) / 64;
-    if (e->frame == 160) vad_packet20_kernel<true><<<grid, 64, 0, (cudaStream_t)stream>>>(e->vad_words, e->vp20, d_pcm, d_vad, n, e->stride);
-    else vad_packet20_kernel<false><<<grid, 64, 0, (cudaStream_t)stream>>>(e->vad_words, e->vp20, d_pcm, d_vad, n, e->stride);
+    if (e->frame == 160) vad_packet20_kernel<true><<<grid, kPktThreads, pkt_smem_bytes<320>(), (cudaStream_t)stream>>>(e->vad_words, e->vp20, d_pcm, d_vad, n, e->stride);
+    else vad_packet20_kernel<false><<<grid, kPktThreads, pkt_smem_bytes<160>(), (cudaStream_t)stream>>>(e->vad_words, e->vp20, d_pcm, d_vad, n, e->stride);
     CK_LAUNCH();
     return WMIXB_OK;
 }
@@ -1312,7 +1348,7 @@ extern "C" int wmixb_vad32_device(wmixb_engine* e, int16_t* d_pcm, uint8_t* d_va
     if (!e->vad_words || e->frame != 160) { snprintf(g_err, sizeof g_err, "vad32: needs a 16 kHz engine created with WMIXB_VAD"); return WMIXB_EINVAL; }
     CK(cudaSetDevice(e->cfg.device));
     const int n = e->cfg.n_streams, grid = (n + 63) / 64;
-    vad_packet32_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>(e->vad_words, e->vp, d_pcm, d_vad, n, e->stride);
+    vad_packet32_kernel<<<grid, kPktThreads, pkt_smem_bytes<320>(), (cudaStream_t)stream>>>(e->vad_words, e->vp, d_pcm, d_vad, n, e->stride);
     CK_LAUNCH();
     return WMIXB_OK;
 }
