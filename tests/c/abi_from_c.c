@@ -13,6 +13,20 @@ int main(void)
     printf("wmixb_create without a GPU -> %d (%s)\n", rc, wmixb_last_error());
     void *h = ns_init(1, 16000, 0);
     printf("ns_init without a GPU -> %p\n", h);
+    {
+        /* the reference's compile-time suppressor switch (MAKE_WEBRTC_NSX) as a run-time call; a 32 kHz engine with the fixed-point core */
+        wmixb_config c32 = { .n_streams = 2, .freq = 32000, .stages = WMIXB_NS, .ns_policy = 2, .ns_core = 1 };
+        wmixb_engine *e32 = 0;
+        if (wmixb_set_default_ns_core(1) != WMIXB_OK || wmixb_default_ns_core() != 1 || wmixb_set_default_ns_core(7) == WMIXB_OK) return 3;
+        {
+            void *hx = ns_init(2, 32000, 0);
+            printf("ns_init (fixed-point core) without a GPU -> %p\n", hx);
+            if (hx) ns_release(hx);
+        }
+        wmixb_set_default_ns_core(0);
+        printf("wmixb_create(32 kHz, ns_core 1) without a GPU -> %d\n", wmixb_create(&c32, &e32));
+        if (e32) wmixb_destroy(e32);
+    }
     wmixb_mix_view v = {0};
     uint32_t tick = 0;
     printf("load_data on a stopped mixer -> %p\n", (void *)wmixb_load_data_host(&v, (const uint8_t *)"ab", 2, 16000, 1, 16, 0, 0, &tick));
