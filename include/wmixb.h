@@ -86,6 +86,18 @@ int wmixb_tick_host_bus(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, ui
 int wmixb_tick_host_submit(wmixb_engine* e, const int16_t* h_in, int16_t* h_out, uint8_t* h_vad, int32_t* h_bus, int stages);
 int wmixb_tick_host_wait(wmixb_engine* e);
 
+/* Host tick for G.711 legs — wmix's RTP PCMA path decodes every 20 ms payload with G711a2PCM before it reaches the mixer and
+ * encodes what goes back with PCM2G711a (R:src/wmixTask.c:1139-1143, :1278-1282; R:src/g711codec.c): here the tick's input
+ * arrives and its output leaves as A-law / mu-law codes, ONE byte per sample over the bus instead of two, and the codecs run
+ * on the device around the configured stages:
+ *     codes -> G711x2PCM -> [NS -> AGC -> VAD] -> bus (wmixb_set_conferences) -> read-out -> PCM2G711x -> codes
+ * h_codes_in / h_codes_out: uint8 [n_streams][frame] (h_codes_out nullable); law: 0 = A-law, 1 = mu-law; h_vad (nullable): uint8
+ * [n_streams]; h_bus (nullable): int32 [n_conf][frame], the exact conference sum of the processed legs.  nminus1 != 0: the leg
+ * handed back is what its conference sounds like WITHOUT it, clamp16(bus - own) (needs conferences); 0: the leg's own processed
+ * PCM.  stages = 0: all configured.  Blocking; buffers should be pinned. */
+int wmixb_tick_host_g711(wmixb_engine* e, int law, const uint8_t* h_codes_in, uint8_t* h_codes_out, uint8_t* h_vad, int32_t* h_bus,
+                         int nminus1, int stages);
+
 /* VAD on 20 ms packets, in place: what wmix itself configures (vad_init(.., WMIX_INTERVAL_MS = 20, ..),
  * R:src/wmix.c:703; 20 ms thresholds of T:.../vad/vad_core.c:149-164).  d_pcm: int16 [n_streams][2*frame],
  * attenuated by the wrapper's mute ramp (R:src/webrtc.c:127-141); d_vad (nullable): uint8 [n_streams].

@@ -126,6 +126,15 @@ def test_nsx_offline_mode_and_every_launch_shape_agree():
         assert np.array_equal(base, run_gpu_nsx(x, 16000, tuning={"nsx_sync": 0, "nsx_cfg": cfg})), cfg
 
 
+def test_nsx_offline_across_a_threshold_relearning():
+    """60 frames per launch over 660 frames: the 512-frame re-learning reads histograms whose last increments were issued as
+    fire-and-forget REDs earlier in the same launch"""
+    x = make_frames(40, 16000, 0, 660, seed=59)
+    assert np.array_equal(oracle_core_run(16000, x[:, :10]), run_gpu_nsx(x, 16000, offline=60)[:, :10])
+    x8 = make_frames(40, 8000, 0, 660, seed=60)
+    assert np.array_equal(oracle_core_run(8000, x8[:, :10]), run_gpu_nsx(x8, 8000, offline=110)[:, :10])
+
+
 def test_nsx_chain_with_agc_and_vad_and_config1_wav():
     """NSX -> AGC -> VAD (the record chain with the switch thrown) against the oracle chain; config 1's wav through NSX"""
     from tests._oracle import RefChain

@@ -1272,3 +1272,50 @@ def test_errors_are_loud():
     assert lib.wmixb_mix_load_plan_device(plan, ring.data_ptr(), n + 8, n + 8, None, 0, None, None, st) != 0   # head outside the ring
     assert lib.wmixb_mix_load_plan_device(plan, ring.data_ptr(), n + 8, 0, None, 2, None, None, st) != 0        # producers without samples
     lib.wmixb_mixplan_destroy(plan)
+
+
+@pytest.mark.parametrize("law,freq,nminus1", [(0, 8000, 1), (1, 8000, 0), (0, 16000, 1)])
+def test_host_tick_with_g711_legs(law, freq, nminus1):
+    """wmixb_tick_host_g711: RTP-style legs arrive and leave as G.711 codes (one byte per sample over the host bus); decode -> NS ->
+    AGC -> VAD -> conference bus -> N-minus-one (or own leg) -> encode on the device, against the oracle's codecs and handles
+    and an int32 numpy bus, bit for bit"""
+    L = oracle()
+    S, T, n = 52, 70, freq // 100
+    bounds = np.array([0, 5, 5, 21, 40, S], np.int32)                       # one empty conference
+    x = make_frames(S, freq, 0, T, seed=103)
+    enc = L.orc_PCM2G711a if law == 0 else L.orc_PCM2G711u
+    dec = L.orc_G711a2PCM if law == 0 else L.orc_G711u2PCM
+    eng = wmix_b200.Engine(S, freq)
+    eng.set_conferences(bounds)
+    n_conf = len(bounds) - 1
+    chains = [RefChain(L, freq, prefix="orc_") for _ in range(S)]
+    codes = np.zeros((S, n), np.uint8)
+    got_codes, got_vad, got_bus = np.zeros((S, n), np.uint8), np.zeros(S, np.uint8), np.zeros((n_conf, n), np.int32)
+    lib = wmix_b200.lib()
+    for t in range(T):
+        pcm_in = np.ascontiguousarray(x[t])
+        enc(P(pcm_in), P(codes), S * n * 2)
+        assert lib.wmixb_tick_host_g711(eng.h, law, codes.ctypes.data, got_codes.ctypes.data, got_vad.ctypes.data, got_bus.ctypes.data,
+                                        nminus1, 0) == 0, lib.wmixb_last_error()
+        dec_pcm = np.zeros((S, n), np.int16)
+        dec(P(codes), P(dec_pcm), S * n)
+        proc = np.stack([chains[s].frame(dec_pcm[s]) for s in range(S)])
+        bus = np.stack([proc[bounds[c]:bounds[c + 1]].astype(np.int32).sum(axis=0) for c in range(n_conf)])
+        assert np.array_equal(got_bus, bus), t
+        if nminus1:
+            conf_of = np.repeat(np.arange(n_conf), np.diff(bounds))
+            leg = np.clip(bus[conf_of] - proc.astype(np.int32), -32768, 32767).astype(np.int16)
+        else:
+            leg = proc
+        want_codes = np.zeros((S, n), np.uint8)
+        enc(P(np.ascontiguousarray(leg)), P(want_codes), S * n * 2)
+        assert np.array_equal(got_codes, want_codes), t
+    for c in chains:
+        c.close()
+    # speech flags come back too, and nothing is written where nothing was asked for
+    assert got_vad.max() <= 1
+    assert lib.wmixb_tick_host_g711(eng.h, law, codes.ctypes.data, None, None, None, 0, 0) != 0
+    eng.close()
+    plain = wmix_b200.Engine(8, freq)
+    assert lib.wmixb_tick_host_g711(plain.h, law, codes.ctypes.data, got_codes.ctypes.data, None, None, 1, 0) != 0    # no conferences set
+    plain.close()

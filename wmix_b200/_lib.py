@@ -102,6 +102,7 @@ def lib():
         "wmixb_set_tuning": (i, [vp, C.c_char_p, i]),
         "wmixb_set_default_device": (i, [i]),
         "wmixb_default_device": (i, []),
+        "wmixb_tick_host_g711": (i, [vp, i, vp, vp, vp, vp, i, i]),
         "wmixb_set_default_ns_core": (i, [i]),
         "wmixb_default_ns_core": (i, []),
         "wmixb_host_alloc": (vp, [sz, i, i]),

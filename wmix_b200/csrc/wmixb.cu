@@ -752,6 +752,7 @@ struct wmixb_engine {
     int frame = 0, ana = 0, sm_count = 0;
     int row = 0;                            // samples per stream and tick in the caller's buffers: frame, or 320 for a 32 kHz engine
     int16_t* pack32 = nullptr;              // [n][160] staging of a 32 kHz engine's NS stage
+    uint8_t* d_codes = nullptr;             // 2 x [n][frame] G.711 codes in / out of wmixb_tick_host_g711
     size_t stride = 0;                      // SoA row pitch (streams rounded up to 32)
     float* ns_rec = nullptr;
     float* ns_hb = nullptr;                 // [n][OVERLAP] high-band history (cfg.ns_high_band: wmix's stereo NS)
@@ -1014,7 +1015,7 @@ extern "C" void wmixb_destroy(wmixb_engine* e)
     cudaFree(e->ns_rec); cudaFree(e->nsx_rec); cudaFree(e->nsx_tables); cudaFree(e->nsx_hb); cudaFree(e->ns_hist); cudaFree(e->ns_tables); cudaFree(e->ns_hb); cudaFree(e->ns_stage);
     cudaFree(e->agc_words); cudaFree(e->vad_words); cudaFree(e->agc_table);
     cudaFree(e->agc_init); cudaFree(e->vad_init);
-    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->pack32); cudaFree(e->d_out2); cudaFree(e->d_vad); cudaFree(e->d_pkt20);
+    cudaFree(e->d_in); cudaFree(e->d_out); cudaFree(e->pack32); cudaFree(e->d_codes); cudaFree(e->d_out2); cudaFree(e->d_vad); cudaFree(e->d_pkt20);
     for (int k = 0; k < kPipe; ++k) if (e->tail_ev[k]) cudaEventDestroy(e->tail_ev[k]);
     for (int k = 0; k < 2; ++k) if (e->done_ev[k]) cudaEventDestroy(e->done_ev[k]);
     cudaFree(e->conf_start); cudaFree(e->conf_of);
@@ -1677,6 +1678,54 @@ extern "C" int wmixb_tick_host_bus(wmixb_engine* e, const int16_t* h_in, int16_t
 {
     if (!h_bus) return WMIXB_EINVAL;
     return tick_host_impl(e, h_in, h_out, h_vad, h_bus, stages);
+}
+
+// G.711 legs in and out (include/wmixb.h): one byte per sample over the host bus, the codecs on the device around the stages
+extern "C" int wmixb_tick_host_g711(wmixb_engine* e, int law, const uint8_t* h_codes_in, uint8_t* h_codes_out, uint8_t* h_vad,
+                                    int32_t* h_bus, int nminus1, int stages)
+{
+    if (!e || !h_codes_in || (law != 0 && law != 1) || (!h_codes_out && !h_vad && !h_bus)) return WMIXB_EINVAL;
+    if (e->row != e->frame) { snprintf(g_err, sizeof g_err, "tick_host_g711: 8 / 16 kHz engines"); return WMIXB_EINVAL; }
+    if ((h_bus || nminus1) && e->n_conf < 1) { snprintf(g_err, sizeof g_err, "tick_host_g711: the bus and the N-minus-one read-out need wmixb_set_conferences"); return WMIXB_EINVAL; }
+    CK(cudaSetDevice(e->cfg.device));
+    const int n = e->cfg.n_streams;
+    const size_t cnt = (size_t)n * e->frame;
+    if (!e->d_codes) CK(cudaMalloc(&e->d_codes, 2 * cnt));
+    uint8_t *c_in = e->d_codes, *c_out = e->d_codes + cnt;
+    cudaStream_t st = e->stream;
+    CK(cudaMemcpyAsync(c_in, h_codes_in, cnt, cudaMemcpyHostToDevice, st));
+    int rc = wmixb_g711_decode_device(law, c_in, e->d_in, cnt, st);
+    if (rc) return rc;
+    rc = run_stages(e, e->d_in, e->d_out, e->d_vad, 1, stages, st);
+    if (rc) return rc;
+    const int16_t* leg = e->d_out;
+    if (h_bus || nminus1) {
+        const size_t bus_bytes = (size_t)e->n_conf * e->frame * sizeof(int32_t);
+        if (e->d_bus_bytes < bus_bytes) {
+            CK(cudaStreamSynchronize(st));
+            cudaFree(e->d_bus);
+            e->d_bus = nullptr;
+            e->d_bus_bytes = 0;
+            CK(cudaMalloc(&e->d_bus, bus_bytes));
+            e->d_bus_bytes = bus_bytes;
+        }
+        rc = wmixb_bus_sum_device(e, e->d_out, e->d_bus, st);
+        if (rc) return rc;
+        if (h_bus) CK(cudaMemcpyAsync(h_bus, e->d_bus, bus_bytes, cudaMemcpyDeviceToHost, st));
+        if (nminus1 && h_codes_out) {
+            rc = wmixb_bus_nminus1_device(e, e->d_bus, e->d_out, e->d_in, st);      // d_in is free again: the read-out lands there
+            if (rc) return rc;
+            leg = e->d_in;
+        }
+    }
+    if (h_codes_out) {
+        rc = wmixb_g711_encode_device(law, leg, c_out, cnt, st);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(h_codes_out, c_out, cnt, cudaMemcpyDeviceToHost, st));
+    }
+    if (h_vad) CK(cudaMemcpyAsync(h_vad, e->d_vad, (size_t)n, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return WMIXB_OK;
 }
 
 // ---- conference bus ----
