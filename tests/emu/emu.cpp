@@ -365,6 +365,17 @@ int emu_nsx_tables(int freq, int policy, void* out, int cap)
     memcpy(out, &T, sizeof T);
     return (int)sizeof T;
 }
+// the VAD's minimum tracker on its own (vad::find_minimum on the packed lists): a feature sequence for one channel, the
+// smoothed value per step in `out`, the channel's 8 + 8 list words and the mean-value word at the end in `words_out[17]`
+void emu_vad_minimum_run(const int16_t* feats, int n, int ch, int16_t* out, int32_t* words_out)
+{
+    std::vector<int32_t> w(vad::N_WORDS, 0);
+    host::vad_initial_words(w.data());
+    SoaWords st{w.data(), 1};
+    for (int t = 0; t < n; ++t) out[t] = vad::find_minimum(st, feats[t], ch, t);
+    for (int k = 0; k < 8; ++k) { words_out[k] = w[vad::W_AGE + ch * 8 + k]; words_out[8 + k] = w[vad::W_LOW + ch * 8 + k]; }
+    words_out[16] = w[vad::W_MEANVAL + (ch >> 1)];
+}
 int emu_ns_rec_floats(int freq) { return freq == 8000 ? ns::Geo<128>::kRecFloats : ns::Geo<256>::kRecFloats; }
 const uint16_t* emu_ns_hist(void* h) { return ((EmuNs*)h)->hist.data(); }
 int emu_agc_gain_table(int32_t* t, int comp, int target, int lim, int at) { return host::agc_gain_table(t, (int16_t)comp, (int16_t)target, lim, (int16_t)at); }

@@ -508,3 +508,47 @@ def test_rtp_host_header_helpers_vs_oracle():
         f = meta.view(np.uint32)
         assert f[0] == ts and f[1] == ssrc and meta[8:10].view(np.uint16)[0] == seq
         assert meta[10] == pt and meta[11] == m and meta[12] == a[0] and meta[13] == int(v == 2 and pt in (0, 8))
+
+
+def test_vad_minimum_tracker_on_packed_lists_vs_oracle():
+    """vad::find_minimum works on the record's packed (age, value) pairs with funnel shifts; against the oracle's list code
+    (pinned to the reference's WebRtcVad_FindMinimum KAT) over feature sequences built to hit its corners: all sixteen initial
+    entries expiring in one frame, the entry behind an expired one skipping its ageing, expiry at even and odd places,
+    insertions at every place, values at and above the 10000 sentinel, long stretches without any insertion"""
+    import ctypes as C
+
+    E, L = emu(), oracle()
+    rng = np.random.default_rng(12)
+    from tests.test_oracle_pin import VadCore
+
+    E.emu_vad_minimum_run.restype = None
+    L.orc_vad_find_minimum.restype = C.c_int16
+
+    def sequences():
+        yield np.full(230, 12000, np.int16)                                   # nothing ever inserted: the 16 initial entries expire together
+        yield np.concatenate([np.arange(3000, 3016), np.full(240, 9000)]).astype(np.int16)       # 16 consecutive inserts, then they expire one per frame
+        yield np.concatenate([np.arange(3016, 3000, -1), np.full(240, 9999)]).astype(np.int16)   # always at place 0
+        yield np.concatenate([np.full(40, 10000), np.arange(100, 140), np.full(150, 10001)]).astype(np.int16)
+        for _ in range(40):
+            n = int(rng.integers(150, 700))
+            base = rng.integers(-2000, 11000, size=n)
+            hold = rng.integers(0, 2, size=n).astype(bool)                     # stretches of large values let entries reach 100
+            seq = np.where(hold, rng.integers(9000, 12000, size=n), base)
+            yield seq.astype(np.int16)
+
+    for k, feats in enumerate(sequences()):
+        ch = k % 6
+        core = VadCore()
+        L.orc_vad_core_init(C.byref(core), 3)
+        want = np.zeros(len(feats), np.int16)
+        for t, f in enumerate(feats):
+            core.frame_counter = t
+            want[t] = L.orc_vad_find_minimum(C.byref(core), int(f), ch)
+        got = np.zeros(len(feats), np.int16)
+        words = np.zeros(17, np.int32)
+        E.emu_vad_minimum_run(P(np.ascontiguousarray(feats)), len(feats), ch, P(got), P(words))
+        assert np.array_equal(got, want), (k, int(np.nonzero(got != want)[0][0]))
+        ages = np.array(core.age[ch * 16:(ch + 1) * 16], np.int16)
+        lows = np.array(core.low_value[ch * 16:(ch + 1) * 16], np.int16)
+        assert np.array_equal(words[:8].view(np.int16), ages), k
+        assert np.array_equal(words[8:16].view(np.int16), lows), k

@@ -219,58 +219,83 @@ WMX_HD int32_t gaussian(int16_t input, int16_t mean, int16_t sd, int16_t& delta)
 #endif
 }
 
-// 16 smallest feature values of the last 100 frames + smoothed "median"
-// (T:.../vad/vad_sp.c:59-177).  The 16-entry lists live in registers; all indices are static
-// after unrolling, the rare age==100 eviction is a real branch.
+// 16 smallest feature values of the last 100 frames + smoothed "median" (T:.../vad/vad_sp.c:59-177).
+// The two 16-entry lists stay PACKED as the record holds them — entry 2w in the low half of word w, 2w+1 in the high half —
+// and every step works on the pairs: a warp carries 32 streams and some lane evicts an entry on most frames, so the
+// "rare" eviction runs for the whole warp; as funnel shifts of eight words it costs a quarter of moving 2 x 15 unpacked
+// entries, and nothing is unpacked on entry or re-packed on exit.  All indices are static after unrolling.
+WMX_HD uint32_t pair_down(uint32_t cur, uint32_t next) { return (cur >> 16) | (next << 16); }   // (cur.hi, next.lo)
 WMX_HD int16_t find_minimum(const SoaWords& st, int16_t feature, int ch, int32_t frame_counter)
 {
-    int16_t age[16], low[16];
+    uint32_t A[8], Lw[8];
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-        int32_t a = st.get(W_AGE + ch * 8 + w), l = st.get(W_LOW + ch * 8 + w);
-        age[2 * w] = lo16(a); age[2 * w + 1] = hi16(a);
-        low[2 * w] = lo16(l); low[2 * w + 1] = hi16(l);
+        A[w] = (uint32_t)st.get(W_AGE + ch * 8 + w);
+        Lw[w] = (uint32_t)st.get(W_LOW + ch * 8 + w);
     }
+    // every entry gets one frame older; an entry that has reached 100 is removed instead: the entries behind it move down
+    // one place on the LIVE list and (age 101, value 10000) enters at the end.  As in the reference the scan then goes on
+    // with the next POSITION, so the entry that moved into the freed place is neither aged nor examined this frame, and its
+    // copy loop's read one past the list lands in the slot the sentinel overwrites (vad_sp.c:78-90).
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
-        if (age[i] != 100) {
-            age[i]++;
+        const int w = i >> 1;
+        const uint32_t age_i = (i & 1) ? A[w] >> 16 : A[w] & 0xFFFFu;
+        if (age_i != 100u) {
+            A[w] = (i & 1) ? A[w] + 0x10000u : (A[w] & 0xFFFF0000u) | ((A[w] + 1u) & 0xFFFFu);
         } else {
-            // the reference's copy loop reads one element past the list for j == 15 and then
-            // overwrites slot 15 (vad_sp.c:83-88), so only j < 15 carries data
 #pragma unroll
-            for (int j = 0; j < 15; ++j)
-                if (j >= i) { low[j] = low[j + 1]; age[j] = age[j + 1]; }
-            age[15] = 101;
-            low[15] = 10000;
+            for (int v = w; v < 8; ++v) {
+                const uint32_t na = v < 7 ? A[v + 1] : 101u, nl = v < 7 ? Lw[v + 1] : 10000u;
+                if (v == w && (i & 1)) {
+                    A[v] = (A[v] & 0xFFFFu) | (na << 16);
+                    Lw[v] = (Lw[v] & 0xFFFFu) | (nl << 16);
+                } else {
+                    A[v] = pair_down(A[v], na);
+                    Lw[v] = pair_down(Lw[v], nl);
+                }
+            }
         }
     }
-    // fixed comparison tree of the reference (vad_sp.c:93-146)
-    int pos = -1;
-    if (feature < low[7]) {
-        if (feature < low[3]) {
-            if (feature < low[1]) pos = (feature < low[0]) ? 0 : 1;
-            else pos = (feature < low[2]) ? 2 : 3;
-        } else if (feature < low[5]) pos = (feature < low[4]) ? 4 : 5;
-        else pos = (feature < low[6]) ? 6 : 7;
-    } else if (feature < low[15]) {
-        if (feature < low[11]) {
-            if (feature < low[9]) pos = (feature < low[8]) ? 8 : 9;
-            else pos = (feature < low[10]) ? 10 : 11;
-        } else if (feature < low[13]) pos = (feature < low[12]) ? 12 : 13;
-        else pos = (feature < low[14]) ? 14 : 15;
+#define WMX_LOW(i) ((int16_t)(((i) & 1) ? Lw[(i) >> 1] >> 16 : Lw[(i) >> 1] & 0xFFFFu))
+    // fixed comparison tree of the reference (vad_sp.c:93-146); 16 = nothing to insert
+    int pos = 16;
+    if (feature < WMX_LOW(7)) {
+        if (feature < WMX_LOW(3)) {
+            if (feature < WMX_LOW(1)) pos = (feature < WMX_LOW(0)) ? 0 : 1;
+            else pos = (feature < WMX_LOW(2)) ? 2 : 3;
+        } else if (feature < WMX_LOW(5)) pos = (feature < WMX_LOW(4)) ? 4 : 5;
+        else pos = (feature < WMX_LOW(6)) ? 6 : 7;
+    } else if (feature < WMX_LOW(15)) {
+        if (feature < WMX_LOW(11)) {
+            if (feature < WMX_LOW(9)) pos = (feature < WMX_LOW(8)) ? 8 : 9;
+            else pos = (feature < WMX_LOW(10)) ? 10 : 11;
+        } else if (feature < WMX_LOW(13)) pos = (feature < WMX_LOW(12)) ? 12 : 13;
+        else pos = (feature < WMX_LOW(14)) ? 14 : 15;
     }
-    if (pos > -1) {
+    // insert (feature, age 1) at pos: the entries from pos on move up one place, the last one drops out (vad_sp.c:150-158).
+    // Downwards over the words so that word w - 1 is still the old one when word w takes its high half.
+    {
+        const uint32_t fv = (uint32_t)(uint16_t)feature;
 #pragma unroll
-        for (int i = 15; i > 0; --i)
-            if (i > pos) { low[i] = low[i - 1]; age[i] = age[i - 1]; }
-#pragma unroll
-        for (int i = 0; i < 16; ++i)
-            if (i == pos) { low[i] = feature; age[i] = 1; }
+        for (int w = 7; w >= 0; --w) {
+            const uint32_t pa = w > 0 ? A[w - 1] : 0u, pl = w > 0 ? Lw[w - 1] : 0u;
+            if (pos < 2 * w) {
+                A[w] = (pa >> 16) | (A[w] << 16);
+                Lw[w] = (pl >> 16) | (Lw[w] << 16);
+            } else if (pos == 2 * w) {
+                A[w] = 1u | (A[w] << 16);
+                Lw[w] = fv | (Lw[w] << 16);
+            } else if (pos == 2 * w + 1) {
+                A[w] = (A[w] & 0xFFFFu) | (1u << 16);
+                Lw[w] = (Lw[w] & 0xFFFFu) | (fv << 16);
+            }
+        }
     }
     int16_t median = 1600, alpha = 0;
-    if (frame_counter > 2) median = low[2];
-    else if (frame_counter > 0) median = low[0];
+    if (frame_counter > 2) median = WMX_LOW(2);
+    else if (frame_counter > 0) median = WMX_LOW(0);
+#undef WMX_LOW
     int w = st.get(W_MEANVAL + (ch >> 1));
     int16_t mv = (ch & 1) ? hi16(w) : lo16(w);
     if (frame_counter > 0) alpha = (median < mv) ? 6553 : 32439;
@@ -281,8 +306,8 @@ WMX_HD int16_t find_minimum(const SoaWords& st, int16_t feature, int ch, int32_t
     st.set(W_MEANVAL + (ch >> 1), (ch & 1) ? pack16(lo16(w), mv) : pack16(mv, hi16(w)));
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        st.set(W_AGE + ch * 8 + k, pack16(age[2 * k], age[2 * k + 1]));
-        st.set(W_LOW + ch * 8 + k, pack16(low[2 * k], low[2 * k + 1]));
+        st.set(W_AGE + ch * 8 + k, (int32_t)A[k]);
+        st.set(W_LOW + ch * 8 + k, (int32_t)Lw[k]);
     }
     return mv;
 }

@@ -520,9 +520,31 @@ post_kernel(int32_t* __restrict__ agc_words, int32_t* __restrict__ vad_words, co
     SoaWords vad_st{vad_words ? vad_words + s : nullptr, stride};
     for (int f = 0; f < n_frames; ++f) {
         __syncthreads();
-        for (int idx = tid; idx < rows * (L / 2); idx += THREADS) {
-            const int r = idx / (L / 2), w = idx - r * (L / 2);
-            tile[r * ROWW + w] = in32[((size_t)(s0 + r) * n_frames + f) * (L / 2) + w];
+        // a warp moves whole rows, a lane the words lane, lane + 32, (lane + 64) of each: no index division, and four rows'
+        // loads are in flight before the first store (the flat idx = r * 40 + w loop was a tenth of the kernel's instructions
+        // and its load -> store pairs waited for DRAM one after the other)
+        {
+            constexpr int WPR = L / 2, NW = THREADS / 32;               // words per row, warps
+            const int wid = tid >> 5, ln = tid & 31;
+#pragma unroll 1
+            for (int r0 = wid; r0 < rows; r0 += 4 * NW) {
+                int32_t v[4][(WPR + 31) / 32];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = r0 + q * NW;
+                    const int32_t* src = in32 + ((size_t)(s0 + r) * n_frames + f) * WPR;
+#pragma unroll
+                    for (int k = 0; k < (WPR + 31) / 32; ++k)
+                        if (r < rows && ln + 32 * k < WPR) v[q][k] = src[ln + 32 * k];
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int r = r0 + q * NW;
+#pragma unroll
+                    for (int k = 0; k < (WPR + 31) / 32; ++k)
+                        if (r < rows && ln + 32 * k < WPR) tile[r * ROWW + ln + 32 * k] = v[q][k];
+                }
+            }
         }
         __syncthreads();
         int16_t* x = reinterpret_cast<int16_t*>(tile + tid * ROWW);
@@ -555,9 +577,16 @@ post_kernel(int32_t* __restrict__ agc_words, int32_t* __restrict__ vad_words, co
             }
         }
         __syncthreads();
-        for (int idx = tid; idx < rows * (L / 2); idx += THREADS) {
-            const int r = idx / (L / 2), w = idx - r * (L / 2);
-            out32[((size_t)(s0 + r) * n_frames + f) * (L / 2) + w] = tile[r * ROWW + w];
+        {
+            constexpr int WPR = L / 2, NW = THREADS / 32;
+            const int wid = tid >> 5, ln = tid & 31;
+#pragma unroll 2
+            for (int r = wid; r < rows; r += NW) {
+                int32_t* dst = out32 + ((size_t)(s0 + r) * n_frames + f) * WPR;
+#pragma unroll
+                for (int k = 0; k < (WPR + 31) / 32; ++k)
+                    if (ln + 32 * k < WPR) dst[ln + 32 * k] = tile[r * ROWW + ln + 32 * k];
+            }
         }
     }
 }
