@@ -31,4 +31,9 @@ ncu --set full --clock-control none --import-source on -k regex:aec_kernel -s 42
 # the staged (persistent offline) NS kernel: DRAM bytes per frame against the tick kernel
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --clock-control none -k regex:ns_cta_kernel -s 600 -c 4 --csv \
     --log-file gpurun_out/${TAG}_offline_dram.csv python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-config4 --no-full-load > /dev/null 2>&1
+# the reports are ~37 MB each and gpurun brings back at most 64 MiB: summarise them here, keep only the NS one
+for k in ns post aec; do
+  python tools/ncu_summary.py gpurun_out/${TAG}_$k.ncu-rep > gpurun_out/${TAG}_${k}_ncu.md 2>/dev/null
+done
+rm -f gpurun_out/${TAG}_post.ncu-rep gpurun_out/${TAG}_aec.ncu-rep
 ls -la gpurun_out | tail -12

@@ -38,8 +38,11 @@ def main():
     g = lambda f: os.path.join(R, "gpurun_out", "%s_%s" % (tag, f))
     b, ref = last_json(g("bench.json")), last_json(g("bench_reference.json"))
     w5 = last_json(g("bench_w5.json")) if os.path.exists(g("bench_w5.json")) else None
-    summ = lambda k: subprocess.run([sys.executable, os.path.join(R, "tools", "ncu_summary.py"), g(k + ".ncu-rep")],
-                                    capture_output=True, text=True).stdout
+    def summ(k):
+        # the summary written on the GPU box (tools/gpu_profile.sh) when the report itself did not travel back
+        if os.path.exists(g(k + "_ncu.md")):
+            return open(g(k + "_ncu.md")).read()
+        return subprocess.run([sys.executable, os.path.join(R, "tools", "ncu_summary.py"), g(k + ".ncu-rep")], capture_output=True, text=True).stdout
     km, e, rf = b["kernel_ms"], b["e2e"], b["roofline"]
     out = ["# Round 2, capture %s" % tag.split("_")[-1].upper(), "",
            "Commands (one B200 via `gpurun`, `tools/gpu_profile.sh %s`): `python bench.py`, `python bench.py --steps 20 --warmup 5` (the driver's flags) and" % tag,
@@ -77,7 +80,7 @@ def main():
     out += ["", "## Launch shares (ncu launch list, cold-cache serialised; agrees with the CUDA-event split above)", "| kernel | mean us | share |", "|---|---|---|"]
     out += ["| %s | %.1f | %.1f %% |" % x for x in launch_shares(g("launches.csv"))]
     for k in ("ns", "post", "aec"):
-        if os.path.exists(g(k + ".ncu-rep")):
+        if os.path.exists(g(k + ".ncu-rep")) or os.path.exists(g(k + "_ncu.md")):
             out += ["", "## %s kernel, `--set full`" % k, summ(k)]
     open(os.path.join(R, "profiles", "%s_summary.md" % tag), "w").write("\n".join(out))
     for f in ("bench.json", "bench_w5.json", "bench_reference.json", "launches.csv", "tests.txt"):
