@@ -1,7 +1,5 @@
 #!/usr/bin/env bash
-# round 2, capture y2: ncu --set full of post_kernel after the packed minimum tracker
 set -u
 mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:post_kernel -s 605 -c 1 -o gpurun_out/r2y_post -f \
-    python bench.py --steps 20 --warmup 10 --no-cpu-baseline --no-config4 --no-full-load --no-offline --no-nsx > /dev/null 2>&1
-ls -la gpurun_out/r2y_post.ncu-rep
+(time timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_multi_gpu.py -x -q -k "bus or conference or host or pipelined or g711") > gpurun_out/r2y_tests.txt 2>&1; tail -3 gpurun_out/r2y_tests.txt
+for i in 1 2; do timeout 900 python bench.py --steps 200 --no-cpu-baseline --no-config4 --no-full-load --no-offline --no-nsx 2> gpurun_out/r2y_bench.err | python -c "import json,sys; d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print(d['ms_per_step'], d['kernel_ms'], 'e2e', d['e2e']['ms_per_step'])"; done
