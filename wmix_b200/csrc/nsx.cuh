@@ -798,19 +798,17 @@ WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, 
     const int shifts = 5 - q_magn_prev + q_noise_prev;
     int32_t p_sum = 0, p_max = 0, p_min = 0x7fffffff;
     WMX_NSX_BINS(k) {
-        uint32_t a = R.magn[k] << 6, b, post = 2048;
+        // (the quotients are formed unconditionally on a safe divisor and selected afterwards: with 32 bins per instruction
+        // some lane needs every one of them, and a branch around a division only adds the divergence bookkeeping)
+        uint32_t a = R.magn[k] << 6, b;
         b = post_shifts < 0 ? xshr(R.noise[k], -post_shifts) : xshl(R.noise[k], post_shifts);
-        if (a > b) {
-            a <<= 11;
-            if (b > 0) { a /= b; post = umin(a, kSatMax); }
-            else post = kSatMax;
-        }
+        const uint32_t q_post = (a << 11) / (b ? b : 1u);
+        const uint32_t post = a > b ? (b > 0 ? umin(q_post, kSatMax) : kSatMax) : 2048u;
         const uint32_t filt = *bin_word<ANA>(rec, A_QF, k, lane) >> 16;
         const uint32_t mprev = *bin_word<ANA>(rec, A_MPREV, k, lane) & 0xFFFFu;
         a = (mprev * filt) << 3;
         b = xshr(*bin_word<ANA>(rec, A_NPREV, k, lane), shifts);
-        if (b > 0) { a /= b; a = umin(a, kSatMax); }
-        else a = kSatMax;
+        a = b > 0 ? umin(a / (b ? b : 1u), kSatMax) : kSatMax;
         R.near_prev[k] = a;
         R.post[k] = post;
         R.prior[k] = 2048u + ((a * 2007u + (post - 2048u) * 41u + 512u) >> 10);
@@ -977,8 +975,7 @@ WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, 
         const int n = norm_u32(post);
         const uint32_t num = post << n;
         const uint32_t den = n > 10 ? xshl(prior, n - 11) : xshr(prior, 11 - n);
-        if (den > 0) bessel -= (int32_t)(num / den);
-        else bessel = 0;
+        bessel = den > 0 ? bessel - (int32_t)(num / (den ? den : 1u)) : 0;
         const int z = norm_u32(prior);
         int32_t frac32 = (int32_t)(((prior << z) & 0x7FFFFFFFu) >> 19);
         int32_t t = (frac32 * frac32 * -43) >> 19;
@@ -1048,7 +1045,7 @@ WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, 
     WMX_NSX_BINS(k) {
         uint32_t ns = 0;
         const int32_t lrt = (int32_t)R.post[k];
-        if (prior_ns > 0 && lrt < 65300) {
+        if (prior_ns > 0) {                                            // warp-uniform
             int32_t t = wmul(lrt, 23637) >> 14;
             int int_part = (int16_t)(t >> 12);
             if (int_part < -8) int_part = -8;
@@ -1057,18 +1054,12 @@ WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, 
             t2 += (frac * 84) >> 7;
             int32_t inv_lrt = (int32_t)xshl(1u, 8 + int_part) + xshift(t2, int_part - 4);
             const int n1 = norm_w32(inv_lrt), n2 = norm_w16((int16_t)(16384 - prior_ns));
-            if (n1 + n2 >= 7) {
-                if (n1 + n2 < 15) {
-                    inv_lrt = xsar(inv_lrt, 15 - n2 - n1);
-                    t = wmul(inv_lrt, 16384 - prior_ns);
-                    inv_lrt = xshift(t, 7 - n1 - n2);
-                } else {
-                    t = wmul(inv_lrt, 16384 - prior_ns);
-                    inv_lrt = t >> 8;
-                }
-                t = prior_ns << 8;
-                ns = (uint32_t)(t / (prior_ns + inv_lrt)) & 0xFFFFu;
-            }
+            const int32_t lo = xshift(wmul(xsar(inv_lrt, 15 - n2 - n1), 16384 - prior_ns), 7 - n1 - n2);
+            const int32_t hi = wmul(inv_lrt, 16384 - prior_ns) >> 8;
+            inv_lrt = n1 + n2 < 15 ? lo : hi;
+            const int32_t den = prior_ns + inv_lrt;
+            const uint32_t q = (uint32_t)((prior_ns << 8) / (den ? den : 1)) & 0xFFFFu;
+            ns = (lrt < 65300 && n1 + n2 >= 7) ? q : 0u;                  // both paths of the reference leave 0 otherwise
         }
         R.nonsp[k] = ns;
         tbins[k < K ? 32 * k + lane : HALF] = ns;
@@ -1136,14 +1127,14 @@ WMX_HD int frame(Warp<ANA>& W, uint32_t* rec, int16_t* hist, const int16_t* in, 
         if (shifts < 0) { m = magn; nz = xshl(noise, -shifts); }
         else if (shifts > 17) { m = magn << 17; nz = xshr(noise, shifts - 17); }
         else { m = xshl(magn, shifts); nz = noise; }
-        if (m > nz) {
-            uint32_t a = m - nz;
+        {
+            uint32_t a = m - nz;                                       // only used when m > nz
             int n = norm_u32(a);
             if (n > 11) n = 11;
             a <<= n;
             const uint32_t b = nz >> (11 - n);
-            if (b > 0) a /= b;
-            cur = umin(a, kSatMax);
+            a /= (b ? b : 1u);                                         // b == 0: the reference skips the division
+            cur = m > nz ? umin(a, kSatMax) : 0u;
         }
         const uint32_t prior = R.near_prev[k] * 2007u + cur * 41u;
         uint32_t a = (uint32_t)T.overdrive + ((prior + 8192u) >> 14);
