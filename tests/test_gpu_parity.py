@@ -1319,3 +1319,33 @@ def test_host_tick_with_g711_legs(law, freq, nminus1):
     plain = wmix_b200.Engine(8, freq)
     assert lib.wmixb_tick_host_g711(plain.h, law, codes.ctypes.data, got_codes.ctypes.data, None, None, 1, 0) != 0    # no conferences set
     plain.close()
+
+
+def test_dropin_handles_at_24khz_fail_the_way_the_reference_does():
+    """24 kHz passes the wrappers' rate test (freq <= 32000 && freq % 8000 == 0, R:src/webrtc.c:43, :563, :711) although no
+    WebRTC module takes it: ns_init gives NULL (WebRtcNs_Init refuses), vad_init and agc_init hand out handles whose every
+    process call fails — vad_process leaves a mono frame untouched and a stereo frame half-averaged, agc_process returns -1
+    with its output untouched.  Same calls through the drop-in library, the oracle and (when it is here) the reference."""
+    lib = wmix_b200.lib()
+    x = ((np.arange(480) % 97) * 50 - 2000).astype(np.int16)
+    assert not lib.ns_init(1, 24000, None) and not lib.aec_init(1, 24000, 10, None)
+    for cname, L, prefix in checkers():
+        for chn in (1, 2):
+            hc = C.c_void_p(L.orc_vad_init(chn, 24000, 10) if prefix else L.vad_init(chn, 24000, 10, None))
+            hg = lib.vad_init(chn, 24000, 10, None)
+            assert hc and hg
+            a, b = x.copy(), x.copy()
+            (L.orc_vad_process if prefix else L.vad_process)(hc, P(a), 240 // chn)
+            lib.vad_process(hg, b.ctypes.data, 240 // chn)
+            assert np.array_equal(a, b) and (chn == 1) == bool(np.array_equal(a, x)), (cname, chn)
+            (L.orc_vad_release if prefix else L.vad_release)(hc)
+            lib.vad_release(hg)
+        hc = C.c_void_p(L.orc_agc_init(1, 24000, 10, 5) if prefix else L.agc_init(1, 24000, 10, 5, None))
+        hg = lib.agc_init(1, 24000, 10, 5, None)
+        assert hc and hg
+        a, b = np.full(240, 7, np.int16), np.full(240, 7, np.int16)
+        rc_c = (L.orc_agc_process if prefix else L.agc_process)(hc, P(x.copy()), P(a), 240)
+        rc_g = lib.agc_process(hg, x.copy().ctypes.data, b.ctypes.data, 240)
+        assert rc_c == rc_g == -1 and np.array_equal(a, b) and (a == 7).all(), cname
+        (L.orc_agc_release if prefix else L.agc_release)(hc)
+        lib.agc_release(hg)

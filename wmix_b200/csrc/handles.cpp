@@ -26,6 +26,7 @@ struct Handle {
     wmixb_engine* eng = nullptr;
     int chn = 1, freq = 0, pkg = 0, stage = 0;
     bool* debug = nullptr;
+    bool bad_rate = false;   // 24 kHz: the reference's vad_init / agc_init hand out a handle whose every process call fails
     std::vector<int16_t> mono, res, far, hb, hb_res;   // hb: right channel of a stereo NS handle
 };
 
@@ -38,7 +39,7 @@ Handle* make(int stage, int chn, int freq, int gain, bool* debug, const char* wh
     wmixb_config c;
     memset(&c, 0, sizeof c);
     c.n_streams = 1;
-    c.freq = freq == 32000 ? 16000 : freq;
+    c.freq = (freq == 32000 || freq == 24000) ? 16000 : freq;
     c.stages = stage;
     c.ns_policy = 2;      // NS_AGGRESSIVE, R:src/webrtc.c:532
     c.agc_gain_db = gain; // compressionGaindB, R:src/webrtc.c:707
@@ -57,6 +58,7 @@ Handle* make(int stage, int chn, int freq, int gain, bool* debug, const char* wh
     h->freq = freq;
     h->pkg = c.freq / 100;
     h->stage = stage;
+    h->bad_rate = freq == 24000;
     h->debug = debug;
     h->mono.resize((size_t)h->pkg);
     h->res.resize((size_t)h->pkg);
@@ -104,6 +106,13 @@ void vad_process(void* fp, int16_t* frame, int frameNum)
             frame[mono++] = (int16_t)(s / h->chn);
         }
     }
+    if (h->bad_rate) {
+        // 24 kHz passes vad_init's rate test (R:src/webrtc.c:43) but WebRtcVad_Process refuses the rate: the reference returns
+        // here, with the frame untouched — or, for a stereo frame, with its first half already averaged to mono and never
+        // expanded again (R:src/webrtc.c:121-127)
+        if (dbg(h->debug)) printf("WebRtcVad_Process failed !!, ret %d \r\n", -1);
+        return;
+    }
     // R:src/webrtc.c:120-141 always hands the detector the START of the buffer and attenuates
     // [cLen, pkgFrame): with more than one packet per call only the first is ever touched.
     for (int pos = 0; pos < mono; pos += h->pkg) {
@@ -139,6 +148,7 @@ void* ns_init(int chn, int freq, bool* debug)
 {
     if (!rate_ok(freq, 32000)) return nullptr;                      // R:src/webrtc.c:563
     if (chn != 1 && chn != 2) return nullptr;                        // the reference only has in[2] / out[2]
+    if (freq == 24000) return nullptr;                               // passes the rate test, WebRtcNs(x)_Init then refuses it (R:src/webrtc.c:569)
     // two channels: the right one is WebRtcNs's "high band" (num_bands = chn, R:src/webrtc.c:624-636) -> wmixb_ns2_host
     Handle* h = make(WMIXB_NS, chn, freq, 0, debug, "ns_init", chn == 2);
     if (!h) return nullptr;
@@ -196,6 +206,12 @@ int agc_process(void* fp, int16_t* frame, int16_t* frameOut, int frameNum)
 {
     Handle* h = (Handle*)fp;
     const int total = frameNum * h->chn, step = h->pkg * h->chn;
+    if (h->bad_rate && total > 0) {
+        // 24 kHz: agc_init succeeds in the reference, WebRtcAgc_Process then fails on the packet length and agc_process returns
+        // its code with frameOut untouched (R:src/webrtc.c:806-811)
+        if (dbg(h->debug)) printf("WebRtcAgc_Process failed !!, ret %d \r\n", -1);
+        return -1;
+    }
     for (int pos = 0; pos < total; pos += step) {                   // R:src/webrtc.c:786-818
         for (int i = 0; i < h->pkg; ++i) {
             int32_t s = 0;
