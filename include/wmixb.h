@@ -204,6 +204,21 @@ int wmixb_peer_bus_connect_local(wmixb_peer_bus* pb, wmixb_peer_bus* const* peer
 int wmixb_peer_bus_tick_device(wmixb_peer_bus* pb, int law, const void* d_in, void* d_out, int32_t* d_bus, void* stream);
 int wmixb_peer_bus_status(wmixb_peer_bus* pb, int* h_error);
 
+/* The same exchange over NCCL, from C: wmixb_*bus_sum_device -> ncclAllReduce(int32, sum) over the node's NVLink / NVSwitch ->
+ * wmixb_*bus_nminus1_device behind one call, for a host that has no communicator of its own.  libnccl is NOT a link-time
+ * dependency of this library: it is opened on first use (dlopen "libnccl.so.2", or the path given to wmixb_nccl_load), and
+ * every entry point below reports WMIXB_ENODEV with a reason when it is not there.  Wiring: rank 0 calls wmixb_nccl_unique_id
+ * and ships the WMIXB_NCCL_ID_BYTES blob to the other ranks over any transport; every rank then calls wmixb_nccl_bus_create
+ * (collective).  Ticks are collective too: same number of calls on every rank, each on a stream of its own device.  Same
+ * arguments and the same bits as wmixb_peer_bus_tick_device (d_bus must be given: the all-reduce runs on it). */
+typedef struct wmixb_nccl_bus wmixb_nccl_bus;
+#define WMIXB_NCCL_ID_BYTES 128
+int wmixb_nccl_load(const char* libnccl_path);          /* optional; NULL = default search */
+int wmixb_nccl_unique_id(void* id_out);
+int wmixb_nccl_bus_create(wmixb_engine* e, int rank, int world, const void* id, wmixb_nccl_bus** out);
+void wmixb_nccl_bus_destroy(wmixb_nccl_bus* nb);
+int wmixb_nccl_bus_tick_device(wmixb_nccl_bus* nb, int law, const void* d_in, void* d_out, int32_t* d_bus, void* stream);
+
 /* G.711 on device buffers (R:src/g711codec.c).  law: 0 = A-law, 1 = mu-law.  n = samples. */
 int wmixb_g711_encode_device(int law, const int16_t* d_pcm, uint8_t* d_codes, size_t n, void* stream);
 int wmixb_g711_decode_device(int law, const uint8_t* d_codes, int16_t* d_pcm, size_t n, void* stream);

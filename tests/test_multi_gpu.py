@@ -155,8 +155,8 @@ def _nccl_worker(rank, world, port, sizes, law, q, opts=None):
         mine = plan.local_members(rank)
         dev = "cuda:%d" % rank
         results = {}
-        for mode in ("peer", "nccl"):
-            conf = ShardedConference(plan, rank, law=law, freq=8000, mode=mode, device=rank, peer_opts=opts)
+        for mode in ("peer", "nccl", "nccl_c"):
+            conf = ShardedConference(plan, rank, law=law, freq=8000, mode=mode, device=rank, peer_opts=opts if mode == "peer" else None)
             d_bus = torch.empty((plan.n_conf, frame), dtype=torch.int32, device=dev)
             outs = []
             for t in range(T):
@@ -172,6 +172,7 @@ def _nccl_worker(rank, world, port, sizes, law, q, opts=None):
             dist.barrier()
             conf.close()
         ok &= all(np.array_equal(a, b) for a, b in zip(results["peer"], results["nccl"]))
+        ok &= all(np.array_equal(a, b) for a, b in zip(results["peer"], results["nccl_c"]))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
@@ -195,3 +196,21 @@ def test_two_processes_peer_and_nccl_modes_agree_with_oracle(law, sizes, opts):
         p.join(timeout=120)
         assert p.exitcode == 0
     assert sorted(res) == [(0, True), (1, True)]
+
+
+@needs2
+def test_nccl_bus_from_plain_c_two_threads_two_gpus(tmp_path):
+    """The NCCL exchange of the conference bus driven from C alone (tests/c/nccl_from_c.c): two host threads, one GPU each,
+    wmixb_nccl_bus_* — the two-GPU result must equal the one-GPU result of the same conferences, every tick."""
+    import subprocess
+
+    libdir = os.path.join(ROOT, "wmix_b200")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = str(tmp_path / "nccl_from_c")
+    subprocess.check_call(["gcc", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"), "-I", cuda + "/include",
+                           os.path.join(ROOT, "tests", "c", "nccl_from_c.c"), "-L", libdir, "-lwmix_b200", "-Wl,-rpath," + libdir,
+                           "-L", cuda + "/lib64", "-lcudart", "-Wl,-rpath," + cuda + "/lib64", "-lpthread", "-o", exe])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    assert "mismatching blocks = 0" in r.stdout

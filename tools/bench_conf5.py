@@ -49,7 +49,7 @@ def main():
     d_bus = torch.empty((plan.n_conf, frame), dtype=torch.int32, device=dev)
     st = torch.cuda.current_stream()
     res = {}
-    for mode in ("peer", "nccl"):
+    for mode in ("peer", "nccl", "nccl_c"):
         conf = ShardedConference(plan, rank, law=a.law, freq=8000, mode=mode, device=local)
         for t in range(a.warmup):
             conf.tick(pool[t % R], d_out, d_bus)
@@ -76,7 +76,8 @@ def main():
             "workload": "BASELINE config 5: N-minus-one conference mix, %d G.711 (%s) participants at 8 kHz over %d GPU(s), "
                         "%d conferences of %d striped over all ranks" % (total, "A-law" if a.law == 0 else "mu-law", world, plan.n_conf, total // n_conf),
             "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_tick": {"peer (one fused kernel, NVLink peer stores)": res["peer"], "nccl (bus_sum -> all_reduce int32 -> nminus1)": res["nccl"]},
+            "ms_per_tick": {"peer (one fused kernel, NVLink peer stores)": res["peer"], "nccl (bus_sum -> all_reduce int32 -> nminus1)": res["nccl"],
+                            "nccl_c (the same three steps behind wmixb_nccl_bus_tick_device, libnccl opened by the library)": res["nccl_c"]},
             "participants_per_10ms_tick_realtime": {k: total * 10.0 / v for k, v in res.items()},
             "bus_bytes_exchanged_per_rank": plan.n_conf * frame * 4 * (world - 1),
             "algorithmic_bytes_per_participant_tick": 160,

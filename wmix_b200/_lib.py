@@ -103,6 +103,11 @@ def lib():
         "wmixb_set_default_device": (i, [i]),
         "wmixb_default_device": (i, []),
         "wmixb_tick_host_g711": (i, [vp, i, vp, vp, vp, vp, i, i]),
+        "wmixb_nccl_load": (i, [C.c_char_p]),
+        "wmixb_nccl_unique_id": (i, [vp]),
+        "wmixb_nccl_bus_create": (i, [vp, i, i, vp, C.POINTER(vp)]),
+        "wmixb_nccl_bus_destroy": (None, [vp]),
+        "wmixb_nccl_bus_tick_device": (i, [vp, i, vp, vp, vp, vp]),
         "wmixb_set_default_ns_core": (i, [i]),
         "wmixb_default_ns_core": (i, []),
         "wmixb_host_alloc": (vp, [sz, i, i]),

@@ -8,7 +8,7 @@ clamp16(bus - own) (N-minus-one), re-encoded to G.711 when the leg is an RTP/PCM
 (R:src/wmixTask.c:1176-1320).  int32 addition is exact, so the result does not depend on the number
 of GPUs or on the placement.
 
-Three exchange modes, same bits:
+Four exchange modes, same bits ('nccl_c' = the NCCL exchange behind the C-ABI, wmixb_nccl_bus_*):
   "peer"  one fused kernel per rank (wmixb_peer_bus_tick_device): partial rows are stored straight
           into every peer's mailbox over NVLink and reduced on arrival — compute and collective in
           one launch, no NCCL on the data path;
@@ -90,6 +90,7 @@ class CudaBackend:
         self.eng = Engine(max(1, n_local), freq, stages=0, device=device)
         self.L = lib()
         self.pb = None
+        self.nb = None
 
     def set_conferences(self, conf_start):
         self.eng.set_conferences(conf_start)
@@ -134,6 +135,23 @@ class CudaBackend:
         check(self.L.wmixb_peer_bus_tick_device(self.pb, law, _ptr(d_in), _ptr(d_out), _ptr(d_bus), _stream_ptr(stream)),
               "wmixb_peer_bus_tick_device")
 
+    # NCCL exchange behind the C-ABI (wmixb_nccl_bus_*): libnccl opened by the library itself, no torch.distributed on the data path
+    def nccl_unique_id(self):
+        blob = (C.c_ubyte * 128)()
+        check(self.L.wmixb_nccl_unique_id(blob), "wmixb_nccl_unique_id")
+        return bytes(blob)
+
+    def nccl_create(self, rank, world, id_blob):
+        h = C.c_void_p()
+        check(self.L.wmixb_nccl_bus_create(self.eng.h, rank, world, id_blob, C.byref(h)), "wmixb_nccl_bus_create")
+        self.nb = h
+
+    def nccl_tick(self, law, d_in, d_out, d_bus, stream):
+        from .engine import _ptr, _stream_ptr
+
+        check(self.L.wmixb_nccl_bus_tick_device(self.nb, law, _ptr(d_in), _ptr(d_out), _ptr(d_bus), _stream_ptr(stream)),
+              "wmixb_nccl_bus_tick_device")
+
     def peer_status(self):
         err = C.c_int(0)
         check(self.L.wmixb_peer_bus_status(self.pb, C.byref(err)), "wmixb_peer_bus_status")
@@ -143,6 +161,9 @@ class CudaBackend:
         if self.pb:
             self.L.wmixb_peer_bus_destroy(self.pb)
             self.pb = None
+        if self.nb:
+            self.L.wmixb_nccl_bus_destroy(self.nb)
+            self.nb = None
         self.eng.close()
 
 
@@ -154,8 +175,8 @@ class ShardedConference:
 
     def __init__(self, plan, rank, law=0, freq=8000, mode="peer", device=None, group=None, backend=None, dist=None,
                  peer_opts=None):
-        if mode not in ("peer", "nccl", "local"):
-            raise ValueError("mode must be 'peer', 'nccl' or 'local'")
+        if mode not in ("peer", "nccl", "nccl_c", "local"):
+            raise ValueError("mode must be 'peer', 'nccl', 'nccl_c' or 'local'")
         if mode == "local" and plan.spans_ranks():
             raise ValueError("mode 'local' needs a plan whose conferences do not span ranks (placement='local')")
         self.plan, self.rank, self.world, self.law, self.mode, self.group = plan, rank, plan.world, law, mode, group
@@ -177,9 +198,19 @@ class ShardedConference:
                 self.dist.all_gather_object(blobs, mine, group=group)
                 self.backend.peer_connect(blobs)
 
+        if mode == "nccl_c":
+            # the library's own communicator (wmixb_nccl_bus_*): rank 0 makes the id, any transport carries it
+            box = [self.backend.nccl_unique_id() if rank == 0 else None]
+            if self.world > 1:
+                self.dist.broadcast_object_list(box, src=0, group=group)
+            self.backend.nccl_create(rank, self.world, box[0])
+
     def tick(self, d_in, d_out, d_bus, stream=None):
         if self.mode == "peer":
             self.backend.peer_tick(self.law, d_in, d_out, d_bus, stream)
+            return
+        if self.mode == "nccl_c":
+            self.backend.nccl_tick(self.law, d_in, d_out, d_bus, stream)
             return
         self.backend.bus_sum(self.law, d_in, d_bus, stream)
         if self.mode == "nccl" and self.world > 1:

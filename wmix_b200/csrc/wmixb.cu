@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <dlfcn.h>
 #include <sched.h>
 #include <unistd.h>
 
@@ -2124,6 +2125,120 @@ extern "C" int wmixb_peer_bus_tick_device(wmixb_peer_bus* pb, int law, const voi
         return fail_cuda(le, "peer_bus kernel launch", __LINE__);
     }
     return WMIXB_OK;
+}
+
+// ---- the conference-bus exchange over NCCL, reachable from C (include/wmixb.h).  libnccl is opened at run time. ----
+namespace {
+struct NcclId { char internal[WMIXB_NCCL_ID_BYTES]; };
+struct NcclApi {
+    void* lib = nullptr;
+    int (*GetUniqueId)(NcclId*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+std::mutex g_nccl_mu;
+constexpr int kNcclInt32 = 2, kNcclSum = 0;              // ncclDataType_t / ncclRedOp_t values (nccl.h, stable across 2.x)
+
+int nccl_open(const char* path)
+{
+    std::lock_guard<std::mutex> lk(g_nccl_mu);
+    if (g_nccl.lib) return WMIXB_OK;
+    const char* names[] = {path, "libnccl.so.2", "libnccl.so"};
+    void* lib = nullptr;
+    for (const char* n : names) {
+        if (!n) continue;
+        lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (lib || n == path) break;
+    }
+    if (!lib) { snprintf(g_err, sizeof g_err, "NCCL is not available: %s", dlerror()); return WMIXB_ENODEV; }
+    NcclApi a;
+    a.lib = lib;
+    a.GetUniqueId = (int (*)(NcclId*))dlsym(lib, "ncclGetUniqueId");
+    a.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(lib, "ncclCommInitRank");
+    a.AllReduce = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(lib, "ncclAllReduce");
+    a.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+    a.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+    if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy) {
+        snprintf(g_err, sizeof g_err, "NCCL library lacks a required symbol");
+        dlclose(lib);
+        return WMIXB_ENODEV;
+    }
+    g_nccl = a;
+    return WMIXB_OK;
+}
+int nccl_fail(int rc, const char* what)
+{
+    snprintf(g_err, sizeof g_err, "%s failed: %s", what, g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error");
+    return WMIXB_ECUDA;
+}
+}  // namespace
+
+struct wmixb_nccl_bus {
+    wmixb_engine* e = nullptr;
+    void* comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+extern "C" int wmixb_nccl_load(const char* libnccl_path) { return nccl_open(libnccl_path); }
+
+extern "C" int wmixb_nccl_unique_id(void* id_out)
+{
+    if (!id_out) return WMIXB_EINVAL;
+    const int rc = nccl_open(nullptr);
+    if (rc) return rc;
+    NcclId id;
+    const int n = g_nccl.GetUniqueId(&id);
+    if (n) return nccl_fail(n, "ncclGetUniqueId");
+    memcpy(id_out, &id, sizeof id);
+    return WMIXB_OK;
+}
+
+extern "C" int wmixb_nccl_bus_create(wmixb_engine* e, int rank, int world, const void* id, wmixb_nccl_bus** out)
+{
+    if (!e || !id || !out || world < 1 || rank < 0 || rank >= world) return WMIXB_EINVAL;
+    *out = nullptr;
+    if (e->n_conf < 1) { snprintf(g_err, sizeof g_err, "nccl_bus: call wmixb_set_conferences first"); return WMIXB_EINVAL; }
+    const int rc = nccl_open(nullptr);
+    if (rc) return rc;
+    CK(cudaSetDevice(e->cfg.device));
+    NcclId nid;
+    memcpy(&nid, id, sizeof nid);
+    void* comm = nullptr;
+    const int n = g_nccl.CommInitRank(&comm, world, nid, rank);
+    if (n) return nccl_fail(n, "ncclCommInitRank");
+    wmixb_nccl_bus* nb = new (std::nothrow) wmixb_nccl_bus();
+    if (!nb) { g_nccl.CommDestroy(comm); return WMIXB_ENOMEM; }
+    nb->e = e; nb->comm = comm; nb->rank = rank; nb->world = world;
+    *out = nb;
+    return WMIXB_OK;
+}
+
+extern "C" void wmixb_nccl_bus_destroy(wmixb_nccl_bus* nb)
+{
+    if (!nb) return;
+    if (nb->comm && g_nccl.CommDestroy) {
+        cudaSetDevice(nb->e->cfg.device);
+        g_nccl.CommDestroy(nb->comm);
+    }
+    delete nb;
+}
+
+extern "C" int wmixb_nccl_bus_tick_device(wmixb_nccl_bus* nb, int law, const void* d_in, void* d_out, int32_t* d_bus, void* stream)
+{
+    if (!nb || !d_in || !d_bus || law < -1 || law > 1) return WMIXB_EINVAL;
+    wmixb_engine* e = nb->e;
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = law < 0 ? bus_sum_impl<-1>(e, d_in, d_bus, st) : (law == 0 ? bus_sum_impl<0>(e, d_in, d_bus, st) : bus_sum_impl<1>(e, d_in, d_bus, st));
+    if (rc) return rc;
+    if (nb->world > 1) {
+        const int n = g_nccl.AllReduce(d_bus, d_bus, (size_t)e->n_conf * e->frame, kNcclInt32, kNcclSum, nb->comm, st);
+        if (n) return nccl_fail(n, "ncclAllReduce");
+    }
+    if (d_out) rc = law < 0 ? nminus1_impl<-1>(e, d_bus, d_in, d_out, st) : (law == 0 ? nminus1_impl<0>(e, d_bus, d_in, d_out, st) : nminus1_impl<1>(e, d_bus, d_in, d_out, st));
+    return rc;
 }
 
 extern "C" int wmixb_peer_bus_status(wmixb_peer_bus* pb, int* h_error)
