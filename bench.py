@@ -194,7 +194,7 @@ def conf5_leg(torch, dist, world, rank, local, dev, conf_size, steps=200, warmup
     pool = torch.randint(0, 256, (R, n_local, frame), generator=g, dtype=torch.uint8).to(dev)
     st = torch.cuda.current_stream()
     res, outs, buses = {}, {}, {}
-    for mode in ("peer", "nccl"):
+    for mode in ("peer", "nccl", "nccl_c"):
         conf = ShardedConference(plan, rank, law=law, freq=8000, mode=mode, device=local)
         d_out = torch.empty_like(pool[0])
         d_bus = torch.empty((plan.n_conf, frame), dtype=torch.int32, device=dev)
@@ -235,19 +235,21 @@ def conf5_leg(torch, dist, world, rank, local, dev, conf_size, steps=200, warmup
     want_codes = torch.empty((n_local, frame), dtype=torch.uint8, device=dev)
     g711_encode(law, want_pcm, want_codes, n_local * frame, st)
     torch.cuda.synchronize()
-    ok = bool(torch.equal(buses["peer"], want_bus)) and bool(torch.equal(buses["nccl"], want_bus)) \
-        and bool(torch.equal(outs["peer"], want_codes)) and bool(torch.equal(outs["nccl"], want_codes)) \
-        and res["peer_ok"] and res["nccl_ok"]
-    stats = torch.tensor([res["peer"], res["nccl"], 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
+    ok = all(bool(torch.equal(buses[m], want_bus)) and bool(torch.equal(outs[m], want_codes)) and res[m + "_ok"]
+             for m in ("peer", "nccl", "nccl_c"))
+    stats = torch.tensor([res["peer"], res["nccl"], res["nccl_c"], 0.0 if ok else 1.0], dtype=torch.float64, device=dev)
     dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-    peer_us, nccl_us, bad = [float(v) for v in stats.cpu()]
+    peer_us, nccl_us, nccl_c_us, bad = [float(v) for v in stats.cpu()]
     return {"participants": total, "conferences": n_conf, "conference_size": total // n_conf, "law": "A-law" if law == 0 else "mu-law",
-            "peer_us": peer_us, "nccl_us": nccl_us, "fused_le_nccl": peer_us <= nccl_us,
+            "peer_us": peer_us, "nccl_us": nccl_us, "nccl_c_us": nccl_c_us, "fused_le_nccl": peer_us <= min(nccl_us, nccl_c_us),
             "bus_bytes": n_conf * frame * 4, "nvlink_bytes_per_rank_per_tick": n_conf * frame * 4 * (world - 1),
             "parity_ok": bad == 0.0, "steps": steps,
-            "participants_realtime_per_10ms_tick": {"peer": total * 10.0 / (peer_us * 1e-3), "nccl": total * 10.0 / (nccl_us * 1e-3)},
+            "participants_realtime_per_10ms_tick": {"peer": total * 10.0 / (peer_us * 1e-3), "nccl": total * 10.0 / (nccl_us * 1e-3),
+                                                    "nccl_c": total * 10.0 / (nccl_c_us * 1e-3)},
             "paths": {"peer": "wmixb_peer_bus_tick_device: one fused kernel per rank, partial rows stored into every peer's mailbox over NVLink",
-                      "nccl": "wmixb_g711_bus_sum_device -> all_reduce(int32, SUM) -> wmixb_g711_nminus1_device"}}
+                      "nccl": "wmixb_g711_bus_sum_device -> torch.distributed all_reduce(int32, SUM) -> wmixb_g711_nminus1_device",
+                      "nccl_c": "wmixb_nccl_bus_tick_device: the same three steps on ONE stream behind the C-ABI, ncclAllReduce from the "
+                                "library's own communicator (libnccl opened at run time)"}}
 
 
 def config4_leg(torch, dev, local, peak, steps=60, warmup=420, streams=16384):

@@ -16,7 +16,7 @@ for f in ("gpurun_out/${TAG}_bench_n$N.json", "gpurun_out/${TAG}_bench_reference
         d = [json.loads(l) for l in open(f) if l.startswith("{")][-1]
         c5 = d.get("conf5") or {}
         print(f, {k: d.get(k) for k in ("value", "ms_per_step", "kernel_ms")}, "e2e", d.get("e2e", {}).get("value"), d.get("e2e", {}).get("ms_per_step"), "ceiling", d.get("e2e", {}).get("copy_ceiling_ms_per_step"),
-              "bus_only", (d.get("e2e", {}).get("bus_only") or {}).get("ms_per_step"), {k: (v["peer_us"], v["nccl_us"], v["parity_ok"]) for k, v in c5.items()}, (d.get("full_load") or {}).get("ms_per_tick"))
+              "bus_only", (d.get("e2e", {}).get("bus_only") or {}).get("ms_per_step"), {k: (v["peer_us"], v["nccl_us"], v.get("nccl_c_us"), v["parity_ok"]) for k, v in c5.items()}, (d.get("full_load") or {}).get("ms_per_tick"))
     except Exception as ex:
         print(f, "unreadable", ex)
 PY
