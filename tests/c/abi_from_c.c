@@ -27,6 +27,14 @@ int main(void)
         printf("wmixb_create(32 kHz, ns_core 1) without a GPU -> %d\n", wmixb_create(&c32, &e32));
         if (e32) wmixb_destroy(e32);
     }
+    {
+        /* the NCCL exchange opens libnccl at run time: a wrong path is an error code and a message, not a link failure */
+        wmixb_nccl_bus *nb = 0;
+        int nrc = wmixb_nccl_load("/nonexistent/libnccl.so.2");
+        printf("wmixb_nccl_load(bad path) -> %d (%s)\n", nrc, wmixb_last_error());
+        if (nrc != WMIXB_ENODEV || wmixb_nccl_bus_create(0, 0, 1, "x", &nb) != WMIXB_EINVAL || nb) return 4;
+        wmixb_nccl_bus_destroy(0);
+    }
     wmixb_mix_view v = {0};
     uint32_t tick = 0;
     printf("load_data on a stopped mixer -> %p\n", (void *)wmixb_load_data_host(&v, (const uint8_t *)"ab", 2, 16000, 1, 16, 0, 0, &tick));

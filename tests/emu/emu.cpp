@@ -55,6 +55,7 @@ struct EmuNsCtaT {
     std::vector<ns::WWarp<ANA>> ww;
     ns::RWarp rw;
     ns::Tables<ANA> T;
+    bool defer_first = false;
     explicit EmuNsCtaT(int w) : W(w), rec((size_t)w * G::kRecFloats, 0.f), tiles((size_t)8 * G::kShFloats, 0.f), hist((size_t)w * 3 * ns::kHistBins, 0),
                                 hptr(8, nullptr), ww(w)
     {
@@ -75,11 +76,19 @@ struct EmuNsCtaT {
             act[j] = ns::w_seg1<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, in + (size_t)j * G::kBlock, out + (size_t)j * G::kBlock, sh, T);
         }
         ns::r_seg1<ANA>(rw, tiles.data(), G::kShFloats, W, T);
+        // r_seg1b runs concurrently with the workers' segment 2 on the device; `defer_first` picks which side goes first here, and
+        // the tests run both orders.  (r_seg2b would be legal behind w_seg3a too — kept in the second order as a check of that.)
+        if (defer_first) ns::r_seg1b<ANA>(rw, tiles.data(), G::kShFloats, T);
         for (int j = 0; j < W; ++j)
             if (act[j]) ns::w_seg2<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, tiles.data() + (size_t)j * G::kShFloats, T);
-        ns::r_seg2<ANA>(rw, tiles.data(), G::kShFloats, hptr.data(), T);
+        if (!defer_first) ns::r_seg1b<ANA>(rw, tiles.data(), G::kShFloats, T);
+        ns::r_seg2a<ANA>(rw, tiles.data(), G::kShFloats, hptr.data(), T);
+        if (defer_first) ns::r_seg2b<ANA>(rw, tiles.data(), G::kShFloats, T);
         for (int j = 0; j < W; ++j)
-            if (act[j]) ns::w_seg3<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, hptr[j], tiles.data() + (size_t)j * G::kShFloats, T);
+            if (act[j]) ns::w_seg3a<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, hptr[j], tiles.data() + (size_t)j * G::kShFloats, T);
+        if (!defer_first) ns::r_seg2b<ANA>(rw, tiles.data(), G::kShFloats, T);
+        for (int j = 0; j < W; ++j)
+            if (act[j]) ns::w_seg3b<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, tiles.data() + (size_t)j * G::kShFloats, T);
         ns::r_seg3<ANA>(rw, tiles.data(), G::kShFloats, T);
         for (int j = 0; j < W; ++j)
             if (act[j]) ns::w_seg4<ANA>(ww[j], rec.data() + (size_t)j * G::kRecFloats, out + (size_t)j * G::kBlock, tiles.data() + (size_t)j * G::kShFloats, T);
@@ -240,6 +249,12 @@ void* emu_nscta_create(int freq, int workers)
     if (e->ana == 256) e->e256 = new EmuNsCtaT<256>(workers);
     else e->e128 = new EmuNsCtaT<128>(workers);
     return e;
+}
+void emu_nscta_order(void* h, int defer_first)
+{
+    EmuNsCta* e = (EmuNsCta*)h;
+    if (e->e256) e->e256->defer_first = defer_first != 0;
+    else e->e128->defer_first = defer_first != 0;
 }
 void emu_nscta_frame(void* h, const int16_t* in, int16_t* out, const uint8_t* live)
 {

@@ -143,13 +143,14 @@ def test_emulated_kernel_bodies_vs_reference(freq, stage):
         assert np.array_equal(ya, yb), (stage, freq, s)
 
 
-@pytest.mark.parametrize("freq,workers", [(16000, 8), (8000, 8), (16000, 3)])
-def test_emulated_cta_ns_equals_single_warp_ns_and_reference(freq, workers):
+@pytest.mark.parametrize("freq,workers,order", [(16000, 8, 0), (16000, 8, 1), (8000, 8, 0), (8000, 8, 1), (16000, 3, 1)])
+def test_emulated_cta_ns_equals_single_warp_ns_and_reference(freq, workers, order):
     """The CTA-cooperative NS (ns_cta.cuh: worker warps + one reducer warp that walks every in-order sum, the scalar model
     and the Nyquist bin of all the CTA's streams) against the single-warp body (ns.cuh) it re-distributes: outputs, the
     whole per-stream record and the feature histograms, bit for bit, over 720 frames (past the start-up model at 50, the
     gain map at 200 and the first histogram re-learning at 500), with an all-zero cohort stream, a stream that joins late
-    and an idle worker slot.  One stream is also checked against the reference itself."""
+    and an idle worker slot.  One stream is also checked against the reference itself.  `order`: the reducer's deferred parts
+    (r_seg1b, r_seg2b) run concurrently with the workers' next segment on the device — here either side goes first."""
     import ctypes as C
 
     E = emu()
@@ -161,6 +162,7 @@ def test_emulated_cta_ns_equals_single_warp_ns_and_reference(freq, workers):
     if workers > 2:
         x[100:140, 2, :] = 0                             # zero frames in the middle of a live stream
     h = C.c_void_p(E.emu_nscta_create(freq, workers))
+    E.emu_nscta_order(h, order)
     singles = [C.c_void_p(E.emu_ns_create(freq)) for _ in range(workers)]
     rec_floats = E.emu_ns_rec_floats(freq)
     live = np.ones(workers, np.uint8)

@@ -28,10 +28,12 @@ def main():
     dev = torch.device("cuda", 0)
     st = torch.cuda.current_stream()
     ticks = int(os.environ.get("SAN_TICKS", "3"))
-    for freq, S in ((16000, 83), (8000, 45)):
+    for freq, S, ns_cfg in ((16000, 83, -1), (8000, 45, -1), (8000, 45, 0)):     # 8 kHz also in the CTA-cooperative shape
         L = freq // 100
         x = make_frames(S, freq, 0, ticks, seed=3)
         eng = wmix_b200.Engine(S, freq)
+        if ns_cfg >= 0:
+            eng.set_tuning("ns_cfg", ns_cfg)
         eng.set_conferences(np.array([0, 7, 7, 40, S], dtype=np.int32))
         d_in = torch.empty((S, L), dtype=torch.int16, device=dev)
         d_out = torch.empty_like(d_in)
@@ -49,6 +51,8 @@ def main():
         torch.cuda.synchronize()
         eng.close()
         print("ns/agc/vad/bus %d Hz ok" % freq, flush=True)
+    if os.environ.get("SAN_ONLY", "") == "ns":
+        return
     # the fixed-point suppressor: mono ticks in the default shape and two others (all-zero stream 1 leaves the frame early),
     # offline frames, the second band, a 32 kHz engine
     if os.environ.get("SAN_ONLY", "") in ("", "nsx"):

@@ -68,6 +68,8 @@ struct WWarp {
 // reducer lane state that lives across its three segments
 struct RLane {
     float re, mag, lm, noise, prev, prob127;
+    float lrt_prev, gain_prior;       // carried from segment 2a to the deferred Nyquist part 2b
+    float mag0;                       // carried from segment 1 to the deferred part 1b
     int frame_idx, active;
 };
 struct RWarp {
@@ -533,19 +535,15 @@ WMX_HD void w_seg2(WarpT& W, float* rec, float* sh, const Tables<ANA>& T)
     WMX_CTA_PHASE_END
 }
 
-// segment 3: probability, noise update, Wiener gain, state back, inverse split, inverse transform, scale.
-// Leaves the scaled time signal in f[] (element pair lane + 32 r -> samples 2c, 2c+1) and its squares in the sum rows.
+// segment 3a: probability, noise update, Wiener gain, state back (everything that does not involve the Nyquist bin)
 template <int ANA, typename WarpT>
-WMX_HD void w_seg3(WarpT& W, float* rec, uint16_t* hist, float* sh, const Tables<ANA>& T)
+WMX_HD void w_seg3a(WarpT& W, float* rec, uint16_t* hist, float* sh, const Tables<ANA>& T)
 {
     typedef Geo<ANA> G;
     typedef WLane<ANA> L;
-    constexpr int NR = G::kNc / 32;
     float* tb = sh + G::kShTime;
-    float* xb = sh + G::kShX;
     float* sv = sh + G::kShSum;
     float* sc = sh + G::kShScal;
-    float* nq = sh + G::kShNyq;
 
     WMX_CTA_PHASE_BEGIN(L)
     {
@@ -592,15 +590,29 @@ WMX_HD void w_seg3(WarpT& W, float* rec, uint16_t* hist, float* sh, const Tables
 #pragma unroll
             for (int s = 0; s < G::kSlots; ++s) rec[G::kOffArrays + a * G::kBody + 32 * s + lane] = R.st[a][s];
         }
-        rec[G::kOffNyq + lane] = lane < 16 ? nq[lane] : 0.f;        // the reducer finished the Nyquist line before barrier 4
     }
     WMX_CTA_PHASE_END
 
     cta_fetch_mirrors<ANA>(W);
+}
+
+// segment 3b: Nyquist line back, inverse split, inverse transform, scale.
+// Leaves the scaled time signal in f[] (element pair lane + 32 r -> samples 2c, 2c+1) and its squares in the sum rows.
+template <int ANA, typename WarpT>
+WMX_HD void w_seg3b(WarpT& W, float* rec, float* sh, const Tables<ANA>& T)
+{
+    typedef Geo<ANA> G;
+    typedef WLane<ANA> L;
+    constexpr int NR = G::kNc / 32;
+    float* xb = sh + G::kShX;
+    float* sv = sh + G::kShSum;
+    float* sc = sh + G::kShScal;
+    float* nq = sh + G::kShNyq;
 
     // inverse real split (rdft isgn<0 head + rftbsub, fft4g.c:345-350, :1259-1283): every lane its elements lane + 32 r
     WMX_CTA_PHASE_BEGIN(L)
     {
+        rec[G::kOffNyq + lane] = lane < 16 ? nq[lane] : 0.f;        // the reducer finished the Nyquist line in segment 2b
         const float nyq_fre = sc[C_NYQ_FRE];
 #pragma unroll
         for (int r = 0; r < NR; ++r) {
@@ -817,37 +829,23 @@ WMX_HD void r_seg1(RWarpT& W, float* tiles, int tile_stride, int n_workers, cons
             sc[C_PNUM] = pnum;
             sc[C_PEXP] = pexp;
             sc[C_USE_PINK] = use_pink;
-            if (frame_idx < kStartupLong) {
-                float f5 = sc[S_FEAT5];
-                f5 *= frame_idx;
-                f5 += sig_e;
-                f5 /= (frame_idx + 1);
-                sc[S_FEAT5] = f5;
-            }
-            // spectral flatness (ns_core.c:523-557); |X|+1 >= 1 so the log(0) escape never fires.  mag of bin 0 is row 1's
-            // first entry
-            {
-                float den = sum_magn;
-                den -= (sh + G::kShSum)[1 * G::kSumStride + 0];
-                float num = sc[C_COUNT_ + 2];
-                den = den / G::kBins;
-                num = num / G::kBins;
-                const float v = exp_f(num, T.dm) / den;
-                float f0 = sc[S_FEAT0];
-                f0 += 0.3f * (v - f0);
-                sc[S_FEAT0] = f0;
-            }
             sc[C_AVGPAUSE] = sc[C_COUNT_ + 3] / nb;
             sc[C_AVGMAGN] = sum_magn / nb;
+            R.mag0 = (sh + G::kShSum)[1 * G::kSumStride + 0];      // mag of bin 0 (row 1's first entry), for the flatness in 1b
         }
     }
     WMX_CTA_PHASE_END
 }
 
-// segment 2: Nyquist SNR / LRT, sums (covariance, two variances, LRT sum), difference feature, histograms and threshold
-// re-learning, indicator functions, prior, Nyquist probability and filter (ns_core.c:566-846, :293-520, :985-1010)
+// The reducer's chains are what the workers wait for, so what the workers do NOT need at a hand-over is taken off that chain.
+//
+// segment 1b: Nyquist SNR / LRT (ns_core.c:566-640) and the two features only the reducer's own segment 2 reads.  The kernel
+// runs it AFTER releasing the workers into their segment 2 (which touches neither the scalar line nor the Nyquist line and
+// writes other columns of the sum rows), i.e. concurrently with it.  Measured: 0.623 against 0.632 ms per 100 000-stream tick.
+// (Deferring the Nyquist probability / filter of segment 2 the same way needs one more meeting point before the workers'
+// inverse transform; that cost more than it hid: 0.672 ms with a barrier per worker, 0.700 ms with one CTA-wide barrier.)
 template <int ANA, typename RWarpT>
-WMX_HD void r_seg2(RWarpT& W, float* tiles, int tile_stride, uint16_t* const* hists, const Tables<ANA>& T)
+WMX_HD void r_seg1b(RWarpT& W, float* tiles, int tile_stride, const Tables<ANA>& T)
 {
     typedef Geo<ANA> G;
     WMX_CTA_PHASE_BEGIN(RLane)
@@ -862,9 +860,38 @@ WMX_HD void r_seg2(RWarpT& W, float* tiles, int tile_stride, uint16_t* const* hi
             bin_snr<ANA>(T, sv, G::kBody, R.frame_idx, sc[C_USE_PINK] != 0.f, sc[S_WHITE], sc[C_PNUM], sc[C_PEXP], sc[C_AVGMAGN], sc[C_AVGPAUSE],
                          R.mag, R.noise, nq[A_MAGN_PREV], nq[A_NOISE_PREV], nq[A_SMOOTH], nq[A_PAUSE], nq[A_LRT], R.prev, pn);
             if (R.frame_idx < kStartupShort) nq[A_PARAM_NOISE] = pn;
+            // the two features only the reducer's own segment 2a reads: long-term signal energy (ns_core.c:1141-1147) ...
+            const int frame_idx = R.frame_idx;
+            if (frame_idx < kStartupLong) {
+                float f5 = sc[S_FEAT5];
+                f5 *= frame_idx;
+                f5 += sc[C_COUNT_ + 0];
+                f5 /= (frame_idx + 1);
+                sc[S_FEAT5] = f5;
+            }
+            // ... and spectral flatness (ns_core.c:523-557); |X|+1 >= 1 so the log(0) escape never fires
+            {
+                float den = sc[C_COUNT_ + 1];
+                den -= R.mag0;
+                float num = sc[C_COUNT_ + 2];
+                den = den / G::kBins;
+                num = num / G::kBins;
+                const float v = exp_f(num, T.dm) / den;
+                float f0 = sc[S_FEAT0];
+                f0 += 0.3f * (v - f0);
+                sc[S_FEAT0] = f0;
+            }
         }
     }
     WMX_CTA_PHASE_END
+}
+
+// segment 2a: sums (covariance, two variances, LRT sum), difference feature, histograms and threshold re-learning,
+// indicator functions, prior (ns_core.c:641-738, :293-520) — ends with everything the workers' segment 3 starts from
+template <int ANA, typename RWarpT>
+WMX_HD void r_seg2a(RWarpT& W, float* tiles, int tile_stride, uint16_t* const* hists, const Tables<ANA>& T)
+{
+    typedef Geo<ANA> G;
     WMX_CTA_PHASE_BEGIN(RLane)
     {
         const int j = lane >> 2, k = lane & 3;
@@ -1011,7 +1038,6 @@ WMX_HD void r_seg2(RWarpT& W, float* tiles, int tile_stride, uint16_t* const* hi
         float* sh = tiles + (size_t)j * tile_stride;
         float* sv = sh + G::kShSum;
         float* sc = sh + G::kShScal;
-        float* nq = sh + G::kShNyq;
         if (R.active && k == 0) {
             // prior update (ns_core.c:731-738)
             const float ind = sc[S_PM4] * sc[C_COUNT_ + 12] + sc[S_PM5] * sc[C_COUNT_ + 13] + sc[S_PM6] * sc[C_COUNT_ + 14];
@@ -1022,9 +1048,31 @@ WMX_HD void r_seg2(RWarpT& W, float* tiles, int tile_stride, uint16_t* const* hi
             sc[S_PRIOR_PROB] = pp;
             const float gain_prior = fdiv(1.f - pp, pp + 0.0001f);
             sc[C_GAIN_PRIOR] = gain_prior;
-            // Nyquist bin: probability (its look-back neighbour, bin kBody-1, is re-derived here from the LRT row the worker
-            // staged — the same arithmetic, so the same value the worker will compute), noise update, gain, filtered value
-            const float p_prev = bin_prob<ANA>(T, sv[3 * G::kSumStride + G::kBody - 1], gain_prior);
+            sc[C_WANT_E] = (T.gainmap == 1 && R.frame_idx > kStartupLong) ? 1.f : 0.f;
+            sc[C_FACTOR] = 1.f;
+            R.gain_prior = gain_prior;
+            R.lrt_prev = sv[3 * G::kSumStride + G::kBody - 1];     // the workers reuse the sum rows from here on
+        }
+    }
+    WMX_CTA_PHASE_END
+}
+
+// segment 2b: Nyquist probability, noise update, gain, filtered value (ns_core.c:741-846, :985-1010)
+template <int ANA, typename RWarpT>
+WMX_HD void r_seg2b(RWarpT& W, float* tiles, int tile_stride, const Tables<ANA>& T)
+{
+    typedef Geo<ANA> G;
+    WMX_CTA_PHASE_BEGIN(RLane)
+    {
+        const int j = lane >> 2, k = lane & 3;
+        float* sh = tiles + (size_t)j * tile_stride;
+        float* sc = sh + G::kShScal;
+        float* nq = sh + G::kShNyq;
+        if (R.active && k == 0) {
+            const float gain_prior = R.gain_prior;
+            // the look-back neighbour, bin kBody-1, is re-derived here from the LRT the worker staged — the same arithmetic,
+            // so the same value the worker computes
+            const float p_prev = bin_prob<ANA>(T, R.lrt_prev, gain_prior);
             const float ps = bin_prob<ANA>(T, nq[A_LRT], gain_prior);
             float init_magn = nq[A_INIT_MAGN];
             const float h = bin_filter<ANA>(T, R.frame_idx, R.mag, ps, p_prev > 0.2f, nq[A_NOISE_PREV], nq[A_PAUSE], R.prev, init_magn,
@@ -1033,8 +1081,6 @@ WMX_HD void r_seg2(RWarpT& W, float* tiles, int tile_stride, uint16_t* const* hi
             nq[A_SMOOTH] = h;
             nq[A_MAGN_PREV] = R.mag;
             sc[C_NYQ_FRE] = R.re * h;
-            sc[C_WANT_E] = (T.gainmap == 1 && R.frame_idx > kStartupLong) ? 1.f : 0.f;
-            sc[C_FACTOR] = 1.f;
         }
     }
     WMX_CTA_PHASE_END

@@ -251,7 +251,10 @@ ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Ta
                 if (act) ns::w_seg2<ANA>(Wk, r, tile, *T);
                 named_bar_arrive(3, kThreads);
                 named_bar_sync(4, kThreads);
-                if (act) ns::w_seg3<ANA>(Wk, r, h, tile, *T);
+                if (act) {
+                    ns::w_seg3a<ANA>(Wk, r, h, tile, *T);
+                    ns::w_seg3b<ANA>(Wk, r, tile, *T);
+                }
                 named_bar_arrive(5, kThreads);
                 named_bar_sync(6, kThreads);
                 if (act) ns::w_seg4<ANA>(Wk, r, po + (size_t)f * G::kBlock, tile, *T);
@@ -271,8 +274,10 @@ ns_cta_kernel(float* __restrict__ rec, uint16_t* __restrict__ hist, const ns::Ta
                 named_bar_sync(1, kThreads);
                 ns::r_seg1<ANA>(Rd, tiles, G::kShFloats, W, *T);
                 named_bar_arrive(2, kThreads);
+                ns::r_seg1b<ANA>(Rd, tiles, G::kShFloats, *T);                 // behind the workers' segment 2, off their critical path
                 named_bar_sync(3, kThreads);
-                ns::r_seg2<ANA>(Rd, tiles, G::kShFloats, hptr, *T);
+                ns::r_seg2a<ANA>(Rd, tiles, G::kShFloats, hptr, *T);
+                ns::r_seg2b<ANA>(Rd, tiles, G::kShFloats, *T);
                 named_bar_arrive(4, kThreads);
                 named_bar_sync(5, kThreads);
                 ns::r_seg3<ANA>(Rd, tiles, G::kShFloats, *T);
