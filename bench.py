@@ -54,8 +54,8 @@ AEC_BYTES_PER_STREAM_TICK = 29.0e3     # AEC at 8 kHz
 NSX_BYTES_PER_STREAM_TICK = 9.93e3     # fixed-point NS: 4.64 KB of record read + 4.64 KB written + PCM in/out
 # dram__bytes_read.sum + dram__bytes_write.sum of one NS launch per stream: a CONSTANT taken from the latest
 # `ncu --set full` capture (it cannot be measured inside an unprofiled run); see NS_TRAFFIC_SOURCE
-NS_DRAM_TRAFFIC_PER_STREAM_NCU = (875.078656e6 + 649.003520e6) / 100_000
-NS_TRAFFIC_SOURCE = "constant from ncu --set full capture r2_z (profiles/r2_z_summary.md), not measured in this run"
+NS_DRAM_TRAFFIC_PER_STREAM_NCU = (874.530048e6 + 650.368000e6) / 100_000
+NS_TRAFFIC_SOURCE = "constant from ncu --set full capture r2zz (profiles/r2zz_summary.md), not measured in this run"
 
 
 def peaks():
