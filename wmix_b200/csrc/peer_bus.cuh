@@ -46,12 +46,39 @@ __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
 {
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ __forceinline__ unsigned long long globaltimer_ns()
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v)
 {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+// Spin until *f == seq.  The time-out runs on the SM's cycle counter (%globaltimer is slow to read and coarse); `timeout`
+// is in cycles.  Returns false when it gave up.
+__device__ __forceinline__ bool wait_flag(const uint32_t* f, uint32_t seq, long long timeout)
+{
+    if (ld_acquire_sys(f) == seq) return true;
+    const long long t0 = clock64();
+    while (ld_acquire_sys(f) != seq) {
+        if (clock64() - t0 > timeout) return false;
+        __nanosleep(20);
+    }
+    return true;
+}
+// Publish: every thread of the CTA has issued its (local and peer) stores; after the CTA barrier ONE warp fences at system
+// scope — cumulativity makes the whole CTA's stores visible before anything that warp writes afterwards — and then sets
+// the flags with plain system-scope stores.  (A fence in every thread and a release per flag cost a system-scope round
+// trip each: fifteen warps' worth instead of one.)
+#define WMX_PEER_PUBLISH(COUNT, FLAG_PTR_EXPR)                                    \
+    __syncthreads();                                                              \
+    if (threadIdx.x < 32) {                                                       \
+        __threadfence_system();                                                   \
+        for (int j = threadIdx.x; j < (COUNT); j += 32) {                         \
+            uint32_t* fp_ = (FLAG_PTR_EXPR);                                      \
+            if (fp_) st_relaxed_sys(fp_, seq);                                    \
+        }                                                                         \
+    }
+
+// sum of the members first + slice, first + slice + S, ... of one sample column: four loads in flight per trip
+template <int LAW>
+__device__ __forceinline__ int32_t sum_members(const void* src, int first, int last, int slice, int S, int frame, int col);
 
 template <int LAW>
 __device__ __forceinline__ int load_sample(const void* src, size_t idx)
@@ -59,6 +86,44 @@ __device__ __forceinline__ int load_sample(const void* src, size_t idx)
     if (LAW < 0) return static_cast<const int16_t*>(src)[idx];
     const uint8_t c = static_cast<const uint8_t*>(src)[idx];
     return LAW == 0 ? alaw2linear(c) : ulaw2linear(c);
+}
+
+template <int LAW>
+__device__ __forceinline__ int32_t sum_members(const void* src, int first, int last, int slice, int S, int frame, int col)
+{
+    int32_t acc = 0;
+    int p = first + slice;
+    for (; p + 3 * S < last; p += 4 * S) {
+        const int a0 = load_sample<LAW>(src, (size_t)p * frame + col), a1 = load_sample<LAW>(src, (size_t)(p + S) * frame + col);
+        const int a2 = load_sample<LAW>(src, (size_t)(p + 2 * S) * frame + col), a3 = load_sample<LAW>(src, (size_t)(p + 3 * S) * frame + col);
+        acc += (a0 + a1) + (a2 + a3);               // int32: exact in any order
+    }
+    for (; p < last; p += S) acc += load_sample<LAW>(src, (size_t)p * frame + col);
+    return acc;
+}
+// N-minus-one read-out of the members first + slice, ... of one sample column against the finished bus value b
+template <int LAW>
+__device__ __forceinline__ void emit_members(const void* src, void* out, int32_t b, int first, int last, int slice, int S, int frame, int col)
+{
+    auto put = [&](size_t idx, int own) {
+        const int16_t v = sat16(b - own);
+        if (LAW < 0) static_cast<int16_t*>(out)[idx] = v;
+        else static_cast<uint8_t*>(out)[idx] = LAW == 0 ? linear2alaw(v) : linear2ulaw(v);
+    };
+    int p = first + slice;
+    for (; p + 3 * S < last; p += 4 * S) {
+        const size_t i0 = (size_t)p * frame + col, i1 = (size_t)(p + S) * frame + col, i2 = (size_t)(p + 2 * S) * frame + col,
+                     i3 = (size_t)(p + 3 * S) * frame + col;
+        const int a0 = load_sample<LAW>(src, i0), a1 = load_sample<LAW>(src, i1), a2 = load_sample<LAW>(src, i2), a3 = load_sample<LAW>(src, i3);
+        put(i0, a0);
+        put(i1, a1);
+        put(i2, a2);
+        put(i3, a3);
+    }
+    for (; p < last; p += S) {
+        const size_t idx = (size_t)p * frame + col;
+        put(idx, load_sample<LAW>(src, idx));
+    }
 }
 
 // LAW < 0: int16 PCM in/out; 0 / 1: A-law / mu-law codes in/out.
@@ -78,7 +143,7 @@ template <int LAW, int TILE>
 __global__ void __launch_bounds__(kThreads)
 peer_bus_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __restrict__ src, void* __restrict__ out,
                 int32_t* __restrict__ bus_out, const int32_t* __restrict__ conf_start, int n_conf, int frame, int S,
-                unsigned long long timeout_ns, int* __restrict__ error)
+                long long timeout, int* __restrict__ error)
 {
     extern __shared__ int32_t sh_all[];             // per group: [S][TILE] partials + [TILE] finished tile
     const int gthreads = TILE * S;
@@ -99,10 +164,7 @@ peer_bus_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __rest
         const bool valid = t < n_tiles;
         const int c = valid ? t / tiles_per_row : 0, x0 = valid ? (t - c * tiles_per_row) * TILE : 0;
         int32_t acc = 0;
-        if (valid) {
-            const int first = conf_start[c], last = conf_start[c + 1];
-            for (int p = first + slice; p < last; p += S) acc += load_sample<LAW>(src, (size_t)p * frame + x0 + tx);
-        }
+        if (valid) acc = sum_members<LAW>(src, conf_start[c], conf_start[c + 1], slice, S, frame, x0 + tx);
         __syncthreads();                            // the previous step's readers are done with sh
         sh[slice * TILE + tx] = acc;
         __syncthreads();
@@ -121,14 +183,11 @@ peer_bus_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __rest
             }
     }
     // one system-scope fence per CTA, then the flags of all of its tiles (a fence per tile would cost an
-    // NVLink round trip each)
-    __threadfence_system();
-    __syncthreads();
-    for (int j = threadIdx.x; j < steps * G * world; j += blockDim.x) {
-        const int r = j % world, k = j / world;                            // k = it * G + g
-        const int t = ((k / G) * gridDim.x + blockIdx.x) * G + (k % G);
-        if (t < n_tiles) st_release_sys(ring.flags[r] + ((size_t)par * world + rank) * n_tiles + t, seq);
-    }
+    // NVLink round trip each); flag j: rank j % world, tile k = j / world = it * G + g
+    WMX_PEER_PUBLISH(steps * G * world,
+                     ((((j / world) / G) * gridDim.x + blockIdx.x) * G + ((j / world) % G)) < n_tiles
+                         ? ring.flags[j % world] + ((size_t)par * world + rank) * n_tiles + ((((j / world) / G) * gridDim.x + blockIdx.x) * G + ((j / world) % G))
+                         : nullptr)
 
     // ---- phase 2: gather, reduce, N-minus-one ----
     const int32_t* my_slots = ring.slots[rank] + (size_t)par * world * row_words;
@@ -137,14 +196,7 @@ peer_bus_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __rest
         const int t = (it * gridDim.x + blockIdx.x) * G + g;
         const bool valid = t < n_tiles;
         const int c = valid ? t / tiles_per_row : 0, x0 = valid ? (t - c * tiles_per_row) * TILE : 0;
-        if (valid && gt < world) {
-            const uint32_t* f = my_flags + (size_t)gt * n_tiles + t;
-            const unsigned long long t0 = globaltimer_ns();
-            while (ld_acquire_sys(f) != seq) {
-                if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(error, 1 + gt); break; }
-                __nanosleep(32);
-            }
-        }
+        if (valid && gt < world && !wait_flag(my_flags + (size_t)gt * n_tiles + t, seq, timeout)) atomicExch(error, 1 + gt);
         __syncthreads();
         if (valid && gt < TILE) {
             int32_t v = 0;
@@ -153,16 +205,7 @@ peer_bus_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __rest
             if (bus_out) bus_out[(size_t)c * frame + x0 + gt] = v;
         }
         __syncthreads();
-        if (valid && out) {
-            const int32_t b = done[tx];
-            const int first = conf_start[c], last = conf_start[c + 1];
-            for (int p = first + slice; p < last; p += S) {
-                const size_t idx = (size_t)p * frame + x0 + tx;
-                const int16_t v = sat16(b - load_sample<LAW>(src, idx));
-                if (LAW < 0) static_cast<int16_t*>(out)[idx] = v;
-                else static_cast<uint8_t*>(out)[idx] = LAW == 0 ? linear2alaw(v) : linear2ulaw(v);
-            }
-        }
+        if (valid && out) emit_members<LAW>(src, out, done[tx], conf_start[c], conf_start[c + 1], slice, S, frame, x0 + tx);
     }
 }
 
@@ -182,7 +225,7 @@ template <int LAW, int TILE>
 __global__ void __launch_bounds__(kThreads)
 peer_bus_rs_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __restrict__ src, void* __restrict__ out,
                    int32_t* __restrict__ bus_out, const int32_t* __restrict__ conf_start, int n_conf, int S,
-                   unsigned long long timeout_ns, int* __restrict__ error)
+                   long long timeout, int* __restrict__ error)
 {
     extern __shared__ int32_t sh_all[];             // per group: [S][TILE] partials + [TILE] finished row
     const int gthreads = TILE * S;
@@ -202,10 +245,7 @@ peer_bus_rs_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __r
         const int c = (it * gridDim.x + blockIdx.x) * G + g;
         const bool valid = c < n_conf;
         int32_t acc = 0;
-        if (valid) {
-            const int first = conf_start[c], last = conf_start[c + 1];
-            for (int p = first + slice; p < last; p += S) acc += load_sample<LAW>(src, (size_t)p * TILE + tx);
-        }
+        if (valid) acc = sum_members<LAW>(src, conf_start[c], conf_start[c + 1], slice, S, TILE, tx);
         __syncthreads();
         sh[slice * TILE + tx] = acc;
         __syncthreads();
@@ -220,12 +260,11 @@ peer_bus_rs_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __r
             for (int j = gt; j < TILE / 4; j += gthreads) dst[j] = reinterpret_cast<const int4*>(done)[j];
         }
     }
-    __threadfence_system();
-    __syncthreads();
-    for (int j = threadIdx.x; j < steps * G; j += blockDim.x) {
-        const int c = ((j / G) * gridDim.x + blockIdx.x) * G + (j % G);
-        if (c < n_conf) st_release_sys(ring.flags[c % world] + ((size_t)par * world + rank) * n_conf + c, seq);
-    }
+    WMX_PEER_PUBLISH(steps * G,
+                     (((j / G) * gridDim.x + blockIdx.x) * G + (j % G)) < n_conf
+                         ? ring.flags[(((j / G) * gridDim.x + blockIdx.x) * G + (j % G)) % world] + ((size_t)par * world + rank) * n_conf +
+                               (((j / G) * gridDim.x + blockIdx.x) * G + (j % G))
+                         : nullptr)
 
     // ---- phase 2a: the rows this rank owns: wait for the partials, reduce, push the finished row to everybody ----
     const int32_t* my_slots = ring.slots[rank] + (size_t)par * world * row_words;
@@ -234,14 +273,7 @@ peer_bus_rs_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __r
         const int k = (it * gridDim.x + blockIdx.x) * G + g;
         const bool valid = k < n_owned;
         const int c = valid ? k * world + rank : 0;
-        if (valid && gt < world) {
-            const uint32_t* f = my_flags + (size_t)gt * n_conf + c;
-            const unsigned long long t0 = globaltimer_ns();
-            while (ld_acquire_sys(f) != seq) {
-                if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(error, 1 + gt); break; }
-                __nanosleep(32);
-            }
-        }
+        if (valid && gt < world && !wait_flag(my_flags + (size_t)gt * n_conf + c, seq, timeout)) atomicExch(error, 1 + gt);
         __syncthreads();
         if (valid && gt < TILE) {
             int32_t v = 0;
@@ -257,13 +289,10 @@ peer_bus_rs_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __r
             }
         __syncthreads();                            // done is rewritten by the next step
     }
-    __threadfence_system();
-    __syncthreads();
-    for (int j = threadIdx.x; j < osteps * G * world; j += blockDim.x) {
-        const int r = j % world, kk = j / world;
-        const int k = ((kk / G) * gridDim.x + blockIdx.x) * G + (kk % G);
-        if (k < n_owned) st_release_sys(ring.rflags[r] + (size_t)par * n_conf + (size_t)k * world + rank, seq);
-    }
+    WMX_PEER_PUBLISH(osteps * G * world,
+                     ((((j / world) / G) * gridDim.x + blockIdx.x) * G + ((j / world) % G)) < n_owned
+                         ? ring.rflags[j % world] + (size_t)par * n_conf + (size_t)((((j / world) / G) * gridDim.x + blockIdx.x) * G + ((j / world) % G)) * world + rank
+                         : nullptr)
 
     // ---- phase 2b: finished rows in, N-minus-one out ----
     const int32_t* my_result = ring.result[rank] + (size_t)par * row_words;
@@ -271,13 +300,7 @@ peer_bus_rs_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __r
     for (int it = 0; it < steps; ++it) {
         const int c = (it * gridDim.x + blockIdx.x) * G + g;
         const bool valid = c < n_conf;
-        if (valid && gt == 0) {
-            const unsigned long long t0 = globaltimer_ns();
-            while (ld_acquire_sys(my_rflags + c) != seq) {
-                if (globaltimer_ns() - t0 > timeout_ns) { atomicExch(error, 1 + c % world); break; }
-                __nanosleep(32);
-            }
-        }
+        if (valid && gt == 0 && !wait_flag(my_rflags + c, seq, timeout)) atomicExch(error, 1 + c % world);
         __syncthreads();
         if (valid && gt < TILE) {
             const int32_t v = __ldcg(my_result + (size_t)c * TILE + gt);
@@ -285,16 +308,7 @@ peer_bus_rs_kernel(Ring ring, int rank, int world, uint32_t seq, const void* __r
             if (bus_out) bus_out[(size_t)c * TILE + gt] = v;
         }
         __syncthreads();
-        if (valid && out) {
-            const int32_t b = done[tx];
-            const int first = conf_start[c], last = conf_start[c + 1];
-            for (int p = first + slice; p < last; p += S) {
-                const size_t idx = (size_t)p * TILE + tx;
-                const int16_t v = sat16(b - load_sample<LAW>(src, idx));
-                if (LAW < 0) static_cast<int16_t*>(out)[idx] = v;
-                else static_cast<uint8_t*>(out)[idx] = LAW == 0 ? linear2alaw(v) : linear2ulaw(v);
-            }
-        }
+        if (valid && out) emit_members<LAW>(src, out, done[tx], conf_start[c], conf_start[c + 1], slice, S, TILE, tx);
     }
 }
 

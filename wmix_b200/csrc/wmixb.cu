@@ -1936,6 +1936,7 @@ struct wmixb_peer_bus {
     uint32_t seq = 0;
     int* d_error = nullptr;
     unsigned long long timeout_ns = 2000000000ull;
+    long long timeout_cycles = 4000000000ll;                 // timeout_ns on the SM cycle counter (set at create)
 };
 
 struct PeerMeta { int32_t magic, world, n_conf, frame; };   // rides behind the 64-byte IPC handle
@@ -1995,6 +1996,11 @@ extern "C" int wmixb_peer_bus_create_ex(wmixb_engine* e, int rank, int world, co
     const int groups = pb->threads / (slices * pb->tile);
     pb->smem = (size_t)groups * (slices + 1) * pb->tile * sizeof(int32_t);
     if (o.timeout_ms > 0) pb->timeout_ns = (unsigned long long)o.timeout_ms * 1000000ull;
+    {
+        int khz = 0;
+        if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, e->cfg.device) != cudaSuccess || khz < 1) khz = 2000000;
+        pb->timeout_cycles = (long long)((double)pb->timeout_ns * (double)khz / 1e6);
+    }
     const size_t mailbox_bytes = pb->slot_bytes + pb->flag_bytes + pb->result_bytes + pb->rflag_bytes;
     cudaError_t ce = cudaMalloc(&pb->mailbox, mailbox_bytes);
     if (ce == cudaSuccess) ce = cudaMemset(pb->mailbox, 0, mailbox_bytes);
@@ -2113,9 +2119,9 @@ extern "C" int wmixb_peer_bus_tick_device(wmixb_peer_bus* pb, int law, const voi
     const uint32_t seq_before = pb->seq;
     if (++pb->seq == 0) pb->seq = 2;     // 0 is the "never written" flag value; keep the parity sequence alternating
     cudaStream_t st = (cudaStream_t)stream;
-#define WMX_PEER(LAW, TILE) peer::peer_bus_kernel<LAW, TILE><<<pb->grid, pb->threads, pb->smem, st>>>(pb->ring, pb->rank, pb->world, pb->seq, d_in, d_out, d_bus, e->conf_start, pb->n_conf, e->frame, pb->slices, pb->timeout_ns, pb->d_error)
+#define WMX_PEER(LAW, TILE) peer::peer_bus_kernel<LAW, TILE><<<pb->grid, pb->threads, pb->smem, st>>>(pb->ring, pb->rank, pb->world, pb->seq, d_in, d_out, d_bus, e->conf_start, pb->n_conf, e->frame, pb->slices, pb->timeout_cycles, pb->d_error)
 #define WMX_PEER_T(TILE) do { if (law < 0) WMX_PEER(-1, TILE); else if (law == 0) WMX_PEER(0, TILE); else WMX_PEER(1, TILE); } while (0)
-#define WMX_PEER_RS(LAW, TILE) peer::peer_bus_rs_kernel<LAW, TILE><<<pb->grid, pb->threads, pb->smem, st>>>(pb->ring, pb->rank, pb->world, pb->seq, d_in, d_out, d_bus, e->conf_start, pb->n_conf, pb->slices, pb->timeout_ns, pb->d_error)
+#define WMX_PEER_RS(LAW, TILE) peer::peer_bus_rs_kernel<LAW, TILE><<<pb->grid, pb->threads, pb->smem, st>>>(pb->ring, pb->rank, pb->world, pb->seq, d_in, d_out, d_bus, e->conf_start, pb->n_conf, pb->slices, pb->timeout_cycles, pb->d_error)
 #define WMX_PEER_RS_T(TILE) do { if (law < 0) WMX_PEER_RS(-1, TILE); else if (law == 0) WMX_PEER_RS(0, TILE); else WMX_PEER_RS(1, TILE); } while (0)
     if (pb->rs) { if (pb->tile == 80) WMX_PEER_RS_T(80); else WMX_PEER_RS_T(160); }
     else if (pb->tile == 16) WMX_PEER_T(16); else if (pb->tile == 80) WMX_PEER_T(80); else WMX_PEER_T(160);
