@@ -173,6 +173,30 @@ def _nccl_worker(rank, world, port, sizes, law, q, opts=None):
             conf.close()
         ok &= all(np.array_equal(a, b) for a, b in zip(results["peer"], results["nccl"]))
         ok &= all(np.array_equal(a, b) for a, b in zip(results["peer"], results["nccl_c"]))
+        # soak: many back-to-back ticks (no host synchronisation in between, both mailbox parities, ranks drifting apart), the
+        # fused exchange against the NCCL one on the same legs, compared on the device every tick
+        a = ShardedConference(plan, rank, law=law, freq=8000, mode="peer", device=rank, peer_opts=opts)
+        b = ShardedConference(plan, rank, law=law, freq=8000, mode="nccl_c", device=rank)
+        g = torch.Generator(device="cpu").manual_seed(77 + rank)
+        n_local = len(mine)
+        pool = (torch.randint(0, 256, (16, n_local, frame), generator=g, dtype=torch.uint8) if law >= 0
+                else torch.randint(-32768, 32768, (16, n_local, frame), generator=g, dtype=torch.int16)).to(dev)
+        out = torch.empty_like(pool[0])
+        bus = torch.empty((plan.n_conf, frame), dtype=torch.int32, device=dev)
+        w_out = torch.randint(1, 1 << 20, out.shape, generator=g, dtype=torch.int64).to(dev)
+        w_bus = torch.randint(1, 1 << 20, bus.shape, generator=g, dtype=torch.int64).to(dev)
+        sums = torch.zeros((2, 400), dtype=torch.int64, device=dev)
+        for k, conf in enumerate((b, a)):                # the fused ticks run alone, nothing else keeps the ranks in step
+            for t in range(400):
+                conf.tick(pool[t % 16], out, bus)
+                sums[k, t] = (out.to(torch.int64) * w_out).sum() + (bus.to(torch.int64) * w_bus).sum()
+            torch.cuda.synchronize()
+            dist.barrier()
+        bad = (sums[0] != sums[1]).sum()
+        ok &= int(bad.item()) == 0 and a.status() == 0
+        dist.barrier()
+        a.close()
+        b.close()
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()

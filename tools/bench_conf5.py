@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--steps", type=int, default=300)
     ap.add_argument("--warmup", type=int, default=30)
     ap.add_argument("--law", type=int, default=0)
+    ap.add_argument("--rs", type=int, default=-1, help="fused kernel: force the reduce-scatter exchange on (1) / off (0); -1 = the library's choice")
+    ap.add_argument("--tile", default="", help="fused kernel: 'row' or 16 (samples per tile); '' = the library's choice")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -50,7 +52,12 @@ def main():
     st = torch.cuda.current_stream()
     res = {}
     for mode in ("peer", "nccl", "nccl_c"):
-        conf = ShardedConference(plan, rank, law=a.law, freq=8000, mode=mode, device=local)
+        opts = {}
+        if a.rs >= 0:
+            opts["reduce_scatter"] = a.rs
+        if a.tile:
+            opts["tile"] = "row" if a.tile == "row" else int(a.tile)
+        conf = ShardedConference(plan, rank, law=a.law, freq=8000, mode=mode, device=local, peer_opts=(opts or None) if mode == "peer" else None)
         for t in range(a.warmup):
             conf.tick(pool[t % R], d_out, d_bus)
         if world > 1:
@@ -75,7 +82,7 @@ def main():
         print(json.dumps({
             "workload": "BASELINE config 5: N-minus-one conference mix, %d G.711 (%s) participants at 8 kHz over %d GPU(s), "
                         "%d conferences of %d striped over all ranks" % (total, "A-law" if a.law == 0 else "mu-law", world, plan.n_conf, total // n_conf),
-            "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "fused_opts": {"reduce_scatter": a.rs, "tile": a.tile or "default"},
             "ms_per_tick": {"peer (one fused kernel, NVLink peer stores)": res["peer"], "nccl (bus_sum -> all_reduce int32 -> nminus1)": res["nccl"],
                             "nccl_c (the same three steps behind wmixb_nccl_bus_tick_device, libnccl opened by the library)": res["nccl_c"]},
             "participants_per_10ms_tick_realtime": {k: total * 10.0 / v for k, v in res.items()},
