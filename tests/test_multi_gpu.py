@@ -28,20 +28,22 @@ def _legs(law, T, total, frame, seed):
 
 @pytest.mark.parametrize("law,freq,sizes", [(0, 8000, [1, 2, 3, 58, 0, 700]), (1, 8000, [16] * 300), (-1, 16000, [5, 1200, 33])])
 def test_peer_bus_world1_matches_oracle(law, freq, sizes):
+    """one rank, no peers: the fused kernel and the C-side NCCL bus (wmixb_nccl_bus_*, which needs no communicator here)"""
     plan = ConferencePlan(sizes, 1)
     frame = freq // 100
     legs = _legs(law, 4, plan.total, frame, 5)
-    conf = ShardedConference(plan, 0, law=law, freq=freq, mode="peer", device=0)
-    d_bus = torch.empty((plan.n_conf, frame), dtype=torch.int32, device="cuda:0")
-    for t in range(4):
-        d_in = torch.from_numpy(legs[t]).to("cuda:0")
-        d_out = torch.empty_like(d_in)
-        conf.tick(d_in, d_out, d_bus)
-        bus, out = conference_oracle(law, legs[t], plan.global_start)
-        assert np.array_equal(d_bus.cpu().numpy(), bus)
-        assert np.array_equal(d_out.cpu().numpy(), out)
-    assert conf.status() == 0
-    conf.close()
+    for mode in ("peer", "nccl_c"):
+        conf = ShardedConference(plan, 0, law=law, freq=freq, mode=mode, device=0)
+        d_bus = torch.empty((plan.n_conf, frame), dtype=torch.int32, device="cuda:0")
+        for t in range(4):
+            d_in = torch.from_numpy(legs[t]).to("cuda:0")
+            d_out = torch.empty_like(d_in)
+            conf.tick(d_in, d_out, d_bus)
+            bus, out = conference_oracle(law, legs[t], plan.global_start)
+            assert np.array_equal(d_bus.cpu().numpy(), bus), mode
+            assert np.array_equal(d_out.cpu().numpy(), out), mode
+        assert conf.status() == 0
+        conf.close()
 
 
 def _run_local_ranks(devices, law, sizes, opts=None, T=5):

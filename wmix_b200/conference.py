@@ -200,7 +200,7 @@ class ShardedConference:
 
         if mode == "nccl_c":
             # the library's own communicator (wmixb_nccl_bus_*): rank 0 makes the id, any transport carries it
-            box = [self.backend.nccl_unique_id() if rank == 0 else None]
+            box = [self.backend.nccl_unique_id() if (rank == 0 and self.world > 1) else bytes(128)]
             if self.world > 1:
                 self.dist.broadcast_object_list(box, src=0, group=group)
             self.backend.nccl_create(rank, self.world, box[0])

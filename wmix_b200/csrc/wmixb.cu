@@ -2212,14 +2212,16 @@ extern "C" int wmixb_nccl_bus_create(wmixb_engine* e, int rank, int world, const
     if (!e || !id || !out || world < 1 || rank < 0 || rank >= world) return WMIXB_EINVAL;
     *out = nullptr;
     if (e->n_conf < 1) { snprintf(g_err, sizeof g_err, "nccl_bus: call wmixb_set_conferences first"); return WMIXB_EINVAL; }
-    const int rc = nccl_open(nullptr);
-    if (rc) return rc;
-    CK(cudaSetDevice(e->cfg.device));
-    NcclId nid;
-    memcpy(&nid, id, sizeof nid);
     void* comm = nullptr;
-    const int n = g_nccl.CommInitRank(&comm, world, nid, rank);
-    if (n) return nccl_fail(n, "ncclCommInitRank");
+    if (world > 1) {                         // a single rank exchanges nothing: no communicator, NCCL need not even be installed
+        const int rc = nccl_open(nullptr);
+        if (rc) return rc;
+        CK(cudaSetDevice(e->cfg.device));
+        NcclId nid;
+        memcpy(&nid, id, sizeof nid);
+        const int n = g_nccl.CommInitRank(&comm, world, nid, rank);
+        if (n) return nccl_fail(n, "ncclCommInitRank");
+    }
     wmixb_nccl_bus* nb = new (std::nothrow) wmixb_nccl_bus();
     if (!nb) { g_nccl.CommDestroy(comm); return WMIXB_ENOMEM; }
     nb->e = e; nb->comm = comm; nb->rank = rank; nb->world = world;
