@@ -10,8 +10,8 @@
 //
 // Phase 1 (per 16-sample tile of a conference row this CTA owns): sum the local members (decoding G.711
 //   in registers) and store the tile into slot [parity][my_rank] of EVERY rank's mailbox (16-byte stores;
-//   peer stores ride NVLink); then one fence at system scope and flags[parity][my_rank][tile] = seq on
-//   every rank for each of the CTA's tiles.
+//   peer stores ride NVLink); then the CTA meets, one warp fences at system scope and sets
+//   flags[parity][my_rank][tile] = seq on every rank for each of the CTA's tiles (WMX_PEER_PUBLISH).
 // Phase 2 (same tiles): wait until all `world` flags of the tile carry `seq`, add the `world` partial
 //   tiles in rank order (int32: exact, so any order gives the same bits), and emit
 //   out = clamp16(bus - own) for the local members (re-encoded for the G.711 variants).
