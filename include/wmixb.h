@@ -298,7 +298,7 @@ int wmixb_set_default_ns_core(int ns_core);
 int wmixb_default_ns_core(void);
 
 /* experiment / test knobs; none changes results.  keys: "ns_cfg", "nsx_cfg", "ns_align", "post_occ", "aec_pf", "aec_grid",
- * "host_chunks", "host_lanes" */
+ * "host_chunks", "host_lanes", "host_zero_copy" (small engines: kernels run on a pinned device-mapped staging block) */
 int wmixb_set_tuning(wmixb_engine* e, const char* key, int value);
 
 /* bookkeeping */
