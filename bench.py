@@ -459,6 +459,9 @@ def run_ours(args):
         eng.set_tuning("ns_cfg", args.ns_cfg)            # kernel-shape experiments (tools/); the default is the library's
     if args.post_occ >= 0:
         eng.set_tuning("post_occ", args.post_occ)
+    for kv in args.tune:
+        k, v = kv.split("=")
+        eng.set_tuning(k, int(v))
     R = args.ring
     # tick inputs live in pinned host memory placed for this GPU (wmixb_host_alloc), the device copy is made from it
     h_pool = HostBuffer((R, S, FRAME), np.int16, device=local)
@@ -696,6 +699,7 @@ def main():
     ap.add_argument("--full-load-streams", type=int, default=1_000_000)
     ap.add_argument("--ns-cfg", type=int, default=-1, help="experiment: NS kernel shape index (wmixb_set_tuning)")
     ap.add_argument("--post-occ", type=int, default=-1, help="experiment: AGC+VAD kernel shape (wmixb_set_tuning)")
+    ap.add_argument("--tune", action="append", default=[], metavar="KEY=VALUE", help="experiment: any wmixb_set_tuning knob of the main engine")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
